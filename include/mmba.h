@@ -1,0 +1,171 @@
+/*
+ * mmba.h — C-ABI of libmmba.so, the B200 (sm_100a) bundle-adjustment engine that replaces the
+ * `scipy.optimize.least_squares(...)` call inside MeatModeler's `bundleAdjuster.adjustPoints`
+ * (reference: bundleAdjuster.py:179-192; caller processor.py:465-470).
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative MMBA_ERR_* code on failure; the message
+ *     is retrievable with mmba_last_error().  No exception crosses this boundary.
+ *   - the caller owns every host buffer; the library owns all device memory.
+ *   - a handle is not thread-safe; distinct handles are independent.  All device work of a handle
+ *     runs on one CUDA stream; every entry point returns only after its work has completed.
+ *   - plain pointers and sizes only: no torch / numpy types.
+ *   - there is NO CPU fallback: entry points that compute fail with MMBA_ERR_CUDA when no sm_100
+ *     device is usable.  Functions in the "host-only" section never touch the GPU.
+ *
+ * Parameter vector layout (bundleAdjuster.py:175-176, 96-97):
+ *   x = [ w0 t0 | w1 t1 | ... (6 doubles per camera) | X0 | X1 | ... (3 doubles per point) ]
+ * Residual layout (bundleAdjuster.py:102): f = [du0, dv0, du1, dv1, ...] in the caller's
+ * observation order.
+ */
+#ifndef MMBA_H
+#define MMBA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMBA_VERSION 100 /* 0.1.0 */
+
+enum {
+    MMBA_OK = 0,
+    MMBA_ERR_ARG = -1,       /* bad argument (null pointer, index out of range, size <= 0) */
+    MMBA_ERR_CUDA = -2,      /* CUDA runtime failure or no usable sm_100 device */
+    MMBA_ERR_STATE = -3,     /* call order (solve before set_problem, ...) */
+    MMBA_ERR_NONFINITE = -4, /* residuals not finite at the initial point
+                                (scipy raises ValueError: least_squares.py:945-946) */
+    MMBA_ERR_TRACK = -5,     /* a point has more observations than one tile can hold */
+    MMBA_ERR_NCCL = -6,      /* NCCL failure (multi-GPU only) */
+    MMBA_ERR_NOMEM = -7
+};
+
+typedef struct mmba_handle mmba_handle;
+typedef struct mmba_plan mmba_plan;
+
+typedef struct mmba_options {
+    int32_t device;       /* CUDA device ordinal */
+    int32_t rank;         /* shard rank in [0, nranks) */
+    int32_t nranks;       /* 1 = single GPU; >1 = observations sharded by point, NCCL allreduce */
+    int32_t verbose;      /* 0 silent, 2 = print scipy's verbose=2 iteration table */
+    double ftol;          /* reference value 1e-4 (bundleAdjuster.py:185) */
+    double xtol;          /* scipy default 1e-8 */
+    double gtol;          /* scipy default 1e-8 */
+    int64_t max_nfev;     /* 0 = scipy default 100*n (trf.py:452-453) */
+    double pcg_rtol;      /* relative residual stop of the reduced-system PCG */
+    int32_t pcg_maxit;
+    int32_t profile;      /* 1 = bracket kernels with CUDA events (mmba_get_profile) */
+    uint8_t nccl_id[128]; /* ncclUniqueId bytes, same on all ranks (nranks > 1 only) */
+} mmba_options;
+
+typedef struct mmba_result {
+    double cost;          /* 0.5 * f.f at the returned x */
+    double initial_cost;
+    double optimality;    /* ||J^T f||_inf, unscaled (trf.py:466) */
+    int64_t nfev, njev, nit;
+    int32_t status;       /* scipy termination codes: 0 max_nfev, 1 gtol, 2 ftol, 3 xtol, 4 both */
+    int32_t reserved;
+    int64_t pcg_iterations; /* total reduced-system PCG iterations */
+    double solve_ms;      /* device time of the solve (CUDA events on the handle's stream) */
+} mmba_result;
+
+/* one row per outer iteration, the columns of scipy's verbose=2 table (common.py:545-563) */
+typedef struct mmba_iter_log {
+    int64_t iteration, nfev;
+    double cost, cost_reduction, step_norm, optimality;
+    double reg, delta;
+    int64_t pcg_iterations;
+} mmba_iter_log;
+
+/* kernel classes of mmba_get_profile */
+enum {
+    MMBA_K_CAMPREP = 0,
+    MMBA_K_BUILD = 1,     /* residual + Jacobian blocks + normal-equation blocks */
+    MMBA_K_RESID = 2,     /* trial residual / cost */
+    MMBA_K_PTINV = 3,     /* damped 3x3 point-block inversion */
+    MMBA_K_RHS = 4,       /* Schur right-hand side + Schur diagonal blocks */
+    MMBA_K_MATVEC = 5,    /* implicit Schur-complement product (PCG) */
+    MMBA_K_BACKSUB = 6,
+    MMBA_K_JV = 7,        /* J*v products (Cauchy step, 2-D subspace Gram) */
+    MMBA_K_VEC = 8,       /* small vector kernels */
+    MMBA_K_ALLREDUCE = 9,
+    MMBA_K_COUNT = 10
+};
+
+int mmba_version(void);
+const char* mmba_last_error(const mmba_handle* h); /* h may be NULL: last error of this thread */
+void mmba_default_options(mmba_options* opt);
+
+/* replaces: the optimiser object scipy builds inside least_squares (least_squares.py:925-934) */
+int mmba_create(mmba_handle** out, const mmba_options* opt);
+void mmba_destroy(mmba_handle* h);
+
+/* replaces: pointAdjustmentSparsity (bundleAdjuster.py:55-78, 179) — the block structure is implied
+ * by the two index arrays.  Copies the problem to the device, narrows indices to int32, reorders
+ * observations into point-aligned tiles and (nranks > 1) keeps only this rank's point range.
+ * All ranks pass the full, identical problem. */
+int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n_obs,
+                     const double K[9], const int64_t* cam_idx, const int64_t* pt_idx,
+                     const double* uv /* n_obs x 2 row-major */);
+
+/* replaces: least_squares(pointFun, x0, jac_sparsity=A, x_scale='jac', ftol=1e-4, method='trf')
+ * (bundleAdjuster.py:180-192).  x is in/out (n = 6*n_cams + 3*n_points); fun_out (2*n_obs, may be
+ * NULL) receives the residuals at the returned x in the caller's observation order. */
+int mmba_solve(mmba_handle* h, double* x, mmba_result* result, double* fun_out);
+
+int mmba_get_log(const mmba_handle* h, mmba_iter_log* out, int capacity); /* returns row count */
+int mmba_get_profile(const mmba_handle* h, int64_t launches[MMBA_K_COUNT], double ms[MMBA_K_COUNT]);
+/* observations / points held by this rank and number of tiles (after set_problem) */
+int mmba_get_shard(const mmba_handle* h, int64_t* n_obs_local, int64_t* n_points_local,
+                   int64_t* n_tiles);
+
+/* ---- evaluation hooks (parity tests; same device code as the solve) ------------------------ */
+/* replaces: pointFun(x, ...) (bundleAdjuster.py:81-102) */
+int mmba_eval_residual(mmba_handle* h, const double* x, double* f /* 2*n_obs */);
+/* replaces: the Jacobian scipy assembles by finite differences (_numdiff.py:770-893); blocks in the
+ * caller's observation order: Jc n_obs x 2 x 6 (columns w0 w1 w2 t0 t1 t2), Jp n_obs x 2 x 3 */
+int mmba_eval_jacobian(mmba_handle* h, const double* x, double* Jc, double* Jp);
+/* J^T J and J^T f block-wise (common.py:590-610): U n_cams x 6 x 6, V n_points x 3 x 3 (full
+ * symmetric), gc n_cams x 6, gp n_points x 3, cost = 0.5 f.f */
+int mmba_eval_blocks(mmba_handle* h, const double* x, double* U, double* V, double* gc, double* gp,
+                     double* cost);
+/* replaces: lsmr(J_h, f, damp=sqrt(reg)) (trf.py:494-495) with J_h = J diag(scale):
+ * solves (J_h^T J_h + reg I) p = J_h^T f by Schur elimination + block-Jacobi PCG. p has n entries. */
+int mmba_eval_gn_step(mmba_handle* h, const double* x, const double* scale, double reg, double* p,
+                      int64_t* pcg_iterations, double* pcg_relres);
+/* J * s for an n-vector s -> 2*n_obs (caller's observation order); test hook for the J*v kernel
+ * (build_quadratic_1d / evaluate_quadratic, common.py:282-288, 348-361): returns ||J s||^2 */
+int mmba_eval_jnorm2(mmba_handle* h, const double* x, const double* s, double* jnorm2);
+/* time `iters` back-to-back launches of one kernel class on the current linearisation
+ * (CUDA events on the handle's stream); used by bench.py for the roofline of each kernel */
+int mmba_bench_kernel(mmba_handle* h, const double* x, int kernel_class, int iters, double* avg_ms);
+
+/* ---- host-only functions (no GPU needed; covered by the CPU test-suite) --------------------- */
+/* replaces: solve_trust_region_2d (common.py:171-219); B = [b00, b01, b11] */
+int mmba_host_tr2d(const double B[3], const double g[2], double delta, double p[2], int* newton);
+/* replaces: minimize_quadratic_1d (common.py:298-322) for y = a t^2 + b t on [lb, ub] */
+int mmba_host_min_quadratic_1d(double a, double b, double lb, double ub, double* t, double* y);
+/* replaces: update_tr_radius (common.py:222-245) */
+int mmba_host_update_tr_radius(double delta, double actual, double predicted, double step_norm,
+                               int bound_hit, double* delta_new, double* ratio);
+/* replaces: check_termination (common.py:705-717); returns 0 for "continue", else 2/3/4 */
+int mmba_host_check_termination(double dF, double F, double dx_norm, double x_norm, double ratio,
+                                double ftol, double xtol);
+
+/* tile plan (observation reordering + point sharding) built on the host */
+int mmba_plan_create(mmba_plan** out, int64_t n_cams, int64_t n_points, int64_t n_obs,
+                     const int64_t* cam_idx, const int64_t* pt_idx, int rank, int nranks);
+void mmba_plan_destroy(mmba_plan* p);
+/* sizes[0..7] = n_tiles, n_obs_local, n_points_local, point_begin, point_end (internal order),
+ * tile_obs, max cameras per tile, padded observation slots */
+int mmba_plan_sizes(const mmba_plan* p, int64_t sizes[8]);
+/* obs_perm: for every padded slot the caller's observation index or -1; point_perm: internal
+ * point -> caller's point index (all n_points); tile_of_slot etc. are implied (slot / tile_obs) */
+int mmba_plan_export(const mmba_plan* p, int64_t* obs_perm, int64_t* point_perm,
+                     int32_t* slot_cam_local, int32_t* slot_point_local);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMBA_H */

@@ -1,0 +1,178 @@
+// Host-side tile plan (see plan.h).
+#include "plan.h"
+
+#include <algorithm>
+#include <numeric>
+
+#include "../../include/mmba.h"
+
+namespace mmba {
+
+int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, const int64_t* cam_idx,
+               const int64_t* pt_idx, int rank, int nranks, std::string& err) {
+    if (n_cams <= 0 || n_points <= 0 || n_obs <= 0 || !cam_idx || !pt_idx) {
+        err = "set_problem: sizes must be positive and index arrays non-null";
+        return MMBA_ERR_ARG;
+    }
+    if (nranks < 1 || rank < 0 || rank >= nranks) {
+        err = "set_problem: rank/nranks out of range";
+        return MMBA_ERR_ARG;
+    }
+    if (n_cams > INT32_MAX / 32 || n_points > INT32_MAX / 16 || n_obs > (int64_t)INT32_MAX * 8) {
+        err = "set_problem: problem too large for 32-bit device indices";
+        return MMBA_ERR_ARG;
+    }
+    plan = Plan();
+    plan.n_cams = n_cams;
+    plan.n_points = n_points;
+    plan.n_obs = n_obs;
+    plan.rank = rank;
+    plan.nranks = nranks;
+
+    // 1. per-point observation count and first (smallest) camera
+    std::vector<int32_t> count(n_points, 0), first_cam(n_points, (int32_t)n_cams);
+    for (int64_t i = 0; i < n_obs; ++i) {
+        const int64_t c = cam_idx[i], p = pt_idx[i];
+        if (c < 0 || c >= n_cams || p < 0 || p >= n_points) {
+            err = "set_problem: index out of range at observation " + std::to_string(i);
+            return MMBA_ERR_ARG;
+        }
+        ++count[p];
+        if (c < first_cam[p]) first_cam[p] = (int32_t)c;
+    }
+    for (int64_t p = 0; p < n_points; ++p) {
+        if (count[p] > kTileObs) {
+            err = "set_problem: point " + std::to_string(p) + " has " + std::to_string(count[p]) +
+                  " observations; one tile holds at most " + std::to_string(kTileObs);
+            return MMBA_ERR_TRACK;
+        }
+    }
+
+    // 2. internal point order: counting sort by first camera (stable -> ties by caller index);
+    //    unobserved points (first_cam == n_cams) go last
+    plan.point_perm.resize(n_points);
+    {
+        std::vector<int64_t> bucket(n_cams + 2, 0);
+        for (int64_t p = 0; p < n_points; ++p) ++bucket[first_cam[p] + 1];
+        for (int64_t c = 0; c <= n_cams; ++c) bucket[c + 1] += bucket[c];
+        for (int64_t p = 0; p < n_points; ++p) plan.point_perm[bucket[first_cam[p]]++] = (int32_t)p;
+    }
+    std::vector<int32_t> point_inv(n_points);
+    for (int64_t q = 0; q < n_points; ++q) point_inv[plan.point_perm[q]] = (int32_t)q;
+
+    // 3. shard cuts: contiguous internal point ranges balanced by observation count
+    plan.shard_begin.assign(nranks + 1, n_points);
+    plan.shard_begin[0] = 0;
+    {
+        int64_t acc = 0;
+        int next = 1;
+        for (int64_t q = 0; q < n_points && next < nranks; ++q) {
+            while (next < nranks && acc >= (n_obs * next + nranks - 1) / nranks) {
+                plan.shard_begin[next++] = q;
+            }
+            acc += count[plan.point_perm[q]];
+        }
+        // remaining cuts (if any) stay at n_points -> empty shards
+    }
+    plan.pt_begin = plan.shard_begin[rank];
+    plan.pt_end = plan.shard_begin[rank + 1];
+    const int64_t npl = plan.pt_end - plan.pt_begin;
+
+    // 4. observations of the local points, grouped by internal point (stable), cameras ascending
+    std::vector<int64_t> start(npl + 1, 0);
+    for (int64_t q = 0; q < npl; ++q) start[q + 1] = start[q] + count[plan.point_perm[plan.pt_begin + q]];
+    plan.n_obs_local = start[npl];
+    std::vector<int64_t> grouped(plan.n_obs_local);
+    {
+        std::vector<int64_t> fill(start.begin(), start.end() - 1);
+        for (int64_t i = 0; i < n_obs; ++i) {
+            const int64_t q = (int64_t)point_inv[pt_idx[i]] - plan.pt_begin;
+            if (q >= 0 && q < npl) grouped[fill[q]++] = i;
+        }
+        for (int64_t q = 0; q < npl; ++q) {
+            std::stable_sort(grouped.begin() + start[q], grouped.begin() + start[q + 1],
+                             [&](int64_t a, int64_t b) { return cam_idx[a] < cam_idx[b]; });
+        }
+    }
+
+    // 5. greedy point-aligned tiles
+    struct Range { int64_t p0, p1; };
+    std::vector<Range> ranges;
+    {
+        int64_t p0 = 0, used = 0;
+        for (int64_t q = 0; q < npl; ++q) {
+            const int64_t L = start[q + 1] - start[q];
+            if (L == 0) continue;  // unobserved points sit at the end of the order; never in a tile
+            if (used + L > kTileObs) {
+                ranges.push_back({p0, q});
+                p0 = q;
+                used = 0;
+            }
+            if (used == 0) p0 = q;
+            used += L;
+        }
+        if (used > 0) {
+            int64_t p1 = npl;
+            while (p1 > p0 && start[p1] - start[p1 - 1] == 0) --p1;
+            ranges.push_back({p0, p1});
+        }
+    }
+    plan.n_tiles = (int64_t)ranges.size();
+    plan.n_slots = plan.n_tiles * kTileObs;
+    plan.tiles.resize(plan.n_tiles);
+    plan.slot_obs.assign(plan.n_slots, -1);
+    plan.slot_cam.assign(plan.n_slots, 0);
+    plan.slot_pt.assign(plan.n_slots, 0xFFFF);   // empty slots carry the pad marker
+    plan.sort_src.resize(plan.n_slots);
+    plan.sort_key.assign(plan.n_slots, kPadKey);
+    plan.tile_cams.reserve(plan.n_tiles * 8);
+
+    // 6. per tile: local camera table, local slots, camera-sorted order
+    std::vector<int32_t> stamp(n_cams, -1), local_of(n_cams, 0);
+    std::vector<int32_t> cams;
+    std::vector<uint16_t> idx(kTileObs);
+    for (int64_t t = 0; t < plan.n_tiles; ++t) {
+        const Range rg = ranges[t];
+        const int64_t o0 = start[rg.p0], o1 = start[rg.p1];
+        const int n = (int)(o1 - o0);
+        const int64_t base = t * kTileObs;
+        cams.clear();
+        for (int i = 0; i < n; ++i) {
+            const int32_t c = (int32_t)cam_idx[grouped[o0 + i]];
+            if (stamp[c] != (int32_t)t) {
+                stamp[c] = (int32_t)t;
+                cams.push_back(c);
+            }
+        }
+        std::sort(cams.begin(), cams.end());
+        for (size_t s = 0; s < cams.size(); ++s) local_of[cams[s]] = (int32_t)s;
+        TileInfo& ti = plan.tiles[t];
+        ti.pt0 = (int32_t)rg.p0;
+        ti.npts = (int32_t)(rg.p1 - rg.p0);
+        ti.cam_off = (int32_t)plan.tile_cams.size();
+        ti.ncams = (int32_t)cams.size();
+        plan.max_tile_cams = std::max(plan.max_tile_cams, ti.ncams);
+        plan.max_tile_pts = std::max(plan.max_tile_pts, ti.npts);
+        plan.tile_cams.insert(plan.tile_cams.end(), cams.begin(), cams.end());
+        int i = 0;
+        for (int64_t q = rg.p0; q < rg.p1; ++q) {
+            for (int64_t o = start[q]; o < start[q + 1]; ++o, ++i) {
+                plan.slot_obs[base + i] = grouped[o];
+                plan.slot_cam[base + i] = (uint16_t)local_of[cam_idx[grouped[o]]];
+                plan.slot_pt[base + i] = (uint16_t)(q - rg.p0);
+            }
+        }
+        std::iota(idx.begin(), idx.begin() + n, (uint16_t)0);
+        std::stable_sort(idx.begin(), idx.begin() + n, [&](uint16_t a, uint16_t b) {
+            return plan.slot_cam[base + a] < plan.slot_cam[base + b];
+        });
+        for (int j = 0; j < n; ++j) {
+            plan.sort_src[base + j] = idx[j];
+            plan.sort_key[base + j] = plan.slot_cam[base + idx[j]];
+        }
+        for (int j = n; j < kTileObs; ++j) plan.sort_src[base + j] = (uint16_t)j;
+    }
+    return MMBA_OK;
+}
+
+}  // namespace mmba

@@ -1,0 +1,49 @@
+// Host-side tile plan: observation reordering into point-aligned tiles + point sharding.
+//
+// Replaces what the reference expresses as a sparsity matrix (bundleAdjuster.py:55-78): the block
+// structure of J is implied by (cam_idx, pt_idx); the plan turns it into the streaming layout the
+// kernels want.  Pure C++ (no CUDA) so that the CPU test-suite covers it.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mmba {
+
+constexpr int kTileObs = 256;          // observation slots per tile == threads per CTA
+constexpr uint16_t kPadKey = 0xFFFF;   // sorted-key of an empty slot
+
+struct TileInfo {       // one int4 on the device
+    int32_t pt0;        // first local (shard-relative, internal-order) point of the tile
+    int32_t npts;       // points in the tile
+    int32_t cam_off;    // offset of the tile's camera list in tile_cams
+    int32_t ncams;      // distinct cameras in the tile
+};
+
+struct Plan {
+    int64_t n_cams = 0, n_points = 0, n_obs = 0;
+    int rank = 0, nranks = 1;
+    // internal point order (all points, identical on every rank): sorted by first camera
+    std::vector<int32_t> point_perm;     // internal -> caller
+    std::vector<int64_t> shard_begin;    // nranks+1 cut positions in internal point order
+    int64_t pt_begin = 0, pt_end = 0;    // this rank's internal point range
+    int64_t n_obs_local = 0;
+    // tiles of this rank
+    int64_t n_tiles = 0, n_slots = 0;
+    int max_tile_cams = 0, max_tile_pts = 0;
+    std::vector<TileInfo> tiles;
+    std::vector<int32_t> tile_cams;      // global camera ids, concatenated per tile (ascending)
+    std::vector<int64_t> slot_obs;       // padded slot -> caller's observation index, -1 = empty
+    std::vector<uint16_t> slot_cam;      // local camera slot of the observation in its tile
+    std::vector<uint16_t> slot_pt;       // local point index of the observation in its tile
+    std::vector<uint16_t> sort_src;      // j-th entry of the tile in camera-sorted order -> slot in tile
+    std::vector<uint16_t> sort_key;      // its local camera slot (kPadKey for empty)
+
+    int64_t n_points_local() const { return pt_end - pt_begin; }
+};
+
+// Returns 0 or a negative MMBA_ERR_* code; `err` receives the message.
+int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, const int64_t* cam_idx,
+               const int64_t* pt_idx, int rank, int nranks, std::string& err);
+
+}  // namespace mmba

@@ -1,0 +1,373 @@
+// Small-vector kernels of the TRF / PCG driver (n-vectors and 6*Nc camera vectors).
+//
+// Replaces numpy vector arithmetic inside scipy's trf_no_bounds (trf.py:433-561), compute_grad /
+// compute_jac_scale (common.py:590-610) and LSMR's vector updates (lsmr.py:373-377).
+//
+// Camera-part reductions of the PCG are *deterministic* (per-block partials summed in a fixed
+// order by every consumer block): with cameras replicated across ranks, every rank then takes
+// bit-identical PCG decisions without exchanging flags.
+#pragma once
+#include "kernels.cuh"
+
+namespace mmba {
+
+constexpr int kCamBlock = 128;   // threads per block of the thread-per-camera kernels
+constexpr int kMaxCamBlocks = 1024;
+
+// per-block partial sums of the PCG (deterministic reductions)
+enum Part { P_RHO0 = 0, P_RHO1, P_PQ, P_RR, P_B2, P_COUNT };
+
+__device__ __forceinline__ double block_sum_det(double v, double* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    return t;
+}
+
+// fixed-order sum of nb per-block partials; every thread of the block gets the same value
+__device__ __forceinline__ double sum_partials(const double* __restrict__ part, int nb, double* s_red) {
+    double v = 0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) v += part[i];
+    return block_sum_det(v, s_red);
+}
+
+__device__ __forceinline__ void sym6_matvec(const double* __restrict__ m, const double (&v)[6], double (&o)[6]) {
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        double s = 0;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) s += m[a <= b ? tri6(a, b) : tri6(b, a)] * v[b];
+        o[a] = s;
+    }
+}
+
+// inverse of a symmetric positive definite 6x6 (packed upper triangle in/out) by Cholesky;
+// falls back to the inverse diagonal when the factorisation breaks down
+__device__ __forceinline__ void sym6_inverse(const double (&s)[21], double (&inv)[21]) {
+    double L[6][6];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double d = s[tri6(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+        if (!(d > 0.0)) { ok = false; d = 1.0; }
+        const double l = sqrt(d);
+        L[j][j] = l;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            double v = s[tri6(j, i)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+            L[i][j] = v / l;
+        }
+    }
+    if (!ok) {
+#pragma unroll
+        for (int i = 0; i < 21; ++i) inv[i] = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) inv[tri6(a, a)] = s[tri6(a, a)] > 0.0 ? 1.0 / s[tri6(a, a)] : 1.0;
+        return;
+    }
+    // W = L^-1 (lower triangular), inverse = W^T W
+    double W[6][6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        W[j][j] = 1.0 / L[j][j];
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            double v = 0;
+#pragma unroll
+            for (int k = j; k < i; ++k) v -= L[i][k] * W[k][j];
+            W[i][j] = v / L[i][i];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) {
+            double v = 0;
+#pragma unroll
+            for (int k = b; k < 6; ++k) v += W[k][a] * W[k][b];
+            inv[tri6(a, b)] = v;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scale update + gradient statistics (compute_jac_scale / compute_grad, common.py:590-610;
+// Delta0 = ||x0 * scale_inv||, trf.py:443)
+//   element e of block b = e / BS: diag of the packed upper-triangle block; g_h = g / scale_inv
+// ---------------------------------------------------------------------------------------------
+template <int BS>
+__global__ void scale_grad_kernel(const double* __restrict__ blk, const double* __restrict__ g,
+                                  const double* __restrict__ x, double* __restrict__ sinv, double* __restrict__ gh,
+                                  int first, int64_t n_elem, double* __restrict__ scal, int accumulate) {
+    __shared__ double s_red[64];
+    constexpr int STRIDE = BS * (BS + 1) / 2;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[3] = {0, 0, 0};
+    double gabs = 0;
+    if (e < n_elem) {
+        const int64_t b = e / BS;
+        const int k = (int)(e - b * BS);
+        const double diag = blk[b * STRIDE + (k * BS - k * (k - 1) / 2)];
+        double si = sqrt(diag);
+        if (first) { if (si == 0.0) si = 1.0; }
+        else si = fmax(si, sinv[e]);
+        sinv[e] = si;
+        const double gv = g[e], xv = x[e];
+        const double h = gv / si;
+        gh[e] = h;
+        gabs = fabs(gv);
+        acc[0] = h * h;
+        acc[1] = (xv * si) * (xv * si);
+        acc[2] = xv * xv;
+    }
+    if (!accumulate) return;
+    double* outp[3] = {scal + S_GH2, scal + S_XSI2, scal + S_X2};
+    block_accumulate<3>(acc, s_red, outp);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) gabs = fmax(gabs, __shfl_xor_sync(kFull, gabs, off));
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(reinterpret_cast<unsigned long long*>(scal + S_GINF), (unsigned long long)__double_as_longlong(gabs));
+}
+
+// out = coef * a / sinv   (unscaled image of a scaled vector: d o a)
+__global__ void unscale_kernel(const double* __restrict__ a, const double* __restrict__ sinv, double coef,
+                               double* __restrict__ out, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = coef * a[e] / sinv[e];
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2-D subspace construction  S = orth[g_h, gn_h]  (trf.py:496-500; scipy uses LAPACK QR, here
+// Gram-Schmidt with one re-orthogonalisation; the subspace and therefore the step are the same)
+// ---------------------------------------------------------------------------------------------
+// gn = src * (sinv if MUL_SINV) ; D0 += gh.gn ; D1 += gn.gn
+template <bool MUL_SINV>
+__global__ void gn_assemble_kernel(const double* __restrict__ src, const double* __restrict__ sinv,
+                                   const double* __restrict__ gh, double* __restrict__ gn, int64_t n,
+                                   double* __restrict__ scal, int accumulate) {
+    __shared__ double s_red[64];
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[2] = {0, 0};
+    if (e < n) {
+        const double v = MUL_SINV ? src[e] * sinv[e] : src[e];
+        gn[e] = v;
+        acc[0] = gh[e] * v;
+        acc[1] = v * v;
+    }
+    if (!accumulate) return;
+    double* outp[2] = {scal + S_DOT0, scal + S_DOT1};
+    block_accumulate<2>(acc, s_red, outp);
+}
+
+// s1 = gh * inv_gh ; s2 = gn - c * s1 ; D2 += s1.s2 ; D3 += s2.s2
+__global__ void orth_a_kernel(const double* __restrict__ gh, const double* __restrict__ gn, double inv_gh, double c,
+                              double* __restrict__ s1, double* __restrict__ s2, int64_t n,
+                              double* __restrict__ scal, int accumulate) {
+    __shared__ double s_red[64];
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[2] = {0, 0};
+    if (e < n) {
+        const double a = gh[e] * inv_gh;
+        const double b = gn[e] - c * a;
+        s1[e] = a;
+        s2[e] = b;
+        acc[0] = a * b;
+        acc[1] = b * b;
+    }
+    if (!accumulate) return;
+    double* outp[2] = {scal + S_DOT2, scal + S_DOT3};
+    block_accumulate<2>(acc, s_red, outp);
+}
+
+// s2 -= c2 * s1 (re-orthogonalisation, left unnormalised); v1 = s1/sinv, v2 = s2/sinv (unscaled);
+// D4 += s2.s2 ; D5 += s2.gh ; D6 += v1.v1 ; D7 += v1.v2 ; D8 += v2.v2 ; D9 += s1.gh
+__global__ void orth_b_kernel(const double* __restrict__ gh, const double* __restrict__ sinv, double c2,
+                              const double* __restrict__ s1, double* __restrict__ s2, double* __restrict__ v1,
+                              double* __restrict__ v2, int64_t n, double* __restrict__ scal, int accumulate) {
+    __shared__ double s_red[64];
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    if (e < n) {
+        const double a = s1[e];
+        const double b = s2[e] - c2 * a;
+        const double si = sinv[e];
+        const double va = a / si, vb = b / si;
+        s2[e] = b;
+        v1[e] = va;
+        v2[e] = vb;
+        acc[0] = b * b;
+        acc[1] = b * gh[e];
+        acc[2] = va * va;
+        acc[3] = va * vb;
+        acc[4] = vb * vb;
+        acc[5] = a * gh[e];
+    }
+    if (!accumulate) return;
+    double* outp[6] = {scal + S_DOT4, scal + S_DOT5, scal + S_DOT6, scal + S_DOT7, scal + S_DOT8, scal + S_DOT9};
+    block_accumulate<6>(acc, s_red, outp);
+}
+
+// trial point x_new = x + p0 * v1 + p1 * v2   (x + d o step_h, trf.py:512-513)
+__global__ void trial_kernel(const double* __restrict__ x, const double* __restrict__ v1, const double* __restrict__ v2,
+                             double p0, double p1, double* __restrict__ xn, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) xn[e] = x[e] + p0 * v1[e] + p1 * v2[e];
+}
+
+// ---------------------------------------------------------------------------------------------
+// PCG on the reduced camera system, one thread per camera (block-Jacobi = 6x6 Schur diagonal)
+// ---------------------------------------------------------------------------------------------
+struct PcgVecs {
+    const double* U;      // [Nc][21]
+    const double* gc;     // [Nc][6]
+    const double* sinv;   // [Nc][6] scale_inv of the camera parameters
+    double* y;            // [Nc][6] scatter target of the schur kernels
+    double* Sd;           // [Nc][21]
+    double* Pinv;         // [Nc][21]
+    double *x, *r, *z, *p, *q, *xt;   // [Nc][6]
+    double* part;         // [P_COUNT][kMaxCamBlocks]
+    int* flags;           // [0] done, [1] iterations
+    int n_cams;
+};
+
+// b = d o (g_c - y) ; Pinv = (d d^T o (U - Sd) + reg I)^-1 ; x = 0, r = b, z = Pinv r, p = z, xt = d o p
+__global__ void __launch_bounds__(kCamBlock) pcg_init_kernel(PcgVecs P, double reg) {
+    __shared__ double s_red[8];
+    const int c = blockIdx.x * kCamBlock + threadIdx.x;
+    double rho = 0, b2 = 0;
+    if (c < P.n_cams) {
+        double d[6], b[6], z[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            d[k] = 1.0 / P.sinv[c * 6 + k];
+            b[k] = d[k] * (P.gc[c * 6 + k] - P.y[c * 6 + k]);
+            P.y[c * 6 + k] = 0.0;
+        }
+        double s[21], inv[21];
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int bb = a; bb < 6; ++bb) {
+                const int i = tri6(a, bb);
+                s[i] = d[a] * d[bb] * (P.U[c * 21 + i] - P.Sd[c * 21 + i]) + (a == bb ? reg : 0.0);
+            }
+        sym6_inverse(s, inv);
+#pragma unroll
+        for (int i = 0; i < 21; ++i) P.Pinv[c * 21 + i] = inv[i];
+        sym6_matvec(inv, b, z);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            P.x[c * 6 + k] = 0.0;
+            P.r[c * 6 + k] = b[k];
+            P.z[c * 6 + k] = z[k];
+            P.p[c * 6 + k] = z[k];
+            P.xt[c * 6 + k] = d[k] * z[k];
+            rho += b[k] * z[k];
+            b2 += b[k] * b[k];
+        }
+    }
+    rho = block_sum_det(rho, s_red);
+    b2 = block_sum_det(b2, s_red);
+    if (threadIdx.x == 0) {
+        P.part[P_RHO0 * kMaxCamBlocks + blockIdx.x] = rho;
+        P.part[P_B2 * kMaxCamBlocks + blockIdx.x] = b2;
+        if (blockIdx.x == 0) { P.flags[0] = 0; P.flags[1] = 0; }
+    }
+}
+
+// q = S p = d o (U xt - y) + reg p ; partial p.q ; y <- 0 for the next product
+__global__ void __launch_bounds__(kCamBlock) pcg_a_kernel(PcgVecs P, double reg) {
+    if (P.flags[0]) return;
+    __shared__ double s_red[8];
+    const int c = blockIdx.x * kCamBlock + threadIdx.x;
+    double pq = 0;
+    if (c < P.n_cams) {
+        double xt[6], ux[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) xt[k] = P.xt[c * 6 + k];
+        sym6_matvec(P.U + c * 21, xt, ux);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double pk = P.p[c * 6 + k];
+            const double qk = (ux[k] - P.y[c * 6 + k]) / P.sinv[c * 6 + k] + reg * pk;
+            P.y[c * 6 + k] = 0.0;
+            P.q[c * 6 + k] = qk;
+            pq += pk * qk;
+        }
+    }
+    pq = block_sum_det(pq, s_red);
+    if (threadIdx.x == 0) P.part[P_PQ * kMaxCamBlocks + blockIdx.x] = pq;
+}
+
+// alpha = rho / p.q ; x += alpha p ; r -= alpha q ; z = Pinv r ; partial r.r, r.z
+__global__ void __launch_bounds__(kCamBlock) pcg_b_kernel(PcgVecs P, int it) {
+    if (P.flags[0]) return;
+    __shared__ double s_red[8];
+    const int nb = gridDim.x;
+    const double rho = sum_partials(P.part + (it & 1 ? P_RHO1 : P_RHO0) * kMaxCamBlocks, nb, s_red);
+    const double pq = sum_partials(P.part + P_PQ * kMaxCamBlocks, nb, s_red);
+    const double alpha = rho / pq;
+    const int c = blockIdx.x * kCamBlock + threadIdx.x;
+    double rr = 0, rz = 0;
+    if (c < P.n_cams) {
+        double r[6], z[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            P.x[c * 6 + k] += alpha * P.p[c * 6 + k];
+            r[k] = P.r[c * 6 + k] - alpha * P.q[c * 6 + k];
+            P.r[c * 6 + k] = r[k];
+        }
+        sym6_matvec(P.Pinv + c * 21, r, z);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            P.z[c * 6 + k] = z[k];
+            rr += r[k] * r[k];
+            rz += r[k] * z[k];
+        }
+    }
+    rr = block_sum_det(rr, s_red);
+    rz = block_sum_det(rz, s_red);
+    if (threadIdx.x == 0) {
+        P.part[P_RR * kMaxCamBlocks + blockIdx.x] = rr;
+        P.part[(it & 1 ? P_RHO0 : P_RHO1) * kMaxCamBlocks + blockIdx.x] = rz;
+    }
+}
+
+// convergence test ; beta = rho_new / rho ; p = z + beta p ; xt = d o p
+__global__ void __launch_bounds__(kCamBlock) pcg_c_kernel(PcgVecs P, int it, double rtol2) {
+    if (P.flags[0]) return;
+    __shared__ double s_red[8];
+    const int nb = gridDim.x;
+    const double rho = sum_partials(P.part + (it & 1 ? P_RHO1 : P_RHO0) * kMaxCamBlocks, nb, s_red);
+    const double rho_new = sum_partials(P.part + (it & 1 ? P_RHO0 : P_RHO1) * kMaxCamBlocks, nb, s_red);
+    const double rr = sum_partials(P.part + P_RR * kMaxCamBlocks, nb, s_red);
+    const double b2 = sum_partials(P.part + P_B2 * kMaxCamBlocks, nb, s_red);
+    const double pq = sum_partials(P.part + P_PQ * kMaxCamBlocks, nb, s_red);
+    int done = 0;
+    if (rr <= rtol2 * b2) done = 1;
+    else if (!(pq > 0.0) || !isfinite(rr) || !(rho_new > 0.0)) done = 2;
+    if (done) {
+        // every block takes the same decision; the flag only gates later launches
+        if (blockIdx.x == 0 && threadIdx.x == 0) { P.flags[1] = it + 1; __threadfence(); P.flags[0] = done; }
+        return;
+    }
+    const double beta = rho_new / rho;
+    const int c = blockIdx.x * kCamBlock + threadIdx.x;
+    if (c < P.n_cams) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double pk = P.z[c * 6 + k] + beta * P.p[c * 6 + k];
+            P.p[c * 6 + k] = pk;
+            P.xt[c * 6 + k] = pk / P.sinv[c * 6 + k];
+        }
+    }
+}
+
+}  // namespace mmba
