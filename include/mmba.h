@@ -99,6 +99,9 @@ void mmba_default_options(mmba_options* opt);
 
 /* replaces: the optimiser object scipy builds inside least_squares (least_squares.py:925-934) */
 int mmba_create(mmba_handle** out, const mmba_options* opt);
+/* nranks > 1: rank 0 obtains the ncclUniqueId here and ships it to the other ranks (the Python
+ * layer broadcasts it with torch.distributed); every rank passes it in mmba_options.nccl_id */
+int mmba_nccl_unique_id(uint8_t out[128]);
 void mmba_destroy(mmba_handle* h);
 
 /* replaces: pointAdjustmentSparsity (bundleAdjuster.py:55-78, 179) — the block structure is implied
@@ -161,9 +164,11 @@ void mmba_plan_destroy(mmba_plan* p);
  * tile_obs, max cameras per tile, padded observation slots */
 int mmba_plan_sizes(const mmba_plan* p, int64_t sizes[8]);
 /* obs_perm: for every padded slot the caller's observation index or -1; point_perm: internal
- * point -> caller's point index (all n_points); tile_of_slot etc. are implied (slot / tile_obs) */
+ * point -> caller's point index (all n_points); slot_cam_global / slot_point_local: the camera id
+ * and the shard-relative internal point index each slot resolves to through the tile tables
+ * (-1 for empty slots); the tile of a slot is slot / tile_obs */
 int mmba_plan_export(const mmba_plan* p, int64_t* obs_perm, int64_t* point_perm,
-                     int32_t* slot_cam_local, int32_t* slot_point_local);
+                     int32_t* slot_cam_global, int32_t* slot_point_local);
 
 #ifdef __cplusplus
 }

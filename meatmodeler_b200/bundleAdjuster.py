@@ -1,0 +1,204 @@
+"""Drop-in replacement for MeatModeler's ``bundleAdjuster`` module, backed by ``libmmba.so``.
+
+Put this directory in front of the reference on ``sys.path`` and ``processor.py`` runs unchanged:
+``import bundleAdjuster`` (processor.py:8) then resolves here, and
+``bundleAdjuster.adjustPoints(extrinsics, K, points_3D, points_2D, frame_indices, point_indices)``
+(processor.py:465-470) keeps the reference signature and return value
+(bundleAdjuster.py:160-194: ``(points (Np,3) float64, list of Nc 4x4 float64 extrinsics)``).
+
+Only O(Nc) parameter packing/unpacking happens on the host (``frameParameters``,
+``reformatPointResult`` — bundleAdjuster.py:105-157).  The residual model, the Jacobian and the
+whole trust-region solve run in hand-written CUDA kernels behind the C-ABI of ``include/mmba.h``.
+There is no CPU fallback: without ``libmmba.so`` or without an sm_100 GPU every solve raises.
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+
+import numpy as np
+
+try:
+    from meatmodeler_b200 import _capi
+except ImportError:  # imported as a top-level module with only this directory on sys.path
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from meatmodeler_b200 import _capi
+
+# Defaults of the reference call site (bundleAdjuster.py:180-192) and of scipy's least_squares.
+FTOL = 1e-4
+XTOL = 1e-8
+GTOL = 1e-8
+VERBOSE = 2          # the reference passes verbose=2: scipy prints its iteration table
+
+#: statistics of the most recent solve (scipy ``OptimizeResult``-like fields)
+last_result = None
+
+_STATUS_MESSAGES = {
+    0: "The maximum number of function evaluations is exceeded.",
+    1: "`gtol` termination condition is satisfied.",
+    2: "`ftol` termination condition is satisfied.",
+    3: "`xtol` termination condition is satisfied.",
+    4: "Both `ftol` and `xtol` termination conditions are satisfied.",
+}
+
+
+class SolveResult(dict):
+    """Attribute-style result, the fields scipy's ``OptimizeResult`` carries for this call."""
+    __getattr__ = dict.__getitem__
+
+
+# --------------------------------------------------------------------------------------------------
+# host-side packing (O(Nc) / O(Np) copies, bundleAdjuster.py:105-157)
+# --------------------------------------------------------------------------------------------------
+
+def frameParameters(frame_extrinsic_matrices):
+    """Extrinsic matrices (Nc, 3 or 4, 4) -> flat ``[rvec0 | tvec0 | rvec1 | tvec1 ...]``.
+
+    Same convention as bundleAdjuster.py:105-134: rotation angle from the trace, axis from the
+    antisymmetric part divided by ``2 sin(angle)``, with 0/0 mapped to 0 (so the identity rotation
+    gives a zero vector).
+    """
+    ext = np.asarray(frame_extrinsic_matrices, dtype=np.float64)
+    R = ext[:, :3, :3]
+    angle = np.arccos((np.trace(R, axis1=1, axis2=2) - 1.0) / 2.0)
+    anti = np.stack((R[:, 2, 1] - R[:, 1, 2], R[:, 0, 2] - R[:, 2, 0], R[:, 1, 0] - R[:, 0, 1]), axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        axis = np.nan_to_num(anti / (2.0 * np.sin(angle))[:, None])
+    out = np.empty((len(ext), 6))
+    out[:, :3] = axis * angle[:, None]
+    out[:, 3:] = ext[:, :3, 3]
+    return out.reshape(-1)
+
+
+def _rodrigues(rvec):
+    """Axis-angle vector -> 3x3 rotation (the matrix ``cv2.Rodrigues`` returns, bundleAdjuster.py:153)."""
+    w = np.asarray(rvec, dtype=np.float64).reshape(3)
+    t = math.sqrt(float(w @ w))
+    if t == 0.0:
+        return np.eye(3)
+    k = w / t
+    Kx = np.array([[0.0, -k[2], k[1]], [k[2], 0.0, -k[0]], [-k[1], k[0], 0.0]])
+    return math.cos(t) * np.eye(3) + math.sin(t) * Kx + (1.0 - math.cos(t)) * np.outer(k, k)
+
+
+def reformatPointResult(result, n_frames, n_points):
+    """``result.x`` -> ((Np,3) points, list of Nc 4x4 extrinsics)   (bundleAdjuster.py:137-157)."""
+    x = np.asarray(result.x)
+    points = x[n_frames * 6:].reshape((n_points, 3))
+    frames = x[:n_frames * 6].reshape((n_frames, 6))
+    extrinsics = []
+    for row in frames:
+        m = np.eye(4)
+        m[:3, :3] = _rodrigues(row[:3])
+        m[:3, 3] = row[3:]
+        extrinsics.append(m)
+    return points, extrinsics
+
+
+def pointAdjustmentSparsity(n_frames, n_points, frame_indices, point_indices):
+    """Structural pattern of the Jacobian (bundleAdjuster.py:55-78) as a scipy CSR matrix.
+
+    The engine never builds it (the block structure is implied by the two index arrays); it is kept
+    for callers that want the pattern itself.
+    """
+    from scipy.sparse import csr_matrix
+
+    fi = np.asarray(frame_indices, dtype=np.int64)
+    pi = np.asarray(point_indices, dtype=np.int64)
+    n_obs = fi.size
+    cols = np.concatenate((6 * fi[:, None] + np.arange(6)[None, :],
+                           6 * n_frames + 3 * pi[:, None] + np.arange(3)[None, :]), axis=1)
+    cols = np.repeat(cols, 2, axis=0).reshape(-1)
+    indptr = 9 * np.arange(2 * n_obs + 1)
+    return csr_matrix((np.ones(cols.size, dtype=int), cols, indptr), shape=(2 * n_obs, 6 * n_frames + 3 * n_points))
+
+
+# --------------------------------------------------------------------------------------------------
+# engine access
+# --------------------------------------------------------------------------------------------------
+
+def _engine(camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D, **options):
+    eng = _capi.Engine(**options)
+    eng.set_problem(n_frames, n_points, camera_matrix, frame_indices, point_indices, points_2D)
+    return eng
+
+
+def pointFun(parameters, camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D):
+    """Reprojection residuals, interleaved (du0, dv0, du1, ...)  (bundleAdjuster.py:81-102),
+    evaluated by the engine's residual kernel."""
+    with _engine(camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D) as eng:
+        return eng.residual(parameters)
+
+
+def _print_table(log, res):
+    """scipy's verbose=2 iteration table (scipy/optimize/_lsq/common.py:545-563) and summary."""
+    print("{:^15}{:^15}{:^15}{:^15}{:^15}{:^15}".format(
+        "Iteration", "Total nfev", "Cost", "Cost reduction", "Step norm", "Optimality"))
+    for row in log:
+        red = "" if math.isnan(row["cost_reduction"]) else f"{row['cost_reduction']:.2e}"
+        stp = "" if math.isnan(row["step_norm"]) else f"{row['step_norm']:.2e}"
+        print(f"{row['iteration']:^15}{row['nfev']:^15}{row['cost']:^15.4e}{red:^15}{stp:^15}"
+              f"{row['optimality']:^15.2e}")
+    print(_STATUS_MESSAGES.get(res.status, ""))
+    print(f"Function evaluations {res.nfev}, initial cost {res.initial_cost:.4e}, final cost "
+          f"{res.cost:.4e}, first-order optimality {res.optimality:.2e}.")
+
+
+def solve(parameters, camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D,
+          ftol=FTOL, xtol=XTOL, gtol=GTOL, max_nfev=None, verbose=0, want_fun=False, engine=None,
+          **options):
+    """The seam: stands where ``least_squares(pointFun, parameters, jac_sparsity=A, x_scale='jac',
+    ftol=1e-4, method='trf', args=...)`` stands in the reference (bundleAdjuster.py:180-192).
+
+    Returns a ``SolveResult`` with ``x, cost, fun, optimality, nfev, njev, nit, status, message,
+    success`` plus engine statistics (``log``, ``pcg_iterations``, ``solve_ms``).
+    """
+    own = engine is None
+    eng = engine if engine is not None else _engine(
+        camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D,
+        ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=0 if max_nfev is None else int(max_nfev), **options)
+    try:
+        try:
+            x, r, fun = eng.solve(parameters, want_fun=want_fun)
+        except _capi.MmbaError as e:
+            if e.code == -4:   # scipy raises ValueError here (least_squares.py:945-946)
+                raise ValueError("Residuals are not finite in the initial point.") from e
+            raise
+        log = eng.log()
+    finally:
+        if own:
+            eng.close()
+    res = SolveResult(x=x, cost=r.cost, initial_cost=r.initial_cost, fun=fun, optimality=r.optimality,
+                      nfev=r.nfev, njev=r.njev, nit=r.nit, status=r.status,
+                      message=_STATUS_MESSAGES.get(r.status, ""), success=r.status > 0, log=log,
+                      pcg_iterations=r.pcg_iterations, solve_ms=r.solve_ms)
+    if verbose >= 2:
+        _print_table(log, res)
+    elif verbose == 1:
+        print(res.message)
+    return res
+
+
+def adjustPoints(frame_extrinsic_matrices, camera_intrinsic_matrix, points_3D, points_2D, frame_indices,
+                 point_indices):
+    """Bundle adjustment of all cameras and points (bundleAdjuster.py:160-194; same signature,
+    same return value, same printed iteration table).
+
+    :param frame_extrinsic_matrices: (Nc, 3|4, 4) extrinsic matrices
+    :param camera_intrinsic_matrix: shared 3x3 intrinsic matrix
+    :param points_3D: (Np, 3) or (Np, 1, 3) triangulated points
+    :param points_2D: (No, 2) image observations
+    :param frame_indices: (No,) camera of each observation
+    :param point_indices: (No,) point of each observation
+    :return: ((Np, 3) adjusted points, list of Nc 4x4 adjusted extrinsics)
+    """
+    global last_result
+    ext = np.asarray(frame_extrinsic_matrices, dtype=np.float64)
+    pts = np.asarray(points_3D, dtype=np.float64)
+    n_frames, n_points = len(ext), len(pts)
+    parameters = np.hstack((frameParameters(ext), pts.reshape((n_points * 3,))))
+    res = solve(parameters, camera_intrinsic_matrix, n_frames, n_points, frame_indices, point_indices,
+                points_2D, ftol=FTOL, verbose=VERBOSE)
+    last_result = res
+    return reformatPointResult(res, n_frames, n_points)

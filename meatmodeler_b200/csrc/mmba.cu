@@ -1,0 +1,1197 @@
+// libmmba.so — C-ABI (include/mmba.h) + host driver of the B200 bundle-adjustment engine.
+//
+// The driver re-implements the outer loop the reference reaches through
+// scipy.optimize.least_squares(method='trf', tr_solver='lsmr', x_scale='jac')
+// (bundleAdjuster.py:180-192 -> scipy/optimize/_lsq/trf.py:415-587): Marquardt column scaling with a
+// monotone scale, Cauchy-step regulariser, a damped Gauss-Newton step (here: Schur elimination of
+// the 3x3 point blocks + block-Jacobi PCG on the camera system instead of LSMR), the 2-D subspace
+// trust-region problem, the radius rule and the termination tests.  Every O(No), O(Np), O(Nc)
+// operation is a CUDA kernel (kernels.cuh, veckernels.cuh); the host only does O(1) scalar work.
+//
+// Multi-GPU (nranks > 1): observations are sharded by point (plan.cpp), cameras are replicated, and
+// the camera-sized partial sums (U, g_c, Schur products) plus a handful of scalars are summed with
+// ncclAllReduce.  NCCL is bound at run time with dlopen so that a single-GPU process never needs it.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mmba.h"
+#include "kernels.cuh"
+#include "plan.h"
+#include "trf_host.h"
+#include "veckernels.cuh"
+
+using namespace mmba;
+
+// ---------------------------------------------------------------------------------------------
+// run-time NCCL binding
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi g_nccl;
+thread_local std::string g_thread_error;
+
+bool load_nccl(std::string& err) {
+    if (g_nccl.lib) return true;
+    // prefer a copy the process has already loaded (torch bundles its own libnccl.so.2)
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+        err = std::string("cannot load libnccl: ") + dlerror();
+        return false;
+    }
+#define MMBA_SYM(name)                                                                  \
+    g_nccl.name = reinterpret_cast<decltype(g_nccl.name)>(dlsym(lib, "nccl" #name));      \
+    if (!g_nccl.name) {                                                                  \
+        err = "libnccl lacks nccl" #name;                                                \
+        return false;                                                                    \
+    }
+    MMBA_SYM(GetUniqueId)
+    MMBA_SYM(CommInitRank)
+    MMBA_SYM(CommDestroy)
+    MMBA_SYM(AllReduce)
+    MMBA_SYM(GroupStart)
+    MMBA_SYM(GroupEnd)
+    MMBA_SYM(GetErrorString)
+#undef MMBA_SYM
+    g_nccl.lib = lib;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device arena: one cudaMalloc per problem, carved into 256-byte aligned arrays
+// ---------------------------------------------------------------------------------------------
+struct Arena {
+    char* base = nullptr;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+struct Dev {
+    // plan
+    int4* tiles;
+    int32_t* tile_cams;
+    uint16_t *slot_cam, *slot_pt, *sort_src, *sort_key;
+    double* uv;
+    // linearisation
+    double *J, *res;
+    double *x, *xn, *camtab, *camtab_n;
+    double *U, *g, *V, *M, *zg, *dp;
+    // n-vectors (camera part first, then the local points)
+    double *sinv, *gh, *gn, *s1, *s2, *v1, *v2, *tmp;
+    // PCG (camera-sized)
+    double *y, *Sd, *Pinv, *px, *pr, *pz, *pp, *pq, *pxt, *part;
+    int* flags;
+    double* scal;
+    double* xp_full;   // all points, internal order (nranks > 1 only)
+};
+
+struct Profile {
+    int64_t launches[MMBA_K_COUNT] = {0};
+    double ms[MMBA_K_COUNT] = {0};
+    std::vector<cudaEvent_t> pool;
+    std::vector<int> cls;   // class of pair i (events 2i, 2i+1)
+    size_t used = 0;
+};
+
+}  // namespace
+
+struct mmba_handle {
+    mmba_options opt;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ncclComm_t comm = nullptr;
+    bool has_problem = false;
+    Plan plan;
+    int64_t Nc = 0, npl = 0, ns = 0, nt = 0, nloc = 0;
+    double K[9];
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    Dev d;
+    TileArgs targs;
+    size_t smem_build = 0, smem_resid = 0, smem_schur = 0, smem_jv1 = 0, smem_jv2 = 0;
+    double* h_stage = nullptr;   // pinned, max(nloc, 2*ns ...) doubles
+    size_t h_stage_n = 0;
+    double* h_scal = nullptr;    // pinned S_COUNT
+    int* h_flags = nullptr;      // pinned 2
+    std::vector<mmba_iter_log> log;
+    Profile prof;
+};
+
+struct mmba_plan {
+    Plan plan;
+};
+
+namespace {
+
+int fail(mmba_handle* h, int code, const std::string& msg) {
+    g_thread_error = msg;
+    if (h) h->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, MMBA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+#define NC(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess)                                                                     \
+            return fail(h, MMBA_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_));  \
+    } while (0)
+
+#define TRY(call)             \
+    do {                      \
+        int rc_ = (call);     \
+        if (rc_ != MMBA_OK) return rc_; \
+    } while (0)
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- profiling -------------------------------------------------------------------------------
+void prof_begin(mmba_handle* h, int cls) {
+    h->prof.launches[cls]++;
+    if (!h->opt.profile) return;
+    Profile& p = h->prof;
+    if (p.used * 2 + 2 > p.pool.size()) {
+        if (p.pool.size() >= 2 * 65536) return;
+        for (int i = 0; i < 512; ++i) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            p.pool.push_back(e);
+        }
+    }
+    if (p.cls.size() <= p.used) p.cls.resize(p.used + 1);
+    p.cls[p.used] = cls;
+    cudaEventRecord(p.pool[2 * p.used], h->stream);
+}
+void prof_end(mmba_handle* h, int) {
+    if (!h->opt.profile) return;
+    Profile& p = h->prof;
+    if (p.used * 2 + 2 > p.pool.size()) return;
+    cudaEventRecord(p.pool[2 * p.used + 1], h->stream);
+    p.used++;
+}
+void prof_collect(mmba_handle* h) {
+    Profile& p = h->prof;
+    if (!h->opt.profile) return;
+    cudaStreamSynchronize(h->stream);
+    for (size_t i = 0; i < p.used; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.pool[2 * i], p.pool[2 * i + 1]) == cudaSuccess) p.ms[p.cls[i]] += ms;
+    }
+    p.used = 0;
+}
+
+#define LAUNCH(cls, kern, grid, block, smem, ...)                         \
+    do {                                                                  \
+        prof_begin(h, cls);                                               \
+        kern<<<(grid), (block), (smem), h->stream>>>(__VA_ARGS__);        \
+        prof_end(h, cls);                                                 \
+    } while (0)
+
+// ---- collectives ------------------------------------------------------------------------------
+struct Red {
+    double* p;
+    size_t n;
+    bool is_max;
+};
+
+// Sum (or max) the listed device arrays over ranks, in place, as one NCCL group.
+int allreduce(mmba_handle* h, std::initializer_list<Red> items) {
+    if (h->opt.nranks <= 1) return MMBA_OK;
+    prof_begin(h, MMBA_K_ALLREDUCE);
+    NC(g_nccl.GroupStart());
+    for (const Red& r : items) {
+        if (r.is_max) {
+            // non-negative doubles order like their bit patterns
+            NC(g_nccl.AllReduce(r.p, r.p, r.n, ncclUint64, ncclMax, h->comm, h->stream));
+        } else {
+            NC(g_nccl.AllReduce(r.p, r.p, r.n, ncclDouble, ncclSum, h->comm, h->stream));
+        }
+    }
+    NC(g_nccl.GroupEnd());
+    prof_end(h, MMBA_K_ALLREDUCE);
+    return MMBA_OK;
+}
+
+int read_scalars(mmba_handle* h) {
+    CU(cudaMemcpyAsync(h->h_scal, h->d.scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MMBA_OK;
+}
+
+int zero(mmba_handle* h, double* p, size_t n) {
+    CU(cudaMemsetAsync(p, 0, n * sizeof(double), h->stream));
+    return MMBA_OK;
+}
+
+// ---- memory layout ----------------------------------------------------------------------------
+void carve(mmba_handle* h, Arena& a) {
+    const Plan& pl = h->plan;
+    Dev& d = h->d;
+    const size_t Nc = h->Nc, npl = std::max<int64_t>(h->npl, 1), ns = std::max<int64_t>(h->ns, 1), nloc = 6 * Nc + 3 * npl;
+    d.tiles = a.take<int4>(std::max<size_t>(pl.tiles.size(), 1));
+    d.tile_cams = a.take<int32_t>(std::max<size_t>(pl.tile_cams.size(), 1));
+    d.slot_cam = a.take<uint16_t>(ns);
+    d.slot_pt = a.take<uint16_t>(ns);
+    d.sort_src = a.take<uint16_t>(ns);
+    d.sort_key = a.take<uint16_t>(ns);
+    d.uv = a.take<double>(2 * ns);
+    d.J = a.take<double>(18 * ns);
+    d.res = a.take<double>(2 * ns);
+    d.x = a.take<double>(nloc);
+    d.xn = a.take<double>(nloc);
+    d.camtab = a.take<double>(kCamTab * Nc);
+    d.camtab_n = a.take<double>(kCamTab * Nc);
+    d.U = a.take<double>(21 * Nc);
+    d.g = a.take<double>(nloc);
+    d.V = a.take<double>(6 * npl);
+    d.M = a.take<double>(6 * npl);
+    d.zg = a.take<double>(3 * npl);
+    d.dp = a.take<double>(3 * npl);
+    d.sinv = a.take<double>(nloc);
+    d.gh = a.take<double>(nloc);
+    d.gn = a.take<double>(nloc);
+    d.s1 = a.take<double>(nloc);
+    d.s2 = a.take<double>(nloc);
+    d.v1 = a.take<double>(nloc);
+    d.v2 = a.take<double>(nloc);
+    d.tmp = a.take<double>(nloc);
+    d.y = a.take<double>(6 * Nc);
+    d.Sd = a.take<double>(21 * Nc);
+    d.Pinv = a.take<double>(21 * Nc);
+    d.px = a.take<double>(6 * Nc);
+    d.pr = a.take<double>(6 * Nc);
+    d.pz = a.take<double>(6 * Nc);
+    d.pp = a.take<double>(6 * Nc);
+    d.pq = a.take<double>(6 * Nc);
+    d.pxt = a.take<double>(6 * Nc);
+    d.part = a.take<double>((size_t)P_COUNT * kMaxCamBlocks);
+    d.flags = a.take<int>(4);
+    d.scal = a.take<double>(S_COUNT);
+    d.xp_full = h->opt.nranks > 1 ? a.take<double>(3 * (size_t)pl.n_points) : nullptr;
+}
+
+void release_problem(mmba_handle* h) {
+    if (h->arena) cudaFree(h->arena);
+    h->arena = nullptr;
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    h->h_stage = nullptr;
+    h->has_problem = false;
+}
+
+template <typename T>
+int upload(mmba_handle* h, T* dst, const std::vector<T>& src) {
+    if (!src.empty()) CU(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return MMBA_OK;
+}
+
+// caller's x (cameras | points in caller order) -> device x (cameras | local points, internal order)
+int put_x(mmba_handle* h, const double* x, double* dst) {
+    const Plan& pl = h->plan;
+    double* s = h->h_stage;
+    std::memcpy(s, x, 6 * h->Nc * sizeof(double));
+    const double* xp = x + 6 * h->Nc;
+    double* o = s + 6 * h->Nc;
+    for (int64_t q = 0; q < h->npl; ++q) {
+        const int64_t p = pl.point_perm[pl.pt_begin + q];
+        o[3 * q] = xp[3 * p];
+        o[3 * q + 1] = xp[3 * p + 1];
+        o[3 * q + 2] = xp[3 * p + 2];
+    }
+    CU(cudaMemcpyAsync(dst, s, h->nloc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));   // the staging buffer is reused
+    return MMBA_OK;
+}
+
+// device n-vector -> caller's layout.  With nranks > 1 the point part is completed over ranks.
+int get_x(mmba_handle* h, const double* src, double* x) {
+    const Plan& pl = h->plan;
+    double* s = h->h_stage;
+    if (h->opt.nranks > 1) {
+        CU(cudaMemsetAsync(h->d.xp_full, 0, 3 * pl.n_points * sizeof(double), h->stream));
+        if (h->npl)
+            CU(cudaMemcpyAsync(h->d.xp_full + 3 * pl.pt_begin, src + 6 * h->Nc, 3 * h->npl * sizeof(double),
+                               cudaMemcpyDeviceToDevice, h->stream));
+        TRY(allreduce(h, {{h->d.xp_full, (size_t)(3 * pl.n_points), false}}));
+        CU(cudaMemcpyAsync(s, src, 6 * h->Nc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(s + 6 * h->Nc, h->d.xp_full, 3 * pl.n_points * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        std::memcpy(x, s, 6 * h->Nc * sizeof(double));
+        const double* o = s + 6 * h->Nc;
+        double* xp = x + 6 * h->Nc;
+        for (int64_t q = 0; q < pl.n_points; ++q) {
+            const int64_t p = pl.point_perm[q];
+            xp[3 * p] = o[3 * q];
+            xp[3 * p + 1] = o[3 * q + 1];
+            xp[3 * p + 2] = o[3 * q + 2];
+        }
+        return MMBA_OK;
+    }
+    CU(cudaMemcpyAsync(s, src, h->nloc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    std::memcpy(x, s, 6 * h->Nc * sizeof(double));
+    const double* o = s + 6 * h->Nc;
+    double* xp = x + 6 * h->Nc;
+    for (int64_t q = 0; q < h->npl; ++q) {
+        const int64_t p = pl.point_perm[pl.pt_begin + q];
+        xp[3 * p] = o[3 * q];
+        xp[3 * p + 1] = o[3 * q + 1];
+        xp[3 * p + 2] = o[3 * q + 2];
+    }
+    return MMBA_OK;
+}
+
+// rows x n_slots SoA on the device -> caller-ordered (n_obs, rows) row-major; local entries only
+int get_slots(mmba_handle* h, const double* src, int rows, double* out, int out_stride, int out_off) {
+    const Plan& pl = h->plan;
+    std::vector<double> tmp((size_t)rows * h->ns);
+    CU(cudaMemcpyAsync(tmp.data(), src, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int64_t s = 0; s < h->ns; ++s) {
+        const int64_t o = pl.slot_obs[s];
+        if (o < 0) continue;
+        for (int r = 0; r < rows; ++r) out[o * out_stride + out_off + r] = tmp[(size_t)r * h->ns + s];
+    }
+    return MMBA_OK;
+}
+
+// ---- device phases ----------------------------------------------------------------------------
+PcgVecs pcg_vecs(mmba_handle* h) {
+    Dev& d = h->d;
+    PcgVecs P;
+    P.U = d.U;
+    P.gc = d.g;
+    P.sinv = d.sinv;
+    P.y = d.y;
+    P.Sd = d.Sd;
+    P.Pinv = d.Pinv;
+    P.x = d.px;
+    P.r = d.pr;
+    P.z = d.pz;
+    P.p = d.pp;
+    P.q = d.pq;
+    P.xt = d.pxt;
+    P.part = d.part;
+    P.flags = d.flags;
+    P.n_cams = (int)h->Nc;
+    return P;
+}
+
+int cam_prep(mmba_handle* h, const double* x, double* camtab) {
+    LAUNCH(MMBA_K_CAMPREP, cam_prep_kernel, cdiv(h->Nc, 128), 128, 0, x, camtab, (int)h->Nc);
+    return MMBA_OK;
+}
+
+// residuals, Jacobian blocks, normal-equation blocks and cost at d.x
+int linearise(mmba_handle* h) {
+    Dev& d = h->d;
+    TRY(cam_prep(h, d.x, d.camtab));
+    TRY(zero(h, d.U, 21 * h->Nc));
+    TRY(zero(h, d.g, 6 * h->Nc));
+    TRY(zero(h, d.scal + S_COST, 1));
+    if (h->nt)
+        LAUNCH(MMBA_K_BUILD, build_kernel, (unsigned)h->nt, kT, h->smem_build, h->targs, d.camtab, d.x + 6 * h->Nc, d.J,
+               d.res, d.U, d.g, d.V, d.g + 6 * h->Nc, d.scal, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    TRY(allreduce(h, {{d.U, (size_t)(21 * h->Nc), false}, {d.g, (size_t)(6 * h->Nc), false}, {d.scal + S_COST, 1, false}}));
+    CU(cudaGetLastError());
+    return MMBA_OK;
+}
+
+// scale_inv (monotone), g_h, ||g_h||^2, ||x*scale_inv||^2, ||x||^2, ||g||_inf
+int scale_and_grad(mmba_handle* h, bool first) {
+    Dev& d = h->d;
+    const int lead = h->opt.rank == 0;
+    TRY(zero(h, d.scal + S_GH2, 4));
+    LAUNCH(MMBA_K_VEC, scale_grad_kernel<6>, cdiv(6 * h->Nc, 256), 256, 0, d.U, d.g, d.x, d.sinv, d.gh, (int)first,
+           6 * h->Nc, d.scal, lead);
+    if (h->npl)
+        LAUNCH(MMBA_K_VEC, scale_grad_kernel<3>, cdiv(3 * h->npl, 256), 256, 0, d.V, d.g + 6 * h->Nc, d.x + 6 * h->Nc,
+               d.sinv + 6 * h->Nc, d.gh + 6 * h->Nc, (int)first, 3 * h->npl, d.scal, 1);
+    TRY(allreduce(h, {{d.scal + S_GH2, 3, false}, {d.scal + S_GINF, 1, true}}));
+    return MMBA_OK;
+}
+
+// ||J v||^2 for the unscaled n-vector v (device, internal layout) -> scal[S_JV00]
+int jv1(mmba_handle* h, const double* v) {
+    Dev& d = h->d;
+    TRY(zero(h, d.scal + S_JV00, 3));
+    if (h->nt) {
+        auto kern = jv_kernel<1, false>;
+        LAUNCH(MMBA_K_JV, kern, (unsigned)h->nt, kT, h->smem_jv1, h->targs, d.J, v, v + 6 * h->Nc, nullptr,
+               nullptr, d.scal, nullptr, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    }
+    TRY(allreduce(h, {{d.scal + S_JV00, 3, false}}));
+    return MMBA_OK;
+}
+
+int jv2(mmba_handle* h, const double* va, const double* vb) {
+    Dev& d = h->d;
+    TRY(zero(h, d.scal + S_JV00, 3));
+    if (h->nt) {
+        auto kern = jv_kernel<2, false>;
+        LAUNCH(MMBA_K_JV, kern, (unsigned)h->nt, kT, h->smem_jv2, h->targs, d.J, va, va + 6 * h->Nc, vb,
+               vb + 6 * h->Nc, d.scal, nullptr, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    }
+    TRY(allreduce(h, {{d.scal + S_JV00, 3, false}}));
+    return MMBA_OK;
+}
+
+int schur_matvec(mmba_handle* h) {
+    Dev& d = h->d;
+    if (h->nt)
+        LAUNCH(MMBA_K_MATVEC, schur_kernel<SCHUR_MATVEC>, (unsigned)h->nt, kT, h->smem_schur, h->targs, d.J, d.pxt, d.M,
+               nullptr, nullptr, d.y, nullptr, nullptr, d.flags, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    TRY(allreduce(h, {{d.y, (size_t)(6 * h->Nc), false}}));
+    return MMBA_OK;
+}
+
+// damped Gauss-Newton step in scaled variables: (D J^T J D + reg I) p = D g.
+// Leaves the camera part in d.px (scaled) and the unscaled point part in d.dp.
+int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
+    Dev& d = h->d;
+    const int camblocks = cdiv(h->Nc, kCamBlock);
+    PcgVecs P = pcg_vecs(h);
+    if (h->npl)
+        LAUNCH(MMBA_K_PTINV, point_invert_kernel, cdiv(h->npl, 256), 256, 0, d.V, d.g + 6 * h->Nc, d.sinv + 6 * h->Nc, reg,
+               d.M, d.zg, h->npl);
+    TRY(zero(h, d.y, 6 * h->Nc));
+    TRY(zero(h, d.Sd, 21 * h->Nc));
+    if (h->nt)
+        LAUNCH(MMBA_K_RHS, schur_kernel<SCHUR_RHS>, (unsigned)h->nt, kT, h->smem_schur, h->targs, d.J, nullptr, d.M, d.zg,
+               nullptr, d.y, d.Sd, nullptr, nullptr, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    TRY(allreduce(h, {{d.y, (size_t)(6 * h->Nc), false}, {d.Sd, (size_t)(21 * h->Nc), false}}));
+    LAUNCH(MMBA_K_VEC, pcg_init_kernel, camblocks, kCamBlock, 0, P, reg);
+
+    const double rtol2 = h->opt.pcg_rtol * h->opt.pcg_rtol;
+    const int maxit = h->opt.pcg_maxit;
+    int it = 0, done = 0;
+    int chunk = 8;
+    while (it < maxit && !done) {
+        const int stop = std::min(maxit, it + chunk);
+        for (; it < stop; ++it) {
+            TRY(schur_matvec(h));
+            LAUNCH(MMBA_K_VEC, pcg_a_kernel, camblocks, kCamBlock, 0, P, reg);
+            LAUNCH(MMBA_K_VEC, pcg_b_kernel, camblocks, kCamBlock, 0, P, it);
+            LAUNCH(MMBA_K_VEC, pcg_c_kernel, camblocks, kCamBlock, 0, P, it, rtol2);
+        }
+        CU(cudaMemcpyAsync(h->h_flags, d.flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        done = h->h_flags[0];
+        chunk = 16;
+    }
+    const int64_t its = done ? h->h_flags[1] : it;
+    if (its_out) *its_out = its;
+    if (relres_out) {
+        std::vector<double> part(2 * kMaxCamBlocks);
+        CU(cudaMemcpyAsync(part.data(), d.part + P_RR * kMaxCamBlocks, 2 * kMaxCamBlocks * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        double rr = 0, b2 = 0;
+        for (int i = 0; i < camblocks; ++i) {
+            rr += part[i];
+            b2 += part[kMaxCamBlocks + i];
+        }
+        *relres_out = (its > 0 && b2 > 0) ? std::sqrt(rr / b2) : (b2 > 0 ? 1.0 : 0.0);
+    }
+    // back-substitution with the unscaled camera step
+    LAUNCH(MMBA_K_VEC, unscale_kernel, cdiv(6 * h->Nc, 256), 256, 0, d.px, d.sinv, 1.0, d.pxt, 6 * h->Nc);
+    if (h->nt)
+        LAUNCH(MMBA_K_BACKSUB, schur_kernel<SCHUR_BACKSUB>, (unsigned)h->nt, kT, h->smem_schur, h->targs, d.J, d.pxt, d.M,
+               nullptr, d.g + 6 * h->Nc, nullptr, nullptr, d.dp, nullptr, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    CU(cudaGetLastError());
+    return MMBA_OK;
+}
+
+int trial_cost(mmba_handle* h, const double* x, double* camtab) {
+    Dev& d = h->d;
+    TRY(cam_prep(h, x, camtab));
+    TRY(zero(h, d.scal + S_COST_NEW, 1));
+    if (h->nt)
+        LAUNCH(MMBA_K_RESID, resid_kernel<false>, (unsigned)h->nt, kT, h->smem_resid, h->targs, camtab, x + 6 * h->Nc,
+               nullptr, d.scal + S_COST_NEW, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    TRY(allreduce(h, {{d.scal + S_COST_NEW, 1, false}}));
+    return MMBA_OK;
+}
+
+double ginf_of(const double* scal) {
+    double v;
+    std::memcpy(&v, scal + S_GINF, sizeof(double));
+    return v;
+}
+
+// ---- the TRF outer loop (trf.py:415-587) --------------------------------------------------------
+int run_trf(mmba_handle* h, mmba_result* out) {
+    Dev& d = h->d;
+    const mmba_options& o = h->opt;
+    const int lead = o.rank == 0;
+    const int64_t n_total = 6 * h->Nc + 3 * h->plan.n_points;
+    const int64_t max_nfev = o.max_nfev > 0 ? o.max_nfev : 100 * n_total;
+    const int64_t nloc = h->nloc, ncam = 6 * h->Nc, npt = 3 * h->npl;
+    const int gv = cdiv(nloc, 256), gc_ = cdiv(ncam, 256), gp_ = std::max(1, cdiv(npt, 256));
+    h->log.clear();
+
+    TRY(linearise(h));
+    TRY(scale_and_grad(h, true));
+    TRY(read_scalars(h));
+    double cost = 0.5 * h->h_scal[S_COST];
+    if (!std::isfinite(cost)) return fail(h, MMBA_ERR_NONFINITE, "Residuals are not finite in the initial point.");
+    double gh2 = h->h_scal[S_GH2], x_norm = std::sqrt(h->h_scal[S_X2]), g_norm = ginf_of(h->h_scal);
+    double Delta = std::sqrt(h->h_scal[S_XSI2]);
+    if (Delta == 0) Delta = 1.0;
+    out->initial_cost = cost;
+    int64_t nfev = 1, njev = 1, nit = 0, pcg_total = 0;
+    int status = -1;   // -1 = running
+    double step_norm = 0, actual = 0;
+    bool have_step = false;
+
+    while (true) {
+        if (g_norm < o.gtol) status = 1;
+        {
+            mmba_iter_log row;
+            row.iteration = nit;
+            row.nfev = nfev;
+            row.cost = cost;
+            row.cost_reduction = have_step ? actual : NAN;
+            row.step_norm = have_step ? step_norm : NAN;
+            row.optimality = g_norm;
+            row.reg = NAN;
+            row.delta = Delta;
+            row.pcg_iterations = 0;
+            h->log.push_back(row);
+        }
+        if (status != -1 || nfev >= max_nfev) break;
+
+        // Cauchy-step regulariser (trf.py:488-492): a = 0.5 ||J_h g_h||^2, b = -||g_h||^2
+        LAUNCH(MMBA_K_VEC, unscale_kernel, gv, 256, 0, d.gh, d.sinv, 1.0, d.tmp, nloc);
+        TRY(jv1(h, d.tmp));
+        TRY(read_scalars(h));
+        const double qa = 0.5 * h->h_scal[S_JV00], qb = -gh2;
+        const double gh_norm = std::sqrt(gh2);
+        double t_best, ag;
+        min_quadratic_1d(qa, qb, 0.0, Delta / gh_norm, &t_best, &ag);
+        const double reg = -ag / (Delta * Delta);
+
+        // damped Gauss-Newton direction (replaces lsmr(J_h, f, damp=sqrt(reg)), trf.py:494-495)
+        int64_t its = 0;
+        TRY(gn_step(h, reg, &its, nullptr));
+        pcg_total += its;
+        h->log.back().reg = reg;
+        h->log.back().pcg_iterations = its;
+
+        // S = orth[g_h, gn_h], B_S = (J_h S)^T (J_h S), g_S = S^T g_h   (trf.py:496-500)
+        TRY(zero(h, d.scal + S_DOT0, 10));
+        LAUNCH(MMBA_K_VEC, gn_assemble_kernel<false>, gc_, 256, 0, d.px, d.sinv, d.gh, d.gn, ncam, d.scal, lead);
+        if (npt)
+            LAUNCH(MMBA_K_VEC, gn_assemble_kernel<true>, gp_, 256, 0, d.dp, d.sinv + ncam, d.gh + ncam, d.gn + ncam, npt,
+                   d.scal, 1);
+        TRY(allreduce(h, {{d.scal + S_DOT0, 2, false}}));
+        TRY(read_scalars(h));
+        const double inv_gh = gh_norm > 0 ? 1.0 / gh_norm : 0.0;
+        const double c1 = h->h_scal[S_DOT0] * inv_gh;
+        LAUNCH(MMBA_K_VEC, orth_a_kernel, gc_, 256, 0, d.gh, d.gn, inv_gh, c1, d.s1, d.s2, ncam, d.scal, lead);
+        if (npt)
+            LAUNCH(MMBA_K_VEC, orth_a_kernel, gp_, 256, 0, d.gh + ncam, d.gn + ncam, inv_gh, c1, d.s1 + ncam, d.s2 + ncam,
+                   npt, d.scal, 1);
+        TRY(allreduce(h, {{d.scal + S_DOT2, 2, false}}));
+        TRY(read_scalars(h));
+        const double c2 = h->h_scal[S_DOT2];
+        LAUNCH(MMBA_K_VEC, orth_b_kernel, gc_, 256, 0, d.gh, d.sinv, c2, d.s1, d.s2, d.v1, d.v2, ncam, d.scal, lead);
+        if (npt)
+            LAUNCH(MMBA_K_VEC, orth_b_kernel, gp_, 256, 0, d.gh + ncam, d.sinv + ncam, c2, d.s1 + ncam, d.s2 + ncam,
+                   d.v1 + ncam, d.v2 + ncam, npt, d.scal, 1);
+        TRY(allreduce(h, {{d.scal + S_DOT4, 6, false}}));
+        TRY(jv2(h, d.v1, d.v2));
+        TRY(read_scalars(h));
+        const double n2 = std::sqrt(h->h_scal[S_DOT4]);
+        // second basis vector is s2/n2; degenerate (gn parallel to g_h) -> 1-D problem along s1
+        const double i2 = (n2 > 1e-300 && std::isfinite(n2)) ? 1.0 / n2 : 0.0;
+        double B[3] = {h->h_scal[S_JV00], h->h_scal[S_JV01] * i2, h->h_scal[S_JV11] * i2 * i2};
+        double gS[2] = {h->h_scal[S_DOT9], h->h_scal[S_DOT5] * i2};
+        const double vv00 = h->h_scal[S_DOT6], vv01 = h->h_scal[S_DOT7] * i2, vv11 = h->h_scal[S_DOT8] * i2 * i2;
+        if (i2 == 0.0) {
+            B[1] = 0.0;
+            B[2] = 1.0;
+            gS[1] = 0.0;
+        }
+
+        actual = -1;
+        double cost_new = cost;
+        while (actual <= 0 && nfev < max_nfev) {
+            double p[2];
+            bool newton;
+            tr2d(B, gS, Delta, p, &newton);
+            if (i2 == 0.0) p[1] = 0.0;
+            const double predicted = -(0.5 * (B[0] * p[0] * p[0] + 2 * B[1] * p[0] * p[1] + B[2] * p[1] * p[1]) +
+                                       gS[0] * p[0] + gS[1] * p[1]);
+            LAUNCH(MMBA_K_VEC, trial_kernel, gv, 256, 0, d.x, d.v1, d.v2, p[0], p[1] * i2, d.xn, nloc);
+            TRY(trial_cost(h, d.xn, d.camtab_n));
+            TRY(read_scalars(h));
+            nfev++;
+            const double step_h_norm = std::hypot(p[0], p[1]);
+            const double f2 = h->h_scal[S_COST_NEW];
+            if (!std::isfinite(f2)) {
+                Delta = 0.25 * step_h_norm;
+                continue;
+            }
+            cost_new = 0.5 * f2;
+            actual = cost - cost_new;
+            double Delta_new, ratio;
+            update_tr_radius(Delta, actual, predicted, step_h_norm, step_h_norm > 0.95 * Delta, &Delta_new, &ratio);
+            step_norm = std::sqrt(std::max(0.0, vv00 * p[0] * p[0] + 2 * vv01 * p[0] * p[1] + vv11 * p[1] * p[1]));
+            have_step = true;
+            const int term = check_termination(actual, cost, step_norm, x_norm, ratio, o.ftol, o.xtol);
+            if (term) {
+                status = term;
+                break;
+            }
+            Delta = Delta_new;
+        }
+        if (actual > 0) {
+            std::swap(d.x, d.xn);
+            cost = cost_new;
+            TRY(linearise(h));
+            njev++;
+            TRY(scale_and_grad(h, false));
+            TRY(read_scalars(h));
+            gh2 = h->h_scal[S_GH2];
+            x_norm = std::sqrt(h->h_scal[S_X2]);
+            g_norm = ginf_of(h->h_scal);
+        } else {
+            step_norm = 0;
+            actual = 0;
+            have_step = true;
+        }
+        nit++;
+    }
+    if (status == -1) status = 0;
+    out->cost = cost;
+    out->optimality = g_norm;
+    out->nfev = nfev;
+    out->njev = njev;
+    out->nit = nit;
+    out->status = status;
+    out->reserved = 0;
+    out->pcg_iterations = pcg_total;
+    return MMBA_OK;
+}
+
+int need_problem(mmba_handle* h) {
+    if (!h) return fail(nullptr, MMBA_ERR_ARG, "null handle");
+    if (!h->has_problem) return fail(h, MMBA_ERR_STATE, "mmba_set_problem has not been called");
+    cudaError_t e = cudaSetDevice(h->opt.device);
+    if (e != cudaSuccess) return fail(h, MMBA_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return MMBA_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+int mmba_version(void) { return MMBA_VERSION; }
+
+const char* mmba_last_error(const mmba_handle* h) { return h ? h->err.c_str() : g_thread_error.c_str(); }
+
+void mmba_default_options(mmba_options* opt) {
+    if (!opt) return;
+    std::memset(opt, 0, sizeof(*opt));
+    opt->device = 0;
+    opt->rank = 0;
+    opt->nranks = 1;
+    opt->verbose = 0;
+    opt->ftol = 1e-4;
+    opt->xtol = 1e-8;
+    opt->gtol = 1e-8;
+    opt->max_nfev = 0;
+    opt->pcg_rtol = 1e-10;
+    opt->pcg_maxit = 1000;
+    opt->profile = 0;
+}
+
+int mmba_nccl_unique_id(uint8_t out[128]) {
+    std::string err;
+    if (!out) return fail(nullptr, MMBA_ERR_ARG, "null output");
+    if (!load_nccl(err)) return fail(nullptr, MMBA_ERR_NCCL, err);
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, MMBA_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+    static_assert(sizeof(id) == 128, "ncclUniqueId size");
+    std::memcpy(out, &id, 128);
+    return MMBA_OK;
+}
+
+int mmba_create(mmba_handle** out, const mmba_options* opt) {
+    if (!out) return fail(nullptr, MMBA_ERR_ARG, "null output handle");
+    *out = nullptr;
+    mmba_options o;
+    if (opt) o = *opt;
+    else mmba_default_options(&o);
+    if (o.nranks < 1 || o.rank < 0 || o.rank >= o.nranks) return fail(nullptr, MMBA_ERR_ARG, "rank/nranks out of range");
+    if (o.pcg_maxit <= 0 || !(o.pcg_rtol > 0)) return fail(nullptr, MMBA_ERR_ARG, "pcg_maxit and pcg_rtol must be positive");
+    mmba_handle* h = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MMBA_ERR_CUDA,
+                    std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                        " (libmmba has no CPU fallback)");
+    if (o.device < 0 || o.device >= ndev) return fail(nullptr, MMBA_ERR_ARG, "device ordinal out of range");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, o.device);
+    if (e != cudaSuccess) return fail(nullptr, MMBA_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, MMBA_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                                std::to_string(prop.minor) + "; libmmba is built for sm_100a only");
+    h = new mmba_handle();
+    h->opt = o;
+    CU(cudaSetDevice(o.device));
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    CU(cudaMallocHost(&h->h_scal, S_COUNT * sizeof(double)));
+    CU(cudaMallocHost(&h->h_flags, 4 * sizeof(int)));
+    if (o.nranks > 1) {
+        std::string err;
+        if (!load_nccl(err)) {
+            delete h;
+            return fail(nullptr, MMBA_ERR_NCCL, err);
+        }
+        ncclUniqueId id;
+        std::memcpy(&id, o.nccl_id, 128);
+        ncclResult_t r = g_nccl.CommInitRank(&h->comm, o.nranks, id, o.rank);
+        if (r != ncclSuccess) {
+            std::string msg = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r);
+            delete h;
+            return fail(nullptr, MMBA_ERR_NCCL, msg);
+        }
+    }
+    *out = h;
+    return MMBA_OK;
+}
+
+void mmba_destroy(mmba_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->opt.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    release_problem(h);
+    if (h->comm) g_nccl.CommDestroy(h->comm);
+    for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n_obs, const double K[9],
+                     const int64_t* cam_idx, const int64_t* pt_idx, const double* uv) {
+    if (!h) return fail(nullptr, MMBA_ERR_ARG, "null handle");
+    if (!K || !uv) return fail(h, MMBA_ERR_ARG, "set_problem: null K or uv");
+    CU(cudaSetDevice(h->opt.device));
+    release_problem(h);
+    std::string err;
+    int rc = build_plan(h->plan, n_cams, n_points, n_obs, cam_idx, pt_idx, h->opt.rank, h->opt.nranks, err);
+    if (rc != MMBA_OK) return fail(h, rc, err);
+    if (n_cams > (int64_t)kMaxCamBlocks * kCamBlock) return fail(h, MMBA_ERR_ARG, "set_problem: too many cameras");
+    const Plan& pl = h->plan;
+    h->Nc = n_cams;
+    h->npl = pl.n_points_local();
+    h->ns = pl.n_slots;
+    h->nt = pl.n_tiles;
+    h->nloc = 6 * h->Nc + 3 * h->npl;
+    std::memcpy(h->K, K, sizeof(h->K));
+
+    Arena measure;
+    carve(h, measure);
+    h->arena_bytes = measure.off + 256;
+    cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
+    if (e != cudaSuccess) {
+        h->arena = nullptr;
+        return fail(h, MMBA_ERR_NOMEM, "set_problem: cudaMalloc of " + std::to_string(h->arena_bytes) + " bytes failed: " +
+                                           cudaGetErrorString(e));
+    }
+    Arena a;
+    a.base = static_cast<char*>(h->arena);
+    carve(h, a);
+    h->h_stage_n = (size_t)std::max<int64_t>(6 * h->Nc + 3 * pl.n_points, 64);
+    CU(cudaMallocHost(&h->h_stage, h->h_stage_n * sizeof(double)));
+
+    Dev& d = h->d;
+    CU(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
+    {
+        std::vector<int4> tiles(pl.tiles.size());
+        for (size_t t = 0; t < tiles.size(); ++t)
+            tiles[t] = make_int4(pl.tiles[t].pt0, pl.tiles[t].npts, pl.tiles[t].cam_off, pl.tiles[t].ncams);
+        TRY(upload(h, d.tiles, tiles));
+        TRY(upload(h, d.tile_cams, pl.tile_cams));
+        TRY(upload(h, d.slot_cam, pl.slot_cam));
+        TRY(upload(h, d.slot_pt, pl.slot_pt));
+        TRY(upload(h, d.sort_src, pl.sort_src));
+        TRY(upload(h, d.sort_key, pl.sort_key));
+        std::vector<double> uvs(2 * (size_t)h->ns, 0.0);
+        for (int64_t s = 0; s < h->ns; ++s) {
+            const int64_t ob = pl.slot_obs[s];
+            if (ob >= 0) {
+                uvs[s] = uv[2 * ob];
+                uvs[h->ns + s] = uv[2 * ob + 1];
+            }
+        }
+        TRY(upload(h, d.uv, uvs));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    TileArgs& A = h->targs;
+    A.tiles = d.tiles;
+    A.tile_cams = d.tile_cams;
+    A.slot_cam = d.slot_cam;
+    A.slot_pt = d.slot_pt;
+    A.sort_src = d.sort_src;
+    A.sort_key = d.sort_key;
+    A.uv = d.uv;
+    A.n_slots = h->ns;
+    std::memcpy(A.K, K, sizeof(A.K));
+
+    const size_t mc = pl.max_tile_cams, mp = pl.max_tile_pts;
+    h->smem_build = (mc * kCamS + mp * 3 + mp * 9 + 9 * kT + 64) * sizeof(double) + mc * sizeof(int);
+    h->smem_resid = (mc * kCamS + mp * 3 + 64) * sizeof(double);
+    h->smem_schur = (mc * kVecS + mp * 3 + 9 * kT) * sizeof(double) + mc * sizeof(int);
+    h->smem_jv1 = (mc * kVecS + mp * 3 + 64) * sizeof(double);
+    h->smem_jv2 = (2 * mc * kVecS + 2 * mp * 3 + 64) * sizeof(double);
+    CU(cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_build));
+    CU(cudaFuncSetAttribute(resid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_resid));
+    CU(cudaFuncSetAttribute(resid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_resid));
+    CU(cudaFuncSetAttribute(schur_kernel<SCHUR_MATVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_schur));
+    CU(cudaFuncSetAttribute(schur_kernel<SCHUR_RHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_schur));
+    CU(cudaFuncSetAttribute(schur_kernel<SCHUR_BACKSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_schur));
+    CU(cudaFuncSetAttribute(jv_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_jv1));
+    CU(cudaFuncSetAttribute(jv_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_jv2));
+    h->has_problem = true;
+    return MMBA_OK;
+}
+
+int mmba_solve(mmba_handle* h, double* x, mmba_result* result, double* fun_out) {
+    TRY(need_problem(h));
+    if (!x || !result) return fail(h, MMBA_ERR_ARG, "solve: null x or result");
+    std::memset(result, 0, sizeof(*result));
+    std::memset(h->prof.launches, 0, sizeof(h->prof.launches));
+    std::memset(h->prof.ms, 0, sizeof(h->prof.ms));
+    TRY(put_x(h, x, h->d.x));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    int rc = run_trf(h, result);
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    result->solve_ms = ms;
+    prof_collect(h);
+    if (rc != MMBA_OK) return rc;
+    TRY(get_x(h, h->d.x, x));
+    if (fun_out) {
+        if (h->opt.nranks > 1) std::memset(fun_out, 0, 2 * h->plan.n_obs * sizeof(double));
+        TRY(get_slots(h, h->d.res, 2, fun_out, 2, 0));
+    }
+    return MMBA_OK;
+}
+
+int mmba_get_log(const mmba_handle* h, mmba_iter_log* out, int capacity) {
+    if (!h) return MMBA_ERR_ARG;
+    const int n = (int)h->log.size();
+    if (out)
+        for (int i = 0; i < n && i < capacity; ++i) out[i] = h->log[i];
+    return n;
+}
+
+int mmba_get_profile(const mmba_handle* h, int64_t launches[MMBA_K_COUNT], double ms[MMBA_K_COUNT]) {
+    if (!h) return MMBA_ERR_ARG;
+    for (int i = 0; i < MMBA_K_COUNT; ++i) {
+        if (launches) launches[i] = h->prof.launches[i];
+        if (ms) ms[i] = h->prof.ms[i];
+    }
+    return MMBA_OK;
+}
+
+int mmba_get_shard(const mmba_handle* h, int64_t* n_obs_local, int64_t* n_points_local, int64_t* n_tiles) {
+    if (!h || !h->has_problem) return MMBA_ERR_STATE;
+    if (n_obs_local) *n_obs_local = h->plan.n_obs_local;
+    if (n_points_local) *n_points_local = h->npl;
+    if (n_tiles) *n_tiles = h->nt;
+    return MMBA_OK;
+}
+
+// ---- evaluation hooks ---------------------------------------------------------------------------
+int mmba_eval_residual(mmba_handle* h, const double* x, double* f) {
+    TRY(need_problem(h));
+    if (!x || !f) return fail(h, MMBA_ERR_ARG, "eval_residual: null argument");
+    Dev& d = h->d;
+    TRY(put_x(h, x, d.x));
+    TRY(cam_prep(h, d.x, d.camtab));
+    TRY(zero(h, d.scal + S_COST_NEW, 1));
+    if (h->nt)
+        LAUNCH(MMBA_K_RESID, resid_kernel<true>, (unsigned)h->nt, kT, h->smem_resid, h->targs, d.camtab, d.x + 6 * h->Nc, d.res,
+               d.scal + S_COST_NEW, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    CU(cudaGetLastError());
+    if (h->opt.nranks > 1) std::memset(f, 0, 2 * h->plan.n_obs * sizeof(double));
+    return get_slots(h, d.res, 2, f, 2, 0);
+}
+
+int mmba_eval_jacobian(mmba_handle* h, const double* x, double* Jc, double* Jp) {
+    TRY(need_problem(h));
+    if (!x || !Jc || !Jp) return fail(h, MMBA_ERR_ARG, "eval_jacobian: null argument");
+    Dev& d = h->d;
+    TRY(put_x(h, x, d.x));
+    TRY(linearise(h));
+    if (h->opt.nranks > 1) {
+        std::memset(Jc, 0, 12 * h->plan.n_obs * sizeof(double));
+        std::memset(Jp, 0, 6 * h->plan.n_obs * sizeof(double));
+    }
+    TRY(get_slots(h, d.J, 12, Jc, 12, 0));
+    return get_slots(h, d.J + 12 * h->ns, 6, Jp, 6, 0);
+}
+
+int mmba_eval_blocks(mmba_handle* h, const double* x, double* U, double* V, double* gc, double* gp, double* cost) {
+    TRY(need_problem(h));
+    if (!x) return fail(h, MMBA_ERR_ARG, "eval_blocks: null x");
+    Dev& d = h->d;
+    const Plan& pl = h->plan;
+    TRY(put_x(h, x, d.x));
+    TRY(linearise(h));
+    std::vector<double> hU(21 * h->Nc), hg(h->nloc), hV(6 * std::max<int64_t>(h->npl, 1));
+    CU(cudaMemcpyAsync(hU.data(), d.U, hU.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(hg.data(), d.g, hg.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->npl) CU(cudaMemcpyAsync(hV.data(), d.V, 6 * h->npl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    TRY(read_scalars(h));
+    if (cost) *cost = 0.5 * h->h_scal[S_COST];
+    if (U)
+        for (int64_t c = 0; c < h->Nc; ++c)
+            for (int a = 0; a < 6; ++a)
+                for (int b = 0; b < 6; ++b) U[c * 36 + a * 6 + b] = hU[c * 21 + (a <= b ? tri6(a, b) : tri6(b, a))];
+    if (gc) std::memcpy(gc, hg.data(), 6 * h->Nc * sizeof(double));
+    if (V && h->opt.nranks > 1) std::memset(V, 0, 9 * pl.n_points * sizeof(double));
+    if (gp && h->opt.nranks > 1) std::memset(gp, 0, 3 * pl.n_points * sizeof(double));
+    for (int64_t q = 0; q < h->npl; ++q) {
+        const int64_t p = pl.point_perm[pl.pt_begin + q];
+        if (V)
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) V[p * 9 + a * 3 + b] = hV[q * 6 + (a <= b ? tri3(a, b) : tri3(b, a))];
+        if (gp)
+            for (int k = 0; k < 3; ++k) gp[p * 3 + k] = hg[6 * h->Nc + q * 3 + k];
+    }
+    return MMBA_OK;
+}
+
+int mmba_eval_gn_step(mmba_handle* h, const double* x, const double* scale, double reg, double* p, int64_t* pcg_iterations,
+                      double* pcg_relres) {
+    TRY(need_problem(h));
+    if (!x || !scale || !p) return fail(h, MMBA_ERR_ARG, "eval_gn_step: null argument");
+    Dev& d = h->d;
+    TRY(put_x(h, x, d.x));
+    TRY(linearise(h));
+    // scale_inv = 1 / scale in the internal layout
+    {
+        std::vector<double> si(6 * h->Nc + 3 * h->plan.n_points);
+        for (size_t i = 0; i < si.size(); ++i) si[i] = 1.0 / scale[i];
+        TRY(put_x(h, si.data(), d.sinv));
+    }
+    TRY(gn_step(h, reg, pcg_iterations, pcg_relres));
+    // p = [px | dp * sinv_p]
+    const int64_t ncam = 6 * h->Nc, npt = 3 * h->npl;
+    TRY(zero(h, d.scal + S_DOT0, 2));
+    LAUNCH(MMBA_K_VEC, gn_assemble_kernel<false>, cdiv(ncam, 256), 256, 0, d.px, d.sinv, d.gh, d.gn, ncam, d.scal, 0);
+    if (npt)
+        LAUNCH(MMBA_K_VEC, gn_assemble_kernel<true>, cdiv(npt, 256), 256, 0, d.dp, d.sinv + ncam, d.gh + ncam, d.gn + ncam, npt,
+               d.scal, 0);
+    CU(cudaGetLastError());
+    return get_x(h, d.gn, p);
+}
+
+int mmba_eval_jnorm2(mmba_handle* h, const double* x, const double* s, double* jnorm2) {
+    TRY(need_problem(h));
+    if (!x || !s || !jnorm2) return fail(h, MMBA_ERR_ARG, "eval_jnorm2: null argument");
+    Dev& d = h->d;
+    TRY(put_x(h, x, d.x));
+    TRY(linearise(h));
+    TRY(put_x(h, s, d.tmp));
+    TRY(jv1(h, d.tmp));
+    TRY(read_scalars(h));
+    *jnorm2 = h->h_scal[S_JV00];
+    return MMBA_OK;
+}
+
+int mmba_bench_kernel(mmba_handle* h, const double* x, int kernel_class, int iters, double* avg_ms) {
+    TRY(need_problem(h));
+    if (!x || !avg_ms || iters <= 0) return fail(h, MMBA_ERR_ARG, "bench_kernel: bad argument");
+    Dev& d = h->d;
+    TRY(put_x(h, x, d.x));
+    TRY(linearise(h));
+    TRY(scale_and_grad(h, true));
+    const double reg = 1e-4;
+    int64_t its;
+    const int saved_maxit = h->opt.pcg_maxit;
+    h->opt.pcg_maxit = 2;
+    int rc = gn_step(h, reg, &its, nullptr);
+    h->opt.pcg_maxit = saved_maxit;
+    TRY(rc);
+    CU(cudaMemsetAsync(d.flags, 0, 2 * sizeof(int), h->stream));
+    LAUNCH(MMBA_K_VEC, unscale_kernel, cdiv(h->nloc, 256), 256, 0, d.gh, d.sinv, 1.0, d.tmp, h->nloc);
+    CU(cudaStreamSynchronize(h->stream));
+    const int mc = h->plan.max_tile_cams, mp = h->plan.max_tile_pts;
+    const unsigned nt = (unsigned)h->nt;
+    if (!nt) return fail(h, MMBA_ERR_STATE, "bench_kernel: this shard has no observations");
+    for (int pass = 0; pass < 2; ++pass) {
+        const int n = pass == 0 ? 2 : iters;
+        if (pass == 1) CU(cudaEventRecord(h->ev0, h->stream));
+        for (int i = 0; i < n; ++i) {
+            switch (kernel_class) {
+                case MMBA_K_BUILD:
+                    build_kernel<<<nt, kT, h->smem_build, h->stream>>>(h->targs, d.camtab, d.x + 6 * h->Nc, d.J, d.res, d.U, d.g,
+                                                                       d.V, d.g + 6 * h->Nc, d.scal, mc, mp);
+                    break;
+                case MMBA_K_RESID:
+                    resid_kernel<false><<<nt, kT, h->smem_resid, h->stream>>>(h->targs, d.camtab, d.x + 6 * h->Nc, nullptr,
+                                                                              d.scal + S_COST_NEW, mc, mp);
+                    break;
+                case MMBA_K_RHS:
+                    schur_kernel<SCHUR_RHS><<<nt, kT, h->smem_schur, h->stream>>>(h->targs, d.J, nullptr, d.M, d.zg, nullptr, d.y,
+                                                                                  d.Sd, nullptr, nullptr, mc, mp);
+                    break;
+                case MMBA_K_MATVEC:
+                    schur_kernel<SCHUR_MATVEC><<<nt, kT, h->smem_schur, h->stream>>>(h->targs, d.J, d.pxt, d.M, nullptr, nullptr,
+                                                                                     d.y, nullptr, nullptr, d.flags, mc, mp);
+                    break;
+                case MMBA_K_BACKSUB:
+                    schur_kernel<SCHUR_BACKSUB><<<nt, kT, h->smem_schur, h->stream>>>(h->targs, d.J, d.pxt, d.M, nullptr,
+                                                                                      d.g + 6 * h->Nc, nullptr, nullptr, d.dp,
+                                                                                      nullptr, mc, mp);
+                    break;
+                case MMBA_K_JV:
+                    jv_kernel<2, false><<<nt, kT, h->smem_jv2, h->stream>>>(h->targs, d.J, d.tmp, d.tmp + 6 * h->Nc, d.gh,
+                                                                            d.gh + 6 * h->Nc, d.scal, nullptr, mc, mp);
+                    break;
+                case MMBA_K_PTINV:
+                    point_invert_kernel<<<cdiv(h->npl, 256), 256, 0, h->stream>>>(d.V, d.g + 6 * h->Nc, d.sinv + 6 * h->Nc, reg,
+                                                                                   d.M, d.zg, h->npl);
+                    break;
+                default:
+                    return fail(h, MMBA_ERR_ARG, "bench_kernel: unsupported kernel class");
+            }
+        }
+        if (pass == 1) CU(cudaEventRecord(h->ev1, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaGetLastError());
+    }
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *avg_ms = ms / iters;
+    return MMBA_OK;
+}
+
+// ---- host-only functions ------------------------------------------------------------------------
+int mmba_host_tr2d(const double B[3], const double g[2], double delta, double p[2], int* newton) {
+    if (!B || !g || !p) return MMBA_ERR_ARG;
+    bool nw = false;
+    tr2d(B, g, delta, p, &nw);
+    if (newton) *newton = nw ? 1 : 0;
+    return MMBA_OK;
+}
+
+int mmba_host_min_quadratic_1d(double a, double b, double lb, double ub, double* t, double* y) {
+    if (!t || !y) return MMBA_ERR_ARG;
+    min_quadratic_1d(a, b, lb, ub, t, y);
+    return MMBA_OK;
+}
+
+int mmba_host_update_tr_radius(double delta, double actual, double predicted, double step_norm, int bound_hit,
+                               double* delta_new, double* ratio) {
+    if (!delta_new || !ratio) return MMBA_ERR_ARG;
+    update_tr_radius(delta, actual, predicted, step_norm, bound_hit != 0, delta_new, ratio);
+    return MMBA_OK;
+}
+
+int mmba_host_check_termination(double dF, double F, double dx_norm, double x_norm, double ratio, double ftol, double xtol) {
+    return check_termination(dF, F, dx_norm, x_norm, ratio, ftol, xtol);
+}
+
+int mmba_plan_create(mmba_plan** out, int64_t n_cams, int64_t n_points, int64_t n_obs, const int64_t* cam_idx,
+                     const int64_t* pt_idx, int rank, int nranks) {
+    if (!out) return fail(nullptr, MMBA_ERR_ARG, "null output plan");
+    *out = nullptr;
+    mmba_plan* p = new mmba_plan();
+    std::string err;
+    int rc = build_plan(p->plan, n_cams, n_points, n_obs, cam_idx, pt_idx, rank, nranks, err);
+    if (rc != MMBA_OK) {
+        delete p;
+        return fail(nullptr, rc, err);
+    }
+    *out = p;
+    return MMBA_OK;
+}
+
+void mmba_plan_destroy(mmba_plan* p) { delete p; }
+
+int mmba_plan_sizes(const mmba_plan* p, int64_t sizes[8]) {
+    if (!p || !sizes) return MMBA_ERR_ARG;
+    const Plan& pl = p->plan;
+    sizes[0] = pl.n_tiles;
+    sizes[1] = pl.n_obs_local;
+    sizes[2] = pl.n_points_local();
+    sizes[3] = pl.pt_begin;
+    sizes[4] = pl.pt_end;
+    sizes[5] = kTileObs;
+    sizes[6] = pl.max_tile_cams;
+    sizes[7] = pl.n_slots;
+    return MMBA_OK;
+}
+
+int mmba_plan_export(const mmba_plan* p, int64_t* obs_perm, int64_t* point_perm, int32_t* slot_cam_global,
+                     int32_t* slot_point_local) {
+    if (!p) return MMBA_ERR_ARG;
+    const Plan& pl = p->plan;
+    if (obs_perm) std::copy(pl.slot_obs.begin(), pl.slot_obs.end(), obs_perm);
+    if (point_perm)
+        for (int64_t q = 0; q < pl.n_points; ++q) point_perm[q] = pl.point_perm[q];
+    for (int64_t t = 0; t < pl.n_tiles; ++t) {
+        for (int j = 0; j < kTileObs; ++j) {
+            const int64_t s = t * kTileObs + j;
+            const bool live = pl.slot_obs[s] >= 0;
+            if (slot_cam_global) slot_cam_global[s] = live ? pl.tile_cams[pl.tiles[t].cam_off + pl.slot_cam[s]] : -1;
+            if (slot_point_local) slot_point_local[s] = live ? pl.tiles[t].pt0 + pl.slot_pt[s] : -1;
+        }
+    }
+    return MMBA_OK;
+}
+
+}  // extern "C"

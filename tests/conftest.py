@@ -1,0 +1,37 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu under gpurun)")
+
+
+@pytest.fixture(scope="session")
+def small():
+    return dict(np.load(os.path.join(GOLDEN, "small.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_c1():
+    return dict(np.load(os.path.join(GOLDEN, "c1.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_mid():
+    return dict(np.load(os.path.join(GOLDEN, "mid.npz")))
+
+
+def problem_x0(prob):
+    """Parameter vector the reference packs (bundleAdjuster.py:172-176) for a synth.Problem."""
+    from meatmodeler_b200 import bundleAdjuster as mm
+    ext, K, pts, uv, fi, pi = prob.args()
+    return np.hstack((mm.frameParameters(ext), np.asarray(pts).reshape(-1)))

@@ -1,0 +1,131 @@
+"""The CPU oracle against outputs of the unmodified reference (tests/golden, make_golden.py)."""
+import numpy as np
+
+from oracle import ba_oracle as ba
+from oracle import schur_trf
+
+
+def _sizes(g):
+    return len(g["ext"]), len(g["pts"])
+
+
+def test_frame_parameters(small):
+    got = ba.frame_parameters(small["ext"])
+    np.testing.assert_allclose(got, small["frame_parameters"], rtol=0, atol=1e-15)
+    assert np.all(got[:3] == 0)          # camera 0 is the identity rotation -> zero rvec (NaN -> 0 rule)
+    np.testing.assert_array_equal(np.hstack((got, small["pts"].reshape(-1))), small["x0"])
+
+
+def test_residuals_float64(small):
+    nc, npts = _sizes(small)
+    for xk, fk in (("x0", "f64"), ("x1", "f64_1")):
+        f = ba.residuals(small[xk], small["K"], nc, npts, small["fi"], small["pi"], small["uv"])
+        scale = np.abs(small["uv"]).max()
+        assert np.abs(f - small[fk]).max() <= 1e-12 * scale
+
+
+def test_residuals_longdouble(small):
+    nc, npts = _sizes(small)
+    f = ba.residuals(small["x0"].astype(np.longdouble), small["K"], nc, npts, small["fi"], small["pi"], small["uv"])
+    assert f.dtype == np.longdouble
+    ref = small["fld"].astype(np.longdouble) + small["fld_lo"].astype(np.longdouble)
+    assert np.abs(f - ref).max() <= 1e-15 * np.abs(small["uv"]).max()
+
+
+def test_theta_zero_rotation_is_exact():
+    X = np.random.default_rng(0).normal(size=(5, 3))
+    np.testing.assert_array_equal(ba.rotate(X, np.zeros((5, 3))), X)
+
+
+def test_sparsity_pattern(small):
+    nc, npts = _sizes(small)
+    A = ba.sparsity(nc, npts, small["fi"], small["pi"]).tocsr()
+    A.sort_indices()
+    np.testing.assert_array_equal(A.indices, small["pattern_indices"])
+    np.testing.assert_array_equal(A.indptr, small["pattern_indptr"])
+
+
+def test_analytic_jacobian_vs_reference_central_differences(small):
+    """Analytic blocks vs longdouble central differences of the reference ``project``; 1e-9 relative
+    per block.  Camera 0 at x0 has rvec == 0: the Taylor branch."""
+    nc, npts = _sizes(small)
+    for xk, jc, jp in (("x0", "Jc", "Jp"), ("x1", "Jc1", "Jp1")):
+        Jc, Jp = ba.jacobian_blocks(small[xk], small["K"], nc, npts, small["fi"], small["pi"])
+        for got, ref in ((Jc, small[jc]), (Jp, small[jp])):
+            err = np.abs(got - ref).max(axis=(1, 2)) / np.abs(ref).max(axis=(1, 2))
+            assert err.max() <= 1e-9
+
+
+def test_own_fd_matches_golden_fd(small):
+    nc, npts = _sizes(small)
+    Jc, Jp = ba.jacobian_blocks_fd(small["x0"], small["K"], nc, npts, small["fi"], small["pi"])
+    assert np.abs(Jc.astype(float) - small["Jc"]).max() <= 1e-9 * np.abs(small["Jc"]).max()
+    assert np.abs(Jp.astype(float) - small["Jp"]).max() <= 1e-9 * np.abs(small["Jp"]).max()
+
+
+def test_reference_path_restatement(small):
+    """``solve_reference_path`` (same scipy call as bundleAdjuster.py:180-192) reproduces the
+    reference run recorded in the golden file: identical nfev/status; costs to 1e-6 (the restated
+    residual rounds differently at 1e-16 and scipy's 2-point finite differences amplify that)."""
+    rec = []
+    res = ba.solve_reference_path(small["ext"], small["K"], small["pts"], small["uv"], small["fi"], small["pi"],
+                                  record=rec)
+    assert res.nfev == int(small["ref_nfev"]) and res.status == int(small["ref_status"])
+    np.testing.assert_allclose(rec, small["ref_costs"][1:], rtol=1e-6)
+    np.testing.assert_allclose(res.x, small["ref_x"], rtol=0, atol=1e-4)
+    pts, ext = ba.adjust_points(small["ext"], small["K"], small["pts"], small["uv"], small["fi"], small["pi"])
+    np.testing.assert_allclose(pts, small["adj_points"], atol=1e-4)
+    np.testing.assert_allclose(np.array(ext), small["adj_extrinsics"], atol=1e-4)
+
+
+def test_schur_trf_restatement_tracks_reference(small):
+    """Schur+PCG inner solve inside the restated TRF loop: same iteration count as the reference,
+    converged cost within 1e-6 relative (north_star bar); intermediate iterations differ only by
+    LSMR's own stopping tolerance (atol=btol=1e-6), bounded here at 1e-4."""
+    nc, npts = _sizes(small)
+    rec = []
+    out = schur_trf.solve(small["x0"], small["K"], nc, npts, small["fi"], small["pi"], small["uv"], record=rec)
+    ref = small["ref_costs"][1:]
+    assert out["nfev"] == int(small["ref_nfev"]) and out["status"] == int(small["ref_status"])
+    assert len(rec) == len(ref)
+    np.testing.assert_allclose(rec, ref, rtol=1e-4)
+    assert abs(out["cost"] - float(small["ref_cost"])) <= 1e-6 * float(small["ref_cost"])
+
+
+def test_schur_trf_on_mid_golden(golden_mid):
+    from meatmodeler_b200 import synth
+    prob = synth.make_problem(60, 1500, 9000, seed=7, hard=True, windowed=False)
+    ext, K, pts, uv, fi, pi = prob.args()
+    x0 = np.hstack((ba.frame_parameters(ext), pts.reshape(-1)))
+    assert abs(x0.sum() - float(golden_mid["x0_checksum"])) < 1e-9
+    rec = []
+    out = schur_trf.solve(x0, K, len(ext), len(pts), fi, pi, uv, record=rec)
+    ref = golden_mid["ref_costs"][1:]
+    assert len(rec) == len(ref) and out["nfev"] == int(golden_mid["ref_nfev"])
+    np.testing.assert_allclose(rec, ref, rtol=1e-4)
+    assert abs(out["cost"] - float(golden_mid["ref_cost"])) <= 1e-6 * float(golden_mid["ref_cost"])
+
+
+def test_block_sums_match_sparse_normal_equations(small):
+    """U, V, g blocks equal the blocks of J^T J and J^T f of the assembled sparse Jacobian."""
+    from scipy.sparse import csr_matrix
+    nc, npts = _sizes(small)
+    fi, pi = small["fi"], small["pi"]
+    x = small["x1"]
+    Jc, Jp = ba.jacobian_blocks(x, small["K"], nc, npts, fi, pi)
+    r = ba.residuals(x, small["K"], nc, npts, fi, pi, small["uv"])
+    n_obs = len(fi)
+    rows = np.repeat(np.arange(2 * n_obs), 9)
+    cols = np.concatenate((6 * fi[:, None] + np.arange(6), 6 * nc + 3 * pi[:, None] + np.arange(3)), axis=1)
+    cols = np.repeat(cols, 2, axis=0).reshape(-1)
+    vals = np.concatenate((Jc, Jp), axis=2).reshape(-1)
+    J = csr_matrix((vals, (rows, cols)), shape=(2 * n_obs, 6 * nc + 3 * npts))
+    H = (J.T @ J).toarray()
+    g = J.T @ r
+    U, V, gc, gp = ba.block_sums(Jc, Jp, r, nc, npts, fi, pi)
+    for c in range(nc):
+        np.testing.assert_allclose(U[c], H[6 * c:6 * c + 6, 6 * c:6 * c + 6], rtol=1e-12, atol=1e-9)
+    for p in range(npts):
+        o = 6 * nc + 3 * p
+        np.testing.assert_allclose(V[p], H[o:o + 3, o:o + 3], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(np.hstack((gc.ravel(), gp.ravel())), g, rtol=1e-12, atol=1e-9)
