@@ -117,6 +117,13 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
  * NULL) receives the residuals at the returned x in the caller's observation order. */
 int mmba_solve(mmba_handle* h, double* x, mmba_result* result, double* fun_out);
 
+/* The same solve with the parameters resident in HBM: mmba_set_x uploads a starting point once,
+ * mmba_solve_resident restarts from it without host<->device parameter traffic (what bench.py
+ * times as the device-resident figure), mmba_get_x downloads the current parameters. */
+int mmba_set_x(mmba_handle* h, const double* x);
+int mmba_solve_resident(mmba_handle* h, mmba_result* result);
+int mmba_get_x(mmba_handle* h, double* x);
+
 int mmba_get_log(const mmba_handle* h, mmba_iter_log* out, int capacity); /* returns row count */
 int mmba_get_profile(const mmba_handle* h, int64_t launches[MMBA_K_COUNT], double ms[MMBA_K_COUNT]);
 /* observations / points held by this rank and number of tiles (after set_problem) */

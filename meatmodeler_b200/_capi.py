@@ -61,6 +61,9 @@ SIGNATURES = {
     "mmba_destroy": (None, [_H]),
     "mmba_set_problem": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, _f64, _i64, _i64, _f64]),
     "mmba_solve": (C.c_int, [_H, _f64, C.POINTER(Result), C.c_void_p]),
+    "mmba_set_x": (C.c_int, [_H, _f64]),
+    "mmba_solve_resident": (C.c_int, [_H, C.POINTER(Result)]),
+    "mmba_get_x": (C.c_int, [_H, _f64]),
     "mmba_get_log": (C.c_int, [_H, C.POINTER(IterLog), C.c_int]),
     "mmba_get_profile": (C.c_int, [_H, C.POINTER(C.c_int64 * K_COUNT), C.POINTER(C.c_double * K_COUNT)]),
     "mmba_get_shard": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -185,6 +188,19 @@ class Engine:
         fun = np.empty(2 * self.sizes[2]) if want_fun else None
         _check(lib().mmba_solve(self._h, x, C.byref(res), fun.ctypes.data if want_fun else None), self._h)
         return x, res, fun
+
+    def set_x(self, x0):
+        _check(lib().mmba_set_x(self._h, self._x(x0)), self._h)
+
+    def solve_resident(self):
+        res = Result()
+        _check(lib().mmba_solve_resident(self._h, C.byref(res)), self._h)
+        return res
+
+    def get_x(self):
+        x = np.empty(self.n)
+        _check(lib().mmba_get_x(self._h, x), self._h)
+        return x
 
     def log(self):
         n = lib().mmba_get_log(self._h, None, 0)

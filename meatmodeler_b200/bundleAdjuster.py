@@ -118,7 +118,26 @@ def pointAdjustmentSparsity(n_frames, n_points, frame_indices, point_indices):
 # engine access
 # --------------------------------------------------------------------------------------------------
 
+def _dist_options():
+    """Shard options when the caller runs one process per GPU under ``torch.distributed``
+    (observations sharded by point, cameras replicated, NCCL all-reduce inside the engine).
+    A single process gets the single-GPU defaults; torch is not imported at all in that case."""
+    dist = getattr(sys.modules.get("torch"), "distributed", None)
+    if dist is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return {}
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    device = torch.cuda.current_device()
+    blob = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{device}")
+    if rank == 0:
+        blob.copy_(torch.frombuffer(bytearray(_capi.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(blob, src=0)
+    return dict(device=device, rank=rank, nranks=world, nccl_id=bytes(blob.cpu().numpy().tobytes()))
+
+
 def _engine(camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D, **options):
+    for k, v in _dist_options().items():
+        options.setdefault(k, v)
     eng = _capi.Engine(**options)
     eng.set_problem(n_frames, n_points, camera_matrix, frame_indices, point_indices, points_2D)
     return eng

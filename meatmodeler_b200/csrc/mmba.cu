@@ -100,7 +100,7 @@ struct Dev {
     double* uv;
     // linearisation
     double *J, *res;
-    double *x, *xn, *camtab, *camtab_n;
+    double *x, *xn, *x0, *camtab, *camtab_n;
     double *U, *g, *V, *M, *zg, *dp;
     // n-vectors (camera part first, then the local points)
     double *sinv, *gh, *gn, *s1, *s2, *v1, *v2, *tmp;
@@ -272,6 +272,7 @@ void carve(mmba_handle* h, Arena& a) {
     d.res = a.take<double>(2 * ns);
     d.x = a.take<double>(nloc);
     d.xn = a.take<double>(nloc);
+    d.x0 = a.take<double>(nloc);
     d.camtab = a.take<double>(kCamTab * Nc);
     d.camtab_n = a.take<double>(kCamTab * Nc);
     d.U = a.take<double>(21 * Nc);
@@ -903,13 +904,11 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     return MMBA_OK;
 }
 
-int mmba_solve(mmba_handle* h, double* x, mmba_result* result, double* fun_out) {
-    TRY(need_problem(h));
-    if (!x || !result) return fail(h, MMBA_ERR_ARG, "solve: null x or result");
+// TRF solve from the parameters in d.x; device time of the solve goes to result->solve_ms
+static int solve_on_device(mmba_handle* h, mmba_result* result) {
     std::memset(result, 0, sizeof(*result));
     std::memset(h->prof.launches, 0, sizeof(h->prof.launches));
     std::memset(h->prof.ms, 0, sizeof(h->prof.ms));
-    TRY(put_x(h, x, h->d.x));
     CU(cudaEventRecord(h->ev0, h->stream));
     int rc = run_trf(h, result);
     CU(cudaEventRecord(h->ev1, h->stream));
@@ -918,13 +917,39 @@ int mmba_solve(mmba_handle* h, double* x, mmba_result* result, double* fun_out) 
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     result->solve_ms = ms;
     prof_collect(h);
-    if (rc != MMBA_OK) return rc;
+    return rc;
+}
+
+int mmba_solve(mmba_handle* h, double* x, mmba_result* result, double* fun_out) {
+    TRY(need_problem(h));
+    if (!x || !result) return fail(h, MMBA_ERR_ARG, "solve: null x or result");
+    TRY(put_x(h, x, h->d.x));
+    TRY(solve_on_device(h, result));
     TRY(get_x(h, h->d.x, x));
     if (fun_out) {
         if (h->opt.nranks > 1) std::memset(fun_out, 0, 2 * h->plan.n_obs * sizeof(double));
         TRY(get_slots(h, h->d.res, 2, fun_out, 2, 0));
     }
     return MMBA_OK;
+}
+
+int mmba_set_x(mmba_handle* h, const double* x) {
+    TRY(need_problem(h));
+    if (!x) return fail(h, MMBA_ERR_ARG, "set_x: null x");
+    return put_x(h, x, h->d.x0);
+}
+
+int mmba_solve_resident(mmba_handle* h, mmba_result* result) {
+    TRY(need_problem(h));
+    if (!result) return fail(h, MMBA_ERR_ARG, "solve_resident: null result");
+    CU(cudaMemcpyAsync(h->d.x, h->d.x0, h->nloc * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return solve_on_device(h, result);
+}
+
+int mmba_get_x(mmba_handle* h, double* x) {
+    TRY(need_problem(h));
+    if (!x) return fail(h, MMBA_ERR_ARG, "get_x: null x");
+    return get_x(h, h->d.x, x);
 }
 
 int mmba_get_log(const mmba_handle* h, mmba_iter_log* out, int capacity) {
