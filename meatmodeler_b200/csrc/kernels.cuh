@@ -1,19 +1,33 @@
-// Device code of libmmba.so — float64 CUDA kernels for sm_100a (B200).
+// Device code of libmmba.so — float64 CUDA kernels for sm_100a (B200): the observation-streaming
+// kernels.  (Small-vector kernels: veckernels.cuh.)
 //
-// Data layout (all in HBM, per shard)
-//   * observations are reordered by the host plan (plan.h) into point-aligned tiles of kT = 256
-//     slots; one CTA of 256 threads owns one tile, one thread one observation slot.
-//   * J   : 18 rows x n_slots doubles, structure-of-arrays.  Rows 0..11 = 2x6 camera block
-//           (row-major, columns w0 w1 w2 t0 t1 t2), rows 12..17 = 2x3 point block.  Every pass
-//           over J is 18 fully coalesced 8-byte streams per warp.
-//   * res : 2 rows x n_slots (du, dv);  uv: 2 rows x n_slots.
-//   * per-slot metadata, 2 bytes each: local camera slot, local point index, and the tile's
-//     camera-sorted order (source slot + key) used by the warp-shuffle segmented scatter.
-//   * cameras: camtab[Nc][24] = R (9) | t (3) | Q (9) produced by cam_prep_kernel; each tile
-//     stages only the cameras it touches in shared memory.
-//   * points: x_p[3*Np] in the plan's internal order; V (6), g_p (3), M (6) per point.
-//   * camera accumulators U (21 upper-triangle doubles), g_c (6), y (6), Sd (21) per camera,
-//     updated with one native f64 RED per (warp-level camera run, component).
+// Data layout in HBM, per shard (built by plan.cpp)
+//   * observations are reordered into point-aligned TILES of kT = 256 slots; a point's observations
+//     are contiguous and never straddle a tile.  Everything per-observation is tile-major, so one
+//     tile is one contiguous block that a single TMA bulk copy moves:
+//       Jt   [tile][18][256] f64   36 864 B/tile   rows 0..11 = 2x6 camera block (row-major, columns
+//                                                  w0 w1 w2 t0 t1 t2), rows 12..17 = 2x3 point block
+//       uv   [tile][2][256]  f64    4 096 B/tile   observed pixel
+//       res  [tile][2][256]  f64                   residual (du, dv)
+//       meta [tile] TileMeta        2 064 B/tile   header + 4 x u16 per slot: local camera slot, local
+//                                                  point, and the tile's camera-sorted order (source
+//                                                  slot, key) that drives the warp-shuffle scatter
+//       tile_cams [tile][cam_stride] i32           global camera ids of the tile's local camera slots
+//   * cameras: camtab[Nc][24] = R (9) | t (3) | Q (9) from cam_prep_kernel (rotate's trigonometry
+//     hoisted from per-observation to per-camera); camera vectors are [Nc][6].
+//   * points (internal order, tile-contiguous): x_p[3], V[6], g_p[3], M[6] (damped inverse), ...
+//
+// Kernel structure: ONE persistent, warp-specialised kernel template (tile_kernel<MODE>).  Each CTA
+// owns a contiguous range of tiles and runs a kStages-deep mbarrier pipeline:
+//   * producer warp (warp 8): cp.async.bulk (TMA bulk copy, SASS UBLKCP) of the tile's J block and
+//     metadata into shared memory, plus the gather of the cameras the tile touches (rotation rows or
+//     PCG vector entries) and of the tile's point payloads, completing on the stage's "full" barrier;
+//   * 8 consumer warps: one thread per observation slot; per-point sums by warp-shuffle segmented
+//     reduction over the contiguous point runs, per-camera sums by re-reading the staged values in
+//     the tile's camera-sorted order, reducing runs with warp shuffles and issuing one f64 RED per
+//     (run, component).
+// Every pass is therefore a streaming pass at 24..184 B/observation with all latency (tile header ->
+// camera list -> camera rows) hidden behind the previous tile's arithmetic.
 //
 // Reference sites replaced: rotate/project/pointFun (bundleAdjuster.py:7-52, 81-102), scipy's
 // finite-difference Jacobian (_numdiff.py:770-893), J^T J / J^T f (common.py:590-610) and the
@@ -27,26 +41,21 @@
 namespace mmba {
 
 constexpr int kT = kTileObs;
-constexpr int kCamTab = 24;   // doubles per camera-table row in HBM
-constexpr int kCamS = 21;     // staged row length in shared memory (odd: conflict-free)
-constexpr int kVecS = 7;      // staged stride of a 6-vector per camera (odd)
+constexpr int kConsumers = kT;            // consumer threads per CTA (one per slot)
+constexpr int kThreads = kConsumers + 32; // + one producer warp
+constexpr int kStages = 2;
+constexpr int kCamTab = 24;               // doubles per camera-table row in HBM
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint16_t kPadPt = 0xFFFF;
+constexpr int kJRows = 18;
+constexpr int kJTileBytes = kJRows * kT * 8;
+constexpr int kUVTileBytes = 2 * kT * 8;
 
-struct TileArgs {
-    const int4* tiles;
-    const int32_t* tile_cams;
-    const uint16_t* slot_cam;
-    const uint16_t* slot_pt;
-    const uint16_t* sort_src;
-    const uint16_t* sort_key;
-    const double* uv;
-    int64_t n_slots;
-    double K[9];
-};
+static_assert(sizeof(TileMeta) == 2064, "TileMeta is bulk-copied: 16-byte multiple");
 
 // scalar slots in device memory (doubles).  Groups that are reduced across ranks together are
-// contiguous: [S_COST..S_X2] sum, S_GINF max, [S_JV00..S_JV11] sum, [S_DOT0..S_DOT9] sum, S_COST_NEW sum.
+// contiguous: [S_COST] sum, [S_GH2..S_X2] sum, S_GINF max, S_COST_NEW sum, [S_JV00..S_JV11] sum,
+// [S_DOT0..S_DOT9] sum.
 enum Scal {
     S_COST = 0,      // sum r^2 (build)
     S_GH2,           // ||g_h||^2
@@ -59,6 +68,133 @@ enum Scal {
     S_COUNT = 24
 };
 
+enum Mode { M_BUILD = 0, M_RESID, M_RESID_STORE, M_MATVEC, M_RHS, M_BACKSUB, M_JV1, M_JV2 };
+
+template <int MODE>
+struct Traits {
+    static constexpr bool kLoadJ = MODE >= M_MATVEC;
+    static constexpr bool kLoadUV = !kLoadJ;
+    // doubles gathered per camera into shared memory, and the (odd, conflict-free) smem stride
+    static constexpr int kCamRows = MODE == M_BUILD ? 21 : (MODE == M_RESID || MODE == M_RESID_STORE) ? 12
+                                  : MODE == M_RHS ? 0 : MODE == M_JV2 ? 12 : 6;
+    static constexpr int kCamStride = kCamRows | 1;
+    // per-point payloads staged by the producer
+    static constexpr int kPA = (MODE == M_MATVEC || MODE == M_RHS || MODE == M_BACKSUB) ? 6 : 3;
+    static constexpr int kPB = (MODE == M_RHS || MODE == M_BACKSUB || MODE == M_JV2) ? 3 : 0;
+    static constexpr bool kScatter = MODE == M_BUILD || MODE == M_MATVEC || MODE == M_RHS;
+    static constexpr int kPtAcc = MODE == M_BUILD ? 9 : (MODE == M_MATVEC || MODE == M_BACKSUB) ? 3 : 0;
+    static constexpr int kStageRows = (MODE == M_BUILD || MODE == M_RHS) ? 9 : MODE == M_MATVEC ? 6 : 0;
+};
+
+struct TileArgs {
+    const TileMeta* meta;
+    const int32_t* tile_cams;
+    const double* uv;
+    int n_tiles, cam_stride, max_cams, max_pts;
+    double K[9];
+};
+
+// operands of one launch; which ones are read depends on MODE
+struct ModeArgs {
+    const double* J;       // Jt (read)                      MATVEC RHS BACKSUB JV
+    double* Jw;            // Jt (written)                   BUILD
+    double* res;           // residuals                      BUILD RESID_STORE
+    const double* cam0;    // camtab / xt / vc0              gathered per tile camera
+    const double* cam1;    // vc1                            JV2
+    const double* ptA;     // x_p / M / vp0
+    const double* ptB;     // zg / g_p / vp1
+    double* y;             // [Nc][6]  scatter target        MATVEC RHS
+    double* Sd;            // [Nc][21]                       RHS
+    double* U;             // [Nc][21]                       BUILD
+    double* gc;            // [Nc][6]                        BUILD
+    double* V;             // [Np][6]                        BUILD
+    double* gp;            // [Np][3]                        BUILD
+    double* dp;            // [Np][3]                        BACKSUB
+    double* scal;          // scalar slots                   BUILD (S_COST) JV (S_JV*)
+    double* cost;          // trial cost slot                RESID
+    const int* done;       // PCG converged flag             MATVEC
+};
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory layout (identical on host and device)
+// ---------------------------------------------------------------------------------------------
+struct SmemLayout {
+    int off_J, off_meta, off_uv, off_camid, off_camvec, off_pa, off_pb, stage_bytes;
+    int off_stages, off_pt, off_z, off_buf, off_red, total;
+};
+
+__host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+template <int MODE>
+__host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts) {
+    using T = Traits<MODE>;
+    SmemLayout L{};
+    int o = 0;
+    L.off_J = o;
+    if (T::kLoadJ) o += kJTileBytes;
+    L.off_meta = o;
+    o += align_up((int)sizeof(TileMeta), 128);
+    L.off_uv = o;
+    if (T::kLoadUV) o += kUVTileBytes;
+    L.off_camid = o;
+    o += align_up(max_cams * 4, 16);
+    L.off_camvec = o;
+    o += align_up(max_cams * T::kCamStride * 8, 16);
+    L.off_pa = o;
+    o += align_up(max_pts * T::kPA * 8, 16);
+    L.off_pb = o;
+    o += align_up(max_pts * T::kPB * 8, 16);
+    L.stage_bytes = align_up(o, 128);
+    L.off_stages = 128;                                   // mbarriers live in the first 128 bytes
+    o = L.off_stages + kStages * L.stage_bytes;
+    L.off_pt = o;
+    o += align_up(max_pts * T::kPtAcc * 8, 16);
+    L.off_z = o;
+    o += align_up(max_pts * 3 * 8, 16);
+    L.off_buf = o;
+    o += 2 * T::kStageRows * kT * 8;
+    L.off_red = o;
+    o += 64 * 8;
+    L.total = o;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + TMA bulk copy + named barrier
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (TMA unit, no register staging); completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// barrier among the consumer warps only (the producer warp never joins)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
@@ -70,10 +206,26 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Block-wide sum of NV values per thread, result added to out[i] with one RED per block.
+// Sum of NV values per consumer thread over the CTA's consumers, added to out[i] with one RED each.
 template <int NV>
-__device__ __forceinline__ void block_accumulate(const double (&v)[NV], double* s_red /* >= 8*NV */,
-                                                 double* const* out) {
+__device__ __forceinline__ void consumer_accumulate(const double (&v)[NV], double* s_red /* >= 8*NV */, double* const* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double w = warp_sum(v[i]);
+        if (lane == 0) s_red[warp * NV + i] = w;
+    }
+    consumer_sync();
+    if (threadIdx.x < NV) {
+        double t = 0;
+        for (int w = 0; w < kConsumers / 32; ++w) t += s_red[w * NV + threadIdx.x];
+        red_add(out[threadIdx.x], t);
+    }
+}
+
+// Block-wide sum for the plain (non-persistent) vector kernels.
+template <int NV>
+__device__ __forceinline__ void block_accumulate(const double (&v)[NV], double* s_red /* >= 8*NV */, double* const* out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -112,9 +264,9 @@ __device__ __forceinline__ bool run_head(unsigned key, int lane) {
 
 // Per-point sums inside a tile: observations of a point are contiguous slots, so a warp-level
 // segmented reduction leaves one partial per (warp, point); partials are combined in shared
-// memory (a point of L observations spans at most ceil(L/32)+1 warps).
+// memory (a point of L observations spans at most ceil(L/32)+1 warps).  s_pt is zero on entry.
 template <int NV>
-__device__ __forceinline__ void tile_point_reduce(double (&v)[NV], unsigned lp, double* s_pt /* [npts][NV], zeroed */) {
+__device__ __forceinline__ void tile_point_reduce(double (&v)[NV], unsigned lp, double* s_pt /* [npts][NV] */) {
     const int lane = threadIdx.x & 31;
     warp_seg_reduce<NV>(v, lp, lane);
     if (run_head(lp, lane) && lp != kPadPt) {
@@ -123,27 +275,26 @@ __device__ __forceinline__ void tile_point_reduce(double (&v)[NV], unsigned lp, 
     }
 }
 
-// Per-camera scatter-add of NV values per observation: stage the values in shared memory, re-read
-// them in the tile's camera-sorted order, reduce runs of equal cameras with warp shuffles and issue
-// one f64 RED per (run, component) to out[cam * stride + offset + i].
+// Per-camera scatter-add of NV values per observation (one "round"): stage the values in shared
+// memory, re-read them in the tile's camera-sorted order, reduce runs of equal cameras with warp
+// shuffles and issue one f64 RED per (run, component) to out[cam * stride + offset + i].
+// Rounds alternate between two staging buffers, so one consumer barrier per round suffices.
 template <int NV>
-__device__ __forceinline__ void tile_camera_scatter(const double (&v)[NV], double* s_stage /* [NV][kT] */,
-                                                    unsigned src, unsigned key, const int* s_camid,
-                                                    double* out, int stride, int offset) {
+__device__ __forceinline__ void camera_scatter_round(const double (&v)[NV], double* s_buf /* [NV][kT] */, unsigned src,
+                                                     unsigned key, const int* s_camid, double* out, int stride, int offset) {
     const int tid = threadIdx.x, lane = tid & 31;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) s_stage[i * kT + tid] = v[i];
-    __syncthreads();
+    for (int i = 0; i < NV; ++i) s_buf[i * kT + tid] = v[i];
+    consumer_sync();
     double w[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) w[i] = s_stage[i * kT + src];
+    for (int i = 0; i < NV; ++i) w[i] = s_buf[i * kT + src];
     warp_seg_reduce<NV>(w, key, lane);
     if (run_head(key, lane) && key != kPadKey) {
         double* dst = out + (int64_t)s_camid[key] * stride + offset;
 #pragma unroll
         for (int i = 0; i < NV; ++i) red_add(dst + i, w[i]);
     }
-    __syncthreads();
 }
 
 // packed upper-triangle index helpers for 6x6 (21) and 3x3 (6)
@@ -152,9 +303,7 @@ __host__ __device__ constexpr int tri3(int a, int b) { return a * 3 - a * (a - 1
 __host__ __device__ constexpr int tri6_row(int idx) {
     return idx < 6 ? 0 : idx < 11 ? 1 : idx < 15 ? 2 : idx < 18 ? 3 : idx < 20 ? 4 : 5;
 }
-__host__ __device__ constexpr int tri6_col(int idx) {
-    return idx - tri6(tri6_row(idx), tri6_row(idx)) + tri6_row(idx);
-}
+__host__ __device__ constexpr int tri6_col(int idx) { return idx - tri6(tri6_row(idx), tri6_row(idx)) + tri6_row(idx); }
 
 // ---------------------------------------------------------------------------------------------
 // K0: per-camera rotation tables  (rotate's trigonometry, bundleAdjuster.py:16-26, hoisted from
@@ -215,25 +364,12 @@ __global__ void cam_prep_kernel(const double* __restrict__ xc, double* __restric
     row[21] = row[22] = row[23] = 0.0;
 }
 
-// ---------------------------------------------------------------------------------------------
-// tile prologue shared by the projection kernels: stage the tile's cameras and points
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_cameras(const TileArgs& A, const int4 ti, const double* __restrict__ camtab,
-                                              double* s_cam, int* s_camid) {
-    for (int i = threadIdx.x; i < ti.w * kCamS; i += blockDim.x) {
-        const int c = i / kCamS, k = i - c * kCamS;
-        s_cam[i] = camtab[(int64_t)A.tile_cams[ti.z + c] * kCamTab + k];
-    }
-    if (s_camid)
-        for (int i = threadIdx.x; i < ti.w; i += blockDim.x) s_camid[i] = A.tile_cams[ti.z + i];
-}
-
 // one observation: residual and (optionally) the analytic 2x6 / 2x3 blocks
 template <bool WITH_JAC>
-__device__ __forceinline__ void project_obs(const double* __restrict__ cam /* smem row: R t Q */,
-                                            const double X0, const double X1, const double X2,
-                                            const double* __restrict__ K, const double u_obs, const double v_obs,
-                                            double (&r)[2], double (&jc)[12], double (&jp)[6]) {
+__device__ __forceinline__ void project_obs(const double* __restrict__ cam /* smem row: R t [Q] */, const double X0,
+                                            const double X1, const double X2, const double* __restrict__ K,
+                                            const double u_obs, const double v_obs, double (&r)[2], double (&jc)[12],
+                                            double (&jp)[6]) {
     const double Y0 = cam[0] * X0 + cam[1] * X1 + cam[2] * X2;
     const double Y1 = cam[3] * X0 + cam[4] * X1 + cam[5] * X2;
     const double Y2 = cam[6] * X0 + cam[7] * X1 + cam[8] * X2;
@@ -271,130 +407,369 @@ __device__ __forceinline__ void project_obs(const double* __restrict__ cam /* sm
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: build — gather, project, residual, Jacobian blocks, and the normal-equation blocks
-//   per slot: 24 B in (indices + uv), 16 B residual + 144 B Jacobian out  -> 184 B/observation
-//   fused: cost, V_p / g_p (point-segment sums), U_c / g_c (camera scatter)
-// dynamic smem: s_cam[max_cams*21] | s_X[max_pts*3] | s_pt[max_pts*9] | s_stage[9*kT] | s_red[64] | s_camid[max_cams]
+// The streaming kernel.  Algorithmic bytes per observation:
+//   BUILD   184  (24 in: metadata + uv; 16 residual + 144 Jacobian out) + fused V/g_p, U/g_c, cost
+//   RESID    24  trial cost only
+//   MATVEC  152  y_c += sum_i Jc_i^T Jp_i M_p (sum_{j in p} Jp_j^T Jc_j xt_c(j))              (PCG)
+//   RHS     152  y_c += sum_i Jc_i^T Jp_i zg_p ;  Sd_c += sum_i E_i M_p E_i^T, E_i = Jc_i^T Jp_i
+//   BACKSUB 152  dp_p = M_p (g_p - sum_{j in p} Jp_j^T Jc_j xt_c(j))
+//   JV1/JV2 152  ||J v||^2 / 2x2 Gram of J [v0 v1]   (build_quadratic_1d, J_h.dot(S): common.py:282-288,
+//                trf.py:498-499); only scalars leave the SM
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kT)
-build_kernel(const TileArgs A, const double* __restrict__ camtab, const double* __restrict__ xp,
-             double* __restrict__ J, double* __restrict__ res, double* __restrict__ U, double* __restrict__ gc,
-             double* __restrict__ V, double* __restrict__ gp, double* __restrict__ scal, int max_cams, int max_pts) {
-    extern __shared__ double smem[];
-    double* s_cam = smem;
-    double* s_X = s_cam + max_cams * kCamS;
-    double* s_pt = s_X + max_pts * 3;
-    double* s_stage = s_pt + max_pts * 9;
-    double* s_red = s_stage + 9 * kT;
-    int* s_camid = reinterpret_cast<int*>(s_red + 64);
-
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) tile_kernel(const TileArgs A, const ModeArgs P) {
+    using T = Traits<MODE>;
+    if (MODE == M_MATVEC && P.done && *P.done) return;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SmemLayout L = smem_layout<MODE>(A.max_cams, A.max_pts);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + kStages;
     const int tid = threadIdx.x;
-    const int4 ti = A.tiles[blockIdx.x];
-    const int64_t slot = (int64_t)blockIdx.x * kT + tid;
-    stage_cameras(A, ti, camtab, s_cam, s_camid);
-    for (int i = tid; i < ti.y * 3; i += kT) s_X[i] = xp[(int64_t)ti.x * 3 + i];
-    for (int i = tid; i < ti.y * 9; i += kT) s_pt[i] = 0.0;
-    const unsigned lp = A.slot_pt[slot], lc = A.slot_cam[slot];
-    const unsigned src = A.sort_src[slot], key = A.sort_key[slot];
-    const bool valid = lp != kPadPt;
-    const double uo = valid ? A.uv[slot] : 0.0, vo = valid ? A.uv[A.n_slots + slot] : 0.0;
+
+    // contiguous tile range of this CTA
+    const int t_begin = (int)(((int64_t)blockIdx.x * A.n_tiles) / gridDim.x);
+    const int t_end = (int)(((int64_t)(blockIdx.x + 1) * A.n_tiles) / gridDim.x);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumers / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // scratch that must start at zero
+    if (T::kPtAcc) {
+        double* s_pt = reinterpret_cast<double*>(smem + L.off_pt);
+        for (int i = tid; i < A.max_pts * T::kPtAcc; i += kThreads) s_pt[i] = 0.0;
+    }
     __syncthreads();
 
-    double r[2] = {0, 0}, jc[12], jp[6];
+    if (tid >= kConsumers) {
+        // ======================= producer warp =======================
+        const int lane = tid - kConsumers;
+        constexpr int kCPL = kT / 32;   // camera ids per lane (registers)
+        int cams_next[kCPL];
+        int4 hdr_next = make_int4(0, 0, 0, 0);
+        auto prefetch = [&](int t) {
+            hdr_next = *reinterpret_cast<const int4*>(&A.meta[t]);
 #pragma unroll
-    for (int i = 0; i < 12; ++i) jc[i] = 0;
+            for (int j = 0; j < kCPL; ++j) {
+                const int c = lane + 32 * j;
+                cams_next[j] = c < A.max_cams ? A.tile_cams[(int64_t)t * A.cam_stride + c] : -1;
+            }
+        };
+        if (t_begin < t_end) prefetch(t_begin);
+        int stage = 0;
+        unsigned phase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            const int4 hdr = hdr_next;
+            int cams[kCPL];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) jp[i] = 0;
-    if (valid) {
-        const double* X = s_X + lp * 3;
-        project_obs<true>(s_cam + lc * kCamS, X[0], X[1], X[2], A.K, uo, vo, r, jc, jp);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) J[(int64_t)i * A.n_slots + slot] = jc[i];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) J[(int64_t)(12 + i) * A.n_slots + slot] = jp[i];
-        res[slot] = r[0];
-        res[A.n_slots + slot] = r[1];
-    }
-    // cost
-    {
-        double c[1] = {r[0] * r[0] + r[1] * r[1]};
-        double* outp[1] = {scal + S_COST};
-        block_accumulate<1>(c, s_red, outp);
-    }
-    // point blocks: V (6) and g_p (3)
-    {
-        double pv[9];
-        pv[0] = jp[0] * jp[0] + jp[3] * jp[3];
-        pv[1] = jp[0] * jp[1] + jp[3] * jp[4];
-        pv[2] = jp[0] * jp[2] + jp[3] * jp[5];
-        pv[3] = jp[1] * jp[1] + jp[4] * jp[4];
-        pv[4] = jp[1] * jp[2] + jp[4] * jp[5];
-        pv[5] = jp[2] * jp[2] + jp[5] * jp[5];
-        pv[6] = jp[0] * r[0] + jp[3] * r[1];
-        pv[7] = jp[1] * r[0] + jp[4] * r[1];
-        pv[8] = jp[2] * r[0] + jp[5] * r[1];
-        tile_point_reduce<9>(pv, lp, s_pt);
-    }
-    // camera blocks: U (21 upper-triangle) + g_c (6) in three rounds of 9
-    {
-        double cv[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) cv[i] = jc[tri6_row(i)] * jc[tri6_col(i)] + jc[6 + tri6_row(i)] * jc[6 + tri6_col(i)];
-        tile_camera_scatter<9>(cv, s_stage, src, key, s_camid, U, 21, 0);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) cv[i] = jc[tri6_row(9 + i)] * jc[tri6_col(9 + i)] + jc[6 + tri6_row(9 + i)] * jc[6 + tri6_col(9 + i)];
-        tile_camera_scatter<9>(cv, s_stage, src, key, s_camid, U, 21, 9);
-        double cw[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) cw[i] = jc[tri6_row(18 + i)] * jc[tri6_col(18 + i)] + jc[6 + tri6_row(18 + i)] * jc[6 + tri6_col(18 + i)];
-        tile_camera_scatter<3>(cw, s_stage, src, key, s_camid, U, 21, 18);
-        double cg[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) cg[i] = jc[i] * r[0] + jc[6 + i] * r[1];
-        tile_camera_scatter<6>(cg, s_stage, src, key, s_camid, gc, 6, 0);
-    }
-    // the tile owns its points: plain coalesced stores
-    for (int i = tid; i < ti.y * 9; i += kT) {
-        const int p = i / 9, k = i - p * 9;
-        if (k < 6) V[((int64_t)ti.x + p) * 6 + k] = s_pt[i];
-        else gp[((int64_t)ti.x + p) * 3 + (k - 6)] = s_pt[i];
-    }
-}
+            for (int j = 0; j < kCPL; ++j) cams[j] = cams_next[j];
+            if (t + 1 < t_end) prefetch(t + 1);
 
-// ---------------------------------------------------------------------------------------------
-// K1r: residual only (trial point) -> cost; optionally stores the residuals
-//   24 B/observation in, one scalar out
-// dynamic smem: s_cam[max_cams*21] | s_X[max_pts*3] | s_red[64]
-// ---------------------------------------------------------------------------------------------
-template <bool STORE>
-__global__ void __launch_bounds__(kT)
-resid_kernel(const TileArgs A, const double* __restrict__ camtab, const double* __restrict__ xp,
-             double* __restrict__ res, double* __restrict__ cost_out, int max_cams, int max_pts) {
-    extern __shared__ double smem[];
-    double* s_cam = smem;
-    double* s_X = s_cam + max_cams * kCamS;
-    double* s_red = s_X + max_pts * 3;
-    const int tid = threadIdx.x;
-    const int4 ti = A.tiles[blockIdx.x];
-    const int64_t slot = (int64_t)blockIdx.x * kT + tid;
-    stage_cameras(A, ti, camtab, s_cam, nullptr);
-    for (int i = tid; i < ti.y * 3; i += kT) s_X[i] = xp[(int64_t)ti.x * 3 + i];
-    const unsigned lp = A.slot_pt[slot], lc = A.slot_cam[slot];
-    const bool valid = lp != kPadPt;
-    const double uo = valid ? A.uv[slot] : 0.0, vo = valid ? A.uv[A.n_slots + slot] : 0.0;
-    __syncthreads();
-    double r[2] = {0, 0}, jc[12], jp[6];
-    if (valid) {
-        const double* X = s_X + lp * 3;
-        project_obs<false>(s_cam + lc * kCamS, X[0], X[1], X[2], A.K, uo, vo, r, jc, jp);
-        if (STORE) {
-            res[slot] = r[0];
-            res[A.n_slots + slot] = r[1];
+            unsigned char* st = smem + L.off_stages + stage * L.stage_bytes;
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (lane == 0) {
+                if (T::kLoadJ) bulk_g2s(st + L.off_J, P.J + (int64_t)t * kJRows * kT, kJTileBytes, &full[stage]);
+                bulk_g2s(st + L.off_meta, &A.meta[t], (unsigned)sizeof(TileMeta), &full[stage]);
+                if (T::kLoadUV) bulk_g2s(st + L.off_uv, A.uv + (int64_t)t * 2 * kT, kUVTileBytes, &full[stage]);
+            }
+            const int npts = hdr.y, ncams = hdr.z;
+            // camera ids, then the gathered camera rows
+            int* s_camid = reinterpret_cast<int*>(st + L.off_camid);
+#pragma unroll
+            for (int j = 0; j < kCPL; ++j) {
+                const int c = lane + 32 * j;
+                if (c < ncams) s_camid[c] = cams[j];
+            }
+            __syncwarp();
+            if (T::kCamRows > 0) {
+                double* s_cv = reinterpret_cast<double*>(st + L.off_camvec);
+                const int total = ncams * T::kCamRows;
+                for (int i = lane; i < total; i += 32) {
+                    const int c = i / T::kCamRows, k = i - c * T::kCamRows;
+                    const int cam = s_camid[c];
+                    double v;
+                    if (MODE == M_BUILD || MODE == M_RESID || MODE == M_RESID_STORE) v = P.cam0[(int64_t)cam * kCamTab + k];
+                    else if (MODE == M_JV2) v = k < 6 ? P.cam0[(int64_t)cam * 6 + k] : P.cam1[(int64_t)cam * 6 + (k - 6)];
+                    else v = P.cam0[(int64_t)cam * 6 + k];
+                    s_cv[c * T::kCamStride + k] = v;
+                }
+            }
+            // point payloads (contiguous slices of the point arrays)
+            {
+                double* s_pa = reinterpret_cast<double*>(st + L.off_pa);
+                const double* src = P.ptA + (int64_t)hdr.x * T::kPA;
+                for (int i = lane; i < npts * T::kPA; i += 32) s_pa[i] = src[i];
+            }
+            if (T::kPB > 0) {
+                double* s_pb = reinterpret_cast<double*>(st + L.off_pb);
+                const double* src = P.ptB + (int64_t)hdr.x * T::kPB;
+                for (int i = lane; i < npts * T::kPB; i += 32) s_pb[i] = src[i];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned tx = (T::kLoadJ ? kJTileBytes : 0) + (unsigned)sizeof(TileMeta) + (T::kLoadUV ? kUVTileBytes : 0);
+                mbar_arrive_expect_tx(&full[stage], tx);
+            }
+            if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+        return;
+    }
+
+    // ======================= consumer warps =======================
+    const int lane = tid & 31;
+    double* s_pt = reinterpret_cast<double*>(smem + L.off_pt);
+    double* s_z = reinterpret_cast<double*>(smem + L.off_z);
+    double* s_buf = reinterpret_cast<double*>(smem + L.off_buf);
+    double* s_red = reinterpret_cast<double*>(smem + L.off_red);
+    int round = 0;                 // staging-buffer parity of camera_scatter_round
+    double acc[3] = {0, 0, 0};     // cost (BUILD / RESID) or Gram (JV)
+    int stage = 0;
+    unsigned phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+        unsigned char* st = smem + L.off_stages + stage * L.stage_bytes;
+        mbar_wait(&full[stage], phase);
+        const TileMeta* mt = reinterpret_cast<const TileMeta*>(st + L.off_meta);
+        const double* sJ = reinterpret_cast<const double*>(st + L.off_J);
+        const double* s_cv = reinterpret_cast<const double*>(st + L.off_camvec);
+        const double* s_pa = reinterpret_cast<const double*>(st + L.off_pa);
+        const double* s_pb = reinterpret_cast<const double*>(st + L.off_pb);
+        const int* s_camid = reinterpret_cast<const int*>(st + L.off_camid);
+        const int pt0 = mt->pt0, npts = mt->npts;
+        const unsigned lp = mt->slot_pt[tid], lc = mt->slot_cam[tid];
+        const bool valid = lp != kPadPt;
+        const int lps = valid ? (int)lp : 0;
+        unsigned src = 0, key = 0;
+        if (T::kScatter) {
+            src = mt->sort_src[tid];
+            key = mt->sort_key[tid];
+        }
+
+        if constexpr (MODE == M_BUILD || MODE == M_RESID || MODE == M_RESID_STORE) {
+            const double* s_uv = reinterpret_cast<const double*>(st + L.off_uv);
+            double r[2] = {0, 0}, jc[12], jp[6];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) jc[i] = 0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) jp[i] = 0;
+            if (valid) {
+                const double* X = s_pa + lp * 3;
+                project_obs<MODE == M_BUILD>(s_cv + lc * T::kCamStride, X[0], X[1], X[2], A.K, s_uv[tid], s_uv[kT + tid], r, jc, jp);
+            }
+            acc[0] += r[0] * r[0] + r[1] * r[1];
+            if (MODE != M_RESID) {
+                double* rt = P.res + (int64_t)t * 2 * kT;
+                rt[tid] = r[0];
+                rt[kT + tid] = r[1];
+            }
+            if constexpr (MODE == M_BUILD) {
+                double* Jt = P.Jw + (int64_t)t * kJRows * kT;
+#pragma unroll
+                for (int i = 0; i < 12; ++i) Jt[i * kT + tid] = jc[i];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) Jt[(12 + i) * kT + tid] = jp[i];
+                // point blocks: V (6) and g_p (3)
+                double pv[9];
+                pv[0] = jp[0] * jp[0] + jp[3] * jp[3];
+                pv[1] = jp[0] * jp[1] + jp[3] * jp[4];
+                pv[2] = jp[0] * jp[2] + jp[3] * jp[5];
+                pv[3] = jp[1] * jp[1] + jp[4] * jp[4];
+                pv[4] = jp[1] * jp[2] + jp[4] * jp[5];
+                pv[5] = jp[2] * jp[2] + jp[5] * jp[5];
+                pv[6] = jp[0] * r[0] + jp[3] * r[1];
+                pv[7] = jp[1] * r[0] + jp[4] * r[1];
+                pv[8] = jp[2] * r[0] + jp[5] * r[1];
+                tile_point_reduce<9>(pv, lp, s_pt);
+                // camera blocks: U (21 upper-triangle) + g_c (6) in four rounds
+                double cv[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) cv[i] = jc[tri6_row(i)] * jc[tri6_col(i)] + jc[6 + tri6_row(i)] * jc[6 + tri6_col(i)];
+                camera_scatter_round<9>(cv, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.U, 21, 0);
+                // the round's barrier also completed the point sums: the tile owns its points
+                for (int i = tid; i < npts * 9; i += kConsumers) {
+                    const int p = i / 9, k = i - p * 9;
+                    const double v = s_pt[i];
+                    s_pt[i] = 0.0;
+                    if (k < 6) P.V[((int64_t)pt0 + p) * 6 + k] = v;
+                    else P.gp[((int64_t)pt0 + p) * 3 + (k - 6)] = v;
+                }
+#pragma unroll
+                for (int i = 0; i < 9; ++i)
+                    cv[i] = jc[tri6_row(9 + i)] * jc[tri6_col(9 + i)] + jc[6 + tri6_row(9 + i)] * jc[6 + tri6_col(9 + i)];
+                camera_scatter_round<9>(cv, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.U, 21, 9);
+                double cw[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    cw[i] = jc[tri6_row(18 + i)] * jc[tri6_col(18 + i)] + jc[6 + tri6_row(18 + i)] * jc[6 + tri6_col(18 + i)];
+                camera_scatter_round<3>(cw, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.U, 21, 18);
+                double cg[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) cg[i] = jc[i] * r[0] + jc[6 + i] * r[1];
+                camera_scatter_round<6>(cg, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.gc, 6, 0);
+            }
+        } else if constexpr (MODE == M_JV1 || MODE == M_JV2) {
+            constexpr int NV = MODE == M_JV2 ? 2 : 1;
+            double e[NV][2];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const double* c = s_cv + lc * T::kCamStride + v * 6;
+                const double* p = (v == 0 ? s_pa : s_pb) + lps * 3;
+                double e0 = 0, e1 = 0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    e0 += sJ[k * kT + tid] * c[k];
+                    e1 += sJ[(6 + k) * kT + tid] * c[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    e0 += sJ[(12 + k) * kT + tid] * p[k];
+                    e1 += sJ[(15 + k) * kT + tid] * p[k];
+                }
+                e[v][0] = valid ? e0 : 0.0;
+                e[v][1] = valid ? e1 : 0.0;
+            }
+            acc[0] += e[0][0] * e[0][0] + e[0][1] * e[0][1];
+            if (NV == 2) {
+                acc[1] += e[0][0] * e[NV - 1][0] + e[0][1] * e[NV - 1][1];
+                acc[2] += e[NV - 1][0] * e[NV - 1][0] + e[NV - 1][1] * e[NV - 1][1];
+            }
+        } else {
+            // ---- Schur passes: MATVEC / RHS / BACKSUB ----
+            double jc[12], jp[6];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) jc[i] = valid ? sJ[i * kT + tid] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) jp[i] = valid ? sJ[(12 + i) * kT + tid] : 0.0;
+            double z0, z1, z2;
+            if constexpr (MODE != M_RHS) {
+                // u = Jc xt_c ; w = Jp^T u ; t_p = sum over the point's observations
+                const double* xc = s_cv + lc * T::kCamStride;
+                double u0 = 0, u1 = 0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    u0 += jc[k] * xc[k];
+                    u1 += jc[6 + k] * xc[k];
+                }
+                double w[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) w[k] = jp[k] * u0 + jp[3 + k] * u1;
+                tile_point_reduce<3>(w, lp, s_pt);
+                consumer_sync();
+                // one thread per point: z = M t  (MATVEC)  or  dp = M (g - t)  (BACKSUB)
+                if (tid < npts) {
+                    double t0 = s_pt[tid * 3], t1 = s_pt[tid * 3 + 1], t2 = s_pt[tid * 3 + 2];
+                    s_pt[tid * 3] = 0.0;
+                    s_pt[tid * 3 + 1] = 0.0;
+                    s_pt[tid * 3 + 2] = 0.0;
+                    if (MODE == M_BACKSUB) {
+                        t0 = s_pb[tid * 3] - t0;
+                        t1 = s_pb[tid * 3 + 1] - t1;
+                        t2 = s_pb[tid * 3 + 2] - t2;
+                    }
+                    const double* m = s_pa + tid * 6;
+                    const double y0 = m[0] * t0 + m[1] * t1 + m[2] * t2;
+                    const double y1 = m[1] * t0 + m[3] * t1 + m[4] * t2;
+                    const double y2 = m[2] * t0 + m[4] * t1 + m[5] * t2;
+                    if (MODE == M_BACKSUB) {
+                        double* o = P.dp + ((int64_t)pt0 + tid) * 3;
+                        o[0] = y0;
+                        o[1] = y1;
+                        o[2] = y2;
+                    } else {
+                        s_z[tid * 3] = y0;
+                        s_z[tid * 3 + 1] = y1;
+                        s_z[tid * 3 + 2] = y2;
+                    }
+                }
+                if (MODE == M_BACKSUB) {
+                    consumer_sync();   // s_pt zeroed before the next tile's atomics; stage reads done
+                } else {
+                    consumer_sync();
+                    z0 = s_z[lps * 3];
+                    z1 = s_z[lps * 3 + 1];
+                    z2 = s_z[lps * 3 + 2];
+                }
+            } else {
+                z0 = s_pb[lps * 3];
+                z1 = s_pb[lps * 3 + 1];
+                z2 = s_pb[lps * 3 + 2];
+            }
+            if constexpr (MODE != M_BACKSUB) {
+                // v = Jp z_p ; contribution Jc^T v to the camera
+                const double v0 = jp[0] * z0 + jp[1] * z1 + jp[2] * z2;
+                const double v1 = jp[3] * z0 + jp[4] * z1 + jp[5] * z2;
+                double cv[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) cv[k] = jc[k] * v0 + jc[6 + k] * v1;
+                camera_scatter_round<6>(cv, s_buf + (round++ & 1) * T::kStageRows * kT, src, key, s_camid, P.y, 6, 0);
+            }
+            if constexpr (MODE == M_RHS) {
+                // Schur diagonal: E = Jc^T Jp (6x3), F = E M (6x3), Sd += F E^T (upper triangle)
+                const double* m = s_pa + lps * 6;
+                const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5];
+                double E[18], F[18];
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) E[a * 3 + k] = jc[a] * jp[k] + jc[6 + a] * jp[3 + k];
+                    F[a * 3 + 0] = E[a * 3] * m0 + E[a * 3 + 1] * m1 + E[a * 3 + 2] * m2;
+                    F[a * 3 + 1] = E[a * 3] * m1 + E[a * 3 + 1] * m3 + E[a * 3 + 2] * m4;
+                    F[a * 3 + 2] = E[a * 3] * m2 + E[a * 3 + 1] * m4 + E[a * 3 + 2] * m5;
+                }
+                double sv[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    const int a = tri6_row(i), b = tri6_col(i);
+                    sv[i] = F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2];
+                }
+                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.Sd, 21, 0);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    const int a = tri6_row(9 + i), b = tri6_col(9 + i);
+                    sv[i] = F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2];
+                }
+                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.Sd, 21, 9);
+                double sw[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int a = tri6_row(18 + i), b = tri6_col(18 + i);
+                    sw[i] = F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2];
+                }
+                camera_scatter_round<3>(sw, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.Sd, 21, 18);
+            }
+        }
+        // all reads of this stage are done: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
         }
     }
-    double c[1] = {r[0] * r[0] + r[1] * r[1]};
-    double* outp[1] = {cost_out};
-    block_accumulate<1>(c, s_red, outp);
+    // per-CTA scalar results
+    if constexpr (MODE == M_BUILD) {
+        double c[1] = {acc[0]};
+        double* outp[1] = {P.scal + S_COST};
+        consumer_accumulate<1>(c, s_red, outp);
+    } else if constexpr (MODE == M_RESID || MODE == M_RESID_STORE) {
+        double c[1] = {acc[0]};
+        double* outp[1] = {P.cost};
+        consumer_accumulate<1>(c, s_red, outp);
+    } else if constexpr (MODE == M_JV1) {
+        double c[1] = {acc[0]};
+        double* outp[1] = {P.scal + S_JV00};
+        consumer_accumulate<1>(c, s_red, outp);
+    } else if constexpr (MODE == M_JV2) {
+        double* outp[3] = {P.scal + S_JV00, P.scal + S_JV01, P.scal + S_JV11};
+        consumer_accumulate<3>(acc, s_red, outp);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -437,214 +812,6 @@ __global__ void point_invert_kernel(const double* __restrict__ V, const double* 
     zg[p * 3 + 0] = m[0] * g0 + m[1] * g1 + m[2] * g2;
     zg[p * 3 + 1] = m[1] * g0 + m[3] * g1 + m[4] * g2;
     zg[p * 3 + 2] = m[2] * g0 + m[4] * g1 + m[5] * g2;
-}
-
-// ---------------------------------------------------------------------------------------------
-// K5 family: one streaming pass over J per launch (144 B Jacobian + 8 B metadata per observation)
-//   SCHUR_MATVEC : y_c += sum_i Jc_i^T Jp_i M_p (sum_{j in p} Jp_j^T Jc_j xt_c(j))       (PCG)
-//   SCHUR_RHS    : y_c += sum_i Jc_i^T Jp_i zg_p ;  Sd_c += sum_i E_i M_p E_i^T, E_i = Jc_i^T Jp_i
-//   SCHUR_BACKSUB: dp_p = M_p (g_p - sum_{j in p} Jp_j^T Jc_j xt_c(j))
-// dynamic smem: s_xc[max_cams*7] | s_pt[max_pts*3] | s_stage[9*kT] | s_camid[max_cams]
-// ---------------------------------------------------------------------------------------------
-enum SchurMode { SCHUR_MATVEC = 0, SCHUR_RHS = 1, SCHUR_BACKSUB = 2 };
-
-template <int MODE>
-__global__ void __launch_bounds__(kT)
-schur_kernel(const TileArgs A, const double* __restrict__ J, const double* __restrict__ xt,
-             const double* __restrict__ M, const double* __restrict__ zg, const double* __restrict__ gp,
-             double* __restrict__ y, double* __restrict__ Sd, double* __restrict__ dp,
-             const int* __restrict__ done, int max_cams, int max_pts) {
-    if (MODE == SCHUR_MATVEC && done && *done) return;
-    extern __shared__ double smem[];
-    double* s_xc = smem;
-    double* s_pt = s_xc + max_cams * kVecS;
-    double* s_stage = s_pt + max_pts * 3;
-    int* s_camid = reinterpret_cast<int*>(s_stage + 9 * kT);
-
-    const int tid = threadIdx.x;
-    const int4 ti = A.tiles[blockIdx.x];
-    const int64_t slot = (int64_t)blockIdx.x * kT + tid;
-    const int64_t ns = A.n_slots;
-    // issue the J loads first: 18 independent coalesced streams
-    double jc[12], jp[6];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) jc[i] = __ldg(J + (int64_t)i * ns + slot);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) jp[i] = __ldg(J + (int64_t)(12 + i) * ns + slot);
-    const unsigned lp = A.slot_pt[slot], lc = A.slot_cam[slot];
-    const unsigned src = A.sort_src[slot], key = A.sort_key[slot];
-    const bool valid = lp != kPadPt;
-
-    if (MODE != SCHUR_BACKSUB)
-        for (int i = tid; i < ti.w; i += kT) s_camid[i] = A.tile_cams[ti.z + i];
-    if (MODE != SCHUR_RHS) {
-        for (int i = tid; i < ti.w * 6; i += kT) {
-            const int c = i / 6, k = i - c * 6;
-            s_xc[c * kVecS + k] = xt[(int64_t)A.tile_cams[ti.z + c] * 6 + k];
-        }
-        for (int i = tid; i < ti.y * 3; i += kT) s_pt[i] = 0.0;
-    } else {
-        for (int i = tid; i < ti.y * 3; i += kT) s_pt[i] = zg[(int64_t)ti.x * 3 + i];
-    }
-    __syncthreads();
-
-    if (MODE != SCHUR_RHS) {
-        // u = Jc xt_c ; w = Jp^T u ; t_p = sum over the point's observations
-        const double* xc = s_xc + lc * kVecS;
-        double u0 = 0, u1 = 0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            u0 += jc[k] * xc[k];
-            u1 += jc[6 + k] * xc[k];
-        }
-        double w[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) w[k] = jp[k] * u0 + jp[3 + k] * u1;
-        tile_point_reduce<3>(w, lp, s_pt);
-        __syncthreads();
-        // one thread per point: z = M t  (MATVEC)  or  dp = M (g - t)  (BACKSUB)
-        if (tid < ti.y) {
-            const int64_t p = (int64_t)ti.x + tid;
-            double t0 = s_pt[tid * 3], t1 = s_pt[tid * 3 + 1], t2 = s_pt[tid * 3 + 2];
-            if (MODE == SCHUR_BACKSUB) {
-                t0 = gp[p * 3] - t0;
-                t1 = gp[p * 3 + 1] - t1;
-                t2 = gp[p * 3 + 2] - t2;
-            }
-            const double* m = M + p * 6;
-            const double z0 = m[0] * t0 + m[1] * t1 + m[2] * t2;
-            const double z1 = m[1] * t0 + m[3] * t1 + m[4] * t2;
-            const double z2 = m[2] * t0 + m[4] * t1 + m[5] * t2;
-            if (MODE == SCHUR_BACKSUB) {
-                dp[p * 3] = z0;
-                dp[p * 3 + 1] = z1;
-                dp[p * 3 + 2] = z2;
-            } else {
-                s_pt[tid * 3] = z0;
-                s_pt[tid * 3 + 1] = z1;
-                s_pt[tid * 3 + 2] = z2;
-            }
-        }
-        if (MODE == SCHUR_BACKSUB) return;
-        __syncthreads();
-    }
-    // v = Jp z_p ; contribution Jc^T v to the camera
-    const int lps = valid ? lp : 0;
-    const double z0 = s_pt[lps * 3], z1 = s_pt[lps * 3 + 1], z2 = s_pt[lps * 3 + 2];
-    const double v0 = jp[0] * z0 + jp[1] * z1 + jp[2] * z2;
-    const double v1 = jp[3] * z0 + jp[4] * z1 + jp[5] * z2;
-    double cv[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) cv[k] = jc[k] * v0 + jc[6 + k] * v1;
-    tile_camera_scatter<6>(cv, s_stage, src, key, s_camid, y, 6, 0);
-
-    if (MODE == SCHUR_RHS) {
-        // Schur diagonal: E = Jc^T Jp (6x3), F = E M (6x3), Sd += F E^T (upper triangle)
-        const double* m = M + ((int64_t)ti.x + lps) * 6;
-        const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5];
-        double E[18], F[18];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) E[a * 3 + k] = jc[a] * jp[k] + jc[6 + a] * jp[3 + k];
-            F[a * 3 + 0] = E[a * 3] * m0 + E[a * 3 + 1] * m1 + E[a * 3 + 2] * m2;
-            F[a * 3 + 1] = E[a * 3] * m1 + E[a * 3 + 1] * m3 + E[a * 3 + 2] * m4;
-            F[a * 3 + 2] = E[a * 3] * m2 + E[a * 3 + 1] * m4 + E[a * 3 + 2] * m5;
-        }
-        double sv[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            const int a = tri6_row(i), b = tri6_col(i);
-            sv[i] = F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2];
-        }
-        tile_camera_scatter<9>(sv, s_stage, src, key, s_camid, Sd, 21, 0);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            const int a = tri6_row(9 + i), b = tri6_col(9 + i);
-            sv[i] = F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2];
-        }
-        tile_camera_scatter<9>(sv, s_stage, src, key, s_camid, Sd, 21, 9);
-        double sw[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int a = tri6_row(18 + i), b = tri6_col(18 + i);
-            sw[i] = F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2];
-        }
-        tile_camera_scatter<3>(sw, s_stage, src, key, s_camid, Sd, 21, 18);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K8: J*v products for NVEC (1 or 2) unscaled n-vectors; only the Gram scalars leave the SM
-//   (build_quadratic_1d / J_h.dot(S), common.py:282-288, trf.py:498-499).  Optionally stores J*v0.
-// dynamic smem: s_vc[NVEC][max_cams*7] | s_vp[NVEC][max_pts*3] | s_red[64]
-// ---------------------------------------------------------------------------------------------
-template <int NVEC, bool STORE>
-__global__ void __launch_bounds__(kT)
-jv_kernel(const TileArgs A, const double* __restrict__ J, const double* __restrict__ vc0,
-          const double* __restrict__ vp0, const double* __restrict__ vc1, const double* __restrict__ vp1,
-          double* __restrict__ scal, double* __restrict__ jv_out, int max_cams, int max_pts) {
-    extern __shared__ double smem[];
-    double* s_vc = smem;
-    double* s_vp = s_vc + NVEC * max_cams * kVecS;
-    double* s_red = s_vp + NVEC * max_pts * 3;
-    const int tid = threadIdx.x;
-    const int4 ti = A.tiles[blockIdx.x];
-    const int64_t slot = (int64_t)blockIdx.x * kT + tid;
-    const int64_t ns = A.n_slots;
-    double jc[12], jp[6];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) jc[i] = __ldg(J + (int64_t)i * ns + slot);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) jp[i] = __ldg(J + (int64_t)(12 + i) * ns + slot);
-    const unsigned lp = A.slot_pt[slot], lc = A.slot_cam[slot];
-    const bool valid = lp != kPadPt;
-#pragma unroll
-    for (int v = 0; v < NVEC; ++v) {
-        const double* vc = v == 0 ? vc0 : vc1;
-        const double* vp = v == 0 ? vp0 : vp1;
-        for (int i = tid; i < ti.w * 6; i += kT) {
-            const int c = i / 6, k = i - c * 6;
-            s_vc[v * max_cams * kVecS + c * kVecS + k] = vc[(int64_t)A.tile_cams[ti.z + c] * 6 + k];
-        }
-        for (int i = tid; i < ti.y * 3; i += kT) s_vp[v * max_pts * 3 + i] = vp[(int64_t)ti.x * 3 + i];
-    }
-    __syncthreads();
-    double e[NVEC][2];
-    const int lps = valid ? lp : 0;
-#pragma unroll
-    for (int v = 0; v < NVEC; ++v) {
-        const double* c = s_vc + v * max_cams * kVecS + lc * kVecS;
-        const double* p = s_vp + v * max_pts * 3 + lps * 3;
-        double e0 = 0, e1 = 0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            e0 += jc[k] * c[k];
-            e1 += jc[6 + k] * c[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            e0 += jp[k] * p[k];
-            e1 += jp[3 + k] * p[k];
-        }
-        e[v][0] = e0;
-        e[v][1] = e1;
-    }
-    if (STORE && valid) {
-        jv_out[slot] = e[0][0];
-        jv_out[ns + slot] = e[0][1];
-    }
-    if (NVEC == 1) {
-        double g[1] = {e[0][0] * e[0][0] + e[0][1] * e[0][1]};
-        double* outp[1] = {scal + S_JV00};
-        block_accumulate<1>(g, s_red, outp);
-    } else {
-        double g[3] = {e[0][0] * e[0][0] + e[0][1] * e[0][1],
-                       e[0][0] * e[NVEC - 1][0] + e[0][1] * e[NVEC - 1][1],
-                       e[NVEC - 1][0] * e[NVEC - 1][0] + e[NVEC - 1][1] * e[NVEC - 1][1]};
-        double* outp[3] = {scal + S_JV00, scal + S_JV01, scal + S_JV11};
-        block_accumulate<3>(g, s_red, outp);
-    }
 }
 
 }  // namespace mmba

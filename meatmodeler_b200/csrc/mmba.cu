@@ -94,9 +94,8 @@ struct Arena {
 
 struct Dev {
     // plan
-    int4* tiles;
+    TileMeta* meta;
     int32_t* tile_cams;
-    uint16_t *slot_cam, *slot_pt, *sort_src, *sort_key;
     double* uv;
     // linearisation
     double *J, *res;
@@ -105,7 +104,7 @@ struct Dev {
     // n-vectors (camera part first, then the local points)
     double *sinv, *gh, *gn, *s1, *s2, *v1, *v2, *tmp;
     // PCG (camera-sized)
-    double *y, *Sd, *Pinv, *px, *pr, *pz, *pp, *pq, *pxt, *part;
+    double *y, *Sd, *Pinv, *px, *pr, *pz, *pp, *pq, *pxt, *part, *state;
     int* flags;
     double* scal;
     double* xp_full;   // all points, internal order (nranks > 1 only)
@@ -135,7 +134,9 @@ struct mmba_handle {
     size_t arena_bytes = 0;
     Dev d;
     TileArgs targs;
-    size_t smem_build = 0, smem_resid = 0, smem_schur = 0, smem_jv1 = 0, smem_jv2 = 0;
+    int sm_count = 148;
+    size_t smem[8] = {0};     // dynamic shared memory of tile_kernel<MODE>
+    int grid[8] = {0};        // persistent grid of tile_kernel<MODE>: min(tiles, SMs x resident CTAs)
     double* h_stage = nullptr;   // pinned, max(nloc, 2*ns ...) doubles
     size_t h_stage_n = 0;
     double* h_scal = nullptr;    // pinned S_COUNT
@@ -261,12 +262,8 @@ void carve(mmba_handle* h, Arena& a) {
     const Plan& pl = h->plan;
     Dev& d = h->d;
     const size_t Nc = h->Nc, npl = std::max<int64_t>(h->npl, 1), ns = std::max<int64_t>(h->ns, 1), nloc = 6 * Nc + 3 * npl;
-    d.tiles = a.take<int4>(std::max<size_t>(pl.tiles.size(), 1));
-    d.tile_cams = a.take<int32_t>(std::max<size_t>(pl.tile_cams.size(), 1));
-    d.slot_cam = a.take<uint16_t>(ns);
-    d.slot_pt = a.take<uint16_t>(ns);
-    d.sort_src = a.take<uint16_t>(ns);
-    d.sort_key = a.take<uint16_t>(ns);
+    d.meta = a.take<TileMeta>(std::max<size_t>(pl.meta.size(), 1));
+    d.tile_cams = a.take<int32_t>(std::max<size_t>(pl.tile_cams.size(), 4));
     d.uv = a.take<double>(2 * ns);
     d.J = a.take<double>(18 * ns);
     d.res = a.take<double>(2 * ns);
@@ -299,6 +296,7 @@ void carve(mmba_handle* h, Arena& a) {
     d.pq = a.take<double>(6 * Nc);
     d.pxt = a.take<double>(6 * Nc);
     d.part = a.take<double>((size_t)P_COUNT * kMaxCamBlocks);
+    d.state = a.take<double>(4);
     d.flags = a.take<int>(4);
     d.scal = a.take<double>(S_COUNT);
     d.xp_full = h->opt.nranks > 1 ? a.take<double>(3 * (size_t)pl.n_points) : nullptr;
@@ -374,7 +372,7 @@ int get_x(mmba_handle* h, const double* src, double* x) {
     return MMBA_OK;
 }
 
-// rows x n_slots SoA on the device -> caller-ordered (n_obs, rows) row-major; local entries only
+// tile-major [tile][rows][256] on the device -> caller-ordered (n_obs, rows) row-major; local entries only
 int get_slots(mmba_handle* h, const double* src, int rows, double* out, int out_stride, int out_off) {
     const Plan& pl = h->plan;
     std::vector<double> tmp((size_t)rows * h->ns);
@@ -383,7 +381,24 @@ int get_slots(mmba_handle* h, const double* src, int rows, double* out, int out_
     for (int64_t s = 0; s < h->ns; ++s) {
         const int64_t o = pl.slot_obs[s];
         if (o < 0) continue;
-        for (int r = 0; r < rows; ++r) out[o * out_stride + out_off + r] = tmp[(size_t)r * h->ns + s];
+        const int64_t t = s / kT, j = s % kT;
+        for (int r = 0; r < rows; ++r) out[o * out_stride + out_off + r] = tmp[((size_t)t * rows + r) * kT + j];
+    }
+    return MMBA_OK;
+}
+
+// Jt [tile][18][256] -> caller-ordered Jc (n_obs,2,6) and Jp (n_obs,2,3); local entries only
+int get_jacobian_slots(mmba_handle* h, double* Jc, double* Jp) {
+    const Plan& pl = h->plan;
+    std::vector<double> tmp((size_t)kJRows * h->ns);
+    CU(cudaMemcpyAsync(tmp.data(), h->d.J, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int64_t s = 0; s < h->ns; ++s) {
+        const int64_t o = pl.slot_obs[s];
+        if (o < 0) continue;
+        const int64_t t = s / kT, j = s % kT;
+        for (int r = 0; r < 12; ++r) Jc[o * 12 + r] = tmp[((size_t)t * kJRows + r) * kT + j];
+        for (int r = 0; r < 6; ++r) Jp[o * 6 + r] = tmp[((size_t)t * kJRows + 12 + r) * kT + j];
     }
     return MMBA_OK;
 }
@@ -406,12 +421,22 @@ PcgVecs pcg_vecs(mmba_handle* h) {
     P.xt = d.pxt;
     P.part = d.part;
     P.flags = d.flags;
+    P.state = d.state;
     P.n_cams = (int)h->Nc;
     return P;
 }
 
 int cam_prep(mmba_handle* h, const double* x, double* camtab) {
     LAUNCH(MMBA_K_CAMPREP, cam_prep_kernel, cdiv(h->Nc, 128), 128, 0, x, camtab, (int)h->Nc);
+    return MMBA_OK;
+}
+
+template <int MODE>
+int launch_tile(mmba_handle* h, int cls, const ModeArgs& P) {
+    if (!h->nt) return MMBA_OK;
+    prof_begin(h, cls);
+    tile_kernel<MODE><<<h->grid[MODE], kThreads, h->smem[MODE], h->stream>>>(h->targs, P);
+    prof_end(h, cls);
     return MMBA_OK;
 }
 
@@ -422,9 +447,17 @@ int linearise(mmba_handle* h) {
     TRY(zero(h, d.U, 21 * h->Nc));
     TRY(zero(h, d.g, 6 * h->Nc));
     TRY(zero(h, d.scal + S_COST, 1));
-    if (h->nt)
-        LAUNCH(MMBA_K_BUILD, build_kernel, (unsigned)h->nt, kT, h->smem_build, h->targs, d.camtab, d.x + 6 * h->Nc, d.J,
-               d.res, d.U, d.g, d.V, d.g + 6 * h->Nc, d.scal, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    ModeArgs P{};
+    P.Jw = d.J;
+    P.res = d.res;
+    P.cam0 = d.camtab;
+    P.ptA = d.x + 6 * h->Nc;
+    P.U = d.U;
+    P.gc = d.g;
+    P.V = d.V;
+    P.gp = d.g + 6 * h->Nc;
+    P.scal = d.scal;
+    TRY(launch_tile<M_BUILD>(h, MMBA_K_BUILD, P));
     TRY(allreduce(h, {{d.U, (size_t)(21 * h->Nc), false}, {d.g, (size_t)(6 * h->Nc), false}, {d.scal + S_COST, 1, false}}));
     CU(cudaGetLastError());
     return MMBA_OK;
@@ -448,11 +481,12 @@ int scale_and_grad(mmba_handle* h, bool first) {
 int jv1(mmba_handle* h, const double* v) {
     Dev& d = h->d;
     TRY(zero(h, d.scal + S_JV00, 3));
-    if (h->nt) {
-        auto kern = jv_kernel<1, false>;
-        LAUNCH(MMBA_K_JV, kern, (unsigned)h->nt, kT, h->smem_jv1, h->targs, d.J, v, v + 6 * h->Nc, nullptr,
-               nullptr, d.scal, nullptr, h->plan.max_tile_cams, h->plan.max_tile_pts);
-    }
+    ModeArgs P{};
+    P.J = d.J;
+    P.cam0 = v;
+    P.ptA = v + 6 * h->Nc;
+    P.scal = d.scal;
+    TRY(launch_tile<M_JV1>(h, MMBA_K_JV, P));
     TRY(allreduce(h, {{d.scal + S_JV00, 3, false}}));
     return MMBA_OK;
 }
@@ -460,22 +494,56 @@ int jv1(mmba_handle* h, const double* v) {
 int jv2(mmba_handle* h, const double* va, const double* vb) {
     Dev& d = h->d;
     TRY(zero(h, d.scal + S_JV00, 3));
-    if (h->nt) {
-        auto kern = jv_kernel<2, false>;
-        LAUNCH(MMBA_K_JV, kern, (unsigned)h->nt, kT, h->smem_jv2, h->targs, d.J, va, va + 6 * h->Nc, vb,
-               vb + 6 * h->Nc, d.scal, nullptr, h->plan.max_tile_cams, h->plan.max_tile_pts);
-    }
+    ModeArgs P{};
+    P.J = d.J;
+    P.cam0 = va;
+    P.ptA = va + 6 * h->Nc;
+    P.cam1 = vb;
+    P.ptB = vb + 6 * h->Nc;
+    P.scal = d.scal;
+    TRY(launch_tile<M_JV2>(h, MMBA_K_JV, P));
     TRY(allreduce(h, {{d.scal + S_JV00, 3, false}}));
     return MMBA_OK;
 }
 
+ModeArgs matvec_args(mmba_handle* h) {
+    Dev& d = h->d;
+    ModeArgs P{};
+    P.J = d.J;
+    P.cam0 = d.pxt;
+    P.ptA = d.M;
+    P.y = d.y;
+    P.done = d.flags;
+    return P;
+}
+
 int schur_matvec(mmba_handle* h) {
     Dev& d = h->d;
-    if (h->nt)
-        LAUNCH(MMBA_K_MATVEC, schur_kernel<SCHUR_MATVEC>, (unsigned)h->nt, kT, h->smem_schur, h->targs, d.J, d.pxt, d.M,
-               nullptr, nullptr, d.y, nullptr, nullptr, d.flags, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    TRY(launch_tile<M_MATVEC>(h, MMBA_K_MATVEC, matvec_args(h)));
     TRY(allreduce(h, {{d.y, (size_t)(6 * h->Nc), false}}));
     return MMBA_OK;
+}
+
+ModeArgs rhs_args(mmba_handle* h) {
+    Dev& d = h->d;
+    ModeArgs P{};
+    P.J = d.J;
+    P.ptA = d.M;
+    P.ptB = d.zg;
+    P.y = d.y;
+    P.Sd = d.Sd;
+    return P;
+}
+
+ModeArgs backsub_args(mmba_handle* h) {
+    Dev& d = h->d;
+    ModeArgs P{};
+    P.J = d.J;
+    P.cam0 = d.pxt;
+    P.ptA = d.M;
+    P.ptB = d.g + 6 * h->Nc;
+    P.dp = d.dp;
+    return P;
 }
 
 // damped Gauss-Newton step in scaled variables: (D J^T J D + reg I) p = D g.
@@ -489,9 +557,7 @@ int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
                d.M, d.zg, h->npl);
     TRY(zero(h, d.y, 6 * h->Nc));
     TRY(zero(h, d.Sd, 21 * h->Nc));
-    if (h->nt)
-        LAUNCH(MMBA_K_RHS, schur_kernel<SCHUR_RHS>, (unsigned)h->nt, kT, h->smem_schur, h->targs, d.J, nullptr, d.M, d.zg,
-               nullptr, d.y, d.Sd, nullptr, nullptr, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    TRY(launch_tile<M_RHS>(h, MMBA_K_RHS, rhs_args(h)));
     TRY(allreduce(h, {{d.y, (size_t)(6 * h->Nc), false}, {d.Sd, (size_t)(21 * h->Nc), false}}));
     LAUNCH(MMBA_K_VEC, pcg_init_kernel, camblocks, kCamBlock, 0, P, reg);
 
@@ -503,9 +569,7 @@ int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
         const int stop = std::min(maxit, it + chunk);
         for (; it < stop; ++it) {
             TRY(schur_matvec(h));
-            LAUNCH(MMBA_K_VEC, pcg_a_kernel, camblocks, kCamBlock, 0, P, reg);
-            LAUNCH(MMBA_K_VEC, pcg_b_kernel, camblocks, kCamBlock, 0, P, it);
-            LAUNCH(MMBA_K_VEC, pcg_c_kernel, camblocks, kCamBlock, 0, P, it, rtol2);
+            LAUNCH(MMBA_K_VEC, pcg_update_kernel, 1, kPcgThreads, 0, P, reg, it, rtol2, camblocks);
         }
         CU(cudaMemcpyAsync(h->h_flags, d.flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -515,22 +579,14 @@ int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
     const int64_t its = done ? h->h_flags[1] : it;
     if (its_out) *its_out = its;
     if (relres_out) {
-        std::vector<double> part(2 * kMaxCamBlocks);
-        CU(cudaMemcpyAsync(part.data(), d.part + P_RR * kMaxCamBlocks, 2 * kMaxCamBlocks * sizeof(double),
-                           cudaMemcpyDeviceToHost, h->stream));
+        double st[4];
+        CU(cudaMemcpyAsync(st, d.state, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        double rr = 0, b2 = 0;
-        for (int i = 0; i < camblocks; ++i) {
-            rr += part[i];
-            b2 += part[kMaxCamBlocks + i];
-        }
-        *relres_out = (its > 0 && b2 > 0) ? std::sqrt(rr / b2) : (b2 > 0 ? 1.0 : 0.0);
+        *relres_out = (its > 0 && st[1] > 0) ? std::sqrt(st[2] / st[1]) : 0.0;
     }
     // back-substitution with the unscaled camera step
     LAUNCH(MMBA_K_VEC, unscale_kernel, cdiv(6 * h->Nc, 256), 256, 0, d.px, d.sinv, 1.0, d.pxt, 6 * h->Nc);
-    if (h->nt)
-        LAUNCH(MMBA_K_BACKSUB, schur_kernel<SCHUR_BACKSUB>, (unsigned)h->nt, kT, h->smem_schur, h->targs, d.J, d.pxt, d.M,
-               nullptr, d.g + 6 * h->Nc, nullptr, nullptr, d.dp, nullptr, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    TRY(launch_tile<M_BACKSUB>(h, MMBA_K_BACKSUB, backsub_args(h)));
     CU(cudaGetLastError());
     return MMBA_OK;
 }
@@ -539,9 +595,11 @@ int trial_cost(mmba_handle* h, const double* x, double* camtab) {
     Dev& d = h->d;
     TRY(cam_prep(h, x, camtab));
     TRY(zero(h, d.scal + S_COST_NEW, 1));
-    if (h->nt)
-        LAUNCH(MMBA_K_RESID, resid_kernel<false>, (unsigned)h->nt, kT, h->smem_resid, h->targs, camtab, x + 6 * h->Nc,
-               nullptr, d.scal + S_COST_NEW, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    ModeArgs P{};
+    P.cam0 = camtab;
+    P.ptA = x + 6 * h->Nc;
+    P.cost = d.scal + S_COST_NEW;
+    TRY(launch_tile<M_RESID>(h, MMBA_K_RESID, P));
     TRY(allreduce(h, {{d.scal + S_COST_NEW, 1, false}}));
     return MMBA_OK;
 }
@@ -708,6 +766,31 @@ int run_trf(mmba_handle* h, mmba_result* out) {
     return MMBA_OK;
 }
 
+template <int MODE>
+int configure_mode(mmba_handle* h) {
+    const SmemLayout L = smem_layout<MODE>(h->targs.max_cams, h->targs.max_pts);
+    h->smem[MODE] = (size_t)L.total;
+    if (L.total > 227 * 1024) return fail(h, MMBA_ERR_NOMEM, "tile_kernel needs " + std::to_string(L.total) + " bytes of shared memory");
+    CU(cudaFuncSetAttribute(tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_kernel<MODE>, kThreads, (size_t)L.total));
+    if (occ < 1) return fail(h, MMBA_ERR_CUDA, "tile_kernel does not fit on an SM");
+    h->grid[MODE] = (int)std::max<int64_t>(1, std::min<int64_t>(h->nt, (int64_t)h->sm_count * occ));
+    return MMBA_OK;
+}
+
+int configure_kernels(mmba_handle* h) {
+    TRY(configure_mode<M_BUILD>(h));
+    TRY(configure_mode<M_RESID>(h));
+    TRY(configure_mode<M_RESID_STORE>(h));
+    TRY(configure_mode<M_MATVEC>(h));
+    TRY(configure_mode<M_RHS>(h));
+    TRY(configure_mode<M_BACKSUB>(h));
+    TRY(configure_mode<M_JV1>(h));
+    TRY(configure_mode<M_JV2>(h));
+    return MMBA_OK;
+}
+
 int need_problem(mmba_handle* h) {
     if (!h) return fail(nullptr, MMBA_ERR_ARG, "null handle");
     if (!h->has_problem) return fail(h, MMBA_ERR_STATE, "mmba_set_problem has not been called");
@@ -779,6 +862,7 @@ int mmba_create(mmba_handle** out, const mmba_options* opt) {
                                                 std::to_string(prop.minor) + "; libmmba is built for sm_100a only");
     h = new mmba_handle();
     h->opt = o;
+    h->sm_count = prop.multiProcessorCount;
     CU(cudaSetDevice(o.device));
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&h->ev0));
@@ -855,51 +939,30 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     Dev& d = h->d;
     CU(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
     {
-        std::vector<int4> tiles(pl.tiles.size());
-        for (size_t t = 0; t < tiles.size(); ++t)
-            tiles[t] = make_int4(pl.tiles[t].pt0, pl.tiles[t].npts, pl.tiles[t].cam_off, pl.tiles[t].ncams);
-        TRY(upload(h, d.tiles, tiles));
+        TRY(upload(h, d.meta, pl.meta));
         TRY(upload(h, d.tile_cams, pl.tile_cams));
-        TRY(upload(h, d.slot_cam, pl.slot_cam));
-        TRY(upload(h, d.slot_pt, pl.slot_pt));
-        TRY(upload(h, d.sort_src, pl.sort_src));
-        TRY(upload(h, d.sort_key, pl.sort_key));
         std::vector<double> uvs(2 * (size_t)h->ns, 0.0);
         for (int64_t s = 0; s < h->ns; ++s) {
             const int64_t ob = pl.slot_obs[s];
             if (ob >= 0) {
-                uvs[s] = uv[2 * ob];
-                uvs[h->ns + s] = uv[2 * ob + 1];
+                const int64_t t = s / kT, j = s % kT;
+                uvs[(t * 2) * kT + j] = uv[2 * ob];
+                uvs[(t * 2 + 1) * kT + j] = uv[2 * ob + 1];
             }
         }
         TRY(upload(h, d.uv, uvs));
         CU(cudaStreamSynchronize(h->stream));
     }
     TileArgs& A = h->targs;
-    A.tiles = d.tiles;
+    A.meta = d.meta;
     A.tile_cams = d.tile_cams;
-    A.slot_cam = d.slot_cam;
-    A.slot_pt = d.slot_pt;
-    A.sort_src = d.sort_src;
-    A.sort_key = d.sort_key;
     A.uv = d.uv;
-    A.n_slots = h->ns;
+    A.n_tiles = (int)h->nt;
+    A.cam_stride = pl.cam_stride;
+    A.max_cams = std::max(pl.max_tile_cams, 1);
+    A.max_pts = std::max(pl.max_tile_pts, 1);
     std::memcpy(A.K, K, sizeof(A.K));
-
-    const size_t mc = pl.max_tile_cams, mp = pl.max_tile_pts;
-    h->smem_build = (mc * kCamS + mp * 3 + mp * 9 + 9 * kT + 64) * sizeof(double) + mc * sizeof(int);
-    h->smem_resid = (mc * kCamS + mp * 3 + 64) * sizeof(double);
-    h->smem_schur = (mc * kVecS + mp * 3 + 9 * kT) * sizeof(double) + mc * sizeof(int);
-    h->smem_jv1 = (mc * kVecS + mp * 3 + 64) * sizeof(double);
-    h->smem_jv2 = (2 * mc * kVecS + 2 * mp * 3 + 64) * sizeof(double);
-    CU(cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_build));
-    CU(cudaFuncSetAttribute(resid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_resid));
-    CU(cudaFuncSetAttribute(resid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_resid));
-    CU(cudaFuncSetAttribute(schur_kernel<SCHUR_MATVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_schur));
-    CU(cudaFuncSetAttribute(schur_kernel<SCHUR_RHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_schur));
-    CU(cudaFuncSetAttribute(schur_kernel<SCHUR_BACKSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_schur));
-    CU(cudaFuncSetAttribute(jv_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_jv1));
-    CU(cudaFuncSetAttribute(jv_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_jv2));
+    TRY(configure_kernels(h));
     h->has_problem = true;
     return MMBA_OK;
 }
@@ -985,9 +1048,14 @@ int mmba_eval_residual(mmba_handle* h, const double* x, double* f) {
     TRY(put_x(h, x, d.x));
     TRY(cam_prep(h, d.x, d.camtab));
     TRY(zero(h, d.scal + S_COST_NEW, 1));
-    if (h->nt)
-        LAUNCH(MMBA_K_RESID, resid_kernel<true>, (unsigned)h->nt, kT, h->smem_resid, h->targs, d.camtab, d.x + 6 * h->Nc, d.res,
-               d.scal + S_COST_NEW, h->plan.max_tile_cams, h->plan.max_tile_pts);
+    {
+        ModeArgs P{};
+        P.res = d.res;
+        P.cam0 = d.camtab;
+        P.ptA = d.x + 6 * h->Nc;
+        P.cost = d.scal + S_COST_NEW;
+        TRY(launch_tile<M_RESID_STORE>(h, MMBA_K_RESID, P));
+    }
     CU(cudaGetLastError());
     if (h->opt.nranks > 1) std::memset(f, 0, 2 * h->plan.n_obs * sizeof(double));
     return get_slots(h, d.res, 2, f, 2, 0);
@@ -1003,8 +1071,7 @@ int mmba_eval_jacobian(mmba_handle* h, const double* x, double* Jc, double* Jp) 
         std::memset(Jc, 0, 12 * h->plan.n_obs * sizeof(double));
         std::memset(Jp, 0, 6 * h->plan.n_obs * sizeof(double));
     }
-    TRY(get_slots(h, d.J, 12, Jc, 12, 0));
-    return get_slots(h, d.J + 12 * h->ns, 6, Jp, 6, 0);
+    return get_jacobian_slots(h, Jc, Jp);
 }
 
 int mmba_eval_blocks(mmba_handle* h, const double* x, double* U, double* V, double* gc, double* gp, double* cost) {
@@ -1093,39 +1160,37 @@ int mmba_bench_kernel(mmba_handle* h, const double* x, int kernel_class, int ite
     CU(cudaMemsetAsync(d.flags, 0, 2 * sizeof(int), h->stream));
     LAUNCH(MMBA_K_VEC, unscale_kernel, cdiv(h->nloc, 256), 256, 0, d.gh, d.sinv, 1.0, d.tmp, h->nloc);
     CU(cudaStreamSynchronize(h->stream));
-    const int mc = h->plan.max_tile_cams, mp = h->plan.max_tile_pts;
-    const unsigned nt = (unsigned)h->nt;
-    if (!nt) return fail(h, MMBA_ERR_STATE, "bench_kernel: this shard has no observations");
+    if (!h->nt) return fail(h, MMBA_ERR_STATE, "bench_kernel: this shard has no observations");
+    ModeArgs Pb{};
+    Pb.Jw = d.J;
+    Pb.res = d.res;
+    Pb.cam0 = d.camtab;
+    Pb.ptA = d.x + 6 * h->Nc;
+    Pb.U = d.U;
+    Pb.gc = d.g;
+    Pb.V = d.V;
+    Pb.gp = d.g + 6 * h->Nc;
+    Pb.scal = d.scal;
+    ModeArgs Pr = Pb;
+    Pr.cost = d.scal + S_COST_NEW;
+    ModeArgs Pj{};
+    Pj.J = d.J;
+    Pj.cam0 = d.tmp;
+    Pj.ptA = d.tmp + 6 * h->Nc;
+    Pj.cam1 = d.gh;
+    Pj.ptB = d.gh + 6 * h->Nc;
+    Pj.scal = d.scal;
     for (int pass = 0; pass < 2; ++pass) {
         const int n = pass == 0 ? 2 : iters;
         if (pass == 1) CU(cudaEventRecord(h->ev0, h->stream));
         for (int i = 0; i < n; ++i) {
             switch (kernel_class) {
-                case MMBA_K_BUILD:
-                    build_kernel<<<nt, kT, h->smem_build, h->stream>>>(h->targs, d.camtab, d.x + 6 * h->Nc, d.J, d.res, d.U, d.g,
-                                                                       d.V, d.g + 6 * h->Nc, d.scal, mc, mp);
-                    break;
-                case MMBA_K_RESID:
-                    resid_kernel<false><<<nt, kT, h->smem_resid, h->stream>>>(h->targs, d.camtab, d.x + 6 * h->Nc, nullptr,
-                                                                              d.scal + S_COST_NEW, mc, mp);
-                    break;
-                case MMBA_K_RHS:
-                    schur_kernel<SCHUR_RHS><<<nt, kT, h->smem_schur, h->stream>>>(h->targs, d.J, nullptr, d.M, d.zg, nullptr, d.y,
-                                                                                  d.Sd, nullptr, nullptr, mc, mp);
-                    break;
-                case MMBA_K_MATVEC:
-                    schur_kernel<SCHUR_MATVEC><<<nt, kT, h->smem_schur, h->stream>>>(h->targs, d.J, d.pxt, d.M, nullptr, nullptr,
-                                                                                     d.y, nullptr, nullptr, d.flags, mc, mp);
-                    break;
-                case MMBA_K_BACKSUB:
-                    schur_kernel<SCHUR_BACKSUB><<<nt, kT, h->smem_schur, h->stream>>>(h->targs, d.J, d.pxt, d.M, nullptr,
-                                                                                      d.g + 6 * h->Nc, nullptr, nullptr, d.dp,
-                                                                                      nullptr, mc, mp);
-                    break;
-                case MMBA_K_JV:
-                    jv_kernel<2, false><<<nt, kT, h->smem_jv2, h->stream>>>(h->targs, d.J, d.tmp, d.tmp + 6 * h->Nc, d.gh,
-                                                                            d.gh + 6 * h->Nc, d.scal, nullptr, mc, mp);
-                    break;
+                case MMBA_K_BUILD: TRY(launch_tile<M_BUILD>(h, MMBA_K_BUILD, Pb)); break;
+                case MMBA_K_RESID: TRY(launch_tile<M_RESID>(h, MMBA_K_RESID, Pr)); break;
+                case MMBA_K_RHS: TRY(launch_tile<M_RHS>(h, MMBA_K_RHS, rhs_args(h))); break;
+                case MMBA_K_MATVEC: TRY(launch_tile<M_MATVEC>(h, MMBA_K_MATVEC, matvec_args(h))); break;
+                case MMBA_K_BACKSUB: TRY(launch_tile<M_BACKSUB>(h, MMBA_K_BACKSUB, backsub_args(h))); break;
+                case MMBA_K_JV: TRY(launch_tile<M_JV2>(h, MMBA_K_JV, Pj)); break;
                 case MMBA_K_PTINV:
                     point_invert_kernel<<<cdiv(h->npl, 256), 256, 0, h->stream>>>(d.V, d.g + 6 * h->Nc, d.sinv + 6 * h->Nc, reg,
                                                                                    d.M, d.zg, h->npl);
@@ -1212,8 +1277,8 @@ int mmba_plan_export(const mmba_plan* p, int64_t* obs_perm, int64_t* point_perm,
         for (int j = 0; j < kTileObs; ++j) {
             const int64_t s = t * kTileObs + j;
             const bool live = pl.slot_obs[s] >= 0;
-            if (slot_cam_global) slot_cam_global[s] = live ? pl.tile_cams[pl.tiles[t].cam_off + pl.slot_cam[s]] : -1;
-            if (slot_point_local) slot_point_local[s] = live ? pl.tiles[t].pt0 + pl.slot_pt[s] : -1;
+            if (slot_cam_global) slot_cam_global[s] = live ? pl.tile_cams[t * pl.cam_stride + pl.meta[t].slot_cam[j]] : -1;
+            if (slot_point_local) slot_point_local[s] = live ? pl.meta[t].pt0 + pl.meta[t].slot_pt[j] : -1;
         }
     }
     return MMBA_OK;

@@ -119,24 +119,19 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
     }
     plan.n_tiles = (int64_t)ranges.size();
     plan.n_slots = plan.n_tiles * kTileObs;
-    plan.tiles.resize(plan.n_tiles);
+    plan.meta.resize(plan.n_tiles);
     plan.slot_obs.assign(plan.n_slots, -1);
-    plan.slot_cam.assign(plan.n_slots, 0);
-    plan.slot_pt.assign(plan.n_slots, 0xFFFF);   // empty slots carry the pad marker
-    plan.sort_src.resize(plan.n_slots);
-    plan.sort_key.assign(plan.n_slots, kPadKey);
-    plan.tile_cams.reserve(plan.n_tiles * 8);
 
     // 6. per tile: local camera table, local slots, camera-sorted order
     std::vector<int32_t> stamp(n_cams, -1), local_of(n_cams, 0);
-    std::vector<int32_t> cams;
+    std::vector<std::vector<int32_t>> cams_of(plan.n_tiles);
     std::vector<uint16_t> idx(kTileObs);
     for (int64_t t = 0; t < plan.n_tiles; ++t) {
         const Range rg = ranges[t];
         const int64_t o0 = start[rg.p0], o1 = start[rg.p1];
         const int n = (int)(o1 - o0);
         const int64_t base = t * kTileObs;
-        cams.clear();
+        std::vector<int32_t>& cams = cams_of[t];
         for (int i = 0; i < n; ++i) {
             const int32_t c = (int32_t)cam_idx[grouped[o0 + i]];
             if (stamp[c] != (int32_t)t) {
@@ -146,32 +141,38 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
         }
         std::sort(cams.begin(), cams.end());
         for (size_t s = 0; s < cams.size(); ++s) local_of[cams[s]] = (int32_t)s;
-        TileInfo& ti = plan.tiles[t];
-        ti.pt0 = (int32_t)rg.p0;
-        ti.npts = (int32_t)(rg.p1 - rg.p0);
-        ti.cam_off = (int32_t)plan.tile_cams.size();
-        ti.ncams = (int32_t)cams.size();
-        plan.max_tile_cams = std::max(plan.max_tile_cams, ti.ncams);
-        plan.max_tile_pts = std::max(plan.max_tile_pts, ti.npts);
-        plan.tile_cams.insert(plan.tile_cams.end(), cams.begin(), cams.end());
+        TileMeta& m = plan.meta[t];
+        m.pt0 = (int32_t)rg.p0;
+        m.npts = (int32_t)(rg.p1 - rg.p0);
+        m.ncams = (int32_t)cams.size();
+        m.nobs = n;
+        plan.max_tile_cams = std::max(plan.max_tile_cams, m.ncams);
+        plan.max_tile_pts = std::max(plan.max_tile_pts, m.npts);
+        for (int j = 0; j < kTileObs; ++j) {
+            m.slot_cam[j] = 0;
+            m.slot_pt[j] = 0xFFFF;   // empty slots carry the pad marker
+            m.sort_src[j] = (uint16_t)j;
+            m.sort_key[j] = kPadKey;
+        }
         int i = 0;
         for (int64_t q = rg.p0; q < rg.p1; ++q) {
             for (int64_t o = start[q]; o < start[q + 1]; ++o, ++i) {
                 plan.slot_obs[base + i] = grouped[o];
-                plan.slot_cam[base + i] = (uint16_t)local_of[cam_idx[grouped[o]]];
-                plan.slot_pt[base + i] = (uint16_t)(q - rg.p0);
+                m.slot_cam[i] = (uint16_t)local_of[cam_idx[grouped[o]]];
+                m.slot_pt[i] = (uint16_t)(q - rg.p0);
             }
         }
         std::iota(idx.begin(), idx.begin() + n, (uint16_t)0);
-        std::stable_sort(idx.begin(), idx.begin() + n, [&](uint16_t a, uint16_t b) {
-            return plan.slot_cam[base + a] < plan.slot_cam[base + b];
-        });
+        std::stable_sort(idx.begin(), idx.begin() + n, [&](uint16_t a, uint16_t b) { return m.slot_cam[a] < m.slot_cam[b]; });
         for (int j = 0; j < n; ++j) {
-            plan.sort_src[base + j] = idx[j];
-            plan.sort_key[base + j] = plan.slot_cam[base + idx[j]];
+            m.sort_src[j] = idx[j];
+            m.sort_key[j] = m.slot_cam[idx[j]];
         }
-        for (int j = n; j < kTileObs; ++j) plan.sort_src[base + j] = (uint16_t)j;
     }
+    plan.cam_stride = std::max(4, (plan.max_tile_cams + 3) / 4 * 4);
+    plan.tile_cams.assign((size_t)plan.n_tiles * plan.cam_stride, -1);
+    for (int64_t t = 0; t < plan.n_tiles; ++t)
+        std::copy(cams_of[t].begin(), cams_of[t].end(), plan.tile_cams.begin() + t * plan.cam_stride);
     return MMBA_OK;
 }
 

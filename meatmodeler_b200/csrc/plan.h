@@ -13,11 +13,16 @@ namespace mmba {
 constexpr int kTileObs = 256;          // observation slots per tile == threads per CTA
 constexpr uint16_t kPadKey = 0xFFFF;   // sorted-key of an empty slot
 
-struct TileInfo {       // one int4 on the device
+// One record per tile, bulk-copied to shared memory as a unit (2064 bytes, 16-byte multiple).
+struct TileMeta {
     int32_t pt0;        // first local (shard-relative, internal-order) point of the tile
     int32_t npts;       // points in the tile
-    int32_t cam_off;    // offset of the tile's camera list in tile_cams
     int32_t ncams;      // distinct cameras in the tile
+    int32_t nobs;       // live observation slots (the rest of the 256 are padding)
+    uint16_t slot_cam[kTileObs];   // local camera slot of the observation in its tile
+    uint16_t slot_pt[kTileObs];    // local point index of the observation in its tile (0xFFFF = empty slot)
+    uint16_t sort_src[kTileObs];   // j-th entry of the tile in camera-sorted order -> slot in tile
+    uint16_t sort_key[kTileObs];   // its local camera slot (kPadKey for empty)
 };
 
 struct Plan {
@@ -31,13 +36,10 @@ struct Plan {
     // tiles of this rank
     int64_t n_tiles = 0, n_slots = 0;
     int max_tile_cams = 0, max_tile_pts = 0;
-    std::vector<TileInfo> tiles;
-    std::vector<int32_t> tile_cams;      // global camera ids, concatenated per tile (ascending)
+    int cam_stride = 0;                  // entries per tile in tile_cams (max_tile_cams rounded up to 4)
+    std::vector<TileMeta> meta;
+    std::vector<int32_t> tile_cams;      // [tile][cam_stride] global camera ids (ascending), -1 padded
     std::vector<int64_t> slot_obs;       // padded slot -> caller's observation index, -1 = empty
-    std::vector<uint16_t> slot_cam;      // local camera slot of the observation in its tile
-    std::vector<uint16_t> slot_pt;       // local point index of the observation in its tile
-    std::vector<uint16_t> sort_src;      // j-th entry of the tile in camera-sorted order -> slot in tile
-    std::vector<uint16_t> sort_key;      // its local camera slot (kPadKey for empty)
 
     int64_t n_points_local() const { return pt_end - pt_begin; }
 };

@@ -3,9 +3,9 @@
 // Replaces numpy vector arithmetic inside scipy's trf_no_bounds (trf.py:433-561), compute_grad /
 // compute_jac_scale (common.py:590-610) and LSMR's vector updates (lsmr.py:373-377).
 //
-// Camera-part reductions of the PCG are *deterministic* (per-block partials summed in a fixed
-// order by every consumer block): with cameras replicated across ranks, every rank then takes
-// bit-identical PCG decisions without exchanging flags.
+// Camera-part reductions of the PCG are *deterministic* (fixed-order sums inside one CTA): with
+// cameras replicated across ranks, every rank then takes bit-identical PCG decisions without
+// exchanging flags.
 #pragma once
 #include "kernels.cuh"
 
@@ -15,7 +15,7 @@ constexpr int kCamBlock = 128;   // threads per block of the thread-per-camera k
 constexpr int kMaxCamBlocks = 1024;
 
 // per-block partial sums of the PCG (deterministic reductions)
-enum Part { P_RHO0 = 0, P_RHO1, P_PQ, P_RR, P_B2, P_COUNT };
+enum Part { P_RHO0 = 0, P_B2, P_COUNT };
 
 __device__ __forceinline__ double block_sum_det(double v, double* s_red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -232,7 +232,8 @@ struct PcgVecs {
     double* Sd;           // [Nc][21]
     double* Pinv;         // [Nc][21]
     double *x, *r, *z, *p, *q, *xt;   // [Nc][6]
-    double* part;         // [P_COUNT][kMaxCamBlocks]
+    double* part;         // [P_COUNT][kMaxCamBlocks] per-block partials of pcg_init
+    double* state;        // [0] rho, [1] ||b||^2, [2] ||r||^2 carried between iterations
     int* flags;           // [0] done, [1] iterations
     int n_cams;
 };
@@ -282,13 +283,27 @@ __global__ void __launch_bounds__(kCamBlock) pcg_init_kernel(PcgVecs P, double r
     }
 }
 
-// q = S p = d o (U xt - y) + reg p ; partial p.q ; y <- 0 for the next product
-__global__ void __launch_bounds__(kCamBlock) pcg_a_kernel(PcgVecs P, double reg) {
+constexpr int kPcgThreads = 1024;
+
+// One PCG iteration's camera-vector work in ONE CTA, so that every reduction is a fixed-order sum
+// and the whole update costs a single launch (LSMR's vector updates, lsmr.py:373-377):
+//   q = S p = d o (U xt - y) + reg p ; alpha = rho / p.q ; x += alpha p ; r -= alpha q ; z = Pinv r ;
+//   stop if ||r|| <= rtol ||b|| ; beta = r.z / rho ; p = z + beta p ; xt = d o p ; y <- 0
+// y holds this iteration's sum_p W V'^-1 W^T xt from the MATVEC pass (all-reduced over ranks).
+__global__ void __launch_bounds__(kPcgThreads) pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init) {
     if (P.flags[0]) return;
-    __shared__ double s_red[8];
-    const int c = blockIdx.x * kCamBlock + threadIdx.x;
+    __shared__ double s_red[32];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    double rho, b2;
+    if (it == 0) {
+        rho = sum_partials(P.part + P_RHO0 * kMaxCamBlocks, nb_init, s_red);
+        b2 = sum_partials(P.part + P_B2 * kMaxCamBlocks, nb_init, s_red);
+    } else {
+        rho = P.state[0];
+        b2 = P.state[1];
+    }
     double pq = 0;
-    if (c < P.n_cams) {
+    for (int c = tid; c < P.n_cams; c += nthr) {
         double xt[6], ux[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) xt[k] = P.xt[c * 6 + k];
@@ -303,20 +318,9 @@ __global__ void __launch_bounds__(kCamBlock) pcg_a_kernel(PcgVecs P, double reg)
         }
     }
     pq = block_sum_det(pq, s_red);
-    if (threadIdx.x == 0) P.part[P_PQ * kMaxCamBlocks + blockIdx.x] = pq;
-}
-
-// alpha = rho / p.q ; x += alpha p ; r -= alpha q ; z = Pinv r ; partial r.r, r.z
-__global__ void __launch_bounds__(kCamBlock) pcg_b_kernel(PcgVecs P, int it) {
-    if (P.flags[0]) return;
-    __shared__ double s_red[8];
-    const int nb = gridDim.x;
-    const double rho = sum_partials(P.part + (it & 1 ? P_RHO1 : P_RHO0) * kMaxCamBlocks, nb, s_red);
-    const double pq = sum_partials(P.part + P_PQ * kMaxCamBlocks, nb, s_red);
     const double alpha = rho / pq;
-    const int c = blockIdx.x * kCamBlock + threadIdx.x;
     double rr = 0, rz = 0;
-    if (c < P.n_cams) {
+    for (int c = tid; c < P.n_cams; c += nthr) {
         double r[6], z[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
@@ -334,33 +338,22 @@ __global__ void __launch_bounds__(kCamBlock) pcg_b_kernel(PcgVecs P, int it) {
     }
     rr = block_sum_det(rr, s_red);
     rz = block_sum_det(rz, s_red);
-    if (threadIdx.x == 0) {
-        P.part[P_RR * kMaxCamBlocks + blockIdx.x] = rr;
-        P.part[(it & 1 ? P_RHO0 : P_RHO1) * kMaxCamBlocks + blockIdx.x] = rz;
-    }
-}
-
-// convergence test ; beta = rho_new / rho ; p = z + beta p ; xt = d o p
-__global__ void __launch_bounds__(kCamBlock) pcg_c_kernel(PcgVecs P, int it, double rtol2) {
-    if (P.flags[0]) return;
-    __shared__ double s_red[8];
-    const int nb = gridDim.x;
-    const double rho = sum_partials(P.part + (it & 1 ? P_RHO1 : P_RHO0) * kMaxCamBlocks, nb, s_red);
-    const double rho_new = sum_partials(P.part + (it & 1 ? P_RHO0 : P_RHO1) * kMaxCamBlocks, nb, s_red);
-    const double rr = sum_partials(P.part + P_RR * kMaxCamBlocks, nb, s_red);
-    const double b2 = sum_partials(P.part + P_B2 * kMaxCamBlocks, nb, s_red);
-    const double pq = sum_partials(P.part + P_PQ * kMaxCamBlocks, nb, s_red);
     int done = 0;
     if (rr <= rtol2 * b2) done = 1;
-    else if (!(pq > 0.0) || !isfinite(rr) || !(rho_new > 0.0)) done = 2;
-    if (done) {
-        // every block takes the same decision; the flag only gates later launches
-        if (blockIdx.x == 0 && threadIdx.x == 0) { P.flags[1] = it + 1; __threadfence(); P.flags[0] = done; }
-        return;
+    else if (!(pq > 0.0) || !isfinite(rr) || !(rz > 0.0)) done = 2;
+    if (tid == 0) {
+        P.state[0] = rz;
+        P.state[1] = b2;
+        P.state[2] = rr;
+        if (done) {
+            P.flags[1] = it + 1;
+            __threadfence();
+            P.flags[0] = done;
+        }
     }
-    const double beta = rho_new / rho;
-    const int c = blockIdx.x * kCamBlock + threadIdx.x;
-    if (c < P.n_cams) {
+    if (done) return;
+    const double beta = rz / rho;
+    for (int c = tid; c < P.n_cams; c += nthr) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             const double pk = P.z[c * 6 + k] + beta * P.p[c * 6 + k];
