@@ -42,8 +42,9 @@ namespace mmba {
 
 constexpr int kT = kTileObs;
 constexpr int kConsumers = kT;            // consumer threads per CTA (one per slot)
-constexpr int kThreads = kConsumers + 32; // + one producer warp
-constexpr int kStages = 2;
+constexpr int kStages = 2;                // pipeline depth; one producer warp per stage
+constexpr int kProducers = kStages;
+constexpr int kThreads = kConsumers + 32 * kProducers;
 constexpr int kCamTab = 24;               // doubles per camera-table row in HBM
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint16_t kPadPt = 0xFFFF;
@@ -51,7 +52,8 @@ constexpr int kJRows = 18;
 constexpr int kJTileBytes = kJRows * kT * 8;
 constexpr int kUVTileBytes = 2 * kT * 8;
 
-static_assert(sizeof(TileMeta) == 2064, "TileMeta is bulk-copied: 16-byte multiple");
+static_assert(sizeof(TileMeta) == 2592 && sizeof(TileMeta) % 16 == 0, "TileMeta is bulk-copied: 16-byte multiple");
+constexpr int kBufStride = kT + 1;         // row stride of the scatter staging buffer (bank spread)
 
 // scalar slots in device memory (doubles).  Groups that are reduced across ranks together are
 // contiguous: [S_COST] sum, [S_GH2..S_X2] sum, S_GINF max, S_COST_NEW sum, [S_JV00..S_JV11] sum,
@@ -120,7 +122,7 @@ struct ModeArgs {
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
     int off_J, off_meta, off_uv, off_camid, off_camvec, off_pa, off_pb, stage_bytes;
-    int off_stages, off_pt, off_z, off_buf, off_red, total;
+    int off_stages, off_pt, off_z, off_buf, off_red, off_ids, total;
 };
 
 __host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -148,13 +150,14 @@ __host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts) {
     L.off_stages = 128;                                   // mbarriers live in the first 128 bytes
     o = L.off_stages + kStages * L.stage_bytes;
     L.off_pt = o;
-    o += align_up(max_pts * T::kPtAcc * 8, 16);
+    o += 2 * align_up(max_pts * T::kPtAcc * 8, 16);       // two parities (see the MATVEC / BACKSUB flow)
     L.off_z = o;
-    o += align_up(max_pts * 3 * 8, 16);
     L.off_buf = o;
-    o += 2 * T::kStageRows * kT * 8;
+    o += 2 * T::kStageRows * kBufStride * 8;
     L.off_red = o;
     o += 64 * 8;
+    L.off_ids = o;
+    o += align_up(kProducers * max_cams * 4, 16);
     L.total = o;
     return L;
 }
@@ -275,25 +278,29 @@ __device__ __forceinline__ void tile_point_reduce(double (&v)[NV], unsigned lp, 
     }
 }
 
-// Per-camera scatter-add of NV values per observation (one "round"): stage the values in shared
-// memory, re-read them in the tile's camera-sorted order, reduce runs of equal cameras with warp
-// shuffles and issue one f64 RED per (run, component) to out[cam * stride + offset + i].
+// Per-camera scatter-add of NV values per observation (one "round"): every consumer stages its
+// values in shared memory; after one barrier, thread (run r, component k) sums the run's values
+// sequentially — the tile's camera-sorted order and its runs (<= kMaxRun observations of one camera)
+// come precomputed in the tile metadata — and issues one f64 RED to out[cam*stride + offset + k].
+// No shuffles, conflict-free staging, 6..9 adjacent lanes RED adjacent doubles of one camera.
 // Rounds alternate between two staging buffers, so one consumer barrier per round suffices.
 template <int NV>
-__device__ __forceinline__ void camera_scatter_round(const double (&v)[NV], double* s_buf /* [NV][kT] */, unsigned src,
-                                                     unsigned key, const int* s_camid, double* out, int stride, int offset) {
-    const int tid = threadIdx.x, lane = tid & 31;
+__device__ __forceinline__ void camera_scatter_round(const double (&v)[NV], double* s_buf /* [NV][kBufStride] */,
+                                                     const TileMeta* mt, const int* s_camid, double* out, int stride,
+                                                     int offset) {
+    const int tid = threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) s_buf[i * kT + tid] = v[i];
+    for (int i = 0; i < NV; ++i) s_buf[i * kBufStride + tid] = v[i];
     consumer_sync();
-    double w[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) w[i] = s_buf[i * kT + src];
-    warp_seg_reduce<NV>(w, key, lane);
-    if (run_head(key, lane) && key != kPadKey) {
-        double* dst = out + (int64_t)s_camid[key] * stride + offset;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) red_add(dst + i, w[i]);
+    const int nruns = mt->nruns, nobs = mt->nobs;
+    for (int idx = tid; idx < nruns * NV; idx += kConsumers) {
+        const int r = idx / NV, k = idx - r * NV;
+        const int j0 = mt->run_start[r];
+        const int j1 = r + 1 < nruns ? (int)mt->run_start[r + 1] : nobs;
+        const double* row = s_buf + k * kBufStride;
+        double sum = 0.0;
+        for (int j = j0; j < j1; ++j) sum += row[mt->sort_src[j]];
+        red_add(out + (int64_t)s_camid[mt->run_cam[r]] * stride + offset + k, sum);
     }
 }
 
@@ -417,7 +424,7 @@ __device__ __forceinline__ void project_obs(const double* __restrict__ cam /* sm
 //                trf.py:498-499); only scalars leave the SM
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) tile_kernel(const TileArgs A, const ModeArgs P) {
+__global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, const ModeArgs P) {
     using T = Traits<MODE>;
     if (MODE == M_MATVEC && P.done && *P.done) return;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -442,82 +449,134 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const TileArgs A, const 
     // scratch that must start at zero
     if (T::kPtAcc) {
         double* s_pt = reinterpret_cast<double*>(smem + L.off_pt);
-        for (int i = tid; i < A.max_pts * T::kPtAcc; i += kThreads) s_pt[i] = 0.0;
+        for (int i = tid; i < 2 * align_up(A.max_pts * T::kPtAcc * 8, 16) / 8; i += kThreads) s_pt[i] = 0.0;
     }
     __syncthreads();
 
     if (tid >= kConsumers) {
-        // ======================= producer warp =======================
-        const int lane = tid - kConsumers;
+        // ======================= producer warps =======================
+        // Producer warp w owns stage w and the CTA's tiles t_begin + w, t_begin + w + kStages, ...
+        // Everything a tile needs besides its bulk-copied blocks is fetched AHEAD of the stage
+        // becoming free: header + camera list two tiles ahead, the first kBatch*32 gathered values
+        // one tile ahead (held in registers while the warp sleeps on the "empty" barrier).  When the
+        // consumers release the stage the producer only issues the bulk copies, stores registers to
+        // shared memory and arrives, so a stage is almost never without a copy in flight.
+        const int pw = (tid - kConsumers) >> 5, lane = tid & 31;
         constexpr int kCPL = kT / 32;   // camera ids per lane (registers)
-        int cams_next[kCPL];
-        int4 hdr_next = make_int4(0, 0, 0, 0);
-        auto prefetch = [&](int t) {
-            hdr_next = *reinterpret_cast<const int4*>(&A.meta[t]);
+        constexpr int kBatch = 8;
+        const int stage = pw;
+        unsigned char* st = smem + L.off_stages + stage * L.stage_bytes;
+        int* s_camid = reinterpret_cast<int*>(st + L.off_camid);
+        double* s_cv = reinterpret_cast<double*>(st + L.off_camvec);
+        double* s_pa = reinterpret_cast<double*>(st + L.off_pa);
+        double* s_pb = reinterpret_cast<double*>(st + L.off_pb);
+        int* s_ids = reinterpret_cast<int*>(smem + L.off_ids) + pw * A.max_cams;   // producer-private camera ids
+
+        int4 hdr_far = make_int4(0, 0, 0, 0);   // header / cameras of the tile after next
+        int cams_far[kCPL];
+        auto fetch_far = [&](int t) {
+            if (t < t_end) {
+                hdr_far = *reinterpret_cast<const int4*>(&A.meta[t]);
+#pragma unroll
+                for (int j = 0; j < kCPL; ++j) {
+                    const int c = lane + 32 * j;
+                    cams_far[j] = c < A.max_cams ? A.tile_cams[(int64_t)t * A.cam_stride + c] : -1;
+                }
+            }
+        };
+        int4 hdr = make_int4(0, 0, 0, 0);       // header / cameras / first gathered batch of the next tile
+        int cams[kCPL];
+        double vals[kBatch];
+        int n_cam = 0, n_pa = 0, n_pb = 0, total = 0;
+        const double *ptA = nullptr, *ptB = nullptr;
+        auto src_of = [&](int i, const int* ids) -> const double* {
+            if (i < n_cam) {
+                const int c = i / (T::kCamRows ? T::kCamRows : 1), k = i - c * T::kCamRows;
+                const int cam = ids[c];
+                if (MODE == M_BUILD || MODE == M_RESID || MODE == M_RESID_STORE) return P.cam0 + (int64_t)cam * kCamTab + k;
+                if (MODE == M_JV2) return k < 6 ? P.cam0 + (int64_t)cam * 6 + k : P.cam1 + (int64_t)cam * 6 + (k - 6);
+                return P.cam0 + (int64_t)cam * 6 + k;
+            }
+            if (i < n_cam + n_pa) return ptA + (i - n_cam);
+            return ptB + (i - n_cam - n_pa);
+        };
+        auto dst_of = [&](int i) -> double* {
+            if (i < n_cam) {
+                const int c = i / (T::kCamRows ? T::kCamRows : 1), k = i - c * T::kCamRows;
+                return s_cv + c * T::kCamStride + k;
+            }
+            if (i < n_cam + n_pa) return s_pa + (i - n_cam);
+            return s_pb + (i - n_cam - n_pa);
+        };
+        // make (hdr_far, cams_far) the current tile and start its first gather batch
+        auto advance = [&]() {
+            hdr = hdr_far;
+#pragma unroll
+            for (int j = 0; j < kCPL; ++j) cams[j] = cams_far[j];
+            n_cam = hdr.z * T::kCamRows;
+            n_pa = hdr.y * T::kPA;
+            n_pb = hdr.y * T::kPB;
+            total = n_cam + n_pa + n_pb;
+            ptA = P.ptA + (int64_t)hdr.x * T::kPA;
+            ptB = T::kPB ? P.ptB + (int64_t)hdr.x * T::kPB : nullptr;
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < kCPL; ++j) {
                 const int c = lane + 32 * j;
-                cams_next[j] = c < A.max_cams ? A.tile_cams[(int64_t)t * A.cam_stride + c] : -1;
+                if (c < hdr.z) s_ids[c] = cams[j];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int i = lane + 32 * u;
+                vals[u] = i < total ? __ldg(src_of(i, s_ids)) : 0.0;
             }
         };
-        if (t_begin < t_end) prefetch(t_begin);
-        int stage = 0;
+        int t = t_begin + pw;
+        fetch_far(t);
+        if (t < t_end) advance();
+        fetch_far(t + kStages);
         unsigned phase = 0;
-        for (int t = t_begin; t < t_end; ++t) {
-            const int4 hdr = hdr_next;
-            int cams[kCPL];
-#pragma unroll
-            for (int j = 0; j < kCPL; ++j) cams[j] = cams_next[j];
-            if (t + 1 < t_end) prefetch(t + 1);
-
-            unsigned char* st = smem + L.off_stages + stage * L.stage_bytes;
+        for (; t < t_end; t += kStages) {
             mbar_wait(&empty[stage], phase ^ 1);
             if (lane == 0) {
                 if (T::kLoadJ) bulk_g2s(st + L.off_J, P.J + (int64_t)t * kJRows * kT, kJTileBytes, &full[stage]);
                 bulk_g2s(st + L.off_meta, &A.meta[t], (unsigned)sizeof(TileMeta), &full[stage]);
                 if (T::kLoadUV) bulk_g2s(st + L.off_uv, A.uv + (int64_t)t * 2 * kT, kUVTileBytes, &full[stage]);
             }
-            const int npts = hdr.y, ncams = hdr.z;
-            // camera ids, then the gathered camera rows
-            int* s_camid = reinterpret_cast<int*>(st + L.off_camid);
 #pragma unroll
             for (int j = 0; j < kCPL; ++j) {
                 const int c = lane + 32 * j;
-                if (c < ncams) s_camid[c] = cams[j];
+                if (c < hdr.z) s_camid[c] = cams[j];
             }
-            __syncwarp();
-            if (T::kCamRows > 0) {
-                double* s_cv = reinterpret_cast<double*>(st + L.off_camvec);
-                const int total = ncams * T::kCamRows;
-                for (int i = lane; i < total; i += 32) {
-                    const int c = i / T::kCamRows, k = i - c * T::kCamRows;
-                    const int cam = s_camid[c];
-                    double v;
-                    if (MODE == M_BUILD || MODE == M_RESID || MODE == M_RESID_STORE) v = P.cam0[(int64_t)cam * kCamTab + k];
-                    else if (MODE == M_JV2) v = k < 6 ? P.cam0[(int64_t)cam * 6 + k] : P.cam1[(int64_t)cam * 6 + (k - 6)];
-                    else v = P.cam0[(int64_t)cam * 6 + k];
-                    s_cv[c * T::kCamStride + k] = v;
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int i = lane + 32 * u;
+                if (i < total) *dst_of(i) = vals[u];
+            }
+            // tiles with more than kBatch*32 gathered values: the rest, batched the same way
+            for (int base = lane + 32 * kBatch; base < total; base += 32 * kBatch) {
+                double v[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const int i = base + 32 * u;
+                    v[u] = i < total ? __ldg(src_of(i, s_ids)) : 0.0;
                 }
-            }
-            // point payloads (contiguous slices of the point arrays)
-            {
-                double* s_pa = reinterpret_cast<double*>(st + L.off_pa);
-                const double* src = P.ptA + (int64_t)hdr.x * T::kPA;
-                for (int i = lane; i < npts * T::kPA; i += 32) s_pa[i] = src[i];
-            }
-            if (T::kPB > 0) {
-                double* s_pb = reinterpret_cast<double*>(st + L.off_pb);
-                const double* src = P.ptB + (int64_t)hdr.x * T::kPB;
-                for (int i = lane; i < npts * T::kPB; i += 32) s_pb[i] = src[i];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const int i = base + 32 * u;
+                    if (i < total) *dst_of(i) = v[u];
+                }
             }
             __syncwarp();
             if (lane == 0) {
                 const unsigned tx = (T::kLoadJ ? kJTileBytes : 0) + (unsigned)sizeof(TileMeta) + (T::kLoadUV ? kUVTileBytes : 0);
                 mbar_arrive_expect_tx(&full[stage], tx);
             }
-            if (++stage == kStages) {
-                stage = 0;
-                phase ^= 1;
+            phase ^= 1;
+            if (t + kStages < t_end) {
+                advance();                       // next tile of this warp: ids + first batch in flight
+                fetch_far(t + 2 * kStages);
             }
         }
         return;
@@ -526,10 +585,10 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const TileArgs A, const 
     // ======================= consumer warps =======================
     const int lane = tid & 31;
     double* s_pt = reinterpret_cast<double*>(smem + L.off_pt);
-    double* s_z = reinterpret_cast<double*>(smem + L.off_z);
     double* s_buf = reinterpret_cast<double*>(smem + L.off_buf);
     double* s_red = reinterpret_cast<double*>(smem + L.off_red);
     int round = 0;                 // staging-buffer parity of camera_scatter_round
+    int par = 0;                   // per-point accumulator parity (MATVEC / BACKSUB)
     double acc[3] = {0, 0, 0};     // cost (BUILD / RESID) or Gram (JV)
     int stage = 0;
     unsigned phase = 0;
@@ -546,11 +605,6 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const TileArgs A, const 
         const unsigned lp = mt->slot_pt[tid], lc = mt->slot_cam[tid];
         const bool valid = lp != kPadPt;
         const int lps = valid ? (int)lp : 0;
-        unsigned src = 0, key = 0;
-        if (T::kScatter) {
-            src = mt->sort_src[tid];
-            key = mt->sort_key[tid];
-        }
 
         if constexpr (MODE == M_BUILD || MODE == M_RESID || MODE == M_RESID_STORE) {
             const double* s_uv = reinterpret_cast<const double*>(st + L.off_uv);
@@ -591,7 +645,7 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const TileArgs A, const 
                 double cv[9];
 #pragma unroll
                 for (int i = 0; i < 9; ++i) cv[i] = jc[tri6_row(i)] * jc[tri6_col(i)] + jc[6 + tri6_row(i)] * jc[6 + tri6_col(i)];
-                camera_scatter_round<9>(cv, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.U, 21, 0);
+                camera_scatter_round<9>(cv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.U, 21, 0);
                 // the round's barrier also completed the point sums: the tile owns its points
                 for (int i = tid; i < npts * 9; i += kConsumers) {
                     const int p = i / 9, k = i - p * 9;
@@ -603,16 +657,16 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const TileArgs A, const 
 #pragma unroll
                 for (int i = 0; i < 9; ++i)
                     cv[i] = jc[tri6_row(9 + i)] * jc[tri6_col(9 + i)] + jc[6 + tri6_row(9 + i)] * jc[6 + tri6_col(9 + i)];
-                camera_scatter_round<9>(cv, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.U, 21, 9);
+                camera_scatter_round<9>(cv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.U, 21, 9);
                 double cw[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
                     cw[i] = jc[tri6_row(18 + i)] * jc[tri6_col(18 + i)] + jc[6 + tri6_row(18 + i)] * jc[6 + tri6_col(18 + i)];
-                camera_scatter_round<3>(cw, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.U, 21, 18);
+                camera_scatter_round<3>(cw, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.U, 21, 18);
                 double cg[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) cg[i] = jc[i] * r[0] + jc[6 + i] * r[1];
-                camera_scatter_round<6>(cg, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.gc, 6, 0);
+                camera_scatter_round<6>(cg, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.gc, 6, 0);
             }
         } else if constexpr (MODE == M_JV1 || MODE == M_JV2) {
             constexpr int NV = MODE == M_JV2 ? 2 : 1;
@@ -649,7 +703,10 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const TileArgs A, const 
             for (int i = 0; i < 6; ++i) jp[i] = valid ? sJ[(12 + i) * kT + tid] : 0.0;
             double z0, z1, z2;
             if constexpr (MODE != M_RHS) {
-                // u = Jc xt_c ; w = Jp^T u ; t_p = sum over the point's observations
+                // u = Jc xt_c ; w = Jp^T u ; t_p = sum over the point's observations.  The per-point
+                // accumulator has two parities: tile i's sums are read after its barrier while tile
+                // i+1 already accumulates into the other one; each parity is re-zeroed by its readers.
+                double* s_ptp = s_pt + par * (align_up(A.max_pts * T::kPtAcc * 8, 16) / 8);
                 const double* xc = s_cv + lc * T::kCamStride;
                 double u0 = 0, u1 = 0;
 #pragma unroll
@@ -660,41 +717,30 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const TileArgs A, const 
                 double w[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) w[k] = jp[k] * u0 + jp[3 + k] * u1;
-                tile_point_reduce<3>(w, lp, s_pt);
+                tile_point_reduce<3>(w, lp, s_ptp);
                 consumer_sync();
-                // one thread per point: z = M t  (MATVEC)  or  dp = M (g - t)  (BACKSUB)
-                if (tid < npts) {
-                    double t0 = s_pt[tid * 3], t1 = s_pt[tid * 3 + 1], t2 = s_pt[tid * 3 + 2];
-                    s_pt[tid * 3] = 0.0;
-                    s_pt[tid * 3 + 1] = 0.0;
-                    s_pt[tid * 3 + 2] = 0.0;
-                    if (MODE == M_BACKSUB) {
-                        t0 = s_pb[tid * 3] - t0;
-                        t1 = s_pb[tid * 3 + 1] - t1;
-                        t2 = s_pb[tid * 3 + 2] - t2;
-                    }
-                    const double* m = s_pa + tid * 6;
-                    const double y0 = m[0] * t0 + m[1] * t1 + m[2] * t2;
-                    const double y1 = m[1] * t0 + m[3] * t1 + m[4] * t2;
-                    const double y2 = m[2] * t0 + m[4] * t1 + m[5] * t2;
-                    if (MODE == M_BACKSUB) {
+                if constexpr (MODE == M_BACKSUB) {
+                    // one thread per point: dp = M (g - t)
+                    if (tid < npts) {
+                        const double t0 = s_pb[tid * 3] - s_ptp[tid * 3], t1 = s_pb[tid * 3 + 1] - s_ptp[tid * 3 + 1],
+                                     t2 = s_pb[tid * 3 + 2] - s_ptp[tid * 3 + 2];
+                        s_ptp[tid * 3] = 0.0;
+                        s_ptp[tid * 3 + 1] = 0.0;
+                        s_ptp[tid * 3 + 2] = 0.0;
+                        const double* m = s_pa + tid * 6;
                         double* o = P.dp + ((int64_t)pt0 + tid) * 3;
-                        o[0] = y0;
-                        o[1] = y1;
-                        o[2] = y2;
-                    } else {
-                        s_z[tid * 3] = y0;
-                        s_z[tid * 3 + 1] = y1;
-                        s_z[tid * 3 + 2] = y2;
+                        o[0] = m[0] * t0 + m[1] * t1 + m[2] * t2;
+                        o[1] = m[1] * t0 + m[3] * t1 + m[4] * t2;
+                        o[2] = m[2] * t0 + m[4] * t1 + m[5] * t2;
                     }
-                }
-                if (MODE == M_BACKSUB) {
-                    consumer_sync();   // s_pt zeroed before the next tile's atomics; stage reads done
+                    z0 = z1 = z2 = 0.0;
                 } else {
-                    consumer_sync();
-                    z0 = s_z[lps * 3];
-                    z1 = s_z[lps * 3 + 1];
-                    z2 = s_z[lps * 3 + 2];
+                    // every observation applies its point's damped inverse itself: z = M_p t_p
+                    const double t0 = s_ptp[lps * 3], t1 = s_ptp[lps * 3 + 1], t2 = s_ptp[lps * 3 + 2];
+                    const double* m = s_pa + lps * 6;
+                    z0 = m[0] * t0 + m[1] * t1 + m[2] * t2;
+                    z1 = m[1] * t0 + m[3] * t1 + m[4] * t2;
+                    z2 = m[2] * t0 + m[4] * t1 + m[5] * t2;
                 }
             } else {
                 z0 = s_pb[lps * 3];
@@ -708,7 +754,12 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const TileArgs A, const 
                 double cv[6];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) cv[k] = jc[k] * v0 + jc[6 + k] * v1;
-                camera_scatter_round<6>(cv, s_buf + (round++ & 1) * T::kStageRows * kT, src, key, s_camid, P.y, 6, 0);
+                camera_scatter_round<6>(cv, s_buf + (round++ & 1) * T::kStageRows * kBufStride, mt, s_camid, P.y, 6, 0);
+                if constexpr (MODE == M_MATVEC) {
+                    // all reads of this parity's point sums happened before the round's barrier
+                    double* s_ptp = s_pt + par * (align_up(A.max_pts * T::kPtAcc * 8, 16) / 8);
+                    for (int i = tid; i < npts * 3; i += kConsumers) s_ptp[i] = 0.0;
+                }
             }
             if constexpr (MODE == M_RHS) {
                 // Schur diagonal: E = Jc^T Jp (6x3), F = E M (6x3), Sd += F E^T (upper triangle)
@@ -729,23 +780,24 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const TileArgs A, const 
                     const int a = tri6_row(i), b = tri6_col(i);
                     sv[i] = F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2];
                 }
-                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.Sd, 21, 0);
+                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.Sd, 21, 0);
 #pragma unroll
                 for (int i = 0; i < 9; ++i) {
                     const int a = tri6_row(9 + i), b = tri6_col(9 + i);
                     sv[i] = F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2];
                 }
-                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.Sd, 21, 9);
+                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.Sd, 21, 9);
                 double sw[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const int a = tri6_row(18 + i), b = tri6_col(18 + i);
                     sw[i] = F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2];
                 }
-                camera_scatter_round<3>(sw, s_buf + (round++ & 1) * 9 * kT, src, key, s_camid, P.Sd, 21, 18);
+                camera_scatter_round<3>(sw, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.Sd, 21, 18);
             }
         }
         // all reads of this stage are done: hand it back to the producer
+        par ^= 1;
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == kStages) {

@@ -148,11 +148,13 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
         m.nobs = n;
         plan.max_tile_cams = std::max(plan.max_tile_cams, m.ncams);
         plan.max_tile_pts = std::max(plan.max_tile_pts, m.npts);
+        m.pad[0] = m.pad[1] = m.pad[2] = 0;
         for (int j = 0; j < kTileObs; ++j) {
             m.slot_cam[j] = 0;
             m.slot_pt[j] = 0xFFFF;   // empty slots carry the pad marker
             m.sort_src[j] = (uint16_t)j;
-            m.sort_key[j] = kPadKey;
+            m.run_start[j] = 0;
+            m.run_cam[j] = 0;
         }
         int i = 0;
         for (int64_t q = rg.p0; q < rg.p1; ++q) {
@@ -164,10 +166,17 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
         }
         std::iota(idx.begin(), idx.begin() + n, (uint16_t)0);
         std::stable_sort(idx.begin(), idx.begin() + n, [&](uint16_t a, uint16_t b) { return m.slot_cam[a] < m.slot_cam[b]; });
+        int nruns = 0;
         for (int j = 0; j < n; ++j) {
             m.sort_src[j] = idx[j];
-            m.sort_key[j] = m.slot_cam[idx[j]];
+            const uint16_t key = m.slot_cam[idx[j]];
+            if (j == 0 || key != m.slot_cam[idx[j - 1]] || j - m.run_start[nruns - 1] >= kMaxRun) {
+                m.run_start[nruns] = (uint16_t)j;
+                m.run_cam[nruns] = key;
+                ++nruns;
+            }
         }
+        m.nruns = nruns;
     }
     plan.cam_stride = std::max(4, (plan.max_tile_cams + 3) / 4 * 4);
     plan.tile_cams.assign((size_t)plan.n_tiles * plan.cam_stride, -1);

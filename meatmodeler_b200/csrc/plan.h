@@ -13,16 +13,21 @@ namespace mmba {
 constexpr int kTileObs = 256;          // observation slots per tile == threads per CTA
 constexpr uint16_t kPadKey = 0xFFFF;   // sorted-key of an empty slot
 
-// One record per tile, bulk-copied to shared memory as a unit (2064 bytes, 16-byte multiple).
+constexpr int kMaxRun = 32;            // longest camera run one thread sums (longer runs are split)
+
+// One record per tile, bulk-copied to shared memory as a unit (2592 bytes, 16-byte multiple).
 struct TileMeta {
     int32_t pt0;        // first local (shard-relative, internal-order) point of the tile
     int32_t npts;       // points in the tile
     int32_t ncams;      // distinct cameras in the tile
     int32_t nobs;       // live observation slots (the rest of the 256 are padding)
+    int32_t nruns;      // camera runs in the tile's camera-sorted order (each at most kMaxRun long)
+    int32_t pad[3];
     uint16_t slot_cam[kTileObs];   // local camera slot of the observation in its tile
     uint16_t slot_pt[kTileObs];    // local point index of the observation in its tile (0xFFFF = empty slot)
     uint16_t sort_src[kTileObs];   // j-th entry of the tile in camera-sorted order -> slot in tile
-    uint16_t sort_key[kTileObs];   // its local camera slot (kPadKey for empty)
+    uint16_t run_start[kTileObs];  // run r covers sorted positions run_start[r] .. run_start[r+1] (or nobs)
+    uint16_t run_cam[kTileObs];    // local camera slot of run r
 };
 
 struct Plan {
