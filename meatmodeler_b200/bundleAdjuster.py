@@ -118,14 +118,19 @@ def pointAdjustmentSparsity(n_frames, n_points, frame_indices, point_indices):
 # engine access
 # --------------------------------------------------------------------------------------------------
 
+def _is_distributed():
+    dist = getattr(sys.modules.get("torch"), "distributed", None)
+    return bool(dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+
+
 def _dist_options():
     """Shard options when the caller runs one process per GPU under ``torch.distributed``
     (observations sharded by point, cameras replicated, NCCL all-reduce inside the engine).
     A single process gets the single-GPU defaults; torch is not imported at all in that case."""
-    dist = getattr(sys.modules.get("torch"), "distributed", None)
-    if dist is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+    if not _is_distributed():
         return {}
     import torch
+    dist = torch.distributed
     rank, world = dist.get_rank(), dist.get_world_size()
     device = torch.cuda.current_device()
     blob = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{device}")
@@ -174,6 +179,7 @@ def solve(parameters, camera_matrix, n_frames, n_points, frame_indices, point_in
     success`` plus engine statistics (``log``, ``pcg_iterations``, ``solve_ms``).
     """
     own = engine is None
+    sharded = engine is None and _is_distributed()
     eng = engine if engine is not None else _engine(
         camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D,
         ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=0 if max_nfev is None else int(max_nfev), **options)
@@ -185,6 +191,12 @@ def solve(parameters, camera_matrix, n_frames, n_points, frame_indices, point_in
                 raise ValueError("Residuals are not finite in the initial point.") from e
             raise
         log = eng.log()
+        if sharded and fun is not None:
+            # each rank holds the residuals of its own observations (zeros elsewhere)
+            import torch
+            t = torch.from_numpy(fun).cuda()
+            torch.distributed.all_reduce(t)
+            fun = t.cpu().numpy()
     finally:
         if own:
             eng.close()

@@ -821,7 +821,7 @@ void mmba_default_options(mmba_options* opt) {
     opt->xtol = 1e-8;
     opt->gtol = 1e-8;
     opt->max_nfev = 0;
-    opt->pcg_rtol = 1e-10;
+    opt->pcg_rtol = 1e-8;
     opt->pcg_maxit = 1000;
     opt->profile = 0;
 }

@@ -1,0 +1,54 @@
+"""Multi-GPU check, run under torchrun (one process per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+Every rank solves its point shard of the same problem (cameras replicated, NCCL all-reduce inside
+libmmba); rank 0 additionally solves the whole problem on one GPU.  The sharded solve must agree
+with the single-GPU solve: same iteration counts, per-iteration costs to 1e-9, x to 1e-7.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from meatmodeler_b200 import _capi, synth  # noqa: E402
+from meatmodeler_b200 import bundleAdjuster as mm  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for name, prob in (("windowed", synth.make_problem(40, 3000, 24000, seed=21, hard=True)),
+                       ("random", synth.make_problem(60, 1500, 9000, seed=7, hard=True, windowed=False)),
+                       ("c2-tenth", synth.make_config("C2", hard=True, scale=0.1))):
+        ext, K, pts, uv, fi, pi = prob.args()
+        nc, npts = len(ext), len(pts)
+        x0 = np.hstack((mm.frameParameters(ext), np.asarray(pts).reshape(-1)))
+        res = mm.solve(x0, K, nc, npts, fi, pi, uv, want_fun=True)       # sharded (torch.distributed is initialised)
+        costs = np.array([r["cost"] for r in res.log])
+        if rank == 0:
+            with _capi.Engine(device=local) as eng:                        # single GPU
+                eng.set_problem(nc, npts, K, fi, pi, uv)
+                x1, r1, f1 = eng.solve(x0, want_fun=True)
+                c1 = np.array([r["cost"] for r in eng.log()])
+            same = (res.nfev == r1.nfev and res.status == r1.status and len(costs) == len(c1)
+                    and np.allclose(costs, c1, rtol=1e-9) and np.abs(res.x - x1).max() < 1e-7
+                    and np.abs(res.fun - f1).max() < 1e-6)
+            print(f"{name}: world={world} nfev {res.nfev}/{r1.nfev} status {res.status}/{r1.status} "
+                  f"cost {res.cost:.12e}/{r1.cost:.12e} max|dx| {np.abs(res.x - x1).max():.2e} "
+                  f"max|df| {np.abs(res.fun - f1).max():.2e} pcg {res.pcg_iterations}/{r1.pcg_iterations} -> {'OK' if same else 'MISMATCH'}",
+                  flush=True)
+            ok = ok and same
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
