@@ -243,7 +243,8 @@ def run_mmba(args):
 
     # ---- per-kernel durations: one extra step with every launch bracketed by CUDA events --------
     eng.close()
-    opts_p = dict(opts)
+    opts_p = mm._dist_options()          # a fresh ncclUniqueId: one id initialises one communicator
+    opts_p.setdefault("device", local)
     opts_p["profile"] = 1
     engp = _capi.Engine(**opts_p)
     engp.set_problem(nc, npts, K, fi, pi, uv)
