@@ -275,7 +275,10 @@ def run_mmba(args):
                 "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"], "avg_launch_ms": kernels[dom]["avg_ms"],
                 "how": "CUDA events around every launch on the engine's stream during one extra, identical step "
                        "(profile=1); the timed steps carry no per-launch events",
-                "kernels": kernels}
+                "kernels": kernels,
+                "other_classes_ms_per_step": {k: {"launches": prof[k]["launches"], "ms": prof[k]["ms"]}
+                                              for k in ("vec", "allreduce", "cam_prep", "point_invert")},
+                "profiled_step_ms": rp.solve_ms}
 
     # ---- end to end through the drop-in adjustPoints with host buffers ---------------------------
     e2e_steps = max(2, min(args.steps, 5))

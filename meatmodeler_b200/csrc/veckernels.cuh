@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kCamBlock) pcg_init_kernel(PcgVecs P, double r
     }
 }
 
-constexpr int kPcgThreads = 1024;
+constexpr int kPcgThreads = 256;
 
 // One PCG iteration's camera-vector work in ONE CTA, so that every reduction is a fixed-order sum
 // and the whole update costs a single launch (LSMR's vector updates, lsmr.py:373-377):
@@ -294,6 +294,90 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update_kernel(PcgVecs P, doub
     if (P.flags[0]) return;
     __shared__ double s_red[32];
     const int tid = threadIdx.x, nthr = blockDim.x;
+    if (P.n_cams <= nthr) {
+        // fast path, one camera per thread: every operand is loaded up front (one memory round trip),
+        // the three reductions then only cost block barriers
+        const int c = tid;
+        const bool live = c < P.n_cams;
+        double xt[6], pv[6], yv[6], si[6], rv[6], xv[6], U[21], Pi[21];
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                xt[k] = P.xt[c * 6 + k];
+                pv[k] = P.p[c * 6 + k];
+                yv[k] = P.y[c * 6 + k];
+                si[k] = P.sinv[c * 6 + k];
+                rv[k] = P.r[c * 6 + k];
+                xv[k] = P.x[c * 6 + k];
+            }
+#pragma unroll
+            for (int i = 0; i < 21; ++i) {
+                U[i] = P.U[c * 21 + i];
+                Pi[i] = P.Pinv[c * 21 + i];
+            }
+        }
+        double rho, b2;
+        if (it == 0) {
+            rho = sum_partials(P.part + P_RHO0 * kMaxCamBlocks, nb_init, s_red);
+            b2 = sum_partials(P.part + P_B2 * kMaxCamBlocks, nb_init, s_red);
+        } else {
+            rho = P.state[0];
+            b2 = P.state[1];
+        }
+        double q[6], pq = 0;
+        if (live) {
+            double ux[6];
+            sym6_matvec(U, xt, ux);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                q[k] = (ux[k] - yv[k]) / si[k] + reg * pv[k];
+                P.y[c * 6 + k] = 0.0;
+                pq += pv[k] * q[k];
+            }
+        }
+        pq = block_sum_det(pq, s_red);
+        const double alpha = rho / pq;
+        double z[6], rr = 0, rz = 0;
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                xv[k] += alpha * pv[k];
+                rv[k] -= alpha * q[k];
+            }
+            sym6_matvec(Pi, rv, z);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                P.x[c * 6 + k] = xv[k];
+                P.r[c * 6 + k] = rv[k];
+                rr += rv[k] * rv[k];
+                rz += rv[k] * z[k];
+            }
+        }
+        rr = block_sum_det(rr, s_red);
+        rz = block_sum_det(rz, s_red);
+        int done = 0;
+        if (rr <= rtol2 * b2) done = 1;
+        else if (!(pq > 0.0) || !isfinite(rr) || !(rz > 0.0)) done = 2;
+        if (tid == 0) {
+            P.state[0] = rz;
+            P.state[1] = b2;
+            P.state[2] = rr;
+            if (done) {
+                P.flags[1] = it + 1;
+                __threadfence();
+                P.flags[0] = done;
+            }
+        }
+        if (done || !live) return;
+        const double beta = rz / rho;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double pk = z[k] + beta * pv[k];
+            P.p[c * 6 + k] = pk;
+            P.xt[c * 6 + k] = pk / si[k];
+        }
+        return;
+    }
     double rho, b2;
     if (it == 0) {
         rho = sum_partials(P.part + P_RHO0 * kMaxCamBlocks, nb_init, s_red);
