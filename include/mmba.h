@@ -103,6 +103,10 @@ int mmba_create(mmba_handle** out, const mmba_options* opt);
  * layer broadcasts it with torch.distributed); every rank passes it in mmba_options.nccl_id */
 int mmba_nccl_unique_id(uint8_t out[128]);
 void mmba_destroy(mmba_handle* h);
+/* change the tolerances / limits / verbosity / profiling of an existing handle (device, rank,
+ * nranks and nccl_id of `opt` are ignored: a handle keeps its device and communicator), so that
+ * one handle — one stream, one NCCL communicator — serves successive problems */
+int mmba_set_options(mmba_handle* h, const mmba_options* opt);
 
 /* replaces: pointAdjustmentSparsity (bundleAdjuster.py:55-78, 179) — the block structure is implied
  * by the two index arrays.  Copies the problem to the device, narrows indices to int32, reorders

@@ -59,6 +59,7 @@ SIGNATURES = {
     "mmba_create": (C.c_int, [C.POINTER(_H), C.POINTER(Options)]),
     "mmba_nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8 * 128)]),
     "mmba_destroy": (None, [_H]),
+    "mmba_set_options": (C.c_int, [_H, C.POINTER(Options)]),
     "mmba_set_problem": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, _f64, _i64, _i64, _f64]),
     "mmba_solve": (C.c_int, [_H, _f64, C.POINTER(Result), C.c_void_p]),
     "mmba_set_x": (C.c_int, [_H, _f64]),
@@ -144,6 +145,15 @@ class Engine:
         self._h = _H()
         _check(lib().mmba_create(C.byref(self._h), C.byref(opt)))
         self.sizes = None
+
+    def set_options(self, **kw):
+        """Change tolerances / limits of the live handle (ftol, xtol, gtol, max_nfev, pcg_rtol, pcg_maxit,
+        verbose, profile)."""
+        for k, v in kw.items():
+            if k in ("device", "rank", "nranks", "nccl_id") or not hasattr(self.options, k):
+                raise TypeError(f"option {k} cannot be changed on a live engine")
+            setattr(self.options, k, v)
+        _check(lib().mmba_set_options(self._h, C.byref(self.options)), self._h)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

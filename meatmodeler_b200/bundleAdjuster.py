@@ -13,6 +13,7 @@ There is no CPU fallback: without ``libmmba.so`` or without an sm_100 GPU every 
 """
 from __future__ import annotations
 
+import atexit
 import math
 import os
 import sys
@@ -140,19 +141,52 @@ def _dist_options():
     return dict(device=device, rank=rank, nranks=world, nccl_id=bytes(blob.cpu().numpy().tobytes()))
 
 
+_ENGINES = {}          # (device, rank, nranks) -> live engine: one stream / NCCL communicator per process
+_TUNABLE = ("ftol", "xtol", "gtol", "max_nfev", "pcg_rtol", "pcg_maxit", "verbose", "profile")
+
+
 def _engine(camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D, **options):
-    for k, v in _dist_options().items():
-        options.setdefault(k, v)
-    eng = _capi.Engine(**options)
+    """The process-wide engine with this problem loaded.  Handles are cached: creating a CUDA stream,
+    pinned staging buffers and (multi-GPU) an NCCL communicator once instead of once per call."""
+    fixed = {k: options.pop(k) for k in ("device", "rank", "nranks", "nccl_id") if k in options}
+    unknown = [k for k in options if k not in _TUNABLE]
+    if unknown:
+        raise TypeError(f"unknown option(s) {unknown}")
+    key = None
+    if not fixed:
+        if _is_distributed():
+            import torch
+            key = (torch.cuda.current_device(), torch.distributed.get_rank(), torch.distributed.get_world_size())
+        else:
+            key = (0, 0, 1)
+    eng = _ENGINES.get(key) if key is not None else None
+    if eng is None:
+        if not fixed:
+            fixed = _dist_options()
+        eng = _capi.Engine(**fixed)
+        if key is not None:
+            _ENGINES[key] = eng
+    defaults = _capi.default_options()
+    eng.set_options(**{k: options.get(k, getattr(defaults, k)) for k in _TUNABLE})
     eng.set_problem(n_frames, n_points, camera_matrix, frame_indices, point_indices, points_2D)
     return eng
+
+
+def release():
+    """Destroy the cached engines (device memory, streams, communicators)."""
+    for eng in _ENGINES.values():
+        eng.close()
+    _ENGINES.clear()
+
+
+atexit.register(release)
 
 
 def pointFun(parameters, camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D):
     """Reprojection residuals, interleaved (du0, dv0, du1, ...)  (bundleAdjuster.py:81-102),
     evaluated by the engine's residual kernel."""
-    with _engine(camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D) as eng:
-        return eng.residual(parameters)
+    eng = _engine(camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D)
+    return eng.residual(parameters)
 
 
 def _print_table(log, res):
@@ -178,28 +212,23 @@ def solve(parameters, camera_matrix, n_frames, n_points, frame_indices, point_in
     Returns a ``SolveResult`` with ``x, cost, fun, optimality, nfev, njev, nit, status, message,
     success`` plus engine statistics (``log``, ``pcg_iterations``, ``solve_ms``).
     """
-    own = engine is None
     sharded = engine is None and _is_distributed()
     eng = engine if engine is not None else _engine(
         camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D,
         ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=0 if max_nfev is None else int(max_nfev), **options)
     try:
-        try:
-            x, r, fun = eng.solve(parameters, want_fun=want_fun)
-        except _capi.MmbaError as e:
-            if e.code == -4:   # scipy raises ValueError here (least_squares.py:945-946)
-                raise ValueError("Residuals are not finite in the initial point.") from e
-            raise
-        log = eng.log()
-        if sharded and fun is not None:
-            # each rank holds the residuals of its own observations (zeros elsewhere)
-            import torch
-            t = torch.from_numpy(fun).cuda()
-            torch.distributed.all_reduce(t)
-            fun = t.cpu().numpy()
-    finally:
-        if own:
-            eng.close()
+        x, r, fun = eng.solve(parameters, want_fun=want_fun)
+    except _capi.MmbaError as e:
+        if e.code == -4:   # scipy raises ValueError here (least_squares.py:945-946)
+            raise ValueError("Residuals are not finite in the initial point.") from e
+        raise
+    log = eng.log()
+    if sharded and fun is not None:
+        # each rank holds the residuals of its own observations (zeros elsewhere)
+        import torch
+        t = torch.from_numpy(fun).cuda()
+        torch.distributed.all_reduce(t)
+        fun = t.cpu().numpy()
     res = SolveResult(x=x, cost=r.cost, initial_cost=r.initial_cost, fun=fun, optimality=r.optimality,
                       nfev=r.nfev, njev=r.njev, nit=r.nit, status=r.status,
                       message=_STATUS_MESSAGES.get(r.status, ""), success=r.status > 0, log=log,

@@ -533,16 +533,21 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, con
             }
         };
         int t = t_begin + pw;
-        fetch_far(t);
-        if (t < t_end) advance();
-        fetch_far(t + kStages);
         unsigned phase = 0;
+        bool first = true;
         for (; t < t_end; t += kStages) {
             mbar_wait(&empty[stage], phase ^ 1);
             if (lane == 0) {
                 if (T::kLoadJ) bulk_g2s(st + L.off_J, P.J + (int64_t)t * kJRows * kT, kJTileBytes, &full[stage]);
                 bulk_g2s(st + L.off_meta, &A.meta[t], (unsigned)sizeof(TileMeta), &full[stage]);
                 if (T::kLoadUV) bulk_g2s(st + L.off_uv, A.uv + (int64_t)t * 2 * kT, kUVTileBytes, &full[stage]);
+            }
+            if (first) {
+                // the first tile's bulk copies are already in flight while its header chain resolves
+                first = false;
+                fetch_far(t);
+                advance();
+                fetch_far(t + kStages);
             }
 #pragma unroll
             for (int j = 0; j < kCPL; ++j) {

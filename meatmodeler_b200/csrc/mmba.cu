@@ -305,8 +305,6 @@ void carve(mmba_handle* h, Arena& a) {
 void release_problem(mmba_handle* h) {
     if (h->arena) cudaFree(h->arena);
     h->arena = nullptr;
-    if (h->h_stage) cudaFreeHost(h->h_stage);
-    h->h_stage = nullptr;
     h->has_problem = false;
 }
 
@@ -888,11 +886,26 @@ int mmba_create(mmba_handle** out, const mmba_options* opt) {
     return MMBA_OK;
 }
 
+int mmba_set_options(mmba_handle* h, const mmba_options* opt) {
+    if (!h || !opt) return fail(h, MMBA_ERR_ARG, "set_options: null argument");
+    if (opt->pcg_maxit <= 0 || !(opt->pcg_rtol > 0)) return fail(h, MMBA_ERR_ARG, "pcg_maxit and pcg_rtol must be positive");
+    h->opt.verbose = opt->verbose;
+    h->opt.ftol = opt->ftol;
+    h->opt.xtol = opt->xtol;
+    h->opt.gtol = opt->gtol;
+    h->opt.max_nfev = opt->max_nfev;
+    h->opt.pcg_rtol = opt->pcg_rtol;
+    h->opt.pcg_maxit = opt->pcg_maxit;
+    h->opt.profile = opt->profile;
+    return MMBA_OK;
+}
+
 void mmba_destroy(mmba_handle* h) {
     if (!h) return;
     cudaSetDevice(h->opt.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     release_problem(h);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->comm) g_nccl.CommDestroy(h->comm);
     for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -933,8 +946,14 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     Arena a;
     a.base = static_cast<char*>(h->arena);
     carve(h, a);
-    h->h_stage_n = (size_t)std::max<int64_t>(6 * h->Nc + 3 * pl.n_points, 64);
-    CU(cudaMallocHost(&h->h_stage, h->h_stage_n * sizeof(double)));
+    const size_t stage_n = (size_t)std::max<int64_t>(6 * h->Nc + 3 * pl.n_points, 64);
+    if (stage_n > h->h_stage_n) {   // pinned staging buffer: grown, never shrunk, freed with the handle
+        if (h->h_stage) cudaFreeHost(h->h_stage);
+        h->h_stage = nullptr;
+        h->h_stage_n = 0;
+        CU(cudaMallocHost(&h->h_stage, stage_n * sizeof(double)));
+        h->h_stage_n = stage_n;
+    }
 
     Dev& d = h->d;
     CU(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
@@ -942,6 +961,7 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
         TRY(upload(h, d.meta, pl.meta));
         TRY(upload(h, d.tile_cams, pl.tile_cams));
         std::vector<double> uvs(2 * (size_t)h->ns, 0.0);
+#pragma omp parallel for schedule(static, 4096)
         for (int64_t s = 0; s < h->ns; ++s) {
             const int64_t ob = pl.slot_obs[s];
             if (ob >= 0) {
@@ -1191,6 +1211,11 @@ int mmba_bench_kernel(mmba_handle* h, const double* x, int kernel_class, int ite
                 case MMBA_K_MATVEC: TRY(launch_tile<M_MATVEC>(h, MMBA_K_MATVEC, matvec_args(h))); break;
                 case MMBA_K_BACKSUB: TRY(launch_tile<M_BACKSUB>(h, MMBA_K_BACKSUB, backsub_args(h))); break;
                 case MMBA_K_JV: TRY(launch_tile<M_JV2>(h, MMBA_K_JV, Pj)); break;
+                case 100: TRY(launch_tile<M_JV1>(h, MMBA_K_JV, Pj)); break;
+                case 101:   // plain streaming read of Jt: the ceiling a trivial kernel reaches on these bytes
+                    stream_read_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(reinterpret_cast<const double2*>(d.J),
+                                                                                (int64_t)kJRows * h->ns / 2, d.scal + S_DOT9);
+                    break;
                 case MMBA_K_PTINV:
                     point_invert_kernel<<<cdiv(h->npl, 256), 256, 0, h->stream>>>(d.V, d.g + 6 * h->Nc, d.sinv + 6 * h->Nc, reg,
                                                                                    d.M, d.zg, h->npl);

@@ -89,9 +89,21 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
             const int64_t q = (int64_t)point_inv[pt_idx[i]] - plan.pt_begin;
             if (q >= 0 && q < npl) grouped[fill[q]++] = i;
         }
+#pragma omp parallel for schedule(static, 1024)
         for (int64_t q = 0; q < npl; ++q) {
-            std::stable_sort(grouped.begin() + start[q], grouped.begin() + start[q + 1],
-                             [&](int64_t a, int64_t b) { return cam_idx[a] < cam_idx[b]; });
+            // tracks are short: insertion sort (stable), usually already ascending
+            int64_t* g = grouped.data() + start[q];
+            const int64_t L = start[q + 1] - start[q];
+            for (int64_t a = 1; a < L; ++a) {
+                const int64_t v = g[a];
+                const int64_t cv = cam_idx[v];
+                int64_t b = a;
+                while (b > 0 && cam_idx[g[b - 1]] > cv) {
+                    g[b] = g[b - 1];
+                    --b;
+                }
+                g[b] = v;
+            }
         }
     }
 
@@ -122,62 +134,74 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
     plan.meta.resize(plan.n_tiles);
     plan.slot_obs.assign(plan.n_slots, -1);
 
-    // 6. per tile: local camera table, local slots, camera-sorted order
-    std::vector<int32_t> stamp(n_cams, -1), local_of(n_cams, 0);
+    // 6. per tile: local camera table, local slots, camera-sorted order (tiles are independent)
     std::vector<std::vector<int32_t>> cams_of(plan.n_tiles);
-    std::vector<uint16_t> idx(kTileObs);
-    for (int64_t t = 0; t < plan.n_tiles; ++t) {
-        const Range rg = ranges[t];
-        const int64_t o0 = start[rg.p0], o1 = start[rg.p1];
-        const int n = (int)(o1 - o0);
-        const int64_t base = t * kTileObs;
-        std::vector<int32_t>& cams = cams_of[t];
-        for (int i = 0; i < n; ++i) {
-            const int32_t c = (int32_t)cam_idx[grouped[o0 + i]];
-            if (stamp[c] != (int32_t)t) {
-                stamp[c] = (int32_t)t;
-                cams.push_back(c);
+    int max_cams = 0, max_pts = 0;
+#pragma omp parallel reduction(max : max_cams, max_pts)
+    {
+        std::vector<int32_t> stamp(n_cams, -1), local_of(n_cams, 0);
+        std::vector<uint16_t> idx(kTileObs);
+        uint16_t cnt[kTileObs + 1];
+#pragma omp for schedule(static, 64)
+        for (int64_t t = 0; t < plan.n_tiles; ++t) {
+            const Range rg = ranges[t];
+            const int64_t o0 = start[rg.p0], o1 = start[rg.p1];
+            const int n = (int)(o1 - o0);
+            const int64_t base = t * kTileObs;
+            std::vector<int32_t>& cams = cams_of[t];
+            for (int i = 0; i < n; ++i) {
+                const int32_t c = (int32_t)cam_idx[grouped[o0 + i]];
+                if (stamp[c] != (int32_t)t) {
+                    stamp[c] = (int32_t)t;
+                    cams.push_back(c);
+                }
             }
-        }
-        std::sort(cams.begin(), cams.end());
-        for (size_t s = 0; s < cams.size(); ++s) local_of[cams[s]] = (int32_t)s;
-        TileMeta& m = plan.meta[t];
-        m.pt0 = (int32_t)rg.p0;
-        m.npts = (int32_t)(rg.p1 - rg.p0);
-        m.ncams = (int32_t)cams.size();
-        m.nobs = n;
-        plan.max_tile_cams = std::max(plan.max_tile_cams, m.ncams);
-        plan.max_tile_pts = std::max(plan.max_tile_pts, m.npts);
-        m.pad[0] = m.pad[1] = m.pad[2] = 0;
-        for (int j = 0; j < kTileObs; ++j) {
-            m.slot_cam[j] = 0;
-            m.slot_pt[j] = 0xFFFF;   // empty slots carry the pad marker
-            m.sort_src[j] = (uint16_t)j;
-            m.run_start[j] = 0;
-            m.run_cam[j] = 0;
-        }
-        int i = 0;
-        for (int64_t q = rg.p0; q < rg.p1; ++q) {
-            for (int64_t o = start[q]; o < start[q + 1]; ++o, ++i) {
-                plan.slot_obs[base + i] = grouped[o];
-                m.slot_cam[i] = (uint16_t)local_of[cam_idx[grouped[o]]];
-                m.slot_pt[i] = (uint16_t)(q - rg.p0);
+            std::sort(cams.begin(), cams.end());
+            for (size_t s = 0; s < cams.size(); ++s) local_of[cams[s]] = (int32_t)s;
+            TileMeta& m = plan.meta[t];
+            m.pt0 = (int32_t)rg.p0;
+            m.npts = (int32_t)(rg.p1 - rg.p0);
+            m.ncams = (int32_t)cams.size();
+            m.nobs = n;
+            max_cams = std::max(max_cams, m.ncams);
+            max_pts = std::max(max_pts, m.npts);
+            m.pad[0] = m.pad[1] = m.pad[2] = 0;
+            for (int j = 0; j < kTileObs; ++j) {
+                m.slot_cam[j] = 0;
+                m.slot_pt[j] = 0xFFFF;   // empty slots carry the pad marker
+                m.sort_src[j] = (uint16_t)j;
+                m.run_start[j] = 0;
+                m.run_cam[j] = 0;
             }
-        }
-        std::iota(idx.begin(), idx.begin() + n, (uint16_t)0);
-        std::stable_sort(idx.begin(), idx.begin() + n, [&](uint16_t a, uint16_t b) { return m.slot_cam[a] < m.slot_cam[b]; });
-        int nruns = 0;
-        for (int j = 0; j < n; ++j) {
-            m.sort_src[j] = idx[j];
-            const uint16_t key = m.slot_cam[idx[j]];
-            if (j == 0 || key != m.slot_cam[idx[j - 1]] || j - m.run_start[nruns - 1] >= kMaxRun) {
-                m.run_start[nruns] = (uint16_t)j;
-                m.run_cam[nruns] = key;
-                ++nruns;
+            int i = 0;
+            for (int64_t q = rg.p0; q < rg.p1; ++q) {
+                for (int64_t o = start[q]; o < start[q + 1]; ++o, ++i) {
+                    plan.slot_obs[base + i] = grouped[o];
+                    m.slot_cam[i] = (uint16_t)local_of[cam_idx[grouped[o]]];
+                    m.slot_pt[i] = (uint16_t)(q - rg.p0);
+                }
             }
+            // stable counting sort of the slots by local camera
+            const int nc = m.ncams;
+            for (int c = 0; c <= nc; ++c) cnt[c] = 0;
+            for (int j = 0; j < n; ++j) ++cnt[m.slot_cam[j] + 1];
+            for (int c = 0; c < nc; ++c) cnt[c + 1] = (uint16_t)(cnt[c + 1] + cnt[c]);
+            for (int j = 0; j < n; ++j) idx[cnt[m.slot_cam[j]]++] = (uint16_t)j;
+            int nruns = 0;
+            for (int j = 0; j < n; ++j) {
+                m.sort_src[j] = idx[j];
+                const uint16_t key = m.slot_cam[idx[j]];
+                if (j == 0 || key != m.slot_cam[idx[j - 1]] || j - m.run_start[nruns - 1] >= kMaxRun) {
+                    m.run_start[nruns] = (uint16_t)j;
+                    m.run_cam[nruns] = key;
+                    ++nruns;
+                }
+            }
+            m.nruns = nruns;
         }
-        m.nruns = nruns;
     }
+    plan.max_tile_cams = max_cams;
+    plan.max_tile_pts = max_pts;
     plan.cam_stride = std::max(4, (plan.max_tile_cams + 3) / 4 * 4);
     plan.tile_cams.assign((size_t)plan.n_tiles * plan.cam_stride, -1);
     for (int64_t t = 0; t < plan.n_tiles; ++t)
