@@ -70,22 +70,27 @@ enum Scal {
     S_COUNT = 24
 };
 
-enum Mode { M_BUILD = 0, M_RESID, M_RESID_STORE, M_MATVEC, M_RHS, M_BACKSUB, M_JV1, M_JV2 };
+enum Mode { M_BUILD = 0, M_RESID, M_RESID_STORE, M_MATVEC, M_RHS, M_BACKSUB, M_JV1, M_JV2, M_BUILD_FULL, M_COUNT };
+__host__ __device__ constexpr bool is_build(int m) { return m == M_BUILD || m == M_BUILD_FULL; }
+__host__ __device__ constexpr bool is_project(int m) { return is_build(m) || m == M_RESID || m == M_RESID_STORE; }
 
 template <int MODE>
 struct Traits {
-    static constexpr bool kLoadJ = MODE >= M_MATVEC;
+    static constexpr bool kLoadJ = !is_project(MODE);
     static constexpr bool kLoadUV = !kLoadJ;
     // doubles gathered per camera into shared memory, and the (odd, conflict-free) smem stride
-    static constexpr int kCamRows = MODE == M_BUILD ? 21 : (MODE == M_RESID || MODE == M_RESID_STORE) ? 12
+    static constexpr int kCamRows = is_build(MODE) ? 21 : (MODE == M_RESID || MODE == M_RESID_STORE) ? 12
                                   : MODE == M_RHS ? 0 : MODE == M_JV2 ? 12 : 6;
     static constexpr int kCamStride = kCamRows | 1;
     // per-point payloads staged by the producer
     static constexpr int kPA = (MODE == M_MATVEC || MODE == M_RHS || MODE == M_BACKSUB) ? 6 : 3;
     static constexpr int kPB = (MODE == M_RHS || MODE == M_BACKSUB || MODE == M_JV2) ? 3 : 0;
-    static constexpr bool kScatter = MODE == M_BUILD || MODE == M_MATVEC || MODE == M_RHS;
-    static constexpr int kPtAcc = MODE == M_BUILD ? 9 : (MODE == M_MATVEC || MODE == M_BACKSUB) ? 3 : 0;
-    static constexpr int kStageRows = (MODE == M_BUILD || MODE == M_RHS) ? 9 : MODE == M_MATVEC ? 6 : 0;
+    static constexpr bool kScatter = is_build(MODE) || MODE == M_MATVEC || MODE == M_RHS;
+    static constexpr int kPtAcc = (MODE == M_MATVEC || MODE == M_BACKSUB) ? 3 : 0;
+    // scatter staging rows: BUILD stages 12 camera + 9 point rows + 1 row of point-run starts in one
+    // single buffer; the Schur passes alternate between two buffers of 6 / 9 rows
+    static constexpr int kStageRows = is_build(MODE) ? 22 : MODE == M_RHS ? 9 : MODE == M_MATVEC ? 6 : 0;
+    static constexpr int kStageBufs = is_build(MODE) ? 1 : 2;
 };
 
 struct TileArgs {
@@ -107,7 +112,8 @@ struct ModeArgs {
     const double* ptB;     // zg / g_p / vp1
     double* y;             // [Nc][6]  scatter target        MATVEC RHS
     double* Sd;            // [Nc][21]                       RHS
-    double* U;             // [Nc][21]                       BUILD
+    double* U;             // [Nc][21] full camera blocks     BUILD_FULL (evaluation hook only)
+    double* Ud;            // [Nc][6]  diag(J_c^T J_c)        BUILD
     double* gc;            // [Nc][6]                        BUILD
     double* V;             // [Np][6]                        BUILD
     double* gp;            // [Np][3]                        BUILD
@@ -153,7 +159,7 @@ __host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts) {
     o += 2 * align_up(max_pts * T::kPtAcc * 8, 16);       // two parities (see the MATVEC / BACKSUB flow)
     L.off_z = o;
     L.off_buf = o;
-    o += 2 * T::kStageRows * kBufStride * 8;
+    o += T::kStageBufs * T::kStageRows * kBufStride * 8;
     L.off_red = o;
     o += 64 * 8;
     L.off_ids = o;
@@ -287,7 +293,9 @@ __device__ __forceinline__ void tile_point_reduce(double (&v)[NV], unsigned lp, 
 template <int NV>
 __device__ __forceinline__ void camera_scatter_round(const double (&v)[NV], double* s_buf /* [NV][kBufStride] */,
                                                      const TileMeta* mt, const int* s_camid, double* out, int stride,
-                                                     int offset) {
+                                                     int offset, int n0 = NV, double* out1 = nullptr, int stride1 = 0,
+                                                     int offset1 = 0) {
+    // components k < n0 go to out[cam*stride + offset + k], the rest to out1[cam*stride1 + offset1 + k - n0]
     const int tid = threadIdx.x;
 #pragma unroll
     for (int i = 0; i < NV; ++i) s_buf[i * kBufStride + tid] = v[i];
@@ -300,7 +308,9 @@ __device__ __forceinline__ void camera_scatter_round(const double (&v)[NV], doub
         const double* row = s_buf + k * kBufStride;
         double sum = 0.0;
         for (int j = j0; j < j1; ++j) sum += row[mt->sort_src[j]];
-        red_add(out + (int64_t)s_camid[mt->run_cam[r]] * stride + offset + k, sum);
+        const int64_t cam = s_camid[mt->run_cam[r]];
+        if (k < n0) red_add(out + cam * stride + offset + k, sum);
+        else red_add(out1 + cam * stride1 + offset1 + (k - n0), sum);
     }
 }
 
@@ -493,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, con
             if (i < n_cam) {
                 const int c = i / (T::kCamRows ? T::kCamRows : 1), k = i - c * T::kCamRows;
                 const int cam = ids[c];
-                if (MODE == M_BUILD || MODE == M_RESID || MODE == M_RESID_STORE) return P.cam0 + (int64_t)cam * kCamTab + k;
+                if (is_project(MODE)) return P.cam0 + (int64_t)cam * kCamTab + k;
                 if (MODE == M_JV2) return k < 6 ? P.cam0 + (int64_t)cam * 6 + k : P.cam1 + (int64_t)cam * 6 + (k - 6);
                 return P.cam0 + (int64_t)cam * 6 + k;
             }
@@ -611,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, con
         const bool valid = lp != kPadPt;
         const int lps = valid ? (int)lp : 0;
 
-        if constexpr (MODE == M_BUILD || MODE == M_RESID || MODE == M_RESID_STORE) {
+        if constexpr (is_project(MODE)) {
             const double* s_uv = reinterpret_cast<const double*>(st + L.off_uv);
             double r[2] = {0, 0}, jc[12], jp[6];
 #pragma unroll
@@ -620,7 +630,7 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, con
             for (int i = 0; i < 6; ++i) jp[i] = 0;
             if (valid) {
                 const double* X = s_pa + lp * 3;
-                project_obs<MODE == M_BUILD>(s_cv + lc * T::kCamStride, X[0], X[1], X[2], A.K, s_uv[tid], s_uv[kT + tid], r, jc, jp);
+                project_obs<is_build(MODE)>(s_cv + lc * T::kCamStride, X[0], X[1], X[2], A.K, s_uv[tid], s_uv[kT + tid], r, jc, jp);
             }
             acc[0] += r[0] * r[0] + r[1] * r[1];
             if (MODE != M_RESID) {
@@ -628,50 +638,72 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, con
                 rt[tid] = r[0];
                 rt[kT + tid] = r[1];
             }
-            if constexpr (MODE == M_BUILD) {
+            if constexpr (is_build(MODE)) {
                 double* Jt = P.Jw + (int64_t)t * kJRows * kT;
 #pragma unroll
                 for (int i = 0; i < 12; ++i) Jt[i * kT + tid] = jc[i];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) Jt[(12 + i) * kT + tid] = jp[i];
-                // point blocks: V (6) and g_p (3)
-                double pv[9];
-                pv[0] = jp[0] * jp[0] + jp[3] * jp[3];
-                pv[1] = jp[0] * jp[1] + jp[3] * jp[4];
-                pv[2] = jp[0] * jp[2] + jp[3] * jp[5];
-                pv[3] = jp[1] * jp[1] + jp[4] * jp[4];
-                pv[4] = jp[1] * jp[2] + jp[4] * jp[5];
-                pv[5] = jp[2] * jp[2] + jp[5] * jp[5];
-                pv[6] = jp[0] * r[0] + jp[3] * r[1];
-                pv[7] = jp[1] * r[0] + jp[4] * r[1];
-                pv[8] = jp[2] * r[0] + jp[5] * r[1];
-                tile_point_reduce<9>(pv, lp, s_pt);
-                // camera blocks: U (21 upper-triangle) + g_c (6) in four rounds
-                double cv[9];
+                // One staging round for everything the normal equations need from this observation:
+                //   rows 0..5   diag(Jc^T Jc)  (column norms of the camera part: the Marquardt scale)
+                //   rows 6..11  Jc^T r         (camera gradient)
+                //   rows 12..17 Jp^T Jp (upper triangle), rows 18..20 Jp^T r   (point block, gradient)
+                //   row  21     first slot of every point of the tile (int)
+                // then thread (camera run, k) / (point, k) sums one run sequentially: no shuffles, no atomics.
+                double* buf = s_buf;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) cv[i] = jc[tri6_row(i)] * jc[tri6_col(i)] + jc[6 + tri6_row(i)] * jc[6 + tri6_col(i)];
-                camera_scatter_round<9>(cv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.U, 21, 0);
-                // the round's barrier also completed the point sums: the tile owns its points
-                for (int i = tid; i < npts * 9; i += kConsumers) {
-                    const int p = i / 9, k = i - p * 9;
-                    const double v = s_pt[i];
-                    s_pt[i] = 0.0;
-                    if (k < 6) P.V[((int64_t)pt0 + p) * 6 + k] = v;
-                    else P.gp[((int64_t)pt0 + p) * 3 + (k - 6)] = v;
+                for (int k = 0; k < 6; ++k) {
+                    buf[k * kBufStride + tid] = jc[k] * jc[k] + jc[6 + k] * jc[6 + k];
+                    buf[(6 + k) * kBufStride + tid] = jc[k] * r[0] + jc[6 + k] * r[1];
                 }
+                buf[12 * kBufStride + tid] = jp[0] * jp[0] + jp[3] * jp[3];
+                buf[13 * kBufStride + tid] = jp[0] * jp[1] + jp[3] * jp[4];
+                buf[14 * kBufStride + tid] = jp[0] * jp[2] + jp[3] * jp[5];
+                buf[15 * kBufStride + tid] = jp[1] * jp[1] + jp[4] * jp[4];
+                buf[16 * kBufStride + tid] = jp[1] * jp[2] + jp[4] * jp[5];
+                buf[17 * kBufStride + tid] = jp[2] * jp[2] + jp[5] * jp[5];
+                buf[18 * kBufStride + tid] = jp[0] * r[0] + jp[3] * r[1];
+                buf[19 * kBufStride + tid] = jp[1] * r[0] + jp[4] * r[1];
+                buf[20 * kBufStride + tid] = jp[2] * r[0] + jp[5] * r[1];
+                int* s_pstart = reinterpret_cast<int*>(buf + 21 * kBufStride);
+                if (valid && (tid == 0 || mt->slot_pt[tid - 1] != lp)) s_pstart[lp] = tid;
+                if (tid == 0) s_pstart[npts] = mt->nobs;
+                consumer_sync();
+                {
+                    const int nruns = mt->nruns, nobs = mt->nobs;
+                    const int n_cam = nruns * 12, n_tot = n_cam + npts * 9;
+                    for (int idx = tid; idx < n_tot; idx += kConsumers) {
+                        if (idx < n_cam) {
+                            const int rr = idx / 12, k = idx - rr * 12;
+                            const int j0 = mt->run_start[rr];
+                            const int j1 = rr + 1 < nruns ? (int)mt->run_start[rr + 1] : nobs;
+                            const double* row = buf + k * kBufStride;
+                            double sum = 0.0;
+                            for (int j = j0; j < j1; ++j) sum += row[mt->sort_src[j]];
+                            const int64_t cam = s_camid[mt->run_cam[rr]];
+                            red_add((k < 6 ? P.Ud : P.gc - 6) + cam * 6 + k, sum);
+                        } else {
+                            const int q = idx - n_cam;
+                            const int p = q / 9, k = q - p * 9;
+                            const double* row = buf + (12 + k) * kBufStride;
+                            const int j1 = s_pstart[p + 1];
+                            double sum = 0.0;
+                            for (int j = s_pstart[p]; j < j1; ++j) sum += row[j];
+                            // the tile owns its points: plain stores
+                            if (k < 6) P.V[((int64_t)pt0 + p) * 6 + k] = sum;
+                            else P.gp[((int64_t)pt0 + p) * 3 + (k - 6)] = sum;
+                        }
+                    }
+                }
+                consumer_sync();   // the single staging buffer is rewritten by the next round
+                if constexpr (MODE == M_BUILD_FULL) {
+                    // evaluation hook only: the full 6x6 camera blocks (upper triangle) in a second round
+                    double cv[21];
 #pragma unroll
-                for (int i = 0; i < 9; ++i)
-                    cv[i] = jc[tri6_row(9 + i)] * jc[tri6_col(9 + i)] + jc[6 + tri6_row(9 + i)] * jc[6 + tri6_col(9 + i)];
-                camera_scatter_round<9>(cv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.U, 21, 9);
-                double cw[3];
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    cw[i] = jc[tri6_row(18 + i)] * jc[tri6_col(18 + i)] + jc[6 + tri6_row(18 + i)] * jc[6 + tri6_col(18 + i)];
-                camera_scatter_round<3>(cw, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.U, 21, 18);
-                double cg[6];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) cg[i] = jc[i] * r[0] + jc[6 + i] * r[1];
-                camera_scatter_round<6>(cg, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.gc, 6, 0);
+                    for (int i = 0; i < 21; ++i) cv[i] = jc[tri6_row(i)] * jc[tri6_col(i)] + jc[6 + tri6_row(i)] * jc[6 + tri6_col(i)];
+                    camera_scatter_round<21>(cv, buf, mt, s_camid, P.U, 21, 0);
+                    consumer_sync();
+                }
             }
         } else if constexpr (MODE == M_JV1 || MODE == M_JV2) {
             constexpr int NV = MODE == M_JV2 ? 2 : 1;
@@ -707,6 +739,8 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, con
 #pragma unroll
             for (int i = 0; i < 6; ++i) jp[i] = valid ? sJ[(12 + i) * kT + tid] : 0.0;
             double z0, z1, z2;
+            double uu0 = 0, uu1 = 0;
+            double cvy[6] = {0, 0, 0, 0, 0, 0};   // RHS: the y contribution rides in the first Sd round
             if constexpr (MODE != M_RHS) {
                 // u = Jc xt_c ; w = Jp^T u ; t_p = sum over the point's observations.  The per-point
                 // accumulator has two parities: tile i's sums are read after its barrier while tile
@@ -719,6 +753,8 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, con
                     u0 += jc[k] * xc[k];
                     u1 += jc[6 + k] * xc[k];
                 }
+                uu0 = u0;
+                uu1 = u1;
                 double w[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) w[k] = jp[k] * u0 + jp[3 + k] * u1;
@@ -753,13 +789,23 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, con
                 z2 = s_pb[lps * 3 + 2];
             }
             if constexpr (MODE != M_BACKSUB) {
-                // v = Jp z_p ; contribution Jc^T v to the camera
-                const double v0 = jp[0] * z0 + jp[1] * z1 + jp[2] * z2;
-                const double v1 = jp[3] * z0 + jp[4] * z1 + jp[5] * z2;
+                // v = Jp z_p.  MATVEC scatters Jc^T (Jc xt - v): the camera's own block U_c xt is folded into
+                // the same pass, so the reduced-system product needs no stored U.  RHS scatters Jc^T v.
+                double v0 = jp[0] * z0 + jp[1] * z1 + jp[2] * z2;
+                double v1 = jp[3] * z0 + jp[4] * z1 + jp[5] * z2;
+                if (MODE == M_MATVEC) {
+                    v0 = uu0 - v0;
+                    v1 = uu1 - v1;
+                }
                 double cv[6];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) cv[k] = jc[k] * v0 + jc[6 + k] * v1;
-                camera_scatter_round<6>(cv, s_buf + (round++ & 1) * T::kStageRows * kBufStride, mt, s_camid, P.y, 6, 0);
+                if constexpr (MODE == M_RHS) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) cvy[k] = cv[k];
+                } else {
+                    camera_scatter_round<6>(cv, s_buf + (round++ & 1) * T::kStageRows * kBufStride, mt, s_camid, P.y, 6, 0);
+                }
                 if constexpr (MODE == M_MATVEC) {
                     // all reads of this parity's point sums happened before the round's barrier
                     double* s_ptp = s_pt + par * (align_up(A.max_pts * T::kPtAcc * 8, 16) / 8);
@@ -767,7 +813,8 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, con
                 }
             }
             if constexpr (MODE == M_RHS) {
-                // Schur diagonal: E = Jc^T Jp (6x3), F = E M (6x3), Sd += F E^T (upper triangle)
+                // Diagonal blocks of the reduced system: S_cc = sum_i (Jc^T Jc - F E^T), E = Jc^T Jp (6x3),
+                // F = E M (6x3); upper triangle, 21 values, scattered in the y round + two more rounds of 9
                 const double* m = s_pa + lps * 6;
                 const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5];
                 double E[18], F[18];
@@ -779,26 +826,23 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, con
                     F[a * 3 + 1] = E[a * 3] * m1 + E[a * 3 + 1] * m3 + E[a * 3 + 2] * m4;
                     F[a * 3 + 2] = E[a * 3] * m2 + E[a * 3 + 1] * m4 + E[a * 3 + 2] * m5;
                 }
+                auto sval = [&](int i) {
+                    const int a = tri6_row(i), b = tri6_col(i);
+                    return jc[a] * jc[b] + jc[6 + a] * jc[6 + b] -
+                           (F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2]);
+                };
                 double sv[9];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    const int a = tri6_row(i), b = tri6_col(i);
-                    sv[i] = F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2];
-                }
-                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.Sd, 21, 0);
+                for (int k = 0; k < 6; ++k) sv[k] = cvy[k];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    const int a = tri6_row(9 + i), b = tri6_col(9 + i);
-                    sv[i] = F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2];
-                }
-                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.Sd, 21, 9);
-                double sw[3];
+                for (int i = 0; i < 3; ++i) sv[6 + i] = sval(i);
+                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.y, 6, 0, 6, P.Sd, 21, 0);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int a = tri6_row(18 + i), b = tri6_col(18 + i);
-                    sw[i] = F[a * 3] * E[b * 3] + F[a * 3 + 1] * E[b * 3 + 1] + F[a * 3 + 2] * E[b * 3 + 2];
-                }
-                camera_scatter_round<3>(sw, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.Sd, 21, 18);
+                for (int i = 0; i < 9; ++i) sv[i] = sval(3 + i);
+                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.Sd, 21, 3);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) sv[i] = sval(12 + i);
+                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.Sd, 21, 12);
             }
         }
         // all reads of this stage are done: hand it back to the producer
@@ -811,7 +855,7 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, con
         }
     }
     // per-CTA scalar results
-    if constexpr (MODE == M_BUILD) {
+    if constexpr (is_build(MODE)) {
         double c[1] = {acc[0]};
         double* outp[1] = {P.scal + S_COST};
         consumer_accumulate<1>(c, s_red, outp);

@@ -100,7 +100,7 @@ struct Dev {
     // linearisation
     double *J, *res;
     double *x, *xn, *x0, *camtab, *camtab_n;
-    double *U, *g, *V, *M, *zg, *dp;
+    double *U, *Ud, *g, *V, *M, *zg, *dp;
     // n-vectors (camera part first, then the local points)
     double *sinv, *gh, *gn, *s1, *s2, *v1, *v2, *tmp;
     // PCG (camera-sized)
@@ -135,8 +135,8 @@ struct mmba_handle {
     Dev d;
     TileArgs targs;
     int sm_count = 148;
-    size_t smem[8] = {0};     // dynamic shared memory of tile_kernel<MODE>
-    int grid[8] = {0};        // persistent grid of tile_kernel<MODE>: min(tiles, SMs x resident CTAs)
+    size_t smem[M_COUNT] = {0};     // dynamic shared memory of tile_kernel<MODE>
+    int grid[M_COUNT] = {0};        // persistent grid of tile_kernel<MODE>: min(tiles, SMs x resident CTAs)
     double* h_stage = nullptr;   // pinned, max(nloc, 2*ns ...) doubles
     size_t h_stage_n = 0;
     double* h_scal = nullptr;    // pinned S_COUNT
@@ -273,6 +273,7 @@ void carve(mmba_handle* h, Arena& a) {
     d.camtab = a.take<double>(kCamTab * Nc);
     d.camtab_n = a.take<double>(kCamTab * Nc);
     d.U = a.take<double>(21 * Nc);
+    d.Ud = a.take<double>(6 * Nc);
     d.g = a.take<double>(nloc);
     d.V = a.take<double>(6 * npl);
     d.M = a.take<double>(6 * npl);
@@ -405,7 +406,6 @@ int get_jacobian_slots(mmba_handle* h, double* Jc, double* Jp) {
 PcgVecs pcg_vecs(mmba_handle* h) {
     Dev& d = h->d;
     PcgVecs P;
-    P.U = d.U;
     P.gc = d.g;
     P.sinv = d.sinv;
     P.y = d.y;
@@ -439,10 +439,11 @@ int launch_tile(mmba_handle* h, int cls, const ModeArgs& P) {
 }
 
 // residuals, Jacobian blocks, normal-equation blocks and cost at d.x
-int linearise(mmba_handle* h) {
+// (full_U: additionally the complete 6x6 camera blocks, for the evaluation hook)
+int linearise(mmba_handle* h, bool full_U = false) {
     Dev& d = h->d;
     TRY(cam_prep(h, d.x, d.camtab));
-    TRY(zero(h, d.U, 21 * h->Nc));
+    TRY(zero(h, d.Ud, 6 * h->Nc));
     TRY(zero(h, d.g, 6 * h->Nc));
     TRY(zero(h, d.scal + S_COST, 1));
     ModeArgs P{};
@@ -450,13 +451,20 @@ int linearise(mmba_handle* h) {
     P.res = d.res;
     P.cam0 = d.camtab;
     P.ptA = d.x + 6 * h->Nc;
-    P.U = d.U;
+    P.Ud = d.Ud;
     P.gc = d.g;
     P.V = d.V;
     P.gp = d.g + 6 * h->Nc;
     P.scal = d.scal;
-    TRY(launch_tile<M_BUILD>(h, MMBA_K_BUILD, P));
-    TRY(allreduce(h, {{d.U, (size_t)(21 * h->Nc), false}, {d.g, (size_t)(6 * h->Nc), false}, {d.scal + S_COST, 1, false}}));
+    if (full_U) {
+        TRY(zero(h, d.U, 21 * h->Nc));
+        P.U = d.U;
+        TRY(launch_tile<M_BUILD_FULL>(h, MMBA_K_BUILD, P));
+        TRY(allreduce(h, {{d.U, (size_t)(21 * h->Nc), false}}));
+    } else {
+        TRY(launch_tile<M_BUILD>(h, MMBA_K_BUILD, P));
+    }
+    TRY(allreduce(h, {{d.Ud, (size_t)(6 * h->Nc), false}, {d.g, (size_t)(6 * h->Nc), false}, {d.scal + S_COST, 1, false}}));
     CU(cudaGetLastError());
     return MMBA_OK;
 }
@@ -466,10 +474,12 @@ int scale_and_grad(mmba_handle* h, bool first) {
     Dev& d = h->d;
     const int lead = h->opt.rank == 0;
     TRY(zero(h, d.scal + S_GH2, 4));
-    LAUNCH(MMBA_K_VEC, scale_grad_kernel<6>, cdiv(6 * h->Nc, 256), 256, 0, d.U, d.g, d.x, d.sinv, d.gh, (int)first,
+    auto sg_cam = scale_grad_kernel<6, false>;
+    auto sg_pt = scale_grad_kernel<3, true>;
+    LAUNCH(MMBA_K_VEC, sg_cam, cdiv(6 * h->Nc, 256), 256, 0, d.Ud, d.g, d.x, d.sinv, d.gh, (int)first,
            6 * h->Nc, d.scal, lead);
     if (h->npl)
-        LAUNCH(MMBA_K_VEC, scale_grad_kernel<3>, cdiv(3 * h->npl, 256), 256, 0, d.V, d.g + 6 * h->Nc, d.x + 6 * h->Nc,
+        LAUNCH(MMBA_K_VEC, sg_pt, cdiv(3 * h->npl, 256), 256, 0, d.V, d.g + 6 * h->Nc, d.x + 6 * h->Nc,
                d.sinv + 6 * h->Nc, d.gh + 6 * h->Nc, (int)first, 3 * h->npl, d.scal, 1);
     TRY(allreduce(h, {{d.scal + S_GH2, 3, false}, {d.scal + S_GINF, 1, true}}));
     return MMBA_OK;
@@ -786,6 +796,7 @@ int configure_kernels(mmba_handle* h) {
     TRY(configure_mode<M_BACKSUB>(h));
     TRY(configure_mode<M_JV1>(h));
     TRY(configure_mode<M_JV2>(h));
+    TRY(configure_mode<M_BUILD_FULL>(h));
     return MMBA_OK;
 }
 
@@ -1100,7 +1111,7 @@ int mmba_eval_blocks(mmba_handle* h, const double* x, double* U, double* V, doub
     Dev& d = h->d;
     const Plan& pl = h->plan;
     TRY(put_x(h, x, d.x));
-    TRY(linearise(h));
+    TRY(linearise(h, true));
     std::vector<double> hU(21 * h->Nc), hg(h->nloc), hV(6 * std::max<int64_t>(h->npl, 1));
     CU(cudaMemcpyAsync(hU.data(), d.U, hU.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(hg.data(), d.g, hg.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1186,7 +1197,7 @@ int mmba_bench_kernel(mmba_handle* h, const double* x, int kernel_class, int ite
     Pb.res = d.res;
     Pb.cam0 = d.camtab;
     Pb.ptA = d.x + 6 * h->Nc;
-    Pb.U = d.U;
+    Pb.Ud = d.Ud;
     Pb.gc = d.g;
     Pb.V = d.V;
     Pb.gp = d.g + 6 * h->Nc;

@@ -100,9 +100,10 @@ __device__ __forceinline__ void sym6_inverse(const double (&s)[21], double (&inv
 // ---------------------------------------------------------------------------------------------
 // scale update + gradient statistics (compute_jac_scale / compute_grad, common.py:590-610;
 // Delta0 = ||x0 * scale_inv||, trf.py:443)
-//   element e of block b = e / BS: diag of the packed upper-triangle block; g_h = g / scale_inv
+//   PACKED: element e of block b = e / BS is the diagonal of a packed upper-triangle block (points: V);
+//   otherwise blk already holds the column sums of squares (cameras: diag(J_c^T J_c)); g_h = g / scale_inv
 // ---------------------------------------------------------------------------------------------
-template <int BS>
+template <int BS, bool PACKED>
 __global__ void scale_grad_kernel(const double* __restrict__ blk, const double* __restrict__ g,
                                   const double* __restrict__ x, double* __restrict__ sinv, double* __restrict__ gh,
                                   int first, int64_t n_elem, double* __restrict__ scal, int accumulate) {
@@ -114,7 +115,7 @@ __global__ void scale_grad_kernel(const double* __restrict__ blk, const double* 
     if (e < n_elem) {
         const int64_t b = e / BS;
         const int k = (int)(e - b * BS);
-        const double diag = blk[b * STRIDE + (k * BS - k * (k - 1) / 2)];
+        const double diag = PACKED ? blk[b * STRIDE + (k * BS - k * (k - 1) / 2)] : blk[e];
         double si = sqrt(diag);
         if (first) { if (si == 0.0) si = 1.0; }
         else si = fmax(si, sinv[e]);
@@ -225,11 +226,10 @@ __global__ void trial_kernel(const double* __restrict__ x, const double* __restr
 // PCG on the reduced camera system, one thread per camera (block-Jacobi = 6x6 Schur diagonal)
 // ---------------------------------------------------------------------------------------------
 struct PcgVecs {
-    const double* U;      // [Nc][21]
     const double* gc;     // [Nc][6]
     const double* sinv;   // [Nc][6] scale_inv of the camera parameters
     double* y;            // [Nc][6] scatter target of the schur kernels
-    double* Sd;           // [Nc][21]
+    double* Sd;           // [Nc][21] diagonal blocks of the reduced system, sum (Jc^T Jc - F E^T), unscaled
     double* Pinv;         // [Nc][21]
     double *x, *r, *z, *p, *q, *xt;   // [Nc][6]
     double* part;         // [P_COUNT][kMaxCamBlocks] per-block partials of pcg_init
@@ -238,7 +238,7 @@ struct PcgVecs {
     int n_cams;
 };
 
-// b = d o (g_c - y) ; Pinv = (d d^T o (U - Sd) + reg I)^-1 ; x = 0, r = b, z = Pinv r, p = z, xt = d o p
+// b = d o (g_c - y) ; Pinv = (d d^T o S_cc + reg I)^-1 ; x = 0, r = b, z = Pinv r, p = z, xt = d o p
 __global__ void __launch_bounds__(kCamBlock) pcg_init_kernel(PcgVecs P, double reg) {
     __shared__ double s_red[8];
     const int c = blockIdx.x * kCamBlock + threadIdx.x;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kCamBlock) pcg_init_kernel(PcgVecs P, double r
 #pragma unroll
             for (int bb = a; bb < 6; ++bb) {
                 const int i = tri6(a, bb);
-                s[i] = d[a] * d[bb] * (P.U[c * 21 + i] - P.Sd[c * 21 + i]) + (a == bb ? reg : 0.0);
+                s[i] = d[a] * d[bb] * P.Sd[c * 21 + i] + (a == bb ? reg : 0.0);
             }
         sym6_inverse(s, inv);
 #pragma unroll
@@ -287,9 +287,9 @@ constexpr int kPcgThreads = 256;
 
 // One PCG iteration's camera-vector work in ONE CTA, so that every reduction is a fixed-order sum
 // and the whole update costs a single launch (LSMR's vector updates, lsmr.py:373-377):
-//   q = S p = d o (U xt - y) + reg p ; alpha = rho / p.q ; x += alpha p ; r -= alpha q ; z = Pinv r ;
+//   q = S p = d o y + reg p ; alpha = rho / p.q ; x += alpha p ; r -= alpha q ; z = Pinv r ;
 //   stop if ||r|| <= rtol ||b|| ; beta = r.z / rho ; p = z + beta p ; xt = d o p ; y <- 0
-// y holds this iteration's sum_p W V'^-1 W^T xt from the MATVEC pass (all-reduced over ranks).
+// y holds this iteration's sum_i Jc_i^T (Jc_i xt - Jp_i z_p) from the MATVEC pass (all-reduced over ranks).
 __global__ void __launch_bounds__(kPcgThreads) pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init) {
     if (P.flags[0]) return;
     __shared__ double s_red[32];
@@ -299,11 +299,10 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update_kernel(PcgVecs P, doub
         // the three reductions then only cost block barriers
         const int c = tid;
         const bool live = c < P.n_cams;
-        double xt[6], pv[6], yv[6], si[6], rv[6], xv[6], U[21], Pi[21];
+        double pv[6], yv[6], si[6], rv[6], xv[6], Pi[21];
         if (live) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                xt[k] = P.xt[c * 6 + k];
                 pv[k] = P.p[c * 6 + k];
                 yv[k] = P.y[c * 6 + k];
                 si[k] = P.sinv[c * 6 + k];
@@ -311,10 +310,7 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update_kernel(PcgVecs P, doub
                 xv[k] = P.x[c * 6 + k];
             }
 #pragma unroll
-            for (int i = 0; i < 21; ++i) {
-                U[i] = P.U[c * 21 + i];
-                Pi[i] = P.Pinv[c * 21 + i];
-            }
+            for (int i = 0; i < 21; ++i) Pi[i] = P.Pinv[c * 21 + i];
         }
         double rho, b2;
         if (it == 0) {
@@ -326,11 +322,9 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update_kernel(PcgVecs P, doub
         }
         double q[6], pq = 0;
         if (live) {
-            double ux[6];
-            sym6_matvec(U, xt, ux);
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                q[k] = (ux[k] - yv[k]) / si[k] + reg * pv[k];
+                q[k] = yv[k] / si[k] + reg * pv[k];
                 P.y[c * 6 + k] = 0.0;
                 pq += pv[k] * q[k];
             }
@@ -388,14 +382,10 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update_kernel(PcgVecs P, doub
     }
     double pq = 0;
     for (int c = tid; c < P.n_cams; c += nthr) {
-        double xt[6], ux[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) xt[k] = P.xt[c * 6 + k];
-        sym6_matvec(P.U + c * 21, xt, ux);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             const double pk = P.p[c * 6 + k];
-            const double qk = (ux[k] - P.y[c * 6 + k]) / P.sinv[c * 6 + k] + reg * pk;
+            const double qk = P.y[c * 6 + k] / P.sinv[c * 6 + k] + reg * pk;
             P.y[c * 6 + k] = 0.0;
             P.q[c * 6 + k] = qk;
             pq += pk * qk;
