@@ -42,9 +42,7 @@ namespace mmba {
 
 constexpr int kT = kTileObs;
 constexpr int kConsumers = kT;            // consumer threads per CTA (one per slot)
-constexpr int kStages = 2;                // pipeline depth; one producer warp per stage
-constexpr int kProducers = kStages;
-constexpr int kThreads = kConsumers + 32 * kProducers;
+constexpr int kMaxStages = 4;             // pipeline depth is per MODE (Traits::kStages); one producer warp per stage
 constexpr int kCamTab = 24;               // doubles per camera-table row in HBM
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint16_t kPadPt = 0xFFFF;
@@ -77,6 +75,10 @@ __host__ __device__ constexpr bool is_project(int m) { return is_build(m) || m =
 template <int MODE>
 struct Traits {
     static constexpr bool kLoadJ = !is_project(MODE);
+    // J-streaming tiles are 39 KB: two stages per CTA, two CTAs per SM.  The residual-only pass moves
+    // 7 KB per tile, so its per-tile latency chain needs more tiles in flight.
+    static constexpr int kStages = (MODE == M_RESID || MODE == M_RESID_STORE) ? 4 : 2;
+    static constexpr int kThreads = kConsumers + 32 * kStages;
     static constexpr bool kLoadUV = !kLoadJ;
     // doubles gathered per camera into shared memory, and the (odd, conflict-free) smem stride
     static constexpr int kCamRows = is_build(MODE) ? 21 : (MODE == M_RESID || MODE == M_RESID_STORE) ? 12
@@ -154,7 +156,7 @@ __host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts) {
     o += align_up(max_pts * T::kPB * 8, 16);
     L.stage_bytes = align_up(o, 128);
     L.off_stages = 128;                                   // mbarriers live in the first 128 bytes
-    o = L.off_stages + kStages * L.stage_bytes;
+    o = L.off_stages + T::kStages * L.stage_bytes;
     L.off_pt = o;
     o += 2 * align_up(max_pts * T::kPtAcc * 8, 16);       // two parities (see the MATVEC / BACKSUB flow)
     L.off_z = o;
@@ -163,7 +165,7 @@ __host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts) {
     L.off_red = o;
     o += 64 * 8;
     L.off_ids = o;
-    o += align_up(kProducers * max_cams * 4, 16);
+    o += align_up(T::kStages * max_cams * 4, 16);
     L.total = o;
     return L;
 }
@@ -434,8 +436,10 @@ __device__ __forceinline__ void project_obs(const double* __restrict__ cam /* sm
 //                trf.py:498-499); only scalars leave the SM
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2) tile_kernel(const TileArgs A, const ModeArgs P) {
+__global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const TileArgs A, const ModeArgs P) {
     using T = Traits<MODE>;
+    constexpr int kStages = T::kStages;
+    constexpr int kThreads = T::kThreads;
     if (MODE == M_MATVEC && P.done && *P.done) return;
     extern __shared__ __align__(128) unsigned char smem[];
     const SmemLayout L = smem_layout<MODE>(A.max_cams, A.max_pts);

@@ -433,7 +433,7 @@ template <int MODE>
 int launch_tile(mmba_handle* h, int cls, const ModeArgs& P) {
     if (!h->nt) return MMBA_OK;
     prof_begin(h, cls);
-    tile_kernel<MODE><<<h->grid[MODE], kThreads, h->smem[MODE], h->stream>>>(h->targs, P);
+    tile_kernel<MODE><<<h->grid[MODE], Traits<MODE>::kThreads, h->smem[MODE], h->stream>>>(h->targs, P);
     prof_end(h, cls);
     return MMBA_OK;
 }
@@ -781,7 +781,7 @@ int configure_mode(mmba_handle* h) {
     if (L.total > 227 * 1024) return fail(h, MMBA_ERR_NOMEM, "tile_kernel needs " + std::to_string(L.total) + " bytes of shared memory");
     CU(cudaFuncSetAttribute(tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_kernel<MODE>, kThreads, (size_t)L.total));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_kernel<MODE>, Traits<MODE>::kThreads, (size_t)L.total));
     if (occ < 1) return fail(h, MMBA_ERR_CUDA, "tile_kernel does not fit on an SM");
     h->grid[MODE] = (int)std::max<int64_t>(1, std::min<int64_t>(h->nt, (int64_t)h->sm_count * occ));
     return MMBA_OK;
