@@ -51,6 +51,7 @@ constexpr int kJTileBytes = kJRows * kT * 8;
 constexpr int kUVTileBytes = 2 * kT * 8;
 
 static_assert(sizeof(TileMeta) == 2592 && sizeof(TileMeta) % 16 == 0, "TileMeta is bulk-copied: 16-byte multiple");
+static_assert(9 * (kTileObs + 1) * 8 <= 18 * kTileObs * 8, "scatter staging rows must fit inside a J block");
 constexpr int kBufStride = kT + 1;         // row stride of the scatter staging buffer (bank spread)
 
 // scalar slots in device memory (doubles).  Groups that are reduced across ranks together are
@@ -89,10 +90,12 @@ struct Traits {
     static constexpr int kPB = (MODE == M_RHS || MODE == M_BACKSUB || MODE == M_JV2) ? 3 : 0;
     static constexpr bool kScatter = is_build(MODE) || MODE == M_MATVEC || MODE == M_RHS;
     static constexpr int kPtAcc = (MODE == M_MATVEC || MODE == M_BACKSUB) ? 3 : 0;
-    // scatter staging rows: BUILD stages 12 camera + 9 point rows + 1 row of point-run starts in one
-    // single buffer; the Schur passes alternate between two buffers of 6 / 9 rows
-    static constexpr int kStageRows = is_build(MODE) ? 22 : MODE == M_RHS ? 9 : MODE == M_MATVEC ? 6 : 0;
-    static constexpr int kStageBufs = is_build(MODE) ? 1 : 2;
+    // scatter staging rows: BUILD stages 12 camera + 9 point rows + 1 row of point-run starts in its
+    // own buffer.  The Schur passes stage 6 / 9 rows INSIDE the current pipeline stage's J block:
+    // every consumer holds its 18 J values in registers by then, the block is dead until the stage
+    // is released, and consecutive tiles use different stages (free double buffering).
+    static constexpr int kStageRows = is_build(MODE) ? 22 : 0;
+    static constexpr int kStageBufs = 1;
 };
 
 struct TileArgs {
@@ -100,6 +103,7 @@ struct TileArgs {
     const int32_t* tile_cams;
     const double* uv;
     int n_tiles, cam_stride, max_cams, max_pts;
+    int n_cams, ytab_cams;   // ytab_cams = n_cams when MATVEC keeps a per-CTA camera table in shared memory, else 0
     double K[9];
 };
 
@@ -130,13 +134,13 @@ struct ModeArgs {
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
     int off_J, off_meta, off_uv, off_camid, off_camvec, off_pa, off_pb, stage_bytes;
-    int off_stages, off_pt, off_z, off_buf, off_red, off_ids, total;
+    int off_stages, off_pt, off_z, off_buf, off_red, off_ids, off_ytab, total;
 };
 
 __host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 template <int MODE>
-__host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts) {
+__host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts, int ytab_cams = 0) {
     using T = Traits<MODE>;
     SmemLayout L{};
     int o = 0;
@@ -166,6 +170,8 @@ __host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts) {
     o += 64 * 8;
     L.off_ids = o;
     o += align_up(T::kStages * max_cams * 4, 16);
+    L.off_ytab = o;
+    if (MODE == M_MATVEC) o += align_up(ytab_cams * 6 * 8, 16);
     L.total = o;
     return L;
 }
@@ -296,7 +302,7 @@ template <int NV>
 __device__ __forceinline__ void camera_scatter_round(const double (&v)[NV], double* s_buf /* [NV][kBufStride] */,
                                                      const TileMeta* mt, const int* s_camid, double* out, int stride,
                                                      int offset, int n0 = NV, double* out1 = nullptr, int stride1 = 0,
-                                                     int offset1 = 0) {
+                                                     int offset1 = 0, double* s_tab = nullptr) {
     // components k < n0 go to out[cam*stride + offset + k], the rest to out1[cam*stride1 + offset1 + k - n0]
     const int tid = threadIdx.x;
 #pragma unroll
@@ -311,7 +317,8 @@ __device__ __forceinline__ void camera_scatter_round(const double (&v)[NV], doub
         double sum = 0.0;
         for (int j = j0; j < j1; ++j) sum += row[mt->sort_src[j]];
         const int64_t cam = s_camid[mt->run_cam[r]];
-        if (k < n0) red_add(out + cam * stride + offset + k, sum);
+        if (s_tab) atomicAdd(s_tab + cam * stride + offset + k, sum);   // per-CTA table, flushed once at the end
+        else if (k < n0) red_add(out + cam * stride + offset + k, sum);
         else red_add(out1 + cam * stride1 + offset1 + (k - n0), sum);
     }
 }
@@ -442,7 +449,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
     constexpr int kThreads = T::kThreads;
     if (MODE == M_MATVEC && P.done && *P.done) return;
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout L = smem_layout<MODE>(A.max_cams, A.max_pts);
+    const SmemLayout L = smem_layout<MODE>(A.max_cams, A.max_pts, A.ytab_cams);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + kStages;
     const int tid = threadIdx.x;
@@ -461,6 +468,10 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     // scratch that must start at zero
+    if (MODE == M_MATVEC && A.ytab_cams) {
+        double* s_ytab = reinterpret_cast<double*>(smem + L.off_ytab);
+        for (int i = tid; i < A.ytab_cams * 6; i += kThreads) s_ytab[i] = 0.0;
+    }
     if (T::kPtAcc) {
         double* s_pt = reinterpret_cast<double*>(smem + L.off_pt);
         for (int i = tid; i < 2 * align_up(A.max_pts * T::kPtAcc * 8, 16) / 8; i += kThreads) s_pt[i] = 0.0;
@@ -808,7 +819,8 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
 #pragma unroll
                     for (int k = 0; k < 6; ++k) cvy[k] = cv[k];
                 } else {
-                    camera_scatter_round<6>(cv, s_buf + (round++ & 1) * T::kStageRows * kBufStride, mt, s_camid, P.y, 6, 0);
+                    camera_scatter_round<6>(cv, const_cast<double*>(sJ), mt, s_camid, P.y, 6, 0, 6,
+                                            nullptr, 0, 0, A.ytab_cams ? reinterpret_cast<double*>(smem + L.off_ytab) : nullptr);
                 }
                 if constexpr (MODE == M_MATVEC) {
                     // all reads of this parity's point sums happened before the round's barrier
@@ -840,13 +852,17 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
                 for (int k = 0; k < 6; ++k) sv[k] = cvy[k];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) sv[6 + i] = sval(i);
-                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.y, 6, 0, 6, P.Sd, 21, 0);
+                double* jbuf = const_cast<double*>(sJ);   // 9 staging rows inside the J block
+                consumer_sync();                          // every consumer has its J values in registers
+                camera_scatter_round<9>(sv, jbuf, mt, s_camid, P.y, 6, 0, 6, P.Sd, 21, 0);
 #pragma unroll
                 for (int i = 0; i < 9; ++i) sv[i] = sval(3 + i);
-                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.Sd, 21, 3);
+                consumer_sync();                          // previous round's sums are done
+                camera_scatter_round<9>(sv, jbuf, mt, s_camid, P.Sd, 21, 3);
 #pragma unroll
                 for (int i = 0; i < 9; ++i) sv[i] = sval(12 + i);
-                camera_scatter_round<9>(sv, s_buf + (round++ & 1) * 9 * kBufStride, mt, s_camid, P.Sd, 21, 12);
+                consumer_sync();
+                camera_scatter_round<9>(sv, jbuf, mt, s_camid, P.Sd, 21, 12);
             }
         }
         // all reads of this stage are done: hand it back to the producer
@@ -856,6 +872,17 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
         if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
+        }
+    }
+    if constexpr (MODE == M_MATVEC) {
+        // few cameras (heavy RED contention on few addresses): the CTA's sums were kept in shared memory
+        if (A.ytab_cams) {
+            consumer_sync();
+            const double* s_ytab = reinterpret_cast<const double*>(smem + L.off_ytab);
+            for (int i = tid; i < A.ytab_cams * 6; i += kConsumers) {
+                const double v = s_ytab[i];
+                if (v != 0.0) red_add(P.y + i, v);
+            }
         }
     }
     // per-CTA scalar results

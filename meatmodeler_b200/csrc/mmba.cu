@@ -577,7 +577,7 @@ int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
         const int stop = std::min(maxit, it + chunk);
         for (; it < stop; ++it) {
             TRY(schur_matvec(h));
-            LAUNCH(MMBA_K_VEC, pcg_update_kernel, 1, kPcgThreads, 0, P, reg, it, rtol2, camblocks);
+            LAUNCH(MMBA_K_VEC, pcg_update_kernel, kPcgCluster, kPcgThreads, 0, P, reg, it, rtol2, camblocks);
         }
         CU(cudaMemcpyAsync(h->h_flags, d.flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -776,7 +776,7 @@ int run_trf(mmba_handle* h, mmba_result* out) {
 
 template <int MODE>
 int configure_mode(mmba_handle* h) {
-    const SmemLayout L = smem_layout<MODE>(h->targs.max_cams, h->targs.max_pts);
+    const SmemLayout L = smem_layout<MODE>(h->targs.max_cams, h->targs.max_pts, h->targs.ytab_cams);
     h->smem[MODE] = (size_t)L.total;
     if (L.total > 227 * 1024) return fail(h, MMBA_ERR_NOMEM, "tile_kernel needs " + std::to_string(L.total) + " bytes of shared memory");
     CU(cudaFuncSetAttribute(tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
@@ -992,6 +992,8 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     A.cam_stride = pl.cam_stride;
     A.max_cams = std::max(pl.max_tile_cams, 1);
     A.max_pts = std::max(pl.max_tile_pts, 1);
+    A.n_cams = (int)h->Nc;
+    A.ytab_cams = h->Nc <= 340 ? (int)h->Nc : 0;   // <= 16 KB of shared memory
     std::memcpy(A.K, K, sizeof(A.K));
     TRY(configure_kernels(h));
     h->has_problem = true;

@@ -7,9 +7,13 @@
 // cameras replicated across ranks, every rank then takes bit-identical PCG decisions without
 // exchanging flags.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "kernels.cuh"
 
 namespace mmba {
+
+namespace cg = cooperative_groups;
 
 constexpr int kCamBlock = 128;   // threads per block of the thread-per-camera kernels
 constexpr int kMaxCamBlocks = 1024;
@@ -284,20 +288,49 @@ __global__ void __launch_bounds__(kCamBlock) pcg_init_kernel(PcgVecs P, double r
 }
 
 constexpr int kPcgThreads = 256;
+constexpr int kPcgCluster = 8;     // CTAs of the update kernel: one thread-block cluster (portable size)
 
-// One PCG iteration's camera-vector work in ONE CTA, so that every reduction is a fixed-order sum
-// and the whole update costs a single launch (LSMR's vector updates, lsmr.py:373-377):
+// Deterministic sum over the whole cluster: fixed-order block sums, exchanged through distributed
+// shared memory and added in cluster-rank order by every CTA (all CTAs, and all ranks, get the same bits).
+template <int NV>
+__device__ __forceinline__ void cluster_sum_det(cg::cluster_group& cluster, double (&v)[NV], double* s_red, double* s_xch /* [NV] */) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = block_sum_det(v[i], s_red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s_xch[i] = v[i];
+    }
+    cluster.sync();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = 0.0;
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r) {
+        const double* rem = cluster.map_shared_rank(s_xch, r);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] += rem[i];
+    }
+}
+
+// One PCG iteration's camera-vector work in ONE launch of one thread-block cluster, so that every
+// reduction is a fixed-order sum (LSMR's vector updates, lsmr.py:373-377):
 //   q = S p = d o y + reg p ; alpha = rho / p.q ; x += alpha p ; r -= alpha q ; z = Pinv r ;
 //   stop if ||r|| <= rtol ||b|| ; beta = r.z / rho ; p = z + beta p ; xt = d o p ; y <- 0
 // y holds this iteration's sum_i Jc_i^T (Jc_i xt - Jp_i z_p) from the MATVEC pass (all-reduced over ranks).
-__global__ void __launch_bounds__(kPcgThreads) pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init) {
-    if (P.flags[0]) return;
+// Up to kPcgCluster*kPcgThreads cameras: one camera per thread, every operand loaded up front (one
+// memory round trip); more cameras: a strided loop with q and z kept in global memory.
+__global__ void __cluster_dims__(kPcgCluster, 1, 1) __launch_bounds__(kPcgThreads)
+pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init) {
+    cg::cluster_group cluster = cg::this_cluster();
+    if (P.flags[0]) return;   // uniform over the cluster: flags are only written by the previous launch
     __shared__ double s_red[32];
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    __shared__ double s_xa[2], s_xb[2];
+    const int tid = threadIdx.x;
+    const int gtid = (int)cluster.block_rank() * kPcgThreads + tid;
+    const int nthr = kPcgCluster * kPcgThreads;
+    const bool lead = gtid == 0;
+    double rho, b2;
+    int done = 0;
     if (P.n_cams <= nthr) {
-        // fast path, one camera per thread: every operand is loaded up front (one memory round trip),
-        // the three reductions then only cost block barriers
-        const int c = tid;
+        const int c = gtid;
         const bool live = c < P.n_cams;
         double pv[6], yv[6], si[6], rv[6], xv[6], Pi[21];
         if (live) {
@@ -312,7 +345,6 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update_kernel(PcgVecs P, doub
 #pragma unroll
             for (int i = 0; i < 21; ++i) Pi[i] = P.Pinv[c * 21 + i];
         }
-        double rho, b2;
         if (it == 0) {
             rho = sum_partials(P.part + P_RHO0 * kMaxCamBlocks, nb_init, s_red);
             b2 = sum_partials(P.part + P_B2 * kMaxCamBlocks, nb_init, s_red);
@@ -320,18 +352,20 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update_kernel(PcgVecs P, doub
             rho = P.state[0];
             b2 = P.state[1];
         }
-        double q[6], pq = 0;
+        double q[6], z[6];
+        double s1[1] = {0};
         if (live) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 q[k] = yv[k] / si[k] + reg * pv[k];
                 P.y[c * 6 + k] = 0.0;
-                pq += pv[k] * q[k];
+                s1[0] += pv[k] * q[k];
             }
         }
-        pq = block_sum_det(pq, s_red);
+        cluster_sum_det<1>(cluster, s1, s_red, s_xa);
+        const double pq = s1[0];
         const double alpha = rho / pq;
-        double z[6], rr = 0, rz = 0;
+        double s2[2] = {0, 0};
         if (live) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
@@ -343,16 +377,15 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update_kernel(PcgVecs P, doub
             for (int k = 0; k < 6; ++k) {
                 P.x[c * 6 + k] = xv[k];
                 P.r[c * 6 + k] = rv[k];
-                rr += rv[k] * rv[k];
-                rz += rv[k] * z[k];
+                s2[0] += rv[k] * rv[k];
+                s2[1] += rv[k] * z[k];
             }
         }
-        rr = block_sum_det(rr, s_red);
-        rz = block_sum_det(rz, s_red);
-        int done = 0;
+        cluster_sum_det<2>(cluster, s2, s_red, s_xb);
+        const double rr = s2[0], rz = s2[1];
         if (rr <= rtol2 * b2) done = 1;
         else if (!(pq > 0.0) || !isfinite(rr) || !(rz > 0.0)) done = 2;
-        if (tid == 0) {
+        if (lead) {
             P.state[0] = rz;
             P.state[1] = b2;
             P.state[2] = rr;
@@ -362,79 +395,81 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update_kernel(PcgVecs P, doub
                 P.flags[0] = done;
             }
         }
-        if (done || !live) return;
-        const double beta = rz / rho;
+        if (!done && live) {
+            const double beta = rz / rho;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const double pk = z[k] + beta * pv[k];
-            P.p[c * 6 + k] = pk;
-            P.xt[c * 6 + k] = pk / si[k];
+            for (int k = 0; k < 6; ++k) {
+                const double pk = z[k] + beta * pv[k];
+                P.p[c * 6 + k] = pk;
+                P.xt[c * 6 + k] = pk / si[k];
+            }
         }
-        return;
-    }
-    double rho, b2;
-    if (it == 0) {
-        rho = sum_partials(P.part + P_RHO0 * kMaxCamBlocks, nb_init, s_red);
-        b2 = sum_partials(P.part + P_B2 * kMaxCamBlocks, nb_init, s_red);
     } else {
-        rho = P.state[0];
-        b2 = P.state[1];
-    }
-    double pq = 0;
-    for (int c = tid; c < P.n_cams; c += nthr) {
+        if (it == 0) {
+            rho = sum_partials(P.part + P_RHO0 * kMaxCamBlocks, nb_init, s_red);
+            b2 = sum_partials(P.part + P_B2 * kMaxCamBlocks, nb_init, s_red);
+        } else {
+            rho = P.state[0];
+            b2 = P.state[1];
+        }
+        double s1[1] = {0};
+        for (int c = gtid; c < P.n_cams; c += nthr) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const double pk = P.p[c * 6 + k];
-            const double qk = P.y[c * 6 + k] / P.sinv[c * 6 + k] + reg * pk;
-            P.y[c * 6 + k] = 0.0;
-            P.q[c * 6 + k] = qk;
-            pq += pk * qk;
+            for (int k = 0; k < 6; ++k) {
+                const double pk = P.p[c * 6 + k];
+                const double qk = P.y[c * 6 + k] / P.sinv[c * 6 + k] + reg * pk;
+                P.y[c * 6 + k] = 0.0;
+                P.q[c * 6 + k] = qk;
+                s1[0] += pk * qk;
+            }
         }
-    }
-    pq = block_sum_det(pq, s_red);
-    const double alpha = rho / pq;
-    double rr = 0, rz = 0;
-    for (int c = tid; c < P.n_cams; c += nthr) {
-        double r[6], z[6];
+        cluster_sum_det<1>(cluster, s1, s_red, s_xa);
+        const double pq = s1[0];
+        const double alpha = rho / pq;
+        double s2[2] = {0, 0};
+        for (int c = gtid; c < P.n_cams; c += nthr) {
+            double r[6], z[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            P.x[c * 6 + k] += alpha * P.p[c * 6 + k];
-            r[k] = P.r[c * 6 + k] - alpha * P.q[c * 6 + k];
-            P.r[c * 6 + k] = r[k];
-        }
-        sym6_matvec(P.Pinv + c * 21, r, z);
+            for (int k = 0; k < 6; ++k) {
+                P.x[c * 6 + k] += alpha * P.p[c * 6 + k];
+                r[k] = P.r[c * 6 + k] - alpha * P.q[c * 6 + k];
+                P.r[c * 6 + k] = r[k];
+            }
+            sym6_matvec(P.Pinv + c * 21, r, z);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            P.z[c * 6 + k] = z[k];
-            rr += r[k] * r[k];
-            rz += r[k] * z[k];
+            for (int k = 0; k < 6; ++k) {
+                P.z[c * 6 + k] = z[k];
+                s2[0] += r[k] * r[k];
+                s2[1] += r[k] * z[k];
+            }
         }
-    }
-    rr = block_sum_det(rr, s_red);
-    rz = block_sum_det(rz, s_red);
-    int done = 0;
-    if (rr <= rtol2 * b2) done = 1;
-    else if (!(pq > 0.0) || !isfinite(rr) || !(rz > 0.0)) done = 2;
-    if (tid == 0) {
-        P.state[0] = rz;
-        P.state[1] = b2;
-        P.state[2] = rr;
-        if (done) {
-            P.flags[1] = it + 1;
-            __threadfence();
-            P.flags[0] = done;
+        cluster_sum_det<2>(cluster, s2, s_red, s_xb);
+        const double rr = s2[0], rz = s2[1];
+        if (rr <= rtol2 * b2) done = 1;
+        else if (!(pq > 0.0) || !isfinite(rr) || !(rz > 0.0)) done = 2;
+        if (lead) {
+            P.state[0] = rz;
+            P.state[1] = b2;
+            P.state[2] = rr;
+            if (done) {
+                P.flags[1] = it + 1;
+                __threadfence();
+                P.flags[0] = done;
+            }
         }
-    }
-    if (done) return;
-    const double beta = rz / rho;
-    for (int c = tid; c < P.n_cams; c += nthr) {
+        if (!done) {
+            const double beta = rz / rho;
+            for (int c = gtid; c < P.n_cams; c += nthr) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const double pk = P.z[c * 6 + k] + beta * P.p[c * 6 + k];
-            P.p[c * 6 + k] = pk;
-            P.xt[c * 6 + k] = pk / P.sinv[c * 6 + k];
+                for (int k = 0; k < 6; ++k) {
+                    const double pk = P.z[c * 6 + k] + beta * P.p[c * 6 + k];
+                    P.p[c * 6 + k] = pk;
+                    P.xt[c * 6 + k] = pk / P.sinv[c * 6 + k];
+                }
+            }
         }
     }
+    cluster.sync();   // no CTA leaves while its exchange slots may still be read remotely
 }
 
 // Reference point for the roofline: a plain grid-stride LDG.128 read of n doubles (what a trivial
