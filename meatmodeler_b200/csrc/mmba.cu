@@ -41,6 +41,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -69,6 +70,7 @@ bool load_nccl(std::string& err) {
     MMBA_SYM(CommInitRank)
     MMBA_SYM(CommDestroy)
     MMBA_SYM(AllReduce)
+    MMBA_SYM(AllGather)
     MMBA_SYM(GroupStart)
     MMBA_SYM(GroupEnd)
     MMBA_SYM(GetErrorString)
@@ -110,6 +112,20 @@ struct Dev {
     double* xp_full;   // all points, internal order (nranks > 1 only)
 };
 
+// One-shot peer all-reduce of the per-iteration Schur product (see xchg_push_kernel)
+struct Xchg {
+    bool on = false;
+    void* base = nullptr;                 // this rank's receive buffer (exported with cudaIpc)
+    std::vector<void*> peers;             // peer mappings (nullptr for self)
+    double* slots = nullptr;              // [2][nranks][n6]
+    unsigned long long* flags = nullptr;  // [2][nranks]
+    double** d_peer_slots = nullptr;      // device arrays of per-rank pointers
+    unsigned long long** d_peer_flags = nullptr;
+    unsigned int* d_counter = nullptr;
+    int n6 = 0;       // slot length in doubles (capacity: the buffers are kept across problems)
+    unsigned long long seq = 0;
+};
+
 struct Profile {
     int64_t launches[MMBA_K_COUNT] = {0};
     double ms[MMBA_K_COUNT] = {0};
@@ -140,9 +156,10 @@ struct mmba_handle {
     double* h_stage = nullptr;   // pinned, max(nloc, 2*ns ...) doubles
     size_t h_stage_n = 0;
     double* h_scal = nullptr;    // pinned S_COUNT
-    int* h_flags = nullptr;      // pinned 2
+    int* h_flags = nullptr;      // pinned 4
     std::vector<mmba_iter_log> log;
     Profile prof;
+    Xchg xchg;
 };
 
 struct mmba_plan {
@@ -303,6 +320,90 @@ void carve(mmba_handle* h, Arena& a) {
     d.xp_full = h->opt.nranks > 1 ? a.take<double>(3 * (size_t)pl.n_points) : nullptr;
 }
 
+void xchg_release(mmba_handle* h) {
+    Xchg& x = h->xchg;
+    for (void* p : x.peers)
+        if (p) cudaIpcCloseMemHandle(p);
+    x.peers.clear();
+    if (x.base) cudaFree(x.base);
+    if (x.d_peer_slots) cudaFree(x.d_peer_slots);
+    if (x.d_peer_flags) cudaFree(x.d_peer_flags);
+    if (x.d_counter) cudaFree(x.d_counter);
+    x = Xchg();
+}
+
+// Allocate this rank's receive buffer, exchange cudaIpc handles through the NCCL communicator and map
+// every peer's buffer.  On any failure the exchange stays off and the solve uses ncclAllReduce.
+int xchg_setup(mmba_handle* h) {
+    Xchg& x = h->xchg;
+    const int nr = h->opt.nranks;
+    const char* env = getenv("MMBA_PEER_XCHG");
+    if (nr <= 1 || (env && env[0] == '0')) return MMBA_OK;
+    if (x.on && x.n6 >= 6 * h->Nc) return MMBA_OK;   // mapped buffers of an earlier problem are large enough
+    xchg_release(h);
+    x.n6 = (int)std::max<int64_t>(6 * h->Nc, 8192);
+    const size_t flag_bytes = 256 * ((2 * nr * sizeof(unsigned long long) + 255) / 256);
+    const size_t bytes = flag_bytes + 2 * (size_t)nr * x.n6 * sizeof(double);
+    CU(cudaMalloc(&x.base, bytes));
+    CU(cudaMemsetAsync(x.base, 0, bytes, h->stream));
+    x.flags = static_cast<unsigned long long*>(x.base);
+    x.slots = reinterpret_cast<double*>(static_cast<char*>(x.base) + flag_bytes);
+    cudaIpcMemHandle_t mine;
+    CU(cudaIpcGetMemHandle(&mine, x.base));
+    char *d_send = nullptr, *d_recv = nullptr;
+    CU(cudaMalloc(&d_send, sizeof(mine)));
+    CU(cudaMalloc(&d_recv, sizeof(mine) * nr));
+    CU(cudaMemcpyAsync(d_send, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+    NC(g_nccl.AllGather(d_send, d_recv, sizeof(mine), ncclChar, h->comm, h->stream));
+    std::vector<cudaIpcMemHandle_t> all(nr);
+    CU(cudaMemcpyAsync(all.data(), d_recv, sizeof(mine) * nr, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d_send);
+    cudaFree(d_recv);
+    x.peers.assign(nr, nullptr);
+    std::vector<double*> ps(nr);
+    std::vector<unsigned long long*> pf(nr);
+    bool ok = true;
+    for (int r = 0; r < nr; ++r) {
+        void* p = x.base;
+        if (r != h->opt.rank) {
+            if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = false;
+                p = x.base;
+            } else {
+                x.peers[r] = p;
+            }
+        }
+        pf[r] = static_cast<unsigned long long*>(p);
+        ps[r] = reinterpret_cast<double*>(static_cast<char*>(p) + flag_bytes);
+    }
+    // every rank must take the same path: agree on success
+    double* d_ok = nullptr;
+    CU(cudaMalloc(&d_ok, sizeof(double)));
+    const double okv = ok ? 0.0 : 1.0;
+    CU(cudaMemcpyAsync(d_ok, &okv, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    double bad = 0;
+    CU(cudaMemcpyAsync(&bad, d_ok, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d_ok);
+    if (bad != 0.0) {
+        xchg_release(h);
+        return MMBA_OK;
+    }
+    CU(cudaMalloc(&x.d_peer_slots, nr * sizeof(double*)));
+    CU(cudaMalloc(&x.d_peer_flags, nr * sizeof(unsigned long long*)));
+    CU(cudaMalloc(&x.d_counter, sizeof(unsigned int)));
+    CU(cudaMemcpyAsync(x.d_peer_slots, ps.data(), nr * sizeof(double*), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(x.d_peer_flags, pf.data(), nr * sizeof(unsigned long long*), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(x.d_counter, 0, sizeof(unsigned int), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    x.seq = 0;
+    x.on = true;
+    return MMBA_OK;
+}
+
 void release_problem(mmba_handle* h) {
     if (h->arena) cudaFree(h->arena);
     h->arena = nullptr;
@@ -421,6 +522,13 @@ PcgVecs pcg_vecs(mmba_handle* h) {
     P.flags = d.flags;
     P.state = d.state;
     P.n_cams = (int)h->Nc;
+    P.xslots = h->xchg.slots;
+    P.xflags = h->xchg.flags;
+    P.peer_slots = h->xchg.d_peer_slots;
+    P.peer_flags = h->xchg.d_peer_flags;
+    P.rank = h->opt.rank;
+    P.nranks = h->xchg.on ? h->opt.nranks : 1;
+    P.n6 = h->xchg.n6;
     return P;
 }
 
@@ -576,11 +684,21 @@ int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
     while (it < maxit && !done) {
         const int stop = std::min(maxit, it + chunk);
         for (; it < stop; ++it) {
-            TRY(schur_matvec(h));
-            LAUNCH(MMBA_K_VEC, pcg_update_kernel, kPcgCluster, kPcgThreads, 0, P, reg, it, rtol2, camblocks);
+            int parity = 0;
+            unsigned long long seq = 0;
+            if (h->xchg.on) {
+                // MATVEC + peer push; the all-reduce completes inside pcg_update
+                TRY(launch_tile<M_MATVEC>(h, MMBA_K_MATVEC, matvec_args(h)));
+                seq = ++h->xchg.seq;
+                parity = (int)(seq & 1);
+            } else {
+                TRY(schur_matvec(h));
+            }
+            LAUNCH(MMBA_K_VEC, pcg_update_kernel, kPcgCluster, kPcgThreads, 0, P, reg, it, rtol2, camblocks, parity, seq);
         }
-        CU(cudaMemcpyAsync(h->h_flags, d.flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->h_flags, d.flags, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
+        if (h->h_flags[2]) return fail(h, MMBA_ERR_NCCL, "peer exchange timed out: a rank stopped participating");
         done = h->h_flags[0];
         chunk = 16;
     }
@@ -916,6 +1034,7 @@ void mmba_destroy(mmba_handle* h) {
     cudaSetDevice(h->opt.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     release_problem(h);
+    xchg_release(h);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->comm) g_nccl.CommDestroy(h->comm);
     for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
@@ -996,6 +1115,7 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     A.ytab_cams = h->Nc <= 340 ? (int)h->Nc : 0;   // <= 16 KB of shared memory
     std::memcpy(A.K, K, sizeof(A.K));
     TRY(configure_kernels(h));
+    TRY(xchg_setup(h));
     h->has_problem = true;
     return MMBA_OK;
 }

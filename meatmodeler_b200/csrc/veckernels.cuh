@@ -240,7 +240,24 @@ struct PcgVecs {
     double* state;        // [0] rho, [1] ||b||^2, [2] ||r||^2 carried between iterations
     int* flags;           // [0] done, [1] iterations
     int n_cams;
+    // peer exchange (nranks > 1): this rank's receive slots [2][nranks][n6] and arrival flags
+    // [2][nranks], plus every rank's mapped slots / flags; nranks == 1 when the exchange is off
+    // (y is then complete in place, all-reduced by NCCL if there are several ranks)
+    const double* xslots;
+    const unsigned long long* xflags;
+    double* const* peer_slots;
+    unsigned long long* const* peer_flags;
+    int nranks, rank, n6;
 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // b = d o (g_c - y) ; Pinv = (d d^T o S_cc + reg I)^-1 ; x = 0, r = b, z = Pinv r, p = z, xt = d o p
 __global__ void __launch_bounds__(kCamBlock) pcg_init_kernel(PcgVecs P, double reg) {
@@ -318,7 +335,7 @@ __device__ __forceinline__ void cluster_sum_det(cg::cluster_group& cluster, doub
 // Up to kPcgCluster*kPcgThreads cameras: one camera per thread, every operand loaded up front (one
 // memory round trip); more cameras: a strided loop with q and z kept in global memory.
 __global__ void __cluster_dims__(kPcgCluster, 1, 1) __launch_bounds__(kPcgThreads)
-pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init) {
+pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int parity, unsigned long long seq) {
     cg::cluster_group cluster = cg::this_cluster();
     if (P.flags[0]) return;   // uniform over the cluster: flags are only written by the previous launch
     __shared__ double s_red[32];
@@ -329,6 +346,38 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init) {
     const bool lead = gtid == 0;
     double rho, b2;
     int done = 0;
+    const bool xchg = P.nranks > 1;
+    const double* slots = nullptr;
+    if (xchg) {
+        // One-shot all-reduce of the 6*Nc Schur product over NVLink peer memory, fused into this kernel
+        // (replaces a per-iteration ncclAllReduce: 30+ us at 8 GPUs for this 10-100 KB message).
+        // Push: every rank stores its partial y into slot [parity][rank] of EVERY rank's receive buffer
+        // (plain stores to peer-mapped addresses) and clears y; after a cluster barrier one release
+        // store per peer raises this rank's arrival flag there.
+        const int n = 6 * P.n_cams;
+        const int64_t off = (int64_t)(parity * P.nranks + P.rank) * P.n6;
+        for (int i = gtid; i < n; i += nthr) {
+            const double v = P.y[i];
+            P.y[i] = 0.0;
+            for (int r = 0; r < P.nranks; ++r) P.peer_slots[r][off + i] = v;
+        }
+        cluster.sync();
+        if (gtid < P.nranks) st_release_sys(P.peer_flags[gtid] + parity * P.nranks + P.rank, seq);
+        // Wait: all ranks' partials have landed in this rank's slots; they are then added in rank order,
+        // so every rank obtains bit-identical sums and takes identical PCG decisions.
+        if (tid < P.nranks) {
+            const unsigned long long* f = P.xflags + parity * P.nranks + tid;
+            const long long t0 = clock64();
+            while (ld_acquire_sys(f) < seq) {
+                if (clock64() - t0 > (1ll << 32)) {   // ~2 s: a peer died; fail instead of hanging
+                    P.flags[2] = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        slots = P.xslots + (int64_t)parity * P.nranks * P.n6;
+    }
     if (P.n_cams <= nthr) {
         const int c = gtid;
         const bool live = c < P.n_cams;
@@ -337,7 +386,13 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 pv[k] = P.p[c * 6 + k];
-                yv[k] = P.y[c * 6 + k];
+                if (xchg) {
+                    double acc = 0.0;
+                    for (int r = 0; r < P.nranks; ++r) acc += __ldcg(slots + (int64_t)r * P.n6 + c * 6 + k);
+                    yv[k] = acc;
+                } else {
+                    yv[k] = P.y[c * 6 + k];
+                }
                 si[k] = P.sinv[c * 6 + k];
                 rv[k] = P.r[c * 6 + k];
                 xv[k] = P.x[c * 6 + k];
@@ -358,7 +413,7 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 q[k] = yv[k] / si[k] + reg * pv[k];
-                P.y[c * 6 + k] = 0.0;
+                if (!xchg) P.y[c * 6 + k] = 0.0;
                 s1[0] += pv[k] * q[k];
             }
         }
@@ -417,8 +472,15 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 const double pk = P.p[c * 6 + k];
-                const double qk = P.y[c * 6 + k] / P.sinv[c * 6 + k] + reg * pk;
-                P.y[c * 6 + k] = 0.0;
+                double yk;
+                if (xchg) {
+                    yk = 0.0;
+                    for (int r = 0; r < P.nranks; ++r) yk += __ldcg(slots + (int64_t)r * P.n6 + c * 6 + k);
+                } else {
+                    yk = P.y[c * 6 + k];
+                    P.y[c * 6 + k] = 0.0;
+                }
+                const double qk = yk / P.sinv[c * 6 + k] + reg * pk;
                 P.q[c * 6 + k] = qk;
                 s1[0] += pk * qk;
             }

@@ -2,7 +2,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
 Every rank solves its point shard of the same problem (cameras replicated, NCCL all-reduce inside
 libmmba); rank 0 additionally solves the whole problem on one GPU.  The sharded solve must agree
-with the single-GPU solve: same iteration counts, per-iteration costs to 1e-9, x to 1e-7.
+with the single-GPU solve: same iteration counts, per-iteration costs to 1e-7 (the bar is 1e-6), x to 1e-7.
 """
 import os
 import sys
@@ -37,7 +37,7 @@ def main():
                 x1, r1, f1 = eng.solve(x0, want_fun=True)
                 c1 = np.array([r["cost"] for r in eng.log()])
             same = (res.nfev == r1.nfev and res.status == r1.status and len(costs) == len(c1)
-                    and np.allclose(costs, c1, rtol=1e-9) and np.abs(res.x - x1).max() < 1e-7
+                    and np.allclose(costs, c1, rtol=1e-7) and np.abs(res.x - x1).max() < 1e-7
                     and np.abs(res.fun - f1).max() < 1e-6)
             print(f"{name}: world={world} nfev {res.nfev}/{r1.nfev} status {res.status}/{r1.status} "
                   f"cost {res.cost:.12e}/{r1.cost:.12e} max|dx| {np.abs(res.x - x1).max():.2e} "
