@@ -121,6 +121,12 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
  * NULL) receives the residuals at the returned x in the caller's observation order. */
 int mmba_solve(mmba_handle* h, double* x, mmba_result* result, double* fun_out);
 
+/* replaces: least_squares(poseFun, parameters, ftol=1e-4) inside adjustPose (bundleAdjuster.py:232-241):
+ * dense-Jacobian defaults, i.e. method='trf', tr_solver='exact', x_scale=1.  Only the 6*n_cams camera
+ * parameters of x are variables; the point coordinates in x are constants (the chessboard).  x has
+ * the layout of mmba_solve; single-GPU handles only. */
+int mmba_solve_pose(mmba_handle* h, double* x, mmba_result* result, double* fun_out);
+
 /* The same solve with the parameters resident in HBM: mmba_set_x uploads a starting point once,
  * mmba_solve_resident restarts from it without host<->device parameter traffic (what bench.py
  * times as the device-resident figure), mmba_get_x downloads the current parameters. */

@@ -62,6 +62,7 @@ SIGNATURES = {
     "mmba_set_options": (C.c_int, [_H, C.POINTER(Options)]),
     "mmba_set_problem": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, _f64, _i64, _i64, _f64]),
     "mmba_solve": (C.c_int, [_H, _f64, C.POINTER(Result), C.c_void_p]),
+    "mmba_solve_pose": (C.c_int, [_H, _f64, C.POINTER(Result), C.c_void_p]),
     "mmba_set_x": (C.c_int, [_H, _f64]),
     "mmba_solve_resident": (C.c_int, [_H, C.POINTER(Result)]),
     "mmba_get_x": (C.c_int, [_H, _f64]),
@@ -197,6 +198,16 @@ class Engine:
         res = Result()
         fun = np.empty(2 * self.sizes[2]) if want_fun else None
         _check(lib().mmba_solve(self._h, x, C.byref(res), fun.ctypes.data if want_fun else None), self._h)
+        return x, res, fun
+
+    def solve_pose(self, x0, want_fun=False):
+        """Pose-only solve: cameras are variables, the points in x0 are constants."""
+        x = np.array(x0, dtype=np.float64, order="C").reshape(-1)
+        if x.size != self.n:
+            raise ValueError(f"x0 has {x.size} entries, expected {self.n}")
+        res = Result()
+        fun = np.empty(2 * self.sizes[2]) if want_fun else None
+        _check(lib().mmba_solve_pose(self._h, x, C.byref(res), fun.ctypes.data if want_fun else None), self._h)
         return x, res, fun
 
     def set_x(self, x0):

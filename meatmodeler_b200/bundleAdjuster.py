@@ -148,12 +148,21 @@ _TUNABLE = ("ftol", "xtol", "gtol", "max_nfev", "pcg_rtol", "pcg_maxit", "verbos
 def _engine(camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D, **options):
     """The process-wide engine with this problem loaded.  Handles are cached: creating a CUDA stream,
     pinned staging buffers and (multi-GPU) an NCCL communicator once instead of once per call."""
+    single = options.pop("single_gpu", False)
     fixed = {k: options.pop(k) for k in ("device", "rank", "nranks", "nccl_id") if k in options}
     unknown = [k for k in options if k not in _TUNABLE]
     if unknown:
         raise TypeError(f"unknown option(s) {unknown}")
     key = None
-    if not fixed:
+    if single and not fixed:
+        # pose-only problems are tiny: every rank solves them whole on its own GPU
+        dev = 0
+        if _is_distributed():
+            import torch
+            dev = torch.cuda.current_device()
+        key = (dev, 0, 1)
+        fixed = dict(device=dev) if key not in _ENGINES else {}
+    elif not fixed:
         if _is_distributed():
             import torch
             key = (torch.cuda.current_device(), torch.distributed.get_rank(), torch.distributed.get_world_size())
@@ -161,7 +170,7 @@ def _engine(camera_matrix, n_frames, n_points, frame_indices, point_indices, poi
             key = (0, 0, 1)
     eng = _ENGINES.get(key) if key is not None else None
     if eng is None:
-        if not fixed:
+        if not fixed and not single:
             fixed = _dist_options()
         eng = _capi.Engine(**fixed)
         if key is not None:
@@ -238,6 +247,82 @@ def solve(parameters, camera_matrix, n_frames, n_points, frame_indices, point_in
     elif verbose == 1:
         print(res.message)
     return res
+
+
+def reformatPoseResult(result, n_frames):
+    """``result.x`` (6 per frame) -> list of n_frames 3x4 extrinsics  (bundleAdjuster.py:197-203)."""
+    frames = np.asarray(result.x)[:n_frames * 6].reshape((n_frames, 6))
+    return [np.hstack((_rodrigues(row[:3]), row[3:].reshape(3, 1))) for row in frames]
+
+
+def _board_points(pattern_size):
+    """The stationary chessboard of adjustPose (bundleAdjuster.py:220-223): a 4x3 grid (times 2) in
+    the x-z plane, built in float32 like the reference (the values are small integers)."""
+    points_3D = np.zeros((pattern_size, 3), np.float32)
+    grid = np.mgrid[0:4, 0:3].T.reshape(-1, 2) * 2
+    points_3D[:, 0] = grid[:, 0]
+    points_3D[:, 2] = grid[:, 1]
+    return points_3D
+
+
+def _pose_problem(n_frames, frame_indices, point_indices, points_3D):
+    """Engine view of a pose-only problem: every observation gets its own (constant) copy of its 3-D
+    point, so that tiles stay point-aligned however many frames see one board corner."""
+    fi = np.ascontiguousarray(frame_indices, dtype=np.int64).reshape(-1)
+    pts = np.asarray(points_3D, dtype=np.float64)[np.asarray(point_indices, dtype=np.int64).reshape(-1)]
+    return fi, np.arange(len(fi), dtype=np.int64), pts
+
+
+def poseFun(parameters, camera_intrinsic_matrix, n_frames, frame_indices, point_indices, points_3D, points_2D):
+    """Residuals of the pose-only problem (bundleAdjuster.py:206-211) from the engine's residual kernel."""
+    fi, pi, pts = _pose_problem(n_frames, frame_indices, point_indices, points_3D)
+    eng = _engine(camera_intrinsic_matrix, n_frames, len(pts), fi, pi, points_2D, single_gpu=True)
+    return eng.residual(np.hstack((np.asarray(parameters, dtype=np.float64).reshape(-1), pts.reshape(-1))))
+
+
+def solve_pose(parameters, camera_intrinsic_matrix, n_frames, frame_indices, point_indices, points_3D, points_2D,
+               ftol=FTOL, xtol=XTOL, gtol=GTOL, max_nfev=None, verbose=0, want_fun=False):
+    """Stands where ``least_squares(poseFun, parameters, verbose=2, ftol=1e-4, args=...)`` stands in the
+    reference's adjustPose (bundleAdjuster.py:232-241): dense defaults (trf, exact trust-region step,
+    x_scale=1), the 3-D points are constants."""
+    fi, pi, pts = _pose_problem(n_frames, frame_indices, point_indices, points_3D)
+    eng = _engine(camera_intrinsic_matrix, n_frames, len(pts), fi, pi, points_2D, single_gpu=True,
+                  ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=0 if max_nfev is None else int(max_nfev))
+    x0 = np.hstack((np.asarray(parameters, dtype=np.float64).reshape(-1), pts.reshape(-1)))
+    try:
+        x, r, fun = eng.solve_pose(x0, want_fun=want_fun)
+    except _capi.MmbaError as e:
+        if e.code == -4:
+            raise ValueError("Residuals are not finite in the initial point.") from e
+        raise
+    log = eng.log()
+    res = SolveResult(x=x[:6 * n_frames], cost=r.cost, initial_cost=r.initial_cost, fun=fun, optimality=r.optimality,
+                      nfev=r.nfev, njev=r.njev, nit=r.nit, status=r.status,
+                      message=_STATUS_MESSAGES.get(r.status, ""), success=r.status > 0, log=log,
+                      pcg_iterations=0, solve_ms=r.solve_ms)
+    if verbose >= 2:
+        _print_table(log, res)
+    elif verbose == 1:
+        print(res.message)
+    return res
+
+
+def adjustPose(frame_extrinsic_matrices, camera_intrinsic_matrix, points_2D):
+    """Pose refinement against the fixed chessboard (bundleAdjuster.py:214-243; same signature and
+    return value: a list of 3x4 extrinsic matrices).  ``points_2D`` holds n_frames copies of the
+    board's image corners."""
+    global last_result
+    ext = np.asarray(frame_extrinsic_matrices, dtype=np.float64)
+    n_frames = len(ext)
+    pattern_size = int(len(points_2D) / n_frames)
+    points_3D = _board_points(pattern_size)
+    frame_indices = np.repeat(np.arange(n_frames), pattern_size)
+    point_indices = np.repeat([np.arange(pattern_size)], n_frames, axis=0).reshape(pattern_size * n_frames)
+    parameters = frameParameters(ext)
+    res = solve_pose(parameters, camera_intrinsic_matrix, n_frames, frame_indices, point_indices, points_3D,
+                     np.asarray(points_2D, dtype=np.float64).reshape(-1, 2), ftol=FTOL, verbose=VERBOSE)
+    last_result = res
+    return reformatPoseResult(res, n_frames)
 
 
 def adjustPoints(frame_extrinsic_matrices, camera_intrinsic_matrix, points_3D, points_2D, frame_indices,

@@ -107,6 +107,7 @@ struct Dev {
     double *sinv, *gh, *gn, *s1, *s2, *v1, *v2, *tmp;
     // PCG (camera-sized)
     double *y, *Sd, *Pinv, *px, *pr, *pz, *pp, *pq, *pxt, *part, *state;
+    double *pose_lam, *pose_suf, *pose_V, *pose_w;   // pose-only adjustment (per-camera eigen data)
     int* flags;
     double* scal;
     double* xp_full;   // all points, internal order (nranks > 1 only)
@@ -315,6 +316,10 @@ void carve(mmba_handle* h, Arena& a) {
     d.pxt = a.take<double>(6 * Nc);
     d.part = a.take<double>((size_t)P_COUNT * kMaxCamBlocks);
     d.state = a.take<double>(4);
+    d.pose_lam = a.take<double>(6 * Nc);
+    d.pose_suf = a.take<double>(6 * Nc);
+    d.pose_V = a.take<double>(36 * Nc);
+    d.pose_w = a.take<double>(6 * Nc);
     d.flags = a.take<int>(4);
     d.scal = a.take<double>(S_COUNT);
     d.xp_full = h->opt.nranks > 1 ? a.take<double>(3 * (size_t)pl.n_points) : nullptr;
@@ -694,7 +699,24 @@ int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
             } else {
                 TRY(schur_matvec(h));
             }
-            LAUNCH(MMBA_K_VEC, pcg_update_kernel, kPcgCluster, kPcgThreads, 0, P, reg, it, rtol2, camblocks, parity, seq);
+            {
+                const unsigned csize = h->Nc <= kPcgThreads ? 1u : (unsigned)kPcgCluster;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(csize);
+                cfg.blockDim = dim3(kPcgThreads);
+                cfg.dynamicSmemBytes = 0;
+                cfg.stream = h->stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = csize;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                prof_begin(h, MMBA_K_VEC);
+                CU(cudaLaunchKernelEx(&cfg, pcg_update_kernel, P, reg, it, rtol2, camblocks, parity, seq));
+                prof_end(h, MMBA_K_VEC);
+            }
         }
         CU(cudaMemcpyAsync(h->h_flags, d.flags, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -915,6 +937,112 @@ int configure_kernels(mmba_handle* h) {
     TRY(configure_mode<M_JV1>(h));
     TRY(configure_mode<M_JV2>(h));
     TRY(configure_mode<M_BUILD_FULL>(h));
+    return MMBA_OK;
+}
+
+// ---- pose-only TRF (adjustPose, bundleAdjuster.py:232-241): dense least_squares defaults ----------
+// method='trf', tr_solver='exact', x_scale=1.0, ftol from the call site; the points are constants.
+// Same outer loop as run_trf (trf.py:415-587) with scale = 1 and the exact trust-region step of
+// solve_lsq_trust_region (common.py:60-164) evaluated per camera block on the device.
+int run_trf_pose(mmba_handle* h, mmba_result* out) {
+    Dev& d = h->d;
+    const mmba_options& o = h->opt;
+    const int64_t ncam = 6 * h->Nc, nloc = h->nloc;
+    const int64_t max_nfev = o.max_nfev > 0 ? o.max_nfev : 100 * ncam;
+    const double m_rows = 2.0 * (double)h->plan.n_obs;
+    h->log.clear();
+    auto sg_cam = scale_grad_kernel<6, false>;
+
+    auto grad_stats = [&]() -> int {
+        // ||g||_inf and ||x||^2 over the camera parameters (the variables of this problem)
+        TRY(zero(h, d.scal + S_GH2, 4));
+        LAUNCH(MMBA_K_VEC, sg_cam, cdiv(ncam, 256), 256, 0, d.Ud, d.g, d.x, d.sinv, d.gh, 1, ncam, d.scal, 1);
+        return MMBA_OK;
+    };
+    TRY(linearise(h, true));
+    TRY(grad_stats());
+    TRY(read_scalars(h));
+    double cost = 0.5 * h->h_scal[S_COST];
+    if (!std::isfinite(cost)) return fail(h, MMBA_ERR_NONFINITE, "Residuals are not finite in the initial point.");
+    double x_norm = std::sqrt(h->h_scal[S_X2]), g_norm = ginf_of(h->h_scal);
+    double Delta = x_norm;   // ||x0 * scale_inv|| with scale_inv = 1 (trf.py:443-445)
+    if (Delta == 0) Delta = 1.0;
+    out->initial_cost = cost;
+    int64_t nfev = 1, njev = 1, nit = 0;
+    int status = -1;
+    double step_norm = 0, actual = 0, alpha = 0.0;
+    bool have_step = false;
+    while (true) {
+        if (g_norm < o.gtol) status = 1;
+        {
+            mmba_iter_log row;
+            row.iteration = nit;
+            row.nfev = nfev;
+            row.cost = cost;
+            row.cost_reduction = have_step ? actual : NAN;
+            row.step_norm = have_step ? step_norm : NAN;
+            row.optimality = g_norm;
+            row.reg = alpha;
+            row.delta = Delta;
+            row.pcg_iterations = 0;
+            h->log.push_back(row);
+        }
+        if (status != -1 || nfev >= max_nfev) break;
+        LAUNCH(MMBA_K_VEC, pose_eig_kernel, cdiv(h->Nc, 128), 128, 0, d.U, d.g, d.pose_lam, d.pose_suf, d.pose_V, (int)h->Nc);
+        actual = -1;
+        double cost_new = cost;
+        while (actual <= 0 && nfev < max_nfev) {
+            LAUNCH(MMBA_K_VEC, pose_tr_kernel, 1, 256, 0, d.pose_lam, d.pose_suf, d.pose_w, (int)ncam, m_rows, Delta, alpha, d.scal);
+            LAUNCH(MMBA_K_VEC, pose_step_kernel, cdiv(nloc, 256), 256, 0, d.x, d.pose_V, d.pose_w, d.xn, (int)h->Nc, nloc);
+            TRY(trial_cost(h, d.xn, d.camtab_n));
+            TRY(read_scalars(h));
+            nfev++;
+            alpha = h->h_scal[PS_ALPHA];
+            const double predicted = h->h_scal[PS_PRED], step_h_norm = h->h_scal[PS_STEPNORM];
+            const double f2 = h->h_scal[S_COST_NEW];
+            if (!std::isfinite(f2)) {
+                Delta = 0.25 * step_h_norm;
+                continue;
+            }
+            cost_new = 0.5 * f2;
+            actual = cost - cost_new;
+            double Delta_new, ratio;
+            update_tr_radius(Delta, actual, predicted, step_h_norm, step_h_norm > 0.95 * Delta, &Delta_new, &ratio);
+            step_norm = step_h_norm;   // scale = 1: the step and the scaled step coincide
+            have_step = true;
+            const int term = check_termination(actual, cost, step_norm, x_norm, ratio, o.ftol, o.xtol);
+            if (term) {
+                status = term;
+                break;
+            }
+            alpha *= Delta / Delta_new;
+            Delta = Delta_new;
+        }
+        if (actual > 0) {
+            std::swap(d.x, d.xn);
+            cost = cost_new;
+            TRY(linearise(h, true));
+            njev++;
+            TRY(grad_stats());
+            TRY(read_scalars(h));
+            x_norm = std::sqrt(h->h_scal[S_X2]);
+            g_norm = ginf_of(h->h_scal);
+        } else {
+            step_norm = 0;
+            actual = 0;
+            have_step = true;
+        }
+        nit++;
+    }
+    if (status == -1) status = 0;
+    out->cost = cost;
+    out->optimality = g_norm;
+    out->nfev = nfev;
+    out->njev = njev;
+    out->nit = nit;
+    out->status = status;
+    out->reserved = 0;
+    out->pcg_iterations = 0;
     return MMBA_OK;
 }
 
@@ -1146,6 +1274,28 @@ int mmba_solve(mmba_handle* h, double* x, mmba_result* result, double* fun_out) 
         if (h->opt.nranks > 1) std::memset(fun_out, 0, 2 * h->plan.n_obs * sizeof(double));
         TRY(get_slots(h, h->d.res, 2, fun_out, 2, 0));
     }
+    return MMBA_OK;
+}
+
+int mmba_solve_pose(mmba_handle* h, double* x, mmba_result* result, double* fun_out) {
+    TRY(need_problem(h));
+    if (!x || !result) return fail(h, MMBA_ERR_ARG, "solve_pose: null x or result");
+    if (h->opt.nranks > 1) return fail(h, MMBA_ERR_STATE, "solve_pose runs on a single-GPU handle (nranks == 1)");
+    TRY(put_x(h, x, h->d.x));
+    std::memset(result, 0, sizeof(*result));
+    std::memset(h->prof.launches, 0, sizeof(h->prof.launches));
+    std::memset(h->prof.ms, 0, sizeof(h->prof.ms));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    int rc = run_trf_pose(h, result);
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    result->solve_ms = ms;
+    prof_collect(h);
+    if (rc != MMBA_OK) return rc;
+    TRY(get_x(h, h->d.x, x));
+    if (fun_out) TRY(get_slots(h, h->d.res, 2, fun_out, 2, 0));
     return MMBA_OK;
 }
 

@@ -313,18 +313,28 @@ template <int NV>
 __device__ __forceinline__ void cluster_sum_det(cg::cluster_group& cluster, double (&v)[NV], double* s_red, double* s_xch /* [NV] */) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = block_sum_det(v[i], s_red);
+    const unsigned nb = cluster.num_blocks();
+    if (nb == 1) return;                       // single CTA: the block sum is the result
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) s_xch[i] = v[i];
     }
     cluster.sync();
+    // lane r of warp 0 fetches CTA r's partial (one remote latency for all of them); the xor tree adds
+    // them in the same order on every CTA
+    if (threadIdx.x < 32) {
+        const double* rem = cluster.map_shared_rank(s_xch, threadIdx.x < nb ? threadIdx.x : 0);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = 0.0;
-    for (unsigned r = 0; r < cluster.num_blocks(); ++r) {
-        const double* rem = cluster.map_shared_rank(s_xch, r);
-#pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] += rem[i];
+        for (int i = 0; i < NV; ++i) {
+            double x = threadIdx.x < nb ? rem[i] : 0.0;
+            x = warp_sum(x);
+            if (threadIdx.x == 0) s_red[i] = x;
+        }
     }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = s_red[i];
+    __syncthreads();
 }
 
 // One PCG iteration's camera-vector work in ONE launch of one thread-block cluster, so that every
@@ -332,9 +342,10 @@ __device__ __forceinline__ void cluster_sum_det(cg::cluster_group& cluster, doub
 //   q = S p = d o y + reg p ; alpha = rho / p.q ; x += alpha p ; r -= alpha q ; z = Pinv r ;
 //   stop if ||r|| <= rtol ||b|| ; beta = r.z / rho ; p = z + beta p ; xt = d o p ; y <- 0
 // y holds this iteration's sum_i Jc_i^T (Jc_i xt - Jp_i z_p) from the MATVEC pass (all-reduced over ranks).
-// Up to kPcgCluster*kPcgThreads cameras: one camera per thread, every operand loaded up front (one
+// Launched as ONE thread-block cluster: 1 CTA for <= 256 cameras, else kPcgCluster CTAs (runtime cluster
+// dimension).  Up to cluster*kPcgThreads cameras: one camera per thread, every operand loaded up front (one
 // memory round trip); more cameras: a strided loop with q and z kept in global memory.
-__global__ void __cluster_dims__(kPcgCluster, 1, 1) __launch_bounds__(kPcgThreads)
+__global__ void __launch_bounds__(kPcgThreads)
 pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int parity, unsigned long long seq) {
     cg::cluster_group cluster = cg::this_cluster();
     if (P.flags[0]) return;   // uniform over the cluster: flags are only written by the previous launch
@@ -342,7 +353,7 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int 
     __shared__ double s_xa[2], s_xb[2];
     const int tid = threadIdx.x;
     const int gtid = (int)cluster.block_rank() * kPcgThreads + tid;
-    const int nthr = kPcgCluster * kPcgThreads;
+    const int nthr = (int)cluster.num_blocks() * kPcgThreads;
     const bool lead = gtid == 0;
     double rho, b2;
     int done = 0;
@@ -532,6 +543,193 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int 
         }
     }
     cluster.sync();   // no CTA leaves while its exchange slots may still be read remotely
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pose-only adjustment (adjustPose, bundleAdjuster.py:214-243: points frozen, dense least_squares
+// with tr_solver='exact', x_scale=1).  With the points fixed J is block diagonal (one 2k x 6 block per
+// camera), so the SVD scipy takes of the whole J (trf.py:480-484) factorises per camera:
+// J_c^T J_c = V_c diag(lambda) V_c^T, s = sqrt(lambda), s*uf = V_c^T g_c.
+// ---------------------------------------------------------------------------------------------
+
+// per camera: cyclic Jacobi eigen-decomposition of the 6x6 block; lam[6], suf[6] = V^T g, V[36] (columns)
+__global__ void __launch_bounds__(128) pose_eig_kernel(const double* __restrict__ U, const double* __restrict__ g,
+                                                       double* __restrict__ lam, double* __restrict__ suf,
+                                                       double* __restrict__ Vout, int n_cams) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cams) return;
+    double A[6][6], V[6][6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            A[a][b] = U[c * 21 + (a <= b ? tri6(a, b) : tri6(b, a))];
+            V[a][b] = a == b ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = 0, diag = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            diag += A[a][a] * A[a][a];
+#pragma unroll
+            for (int b = a + 1; b < 6; ++b) off += A[a][b] * A[a][b];
+        }
+        if (off <= 1e-34 * diag) break;
+#pragma unroll
+        for (int p = 0; p < 5; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 6; ++q) {
+                const double apq = A[p][q];
+                if (apq != 0.0) {
+                    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                    const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const double akp = A[k][p], akq = A[k][q];
+                        A[k][p] = cs * akp - sn * akq;
+                        A[k][q] = sn * akp + cs * akq;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const double apk = A[p][k], aqk = A[q][k];
+                        A[p][k] = cs * apk - sn * aqk;
+                        A[q][k] = sn * apk + cs * aqk;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const double vkp = V[k][p], vkq = V[k][q];
+                        V[k][p] = cs * vkp - sn * vkq;
+                        V[k][q] = sn * vkp + cs * vkq;
+                    }
+                }
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        lam[c * 6 + k] = fmax(A[k][k], 0.0);
+        double sv = 0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            sv += V[j][k] * g[c * 6 + j];
+            Vout[c * 36 + j * 6 + k] = V[j][k];
+        }
+        suf[c * 6 + k] = sv;
+    }
+}
+
+// results of pose_tr_kernel in the scalar array
+enum PoseScal { PS_ALPHA = S_DOT0, PS_NITER = S_DOT1, PS_PRED = S_DOT2, PS_STEPNORM = S_DOT3, PS_GNORM = S_DOT4 };
+
+// One CTA: scipy's solve_lsq_trust_region (common.py:106-164) on the n = 6*Nc (lambda, suf) pairs:
+// Gauss-Newton step if it is inside the radius, else More's root-finding for alpha with
+// ||p(alpha)|| = Delta, p = -V (suf / (lambda + alpha)), rescaled onto the boundary.  Writes the step
+// coefficients w in the eigenbasis, alpha, the iteration count, the predicted reduction
+// -(0.5 p^T H p + g^T p) and ||p||.
+__global__ void __launch_bounds__(256) pose_tr_kernel(const double* __restrict__ lam, const double* __restrict__ suf,
+                                                      double* __restrict__ w, int n, double m_rows, double Delta,
+                                                      double alpha_in, double* __restrict__ scal) {
+    __shared__ double s_red[32];
+    const int tid = threadIdx.x;
+    auto bsum = [&](double v) { return block_sum_det(v, s_red); };
+    auto bmax = [&](double v) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, off));
+        __syncthreads();
+        if ((tid & 31) == 0) s_red[tid >> 5] = v;
+        __syncthreads();
+        double t = s_red[0];
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) t = fmax(t, s_red[i]);
+        return t;
+    };
+    double lmax = 0, lmin_neg = -1e300, suf2 = 0, gn2 = 0, d0 = 0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double l = lam[i], sf = suf[i];
+        lmax = fmax(lmax, l);
+        lmin_neg = fmax(lmin_neg, -l);
+        suf2 += sf * sf;
+        if (l > 0) {
+            gn2 += sf * sf / (l * l);
+            d0 += sf * sf / (l * l * l);
+        }
+    }
+    lmax = bmax(lmax);
+    const double lmin = -bmax(lmin_neg);
+    suf2 = bsum(suf2);
+    gn2 = bsum(gn2);
+    d0 = bsum(d0);
+    const double EPS = 2.220446049250313e-16;
+    const bool full_rank = m_rows >= n && sqrt(lmin) > EPS * m_rows * sqrt(lmax);
+    double alpha = 0.0, scale = 1.0;
+    int n_iter = 0;
+    if (!(full_rank && sqrt(gn2) <= Delta)) {
+        double alpha_upper = sqrt(suf2) / Delta;
+        double alpha_lower = 0.0;
+        if (full_rank) {
+            const double pn = sqrt(gn2);
+            alpha_lower = -(pn - Delta) / (-d0 / pn);
+        }
+        if (!full_rank && alpha_in == 0.0) alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
+        else alpha = alpha_in;
+        for (int it = 0; it < 10; ++it) {
+            if (alpha < alpha_lower || alpha > alpha_upper) alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
+            double a2 = 0, a3 = 0;
+            for (int i = tid; i < n; i += blockDim.x) {
+                const double dn = lam[i] + alpha, sf = suf[i];
+                a2 += sf * sf / (dn * dn);
+                a3 += sf * sf / (dn * dn * dn);
+            }
+            a2 = bsum(a2);
+            a3 = bsum(a3);
+            const double pn = sqrt(a2);
+            const double phi = pn - Delta, phi_prime = -a3 / pn;
+            if (phi < 0) alpha_upper = alpha;
+            const double ratio = phi / phi_prime;
+            alpha_lower = fmax(alpha_lower, alpha - ratio);
+            alpha -= (phi + Delta) * ratio / Delta;
+            n_iter = it + 1;
+            if (fabs(phi) < 0.01 * Delta) break;
+        }
+        double pn2 = 0;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const double v = suf[i] / (lam[i] + alpha);
+            pn2 += v * v;
+        }
+        pn2 = bsum(pn2);
+        scale = Delta / sqrt(pn2);
+    }
+    double pred = 0, wn2 = 0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double l = lam[i], sf = suf[i];
+        const double wi = -scale * sf / (l + alpha);
+        w[i] = wi;
+        pred += 0.5 * l * wi * wi + sf * wi;
+        wn2 += wi * wi;
+    }
+    pred = bsum(pred);
+    wn2 = bsum(wn2);
+    if (tid == 0) {
+        scal[PS_ALPHA] = alpha;
+        scal[PS_NITER] = (double)n_iter;
+        scal[PS_PRED] = -pred;
+        scal[PS_STEPNORM] = sqrt(wn2);
+    }
+}
+
+// x_new (cameras) = x + V w ; the frozen points are copied
+__global__ void pose_step_kernel(const double* __restrict__ x, const double* __restrict__ V, const double* __restrict__ w,
+                                 double* __restrict__ xn, int n_cams, int64_t n_total) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_total) return;
+    if (e >= 6 * (int64_t)n_cams) {
+        xn[e] = x[e];
+        return;
+    }
+    const int c = (int)(e / 6), j = (int)(e - 6 * c);
+    double p = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) p += V[c * 36 + j * 6 + k] * w[c * 6 + k];
+    xn[e] = x[e] + p;
 }
 
 // Reference point for the roofline: a plain grid-stride LDG.128 read of n doubles (what a trivial

@@ -165,6 +165,47 @@ def adjust_points(extrinsics, camera_matrix, points_3d, points_2d, frame_indices
 
 
 # ----------------------------------------------------------------------------------------------
+# the pose-only path (bundleAdjuster.py:197-243)
+# ----------------------------------------------------------------------------------------------
+
+def board_points(pattern_size):
+    """Chessboard of adjustPose: 4x3 grid times 2 in the x-z plane, float32 (bundleAdjuster.py:220-223)."""
+    pts = np.zeros((pattern_size, 3), np.float32)
+    grid = np.mgrid[0:4, 0:3].T.reshape(-1, 2) * 2
+    pts[:, 0] = grid[:, 0]
+    pts[:, 2] = grid[:, 1]
+    return pts
+
+
+def pose_residuals(x, camera_matrix, n_frames, frame_indices, point_indices, points_3d, points_2d):
+    """poseFun (bundleAdjuster.py:206-211)."""
+    cams = x.reshape(n_frames, 6)
+    uv = project(points_3d[point_indices], cams[frame_indices], camera_matrix)
+    return (uv - points_2d).ravel()
+
+
+def solve_pose_reference_path(extrinsics, camera_matrix, points_2d, verbose=0, record=None):
+    """CPU restatement of ``adjustPose`` (bundleAdjuster.py:214-243): dense
+    ``least_squares(poseFun, parameters, ftol=1e-4)`` -> trf, 2-point dense finite differences,
+    tr_solver='exact', x_scale=1.  Returns the scipy result."""
+    from scipy.optimize import least_squares
+
+    ext = np.asarray(extrinsics, dtype=np.float64)
+    n_frames = len(ext)
+    pattern = int(len(points_2d) / n_frames)
+    pts = board_points(pattern)
+    fi = np.repeat(np.arange(n_frames), pattern)
+    pi = np.repeat([np.arange(pattern)], n_frames, axis=0).reshape(pattern * n_frames)
+
+    def on_iter(intermediate_result):
+        if record is not None:
+            record.append(float(intermediate_result.cost))
+
+    return least_squares(pose_residuals, frame_parameters(ext), verbose=verbose, ftol=1e-4, callback=on_iter,
+                         args=(camera_matrix, n_frames, fi, pi, pts, points_2d))
+
+
+# ----------------------------------------------------------------------------------------------
 # Jacobian blocks
 # ----------------------------------------------------------------------------------------------
 

@@ -21,7 +21,7 @@ Parity status: pinned against the reference's cost trajectory on the committed g
 from __future__ import annotations
 
 import numpy as np
-from scipy.optimize._lsq.common import (check_termination, minimize_quadratic_1d,
+from scipy.optimize._lsq.common import (check_termination, minimize_quadratic_1d, solve_lsq_trust_region,
                                         solve_trust_region_2d, update_tr_radius)
 
 from . import ba_oracle as ba
@@ -213,3 +213,79 @@ def solve(x0, K, Nc, Np, fi, pi, uv, ftol=1e-4, xtol=1e-8, gtol=1e-8, max_nfev=N
         status = 0
     return dict(x=x, cost=cost, fun=lin.r, nfev=nfev, njev=njev, nit=nit, status=status,
                 optimality=g_norm, log=log)
+
+
+def solve_pose(x0, K, Nc, fi, pts_obs, uv, ftol=1e-4, xtol=1e-8, gtol=1e-8, max_nfev=None, record=None):
+    """Pose-only TRF with the exact trust-region step (trf.py:415-587 with tr_solver='exact', x_scale=1;
+    the reference reaches it from adjustPose, bundleAdjuster.py:232-241) and the analytic camera
+    blocks.  ``pts_obs`` (No,3) are the constant 3-D points of the observations.  The dense SVD and
+    ``solve_lsq_trust_region`` are scipy's own."""
+    n_obs = len(fi)
+    pi = np.arange(n_obs)
+
+    def lin(xc):
+        x = np.hstack((xc, pts_obs.reshape(-1)))
+        r = ba.residuals(x, K, Nc, n_obs, fi, pi, uv)
+        Jc, _ = ba.jacobian_blocks(x, K, Nc, n_obs, fi, pi)
+        J = np.zeros((2 * n_obs, 6 * Nc))
+        rows = np.arange(n_obs)
+        for a in range(2):
+            for k in range(6):
+                J[2 * rows + a, 6 * fi + k] = Jc[:, a, k]
+        return r, J
+
+    x = np.array(x0, dtype=np.float64)
+    f, J = lin(x)
+    if not np.all(np.isfinite(f)):
+        raise ValueError("Residuals are not finite in the initial point.")
+    m, n = J.shape
+    nfev = njev = 1
+    cost = 0.5 * float(f @ f)
+    g = J.T @ f
+    Delta = np.linalg.norm(x)
+    if Delta == 0:
+        Delta = 1.0
+    if max_nfev is None:
+        max_nfev = x.size * 100
+    alpha = 0.0
+    status = None
+    nit = 0
+    while True:
+        g_norm = np.abs(g).max()
+        if g_norm < gtol:
+            status = 1
+        if status is not None or nfev == max_nfev:
+            break
+        U, s, Vt = np.linalg.svd(J, full_matrices=False)
+        V = Vt.T
+        uf = U.T @ f
+        actual = -1
+        while actual <= 0 and nfev < max_nfev:
+            step, alpha, _ = solve_lsq_trust_region(n, m, uf, s, V, Delta, initial_alpha=alpha)
+            Js = J @ step
+            predicted = -(0.5 * float(Js @ Js) + float(g @ step))
+            x_new = x + step
+            f_new, J_new = lin(x_new)
+            nfev += 1
+            step_norm = np.linalg.norm(step)
+            if not np.all(np.isfinite(f_new)):
+                Delta = 0.25 * step_norm
+                continue
+            cost_new = 0.5 * float(f_new @ f_new)
+            actual = cost - cost_new
+            Delta_new, ratio = update_tr_radius(Delta, actual, predicted, step_norm, step_norm > 0.95 * Delta)
+            status = check_termination(actual, cost, step_norm, np.linalg.norm(x), ratio, ftol, xtol)
+            if status is not None:
+                break
+            alpha *= Delta / Delta_new
+            Delta = Delta_new
+        if actual > 0:
+            x, f, J, cost = x_new, f_new, J_new, cost_new
+            g = J.T @ f
+            njev += 1
+        nit += 1
+        if record is not None:
+            record.append(cost)
+    if status is None:
+        status = 0
+    return dict(x=x, cost=cost, fun=f, nfev=nfev, njev=njev, nit=nit, status=status, optimality=g_norm)

@@ -26,6 +26,11 @@ def golden_c1():
 
 
 @pytest.fixture(scope="session")
+def golden_pose():
+    return dict(np.load(os.path.join(GOLDEN, "pose.npz")))
+
+
+@pytest.fixture(scope="session")
 def golden_mid():
     return dict(np.load(os.path.join(GOLDEN, "mid.npz")))
 

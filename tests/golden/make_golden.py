@@ -13,6 +13,8 @@ Files
   c1.npz      BASELINE configs[0] (20 / 2 000 / 40 000, seed 1, hard init): reference cost
               trajectory, nfev, final cost / optimality, final points checksum, LSMR iterations.
   mid.npz     Nc=60, Np=1500, No=9000 sparse-visibility problem: same scalars.
+  pose.npz    adjustPose (pose-only, dense least_squares) on a 9-frame synthetic chessboard sequence:
+              inputs, poseFun at x0, per-iteration costs, final parameters and returned 3x4 matrices.
 """
 import contextlib
 import io
@@ -155,5 +157,44 @@ def main():
         print(name, costs, res.nfev, res.status, rms, lsmr_its)
 
 
+def pose_golden():
+    """adjustPose of the unmodified reference on a synthetic chessboard sequence -> pose.npz."""
+    rng = np.random.default_rng(23)
+    n_frames = 9
+    K = np.array([[950.0, 0, 320.0], [0, 940.0, 240.0], [0, 0, 1.0]])
+    board = np.zeros((12, 3), np.float32)
+    grid = np.mgrid[0:4, 0:3].T.reshape(-1, 2) * 2
+    board[:, 0] = grid[:, 0]
+    board[:, 2] = grid[:, 1]
+    ext = np.zeros((n_frames, 3, 4))
+    for c in range(n_frames):
+        w = rng.normal(0, 0.3, 3) + np.array([0.9, 0.0, 0.0])     # look down at the x-z plane
+        th = np.linalg.norm(w)
+        k = w / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        ext[c, :, :3] = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+        ext[c, :, 3] = np.array([-3.0, -1.0, 14.0]) + rng.normal(0, 0.8, 3)
+    params = ref.frameParameters(ext).reshape(n_frames, 6)
+    fi = np.repeat(np.arange(n_frames), 12)
+    pi = np.tile(np.arange(12), n_frames)
+    uv = ref.project(board[pi].astype(np.float64), params[fi], K) + rng.normal(0, 0.3, (len(fi), 2))
+    ext0 = ext.copy()
+    ext0[:, :, 3] += rng.normal(0, 0.4, (n_frames, 3))
+    costs = []
+    x0 = ref.frameParameters(ext0)
+    res = least_squares(ref.poseFun, x0, verbose=0, ftol=1e-4,
+                        args=(K, n_frames, fi, pi, board, uv),
+                        callback=lambda intermediate_result: costs.append(float(intermediate_result.cost)))
+    f0 = ref.poseFun(x0, K, n_frames, fi, pi, board, uv)
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = ref.adjustPose(ext0, K, uv)
+    np.savez_compressed(os.path.join(HERE, "pose.npz"), ext0=ext0, K=K, uv=uv, x0=x0, f0=f0,
+                        ref_costs=np.array([0.5 * f0 @ f0] + costs), ref_x=res.x, ref_cost=res.cost, ref_nfev=res.nfev,
+                        ref_status=res.status, ref_optimality=res.optimality, adj_extrinsics=np.array(out),
+                        versions=np.array([np.__version__, scipy.__version__]))
+    print("pose:", np.array([0.5 * f0 @ f0] + costs), res.nfev, res.status)
+
+
 if __name__ == "__main__":
     main()
+    pose_golden()

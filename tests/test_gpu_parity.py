@@ -235,3 +235,63 @@ def test_full_size_config2_properties():
     assert 0.5 * float(res.fun @ res.fun) == pytest.approx(res.cost, rel=1e-12)
     rms = np.sqrt(np.mean(np.sum(res.fun.reshape(-1, 2) ** 2, axis=1)))
     assert 0.6 < rms < 0.8                     # 0.5 px noise per coordinate -> ~0.7 px
+
+
+# ---- pose-only adjustment (adjustPose) ----------------------------------------------
+
+def test_adjust_pose_vs_reference_golden(golden_pose, capsys):
+    g = golden_pose
+    n_frames = len(g["ext0"])
+    out = mm.adjustPose(g["ext0"], g["K"], g["uv"])
+    text = capsys.readouterr().out
+    assert "Iteration" in text and "termination condition is satisfied" in text
+    assert isinstance(out, list) and len(out) == n_frames and out[0].shape == (3, 4)
+    res = mm.last_result
+    costs = np.array([row["cost"] for row in res.log])
+    assert res.nfev == int(g["ref_nfev"]) and res.status == int(g["ref_status"]) and len(costs) == len(g["ref_costs"])
+    assert costs[0] == pytest.approx(g["ref_costs"][0], rel=1e-12)
+    np.testing.assert_allclose(costs, g["ref_costs"], rtol=1e-6)
+    assert res.cost == pytest.approx(float(g["ref_cost"]), rel=1e-6)
+    np.testing.assert_allclose(res.x, g["ref_x"], atol=1e-5)
+    np.testing.assert_allclose(np.array(out), g["adj_extrinsics"], atol=1e-5)
+
+
+def test_pose_solve_vs_oracle(golden_pose):
+    g = golden_pose
+    n_frames = len(g["ext0"])
+    fi = np.repeat(np.arange(n_frames), 12)
+    pi = np.tile(np.arange(12), n_frames)
+    board = ba.board_points(12)
+    rec = []
+    ref = schur_trf.solve_pose(g["x0"], g["K"], n_frames, fi, board[pi].astype(np.float64), g["uv"], record=rec)
+    res = mm.solve_pose(g["x0"], g["K"], n_frames, fi, pi, board, g["uv"], want_fun=True)
+    costs = [row["cost"] for row in res.log][1:]
+    assert res.nfev == ref["nfev"] and res.status == ref["status"] and len(costs) == len(rec)
+    np.testing.assert_allclose(costs, rec, rtol=1e-9)
+    np.testing.assert_allclose(res.x, ref["x"], atol=1e-8)
+    assert np.abs(res.fun - ref["fun"]).max() <= 1e-8
+    f = mm.poseFun(g["x0"], g["K"], n_frames, fi, pi, board, g["uv"])
+    assert np.abs(f - g["f0"]).max() <= 1e-9 * np.abs(g["uv"]).max()
+
+
+def test_pose_many_frames():
+    """More frames than one tile has slots per point: every board corner is seen by all 400 frames."""
+    rng = np.random.default_rng(3)
+    n_frames = 400
+    g_small = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "pose.npz"))
+    K = g_small["K"]
+    ext = np.repeat(g_small["ext0"][:1], n_frames, axis=0).copy()
+    ext[:, :, 3] += rng.normal(0, 0.5, (n_frames, 3))
+    board = ba.board_points(12).astype(np.float64)
+    fi = np.repeat(np.arange(n_frames), 12)
+    pi = np.tile(np.arange(12), n_frames)
+    params = mm.frameParameters(ext).reshape(n_frames, 6)
+    uv = ba.project(board[pi], params[fi], K) + rng.normal(0, 0.3, (len(fi), 2))
+    ext0 = ext.copy()
+    ext0[:, :, 3] += rng.normal(0, 0.2, (n_frames, 3))
+    x0 = mm.frameParameters(ext0)
+    ref = schur_trf.solve_pose(x0, K, n_frames, fi, board[pi], uv)
+    res = mm.solve_pose(x0, K, n_frames, fi, pi, board, uv)
+    assert res.nfev == ref["nfev"] and res.status == ref["status"]
+    assert res.cost == pytest.approx(ref["cost"], rel=1e-9)
+    np.testing.assert_allclose(res.x, ref["x"], atol=1e-7)

@@ -129,3 +129,41 @@ def test_block_sums_match_sparse_normal_equations(small):
         o = 6 * nc + 3 * p
         np.testing.assert_allclose(V[p], H[o:o + 3, o:o + 3], rtol=1e-12, atol=1e-9)
     np.testing.assert_allclose(np.hstack((gc.ravel(), gp.ravel())), g, rtol=1e-12, atol=1e-9)
+
+
+# ---- pose-only path (adjustPose) --------------------------------------------------------------
+
+def _pose_inputs(g):
+    n_frames = len(g["ext0"])
+    fi = np.repeat(np.arange(n_frames), 12)
+    pi = np.tile(np.arange(12), n_frames)
+    return n_frames, fi, pi, ba.board_points(12)
+
+
+def test_pose_residuals_vs_reference(golden_pose):
+    g = golden_pose
+    n_frames, fi, pi, board = _pose_inputs(g)
+    np.testing.assert_array_equal(ba.frame_parameters(g["ext0"]), g["x0"])
+    f = ba.pose_residuals(g["x0"], g["K"], n_frames, fi, pi, board, g["uv"])
+    assert np.abs(f - g["f0"]).max() <= 1e-12 * np.abs(g["uv"]).max()
+
+
+def test_pose_reference_path_restatement(golden_pose):
+    g = golden_pose
+    rec = []
+    res = ba.solve_pose_reference_path(g["ext0"], g["K"], g["uv"], record=rec)
+    assert res.nfev == int(g["ref_nfev"]) and res.status == int(g["ref_status"])
+    np.testing.assert_allclose(rec, g["ref_costs"][1:], rtol=1e-6)
+    np.testing.assert_allclose(res.x, g["ref_x"], atol=1e-5)
+
+
+def test_pose_trf_restatement_tracks_reference(golden_pose):
+    """Exact-step TRF with analytic blocks vs the reference's finite-difference run: same iteration
+    count, costs within 1e-6 (north_star bar)."""
+    g = golden_pose
+    n_frames, fi, pi, board = _pose_inputs(g)
+    rec = []
+    out = schur_trf.solve_pose(g["x0"], g["K"], n_frames, fi, board[pi].astype(np.float64), g["uv"], record=rec)
+    assert out["nfev"] == int(g["ref_nfev"]) and out["status"] == int(g["ref_status"])
+    np.testing.assert_allclose(rec, g["ref_costs"][1:], rtol=1e-6)
+    np.testing.assert_allclose(out["x"], g["ref_x"], atol=1e-5)

@@ -25,6 +25,7 @@ def main():
     ok = True
     for name, prob in (("windowed", synth.make_problem(40, 3000, 24000, seed=21, hard=True)),
                        ("random", synth.make_problem(60, 1500, 9000, seed=7, hard=True, windowed=False)),
+                       ("many-cameras", synth.make_problem(300, 900, 4000, seed=9, windowed=False)),   # cluster update path
                        ("c2-tenth", synth.make_config("C2", hard=True, scale=0.1))):
         ext, K, pts, uv, fi, pi = prob.args()
         nc, npts = len(ext), len(pts)
