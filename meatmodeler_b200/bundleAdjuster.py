@@ -72,15 +72,21 @@ def frameParameters(frame_extrinsic_matrices):
     return out.reshape(-1)
 
 
-def _rodrigues(rvec):
-    """Axis-angle vector -> 3x3 rotation (the matrix ``cv2.Rodrigues`` returns, bundleAdjuster.py:153)."""
-    w = np.asarray(rvec, dtype=np.float64).reshape(3)
-    t = math.sqrt(float(w @ w))
-    if t == 0.0:
-        return np.eye(3)
-    k = w / t
-    Kx = np.array([[0.0, -k[2], k[1]], [k[2], 0.0, -k[0]], [-k[1], k[0], 0.0]])
-    return math.cos(t) * np.eye(3) + math.sin(t) * Kx + (1.0 - math.cos(t)) * np.outer(k, k)
+def _rodrigues(rvecs):
+    """Axis-angle vectors (N,3) -> rotations (N,3,3): the matrices ``cv2.Rodrigues`` returns
+    (bundleAdjuster.py:153), all frames at once."""
+    w = np.asarray(rvecs, dtype=np.float64).reshape(-1, 3)
+    t = np.sqrt((w * w).sum(axis=1))
+    safe = np.where(t > 0, t, 1.0)
+    k = w / safe[:, None]
+    Kx = np.zeros((len(w), 3, 3))
+    Kx[:, 0, 1], Kx[:, 0, 2] = -k[:, 2], k[:, 1]
+    Kx[:, 1, 0], Kx[:, 1, 2] = k[:, 2], -k[:, 0]
+    Kx[:, 2, 0], Kx[:, 2, 1] = -k[:, 1], k[:, 0]
+    c, s_ = np.cos(t)[:, None, None], np.sin(t)[:, None, None]
+    R = c * np.eye(3)[None] + s_ * Kx + (1.0 - c) * (k[:, :, None] * k[:, None, :])
+    R[t == 0] = np.eye(3)
+    return R
 
 
 def reformatPointResult(result, n_frames, n_points):
@@ -88,13 +94,11 @@ def reformatPointResult(result, n_frames, n_points):
     x = np.asarray(result.x)
     points = x[n_frames * 6:].reshape((n_points, 3))
     frames = x[:n_frames * 6].reshape((n_frames, 6))
-    extrinsics = []
-    for row in frames:
-        m = np.eye(4)
-        m[:3, :3] = _rodrigues(row[:3])
-        m[:3, 3] = row[3:]
-        extrinsics.append(m)
-    return points, extrinsics
+    ext = np.zeros((n_frames, 4, 4))
+    ext[:, :3, :3] = _rodrigues(frames[:, :3])
+    ext[:, :3, 3] = frames[:, 3:]
+    ext[:, 3, 3] = 1.0
+    return points, list(ext)
 
 
 def pointAdjustmentSparsity(n_frames, n_points, frame_indices, point_indices):
@@ -252,7 +256,7 @@ def solve(parameters, camera_matrix, n_frames, n_points, frame_indices, point_in
 def reformatPoseResult(result, n_frames):
     """``result.x`` (6 per frame) -> list of n_frames 3x4 extrinsics  (bundleAdjuster.py:197-203)."""
     frames = np.asarray(result.x)[:n_frames * 6].reshape((n_frames, 6))
-    return [np.hstack((_rodrigues(row[:3]), row[3:].reshape(3, 1))) for row in frames]
+    return list(np.concatenate((_rodrigues(frames[:, :3]), frames[:, 3:, None]), axis=2))
 
 
 def _board_points(pattern_size):

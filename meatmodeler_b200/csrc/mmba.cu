@@ -1219,15 +1219,16 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
         TRY(upload(h, d.meta, pl.meta));
         TRY(upload(h, d.tile_cams, pl.tile_cams));
         std::vector<double> uvs(2 * (size_t)h->ns, 0.0);
-#pragma omp parallel for schedule(static, 4096)
-        for (int64_t s = 0; s < h->ns; ++s) {
-            const int64_t ob = pl.slot_obs[s];
-            if (ob >= 0) {
-                const int64_t t = s / kT, j = s % kT;
-                uvs[(t * 2) * kT + j] = uv[2 * ob];
-                uvs[(t * 2 + 1) * kT + j] = uv[2 * ob + 1];
+        parallel_ranges(h->ns, 65536, [&](int64_t s0, int64_t s1, int) {
+            for (int64_t s = s0; s < s1; ++s) {
+                const int64_t ob = pl.slot_obs[s];
+                if (ob >= 0) {
+                    const int64_t t = s / kT, j = s % kT;
+                    uvs[(t * 2) * kT + j] = uv[2 * ob];
+                    uvs[(t * 2 + 1) * kT + j] = uv[2 * ob + 1];
+                }
             }
-        }
+        });
         TRY(upload(h, d.uv, uvs));
         CU(cudaStreamSynchronize(h->stream));
     }

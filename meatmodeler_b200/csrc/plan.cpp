@@ -89,22 +89,23 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
             const int64_t q = (int64_t)point_inv[pt_idx[i]] - plan.pt_begin;
             if (q >= 0 && q < npl) grouped[fill[q]++] = i;
         }
-#pragma omp parallel for schedule(static, 1024)
-        for (int64_t q = 0; q < npl; ++q) {
-            // tracks are short: insertion sort (stable), usually already ascending
-            int64_t* g = grouped.data() + start[q];
-            const int64_t L = start[q + 1] - start[q];
-            for (int64_t a = 1; a < L; ++a) {
-                const int64_t v = g[a];
-                const int64_t cv = cam_idx[v];
-                int64_t b = a;
-                while (b > 0 && cam_idx[g[b - 1]] > cv) {
-                    g[b] = g[b - 1];
-                    --b;
+        parallel_ranges(npl, 4096, [&](int64_t q0, int64_t q1, int) {
+            for (int64_t q = q0; q < q1; ++q) {
+                // tracks are short: insertion sort (stable), usually already ascending
+                int64_t* g = grouped.data() + start[q];
+                const int64_t L = start[q + 1] - start[q];
+                for (int64_t a = 1; a < L; ++a) {
+                    const int64_t v = g[a];
+                    const int64_t cv = cam_idx[v];
+                    int64_t b = a;
+                    while (b > 0 && cam_idx[g[b - 1]] > cv) {
+                        g[b] = g[b - 1];
+                        --b;
+                    }
+                    g[b] = v;
                 }
-                g[b] = v;
             }
-        }
+        });
     }
 
     // 5. greedy point-aligned tiles
@@ -136,14 +137,13 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
 
     // 6. per tile: local camera table, local slots, camera-sorted order (tiles are independent)
     std::vector<std::vector<int32_t>> cams_of(plan.n_tiles);
-    int max_cams = 0, max_pts = 0;
-#pragma omp parallel reduction(max : max_cams, max_pts)
-    {
+    int max_cams_w[8] = {0}, max_pts_w[8] = {0};
+    parallel_ranges(plan.n_tiles, 256, [&](int64_t t0, int64_t t1, int worker) {
         std::vector<int32_t> stamp(n_cams, -1), local_of(n_cams, 0);
         std::vector<uint16_t> idx(kTileObs);
         uint16_t cnt[kTileObs + 1];
-#pragma omp for schedule(static, 64)
-        for (int64_t t = 0; t < plan.n_tiles; ++t) {
+        int max_cams = 0, max_pts = 0;
+        for (int64_t t = t0; t < t1; ++t) {
             const Range rg = ranges[t];
             const int64_t o0 = start[rg.p0], o1 = start[rg.p1];
             const int n = (int)(o1 - o0);
@@ -199,9 +199,13 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
             }
             m.nruns = nruns;
         }
+        max_cams_w[worker] = max_cams;
+        max_pts_w[worker] = max_pts;
+    });
+    for (int w = 0; w < 8; ++w) {
+        plan.max_tile_cams = std::max(plan.max_tile_cams, max_cams_w[w]);
+        plan.max_tile_pts = std::max(plan.max_tile_pts, max_pts_w[w]);
     }
-    plan.max_tile_cams = max_cams;
-    plan.max_tile_pts = max_pts;
     plan.cam_stride = std::max(4, (plan.max_tile_cams + 3) / 4 * 4);
     plan.tile_cams.assign((size_t)plan.n_tiles * plan.cam_stride, -1);
     for (int64_t t = 0; t < plan.n_tiles; ++t)

@@ -5,7 +5,9 @@
 // kernels want.  Pure C++ (no CUDA) so that the CPU test-suite covers it.
 #pragma once
 #include <cstdint>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace mmba {
@@ -48,6 +50,27 @@ struct Plan {
 
     int64_t n_points_local() const { return pt_end - pt_begin; }
 };
+
+// Static-chunked parallel loop over [0, n) on short-lived std::threads (at most 8): fn(begin, end, worker).
+// No thread pool is left spinning between calls (an OpenMP runtime's idle workers were measured to slow
+// the surrounding CUDA calls by several times).
+template <typename F>
+inline void parallel_ranges(int64_t n, int64_t min_chunk, F&& fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int64_t workers = std::min<int64_t>(std::max(1u, std::min(8u, hw ? hw / 2 : 1u)), std::max<int64_t>(1, n / std::max<int64_t>(1, min_chunk)));
+    if (workers <= 1) {
+        fn((int64_t)0, n, 0);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const int64_t step = (n + workers - 1) / workers;
+    for (int64_t w = 0; w < workers; ++w) {
+        const int64_t b = w * step, e = std::min(n, b + step);
+        if (b >= e) break;
+        pool.emplace_back([&fn, b, e, w]() { fn(b, e, (int)w); });
+    }
+    for (auto& t : pool) t.join();
+}
 
 // Returns 0 or a negative MMBA_ERR_* code; `err` receives the message.
 int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, const int64_t* cam_idx,
