@@ -36,6 +36,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pcg.cuh"
 #include "plan.h"
 
 namespace mmba {
@@ -322,14 +323,6 @@ __device__ __forceinline__ void camera_scatter_round(const double (&v)[NV], doub
         else red_add(out1 + cam * stride1 + offset1 + (k - n0), sum);
     }
 }
-
-// packed upper-triangle index helpers for 6x6 (21) and 3x3 (6)
-__host__ __device__ constexpr int tri6(int a, int b) { return a * 6 - a * (a - 1) / 2 + (b - a); }
-__host__ __device__ constexpr int tri3(int a, int b) { return a * 3 - a * (a - 1) / 2 + (b - a); }
-__host__ __device__ constexpr int tri6_row(int idx) {
-    return idx < 6 ? 0 : idx < 11 ? 1 : idx < 15 ? 2 : idx < 18 ? 3 : idx < 20 ? 4 : 5;
-}
-__host__ __device__ constexpr int tri6_col(int idx) { return idx - tri6(tri6_row(idx), tri6_row(idx)) + tri6_row(idx); }
 
 // ---------------------------------------------------------------------------------------------
 // K0: per-camera rotation tables  (rotate's trigonometry, bundleAdjuster.py:16-26, hoisted from
