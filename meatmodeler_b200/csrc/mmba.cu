@@ -148,7 +148,7 @@ struct mmba_handle {
     int64_t Nc = 0, npl = 0, ns = 0, nt = 0, nloc = 0;
     double K[9];
     void* arena = nullptr;
-    size_t arena_bytes = 0;
+    size_t arena_bytes = 0, arena_cap = 0;
     Dev d;
     TileArgs targs;
     int sm_count = 148;
@@ -409,9 +409,9 @@ int xchg_setup(mmba_handle* h) {
     return MMBA_OK;
 }
 
+// The device arena survives a change of problem (mmba_set_problem reuses it when it is large enough):
+// repeated adjustPoints calls do not pay cudaFree/cudaMalloc of hundreds of MB each time.
 void release_problem(mmba_handle* h) {
-    if (h->arena) cudaFree(h->arena);
-    h->arena = nullptr;
     h->has_problem = false;
 }
 
@@ -1162,6 +1162,8 @@ void mmba_destroy(mmba_handle* h) {
     cudaSetDevice(h->opt.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     release_problem(h);
+    if (h->arena) cudaFree(h->arena);
+    h->arena = nullptr;
     xchg_release(h);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->comm) g_nccl.CommDestroy(h->comm);
@@ -1194,13 +1196,20 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
 
     Arena measure;
     carve(h, measure);
-    h->arena_bytes = measure.off + 256;
-    cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
-    if (e != cudaSuccess) {
+    const size_t need = measure.off + 256;
+    if (!h->arena || h->arena_cap < need) {
+        if (h->arena) cudaFree(h->arena);
         h->arena = nullptr;
-        return fail(h, MMBA_ERR_NOMEM, "set_problem: cudaMalloc of " + std::to_string(h->arena_bytes) + " bytes failed: " +
-                                           cudaGetErrorString(e));
+        h->arena_cap = 0;
+        cudaError_t e = cudaMalloc(&h->arena, need);
+        if (e != cudaSuccess) {
+            h->arena = nullptr;
+            return fail(h, MMBA_ERR_NOMEM, "set_problem: cudaMalloc of " + std::to_string(need) + " bytes failed: " +
+                                               cudaGetErrorString(e));
+        }
+        h->arena_cap = need;
     }
+    h->arena_bytes = need;
     Arena a;
     a.base = static_cast<char*>(h->arena);
     carve(h, a);

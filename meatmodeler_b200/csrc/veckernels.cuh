@@ -294,8 +294,14 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int 
     if (P.n_cams <= nthr) {
         const int c = gtid;
         const bool live = c < P.n_cams;
-        double pv[6], yv[6], si[6], rv[6], xv[6], Pi[21];
+        // register-lean: the 6x6 preconditioner block is prefetched into L1 and read when needed
+        double pv[6], yv[6], si[6], rv[6], xv[6];
         if (live) {
+            const char* pin = reinterpret_cast<const char*>(P.Pinv + c * 21);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pin));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pin + 64));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pin + 128));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pin + 160));
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 pv[k] = P.p[c * 6 + k];
@@ -310,8 +316,6 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int 
                 rv[k] = P.r[c * 6 + k];
                 xv[k] = P.x[c * 6 + k];
             }
-#pragma unroll
-            for (int i = 0; i < 21; ++i) Pi[i] = P.Pinv[c * 21 + i];
         }
         if (it == 0) {
             rho = sum_partials(P.part + P_RHO0 * kMaxCamBlocks, nb_init, s_red);
@@ -340,7 +344,7 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int 
                 xv[k] += alpha * pv[k];
                 rv[k] -= alpha * q[k];
             }
-            sym6_matvec(Pi, rv, z);
+            sym6_matvec(P.Pinv + c * 21, rv, z);
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 P.x[c * 6 + k] = xv[k];
