@@ -77,9 +77,10 @@ __host__ __device__ constexpr bool is_project(int m) { return is_build(m) || m =
 template <int MODE>
 struct Traits {
     static constexpr bool kLoadJ = !is_project(MODE);
-    // J-streaming tiles are 39 KB: two stages per CTA, two CTAs per SM.  The residual-only pass moves
-    // 7 KB per tile, so its per-tile latency chain needs more tiles in flight.
-    static constexpr int kStages = (MODE == M_RESID || MODE == M_RESID_STORE) ? 4 : 2;
+    // J-streaming tiles are 39 KB: two stages per CTA, two CTAs per SM.  The projection passes (BUILD, RESID)
+    // stage only 7-13 KB per tile but gather 12-21 doubles per camera, so their per-tile latency chains need
+    // more tiles (and producer warps) in flight.
+    static constexpr int kStages = is_project(MODE) ? 4 : 2;
     static constexpr int kThreads = kConsumers + 32 * kStages;
     static constexpr bool kLoadUV = !kLoadJ;
     // doubles gathered per camera into shared memory, and the (odd, conflict-free) smem stride

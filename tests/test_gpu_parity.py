@@ -295,3 +295,28 @@ def test_pose_many_frames():
     assert res.nfev == ref["nfev"] and res.status == ref["status"]
     assert res.cost == pytest.approx(ref["cost"], rel=1e-9)
     np.testing.assert_allclose(res.x, ref["x"], atol=1e-7)
+
+
+# ---- size-independent properties at BASELINE sizes ----------------------------------------------
+
+def test_noise_free_problem_is_solved_to_zero_residual():
+    """Round trip: observations generated without noise from the true cameras/points, solve from a
+    perturbed start -> the reprojection error must vanish (gauge freedom leaves x itself free)."""
+    prob = synth.make_problem(200, 5000, 100_000, seed=12, noise_px=0.0, hard=False)
+    res = _solve(prob, max_nfev=60)
+    assert res.cost < 1e-9 * res.initial_cost
+    rms = np.sqrt(np.mean(np.sum(res.fun.reshape(-1, 2) ** 2, axis=1)))
+    assert rms < 1e-5
+
+
+def test_full_size_config4_properties():
+    """BASELINE configs[3] (1 778 cameras / 993 k points / 5 M observations) at full size: monotone cost,
+    returned residual vector reproduces the cost, RMS at the noise level, every tile slot accounted for."""
+    prob = synth.make_config("C4", hard=True)
+    res = _solve(prob)
+    costs = np.array([row["cost"] for row in res.log])
+    assert np.all(np.diff(costs) < 0) and res.status in (2, 4)
+    assert 0.5 * float(res.fun @ res.fun) == pytest.approx(res.cost, rel=1e-12)
+    rms = np.sqrt(np.mean(np.sum(res.fun.reshape(-1, 2) ** 2, axis=1)))
+    assert 0.55 < rms < 0.8
+    assert res.x.shape == (6 * 1778 + 3 * 993_000,) and np.all(np.isfinite(res.x))
