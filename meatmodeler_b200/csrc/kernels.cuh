@@ -47,6 +47,7 @@ constexpr int kMaxStages = 4;             // pipeline depth is per MODE (Traits:
 constexpr int kCamTab = 24;               // doubles per camera-table row in HBM
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint16_t kPadPt = 0xFFFF;
+constexpr int kProducerShare = 1024;      // gathered values per tile the producer warp stages itself
 constexpr int kJRows = 18;
 constexpr int kJTileBytes = kJRows * kT * 8;
 constexpr int kUVTileBytes = 2 * kT * 8;
@@ -578,18 +579,20 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
                 const int i = lane + 32 * u;
                 if (i < total) *dst_of(i) = vals[u];
             }
-            // tiles with more than kBatch*32 gathered values: the rest, batched the same way
-            for (int base = lane + 32 * kBatch; base < total; base += 32 * kBatch) {
+            // up to three more batches here (one memory round trip each, overlapped with the other stages'
+            // arithmetic); values beyond kProducerShare (tiles touching many cameras) are fetched cooperatively
+            // by the 256 consumer threads once the stage is full
+            for (int base = 32 * kBatch + lane; base < min(total, kProducerShare); base += 32 * kBatch) {
                 double v[kBatch];
 #pragma unroll
                 for (int u = 0; u < kBatch; ++u) {
                     const int i = base + 32 * u;
-                    v[u] = i < total ? __ldg(src_of(i, s_ids)) : 0.0;
+                    v[u] = i < min(total, kProducerShare) ? __ldg(src_of(i, s_ids)) : 0.0;
                 }
 #pragma unroll
                 for (int u = 0; u < kBatch; ++u) {
                     const int i = base + 32 * u;
-                    if (i < total) *dst_of(i) = v[u];
+                    if (i < min(total, kProducerShare)) *dst_of(i) = v[u];
                 }
             }
             __syncwarp();
@@ -626,6 +629,33 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
         const double* s_pb = reinterpret_cast<const double*>(st + L.off_pb);
         const int* s_camid = reinterpret_cast<const int*>(st + L.off_camid);
         const int pt0 = mt->pt0, npts = mt->npts;
+        {
+            // remainder of the tile's gathered operands (see the producer): index space
+            // (camera rows | point payload A | point payload B), entries >= kProducerShare
+            const int n_cam = mt->ncams * T::kCamRows, n_pa = npts * T::kPA, n_pb = npts * T::kPB;
+            const int total = n_cam + n_pa + n_pb;
+            if (total > kProducerShare) {
+                double* w_cv = reinterpret_cast<double*>(st + L.off_camvec);
+                double* w_pa = reinterpret_cast<double*>(st + L.off_pa);
+                double* w_pb = reinterpret_cast<double*>(st + L.off_pb);
+                for (int i = kProducerShare + tid; i < total; i += kConsumers) {
+                    if (i < n_cam) {
+                        const int c = i / (T::kCamRows ? T::kCamRows : 1), k = i - c * T::kCamRows;
+                        const int cam = s_camid[c];
+                        double v;
+                        if (is_project(MODE)) v = __ldg(P.cam0 + (int64_t)cam * kCamTab + k);
+                        else if (MODE == M_JV2) v = k < 6 ? __ldg(P.cam0 + (int64_t)cam * 6 + k) : __ldg(P.cam1 + (int64_t)cam * 6 + (k - 6));
+                        else v = __ldg(P.cam0 + (int64_t)cam * 6 + k);
+                        w_cv[c * T::kCamStride + k] = v;
+                    } else if (i < n_cam + n_pa) {
+                        w_pa[i - n_cam] = __ldg(P.ptA + (int64_t)pt0 * T::kPA + (i - n_cam));
+                    } else if (T::kPB) {
+                        w_pb[i - n_cam - n_pa] = __ldg(P.ptB + (int64_t)pt0 * T::kPB + (i - n_cam - n_pa));
+                    }
+                }
+                consumer_sync();
+            }
+        }
         const unsigned lp = mt->slot_pt[tid], lc = mt->slot_cam[tid];
         const bool valid = lp != kPadPt;
         const int lps = valid ? (int)lp : 0;
