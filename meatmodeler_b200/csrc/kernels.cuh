@@ -442,6 +442,8 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
     using T = Traits<MODE>;
     constexpr int kStages = T::kStages;
     constexpr int kThreads = T::kThreads;
+    // programmatic dependent launch: this grid may have been scheduled while its predecessor drains
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (MODE == M_MATVEC && P.done && *P.done) return;
     extern __shared__ __align__(128) unsigned char smem[];
     const SmemLayout L = smem_layout<MODE>(A.max_cams, A.max_pts, A.ytab_cams);

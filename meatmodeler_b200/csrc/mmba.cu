@@ -542,11 +542,27 @@ int cam_prep(mmba_handle* h, const double* x, double* camtab) {
     return MMBA_OK;
 }
 
+// `overlap`: programmatic dependent launch — the grid may be scheduled while the previous kernel in the
+// stream drains; every kernel starts with griddepcontrol.wait, so only the launch latency overlaps.
 template <int MODE>
-int launch_tile(mmba_handle* h, int cls, const ModeArgs& P) {
+int launch_tile(mmba_handle* h, int cls, const ModeArgs& P, bool overlap = false) {
     if (!h->nt) return MMBA_OK;
     prof_begin(h, cls);
-    tile_kernel<MODE><<<h->grid[MODE], Traits<MODE>::kThreads, h->smem[MODE], h->stream>>>(h->targs, P);
+    if (overlap) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(h->grid[MODE]);
+        cfg.blockDim = dim3(Traits<MODE>::kThreads);
+        cfg.dynamicSmemBytes = h->smem[MODE];
+        cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, tile_kernel<MODE>, h->targs, P));
+    } else {
+        tile_kernel<MODE><<<h->grid[MODE], Traits<MODE>::kThreads, h->smem[MODE], h->stream>>>(h->targs, P);
+    }
     prof_end(h, cls);
     return MMBA_OK;
 }
@@ -640,7 +656,7 @@ ModeArgs matvec_args(mmba_handle* h) {
 
 int schur_matvec(mmba_handle* h) {
     Dev& d = h->d;
-    TRY(launch_tile<M_MATVEC>(h, MMBA_K_MATVEC, matvec_args(h)));
+    TRY(launch_tile<M_MATVEC>(h, MMBA_K_MATVEC, matvec_args(h), !h->opt.profile));
     TRY(allreduce(h, {{d.y, (size_t)(6 * h->Nc), false}}));
     return MMBA_OK;
 }
@@ -693,7 +709,7 @@ int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
             unsigned long long seq = 0;
             if (h->xchg.on) {
                 // MATVEC + peer push; the all-reduce completes inside pcg_update
-                TRY(launch_tile<M_MATVEC>(h, MMBA_K_MATVEC, matvec_args(h)));
+                TRY(launch_tile<M_MATVEC>(h, MMBA_K_MATVEC, matvec_args(h), !h->opt.profile));
                 seq = ++h->xchg.seq;
                 parity = (int)(seq & 1);
             } else {
@@ -706,13 +722,15 @@ int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
                 cfg.blockDim = dim3(kPcgThreads);
                 cfg.dynamicSmemBytes = 0;
                 cfg.stream = h->stream;
-                cudaLaunchAttribute attr[1];
+                cudaLaunchAttribute attr[2];
                 attr[0].id = cudaLaunchAttributeClusterDimension;
                 attr[0].val.clusterDim.x = csize;
                 attr[0].val.clusterDim.y = 1;
                 attr[0].val.clusterDim.z = 1;
+                attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[1].val.programmaticStreamSerializationAllowed = 1;
                 cfg.attrs = attr;
-                cfg.numAttrs = 1;
+                cfg.numAttrs = h->opt.profile ? 1 : 2;   // profile mode brackets launches with events: no overlap
                 prof_begin(h, MMBA_K_VEC);
                 CU(cudaLaunchKernelEx(&cfg, pcg_update_kernel, P, reg, it, rtol2, camblocks, parity, seq));
                 prof_end(h, MMBA_K_VEC);

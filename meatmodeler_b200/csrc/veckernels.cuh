@@ -249,6 +249,7 @@ __device__ __forceinline__ void cluster_sum_det(cg::cluster_group& cluster, doub
 // memory round trip); more cameras: a strided loop with q and z kept in global memory.
 __global__ void __launch_bounds__(kPcgThreads)
 pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int parity, unsigned long long seq) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch (see launch_tile)
     cg::cluster_group cluster = cg::this_cluster();
     if (P.flags[0]) return;   // uniform over the cluster: flags are only written by the previous launch
     __shared__ double s_red[32];
