@@ -249,9 +249,11 @@ __device__ __forceinline__ void cluster_sum_det(cg::cluster_group& cluster, doub
 // memory round trip); more cameras: a strided loop with q and z kept in global memory.
 __global__ void __launch_bounds__(kPcgThreads)
 pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int parity, unsigned long long seq) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch (see launch_tile)
+    // Programmatic dependent launch (see launch_tile): this grid may be scheduled while the MATVEC pass still
+    // drains.  Everything written by the PREVIOUS update (flags, p, r, x, state) or earlier (sinv, Pinv) is
+    // complete by then and may be read at once; y and every store wait for griddepcontrol.wait below.
     cg::cluster_group cluster = cg::this_cluster();
-    if (P.flags[0]) return;   // uniform over the cluster: flags are only written by the previous launch
+    if (P.flags[0]) return;   // uniform over the cluster: flags are only written by the previous update
     __shared__ double s_red[32];
     __shared__ double s_xa[2], s_xb[2];
     const int tid = threadIdx.x;
@@ -262,7 +264,7 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int 
     int done = 0;
     const bool xchg = P.nranks > 1;
     const double* slots = nullptr;
-    if (xchg) {
+    auto exchange = [&]() {
         // One-shot all-reduce of the 6*Nc Schur product over NVLink peer memory, fused into this kernel
         // (replaces a per-iteration ncclAllReduce: 30+ us at 8 GPUs for this 10-100 KB message).
         // Push: every rank stores its partial y into slot [parity][rank] of EVERY rank's receive buffer
@@ -291,7 +293,7 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int 
         }
         __syncthreads();
         slots = P.xslots + (int64_t)parity * P.nranks * P.n6;
-    }
+    };
     if (P.n_cams <= nthr) {
         const int c = gtid;
         const bool live = c < P.n_cams;
@@ -306,13 +308,6 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int 
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 pv[k] = P.p[c * 6 + k];
-                if (xchg) {
-                    double acc = 0.0;
-                    for (int r = 0; r < P.nranks; ++r) acc += __ldcg(slots + (int64_t)r * P.n6 + c * 6 + k);
-                    yv[k] = acc;
-                } else {
-                    yv[k] = P.y[c * 6 + k];
-                }
                 si[k] = P.sinv[c * 6 + k];
                 rv[k] = P.r[c * 6 + k];
                 xv[k] = P.x[c * 6 + k];
@@ -324,6 +319,20 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int 
         } else {
             rho = P.state[0];
             b2 = P.state[1];
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // the MATVEC pass (and its memory) is complete
+        if (xchg) exchange();
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                if (xchg) {
+                    double acc = 0.0;
+                    for (int r = 0; r < P.nranks; ++r) acc += __ldcg(slots + (int64_t)r * P.n6 + c * 6 + k);
+                    yv[k] = acc;
+                } else {
+                    yv[k] = __ldcg(P.y + c * 6 + k);
+                }
+            }
         }
         double q[6], z[6];
         double s1[1] = {0};
@@ -385,6 +394,8 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int 
             rho = P.state[0];
             b2 = P.state[1];
         }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (xchg) exchange();
         double s1[1] = {0};
         for (int c = gtid; c < P.n_cams; c += nthr) {
 #pragma unroll
