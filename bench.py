@@ -108,7 +108,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_sample(n_gpus_label, seconds_target=15.0, scale=None):
+def cpu_reference_sample(scale=None):
     """The reference's CPU path on a bounded sample: C2 scaled down (all 200 cameras kept, points
     and observations x scale), full solve with the reference's least_squares arguments."""
     from threadpoolctl import threadpool_info
@@ -143,7 +143,7 @@ def run_reference(args):
     del prob
     samples = []
     for i in range(args.warmup + args.steps):
-        s = cpu_reference_sample(args.gpus, scale=args.ref_scale)
+        s = cpu_reference_sample(scale=args.ref_scale)
         if i >= args.warmup:
             samples.append(s)
     wall = sum(s["wall_s"] for s in samples)
@@ -317,7 +317,7 @@ def run_mmba(args):
             "gpu_launches": launches, "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = {k: v for k, v in cpu_reference_sample(1, scale=args.ref_scale).items()
+            line["cpu_baseline"] = {k: v for k, v in cpu_reference_sample(scale=args.ref_scale).items()
                                     if k not in ("wall_s", "lm_iterations", "cost", "n_obs")}
         print(json.dumps(line))
     if world > 1:

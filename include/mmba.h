@@ -161,6 +161,14 @@ int mmba_eval_jnorm2(mmba_handle* h, const double* x, const double* s, double* j
  * (CUDA events on the handle's stream); used by bench.py for the roofline of each kernel */
 int mmba_bench_kernel(mmba_handle* h, const double* x, int kernel_class, int iters, double* avg_ms);
 
+/* ---- batched two-view triangulation ----------------------------------------------
+ * replaces: the per-track cv2.triangulatePoints(projection1, projection2, feature, correspondent) loop of
+ * processor.triangulatePoints (processor.py:246-261).  projections: n_frames x 3 x 4 row-major; f1 / f2:
+ * frame of the first / last observation of each of the n tracks; uv1 / uv2: n x 2; points: n x 3
+ * (dehomogenised, as processor.py:259 does); kernel_ms (may be NULL): device time of the kernel. */
+int mmba_triangulate(int device, int64_t n_frames, const double* projections, int64_t n, const int64_t* f1,
+                     const int64_t* f2, const double* uv1, const double* uv2, double* points, double* kernel_ms);
+
 /* ---- host-only functions (no GPU needed; covered by the CPU test-suite) --------------------- */
 /* replaces: solve_trust_region_2d (common.py:171-219); B = [b00, b01, b11] */
 int mmba_host_tr2d(const double B[3], const double g[2], double delta, double p[2], int* newton);

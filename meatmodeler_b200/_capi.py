@@ -75,6 +75,7 @@ SIGNATURES = {
     "mmba_eval_gn_step": (C.c_int, [_H, _f64, _f64, C.c_double, _f64, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "mmba_eval_jnorm2": (C.c_int, [_H, _f64, _f64, C.POINTER(C.c_double)]),
     "mmba_bench_kernel": (C.c_int, [_H, _f64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "mmba_triangulate": (C.c_int, [C.c_int, C.c_int64, _f64, C.c_int64, _i64, _i64, _f64, _f64, _f64, C.POINTER(C.c_double)]),
     "mmba_host_tr2d": (C.c_int, [C.POINTER(C.c_double * 3), C.POINTER(C.c_double * 2), C.c_double,
                                  C.POINTER(C.c_double * 2), C.POINTER(C.c_int)]),
     "mmba_host_min_quadratic_1d": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_double,
@@ -277,6 +278,25 @@ class Engine:
         out = C.c_double()
         _check(lib().mmba_bench_kernel(self._h, self._x(x), int(kernel_class), int(iters), C.byref(out)), self._h)
         return out.value
+
+
+def triangulate(projections, f1, f2, uv1, uv2, device=0, return_ms=False):
+    """Two-view DLT triangulation of n tracks at once -> (n,3) points (processor.py:246-261)."""
+    proj = _c(projections, np.float64).reshape(-1, 12)
+    f1 = _c(f1, np.int64).reshape(-1)
+    f2 = _c(f2, np.int64).reshape(-1)
+    uv1 = _c(uv1, np.float64).reshape(-1, 2)
+    uv2 = _c(uv2, np.float64).reshape(-1, 2)
+    n = len(f1)
+    if not (len(f2) == len(uv1) == len(uv2) == n):
+        raise ValueError("f1, f2, uv1, uv2 must have one entry per track")
+    out = np.empty((max(n, 1), 3))
+    ms = C.c_double()
+    _check(lib().mmba_triangulate(int(device), len(proj), proj.reshape(-1), n, f1 if n else np.zeros(1, np.int64),
+                                  f2 if n else np.zeros(1, np.int64), uv1.reshape(-1) if n else np.zeros(2),
+                                  uv2.reshape(-1) if n else np.zeros(2), out.reshape(-1), C.byref(ms)))
+    out = out[:n]
+    return (out, ms.value) if return_ms else out
 
 
 # -- host-only helpers (no GPU) -------------------------------------------------------------------

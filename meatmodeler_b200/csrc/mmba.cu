@@ -122,7 +122,6 @@ struct Xchg {
     unsigned long long* flags = nullptr;  // [2][nranks]
     double** d_peer_slots = nullptr;      // device arrays of per-rank pointers
     unsigned long long** d_peer_flags = nullptr;
-    unsigned int* d_counter = nullptr;
     int n6 = 0;       // slot length in doubles (capacity: the buffers are kept across problems)
     unsigned long long seq = 0;
 };
@@ -333,7 +332,6 @@ void xchg_release(mmba_handle* h) {
     if (x.base) cudaFree(x.base);
     if (x.d_peer_slots) cudaFree(x.d_peer_slots);
     if (x.d_peer_flags) cudaFree(x.d_peer_flags);
-    if (x.d_counter) cudaFree(x.d_counter);
     x = Xchg();
 }
 
@@ -399,10 +397,8 @@ int xchg_setup(mmba_handle* h) {
     }
     CU(cudaMalloc(&x.d_peer_slots, nr * sizeof(double*)));
     CU(cudaMalloc(&x.d_peer_flags, nr * sizeof(unsigned long long*)));
-    CU(cudaMalloc(&x.d_counter, sizeof(unsigned int)));
     CU(cudaMemcpyAsync(x.d_peer_slots, ps.data(), nr * sizeof(double*), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(x.d_peer_flags, pf.data(), nr * sizeof(unsigned long long*), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemsetAsync(x.d_counter, 0, sizeof(unsigned int), h->stream));
     CU(cudaStreamSynchronize(h->stream));
     x.seq = 0;
     x.on = true;
@@ -1542,6 +1538,69 @@ int mmba_bench_kernel(mmba_handle* h, const double* x, int kernel_class, int ite
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     *avg_ms = ms / iters;
+    return MMBA_OK;
+}
+
+// ---- batched two-view triangulation (no handle: a free function on one device) --------------------
+int mmba_triangulate(int device, int64_t n_frames, const double* projections, int64_t n, const int64_t* f1,
+                     const int64_t* f2, const double* uv1, const double* uv2, double* points, double* kernel_ms) {
+    mmba_handle* h = nullptr;
+    if (n_frames <= 0 || n < 0 || !projections || (n > 0 && (!f1 || !f2 || !uv1 || !uv2 || !points)))
+        return fail(h, MMBA_ERR_ARG, "triangulate: bad argument");
+    for (int64_t i = 0; i < n; ++i)
+        if (f1[i] < 0 || f1[i] >= n_frames || f2[i] < 0 || f2[i] >= n_frames)
+            return fail(h, MMBA_ERR_ARG, "triangulate: frame index out of range at track " + std::to_string(i));
+    if (n == 0) return MMBA_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(h, MMBA_ERR_CUDA, "no CUDA device (libmmba has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    double *d_proj = nullptr, *d_uv1 = nullptr, *d_uv2 = nullptr, *d_out = nullptr;
+    int64_t *d_f1 = nullptr, *d_f2 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_proj);
+        cudaFree(d_uv1);
+        cudaFree(d_uv2);
+        cudaFree(d_out);
+        cudaFree(d_f1);
+        cudaFree(d_f2);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+#define TRI(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            cleanup();                                                                             \
+            return fail(h, MMBA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+        }                                                                                          \
+    } while (0)
+    TRI(cudaMalloc(&d_proj, n_frames * 12 * sizeof(double)));
+    TRI(cudaMalloc(&d_uv1, n * 2 * sizeof(double)));
+    TRI(cudaMalloc(&d_uv2, n * 2 * sizeof(double)));
+    TRI(cudaMalloc(&d_out, n * 3 * sizeof(double)));
+    TRI(cudaMalloc(&d_f1, n * sizeof(int64_t)));
+    TRI(cudaMalloc(&d_f2, n * sizeof(int64_t)));
+    TRI(cudaEventCreate(&e0));
+    TRI(cudaEventCreate(&e1));
+    TRI(cudaMemcpy(d_proj, projections, n_frames * 12 * sizeof(double), cudaMemcpyHostToDevice));
+    TRI(cudaMemcpy(d_uv1, uv1, n * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    TRI(cudaMemcpy(d_uv2, uv2, n * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    TRI(cudaMemcpy(d_f1, f1, n * sizeof(int64_t), cudaMemcpyHostToDevice));
+    TRI(cudaMemcpy(d_f2, f2, n * sizeof(int64_t), cudaMemcpyHostToDevice));
+    TRI(cudaEventRecord(e0));
+    triangulate_kernel<<<cdiv(n, 128), 128>>>(d_proj, d_f1, d_f2, d_uv1, d_uv2, d_out, n);
+    TRI(cudaEventRecord(e1));
+    TRI(cudaGetLastError());
+    TRI(cudaMemcpy(points, d_out, n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (kernel_ms) {
+        float ms = 0;
+        TRI(cudaEventElapsedTime(&ms, e0, e1));
+        *kernel_ms = ms;
+    }
+#undef TRI
+    cleanup();
     return MMBA_OK;
 }
 

@@ -650,6 +650,87 @@ __global__ void pose_step_kernel(const double* __restrict__ x, const double* __r
     xn[e] = x[e] + p;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched two-view triangulation: the per-track cv2.triangulatePoints call of
+// processor.triangulatePoints (processor.py:246-261).  DLT: A = [u1 P1[2]-P1[0]; v1 P1[2]-P1[1];
+// u2 P2[2]-P2[0]; v2 P2[2]-P2[1]] (4x4), X = right singular vector of the smallest singular value,
+// dehomogenised.  One thread per track; one-sided (Hestenes) Jacobi SVD in registers, which keeps the
+// accuracy of an SVD of A itself (no A^T A).  48 B in (2 x uv + 2 x frame index), 24 B out per track;
+// the projection matrices (96 B per frame) stay in L1/L2.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) triangulate_kernel(const double* __restrict__ proj, const int64_t* __restrict__ f1,
+                                                          const int64_t* __restrict__ f2, const double* __restrict__ uv1,
+                                                          const double* __restrict__ uv2, double* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* P1 = proj + f1[i] * 12;
+    const double* P2 = proj + f2[i] * 12;
+    const double u1 = uv1[2 * i], v1 = uv1[2 * i + 1], u2 = uv2[2 * i], v2 = uv2[2 * i + 1];
+    double A[4][4], V[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double p10 = __ldg(P1 + k), p11 = __ldg(P1 + 4 + k), p12 = __ldg(P1 + 8 + k);
+        const double p20 = __ldg(P2 + k), p21 = __ldg(P2 + 4 + k), p22 = __ldg(P2 + 8 + k);
+        A[0][k] = u1 * p12 - p10;
+        A[1][k] = v1 * p12 - p11;
+        A[2][k] = u2 * p22 - p20;
+        A[3][k] = v2 * p22 - p21;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) V[j][k] = j == k ? 1.0 : 0.0;
+    }
+    // rotate column pairs until all columns of A V are mutually orthogonal
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                double app = 0, aqq = 0, apq = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    app += A[r][p] * A[r][p];
+                    aqq += A[r][q] * A[r][q];
+                    apq += A[r][p] * A[r][q];
+                }
+                if (fabs(apq) > 1e-17 * sqrt(app * aqq) && apq != 0.0) {
+                    off = fmax(off, fabs(apq) / sqrt(app * aqq));
+                    const double zeta = (aqq - app) / (2.0 * apq);
+                    const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const double ap = A[r][p], aq = A[r][q];
+                        A[r][p] = cs * ap - sn * aq;
+                        A[r][q] = sn * ap + cs * aq;
+                        const double vp = V[r][p], vq = V[r][q];
+                        V[r][p] = cs * vp - sn * vq;
+                        V[r][q] = sn * vp + cs * vq;
+                    }
+                }
+            }
+        if (off < 1e-15) break;
+    }
+    int best = 0;
+    double smin = 1e300;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double nk = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) nk += A[r][k] * A[r][k];
+        if (nk < smin) {
+            smin = nk;
+            best = k;
+        }
+    }
+    double x[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) x[r] = best == 0 ? V[r][0] : best == 1 ? V[r][1] : best == 2 ? V[r][2] : V[r][3];
+    const double iw = 1.0 / x[3];
+    out[3 * i] = x[0] * iw;
+    out[3 * i + 1] = x[1] * iw;
+    out[3 * i + 2] = x[2] * iw;
+}
+
 // Reference point for the roofline: a plain grid-stride LDG.128 read of n doubles (what a trivial
 // streaming kernel achieves on the same bytes, launch overhead included).  bench/diagnostics only.
 __global__ void __launch_bounds__(256) stream_read_kernel(const double2* __restrict__ src, int64_t n2, double* __restrict__ out) {

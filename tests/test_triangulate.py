@@ -1,0 +1,107 @@
+"""Batched two-view triangulation: oracle vs cv2 golden (CPU), kernel vs both (GPU)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from meatmodeler_b200 import _capi
+from meatmodeler_b200 import processor as mp
+from oracle import triangulate_oracle as tri   # checker only
+
+
+@pytest.fixture(scope="module")
+def golden_tri():
+    return dict(np.load(os.path.join(GOLDEN, "triangulate.npz")))
+
+
+class _Track:
+    """The reference's track.Track interface (track.py:1-41), re-stated for the tests."""
+
+    def __init__(self, coords):
+        self.coordinates = dict(coords)
+        self.point = None
+
+    def getTriangulationData(self):
+        frames = list(self.coordinates.keys())
+        return frames[0], frames[-1], self.coordinates.get(frames[0]), self.coordinates.get(frames[-1])
+
+    def getCoordinates(self):
+        return self.coordinates
+
+    def setPoint(self, point):
+        self.point = point
+
+    def getPoint(self):
+        return self.point
+
+
+def test_oracle_matches_cv2_golden(golden_tri):
+    g = golden_tri
+    out = tri.triangulate(g["projections"], g["f1"], g["f2"], g["uv1"], g["uv2"])
+    assert np.abs(out - g["points"]).max() <= 1e-11 * np.abs(g["points"]).max()
+
+
+def test_manage_points_matches_reference_order():
+    # processor.py:264-291: one observation per (track, frame), track order, dict insertion order
+    tracks = [_Track({3: (1.0, 2.0), 5: (3.0, 4.0), 4: (9.0, 9.5)}), _Track({0: (5.0, 6.0), 1: (7.0, 8.0)})]
+    tracks[0].setPoint(np.array([[1.0, 2.0, 3.0]]))
+    tracks[1].setPoint(np.array([[4.0, 5.0, 6.0]]))
+    points, coordinates, frame_indices, point_indices = mp.managePoints(tracks)
+    assert [p.tolist() for p in points] == [[[1.0, 2.0, 3.0]], [[4.0, 5.0, 6.0]]]
+    assert coordinates == [(1.0, 2.0), (3.0, 4.0), (9.0, 9.5), (5.0, 6.0), (7.0, 8.0)]
+    assert frame_indices == [3, 5, 4, 0, 1]
+    assert point_indices == [0, 0, 0, 1, 1]
+
+
+def test_triangulation_arrays_take_first_and_last_frame():
+    t = _Track({7: (1.0, 2.0), 9: (3.0, 4.0), 8: (5.0, 6.0)})
+    f1, f2, uv1, uv2 = mp.triangulationArrays([t])
+    assert (f1[0], f2[0]) == (7, 8) and uv1[0].tolist() == [1.0, 2.0] and uv2[0].tolist() == [5.0, 6.0]
+
+
+@pytest.mark.gpu
+def test_kernel_vs_cv2_golden_and_oracle(golden_tri):
+    g = golden_tri
+    out = _capi.triangulate(g["projections"], g["f1"], g["f2"], g["uv1"], g["uv2"])
+    scale = np.abs(g["points"]).max()
+    assert np.abs(out - g["points"]).max() <= 1e-9 * scale           # bar: 1e-9 relative in float64
+    assert np.abs(out - tri.triangulate(g["projections"], g["f1"], g["f2"], g["uv1"], g["uv2"])).max() <= 1e-9 * scale
+
+
+@pytest.mark.gpu
+def test_triangulate_points_dropin(golden_tri):
+    g = golden_tri
+    n = 50
+    tracks = [_Track({int(g["f1"][i]): tuple(g["uv1"][i]), int(g["f2"][i]): tuple(g["uv2"][i])}) for i in range(n)]
+    mp.triangulatePoints(tracks, g["projections"])
+    for i, t in enumerate(tracks):
+        assert t.getPoint().shape == (1, 3)
+        assert np.abs(t.getPoint()[0] - g["points"][i]).max() <= 1e-9 * np.abs(g["points"]).max()
+    # projections as a {frame_ID: P} mapping
+    tracks2 = [_Track({int(g["f1"][i]): tuple(g["uv1"][i]), int(g["f2"][i]): tuple(g["uv2"][i])}) for i in range(n)]
+    mp.triangulatePoints(tracks2, {k: P for k, P in enumerate(g["projections"])})
+    assert all(np.array_equal(a.getPoint(), b.getPoint()) for a, b in zip(tracks, tracks2))
+    mp.triangulatePoints([], g["projections"])   # empty: no-op, as the reference loop
+
+
+@pytest.mark.gpu
+def test_triangulate_edge_cases_and_large_batch(golden_tri):
+    g = golden_tri
+    assert _capi.triangulate(g["projections"], [], [], np.zeros((0, 2)), np.zeros((0, 2))).shape == (0, 3)
+    with pytest.raises(_capi.MmbaError):
+        _capi.triangulate(g["projections"], [len(g["projections"])], [0], np.zeros((1, 2)), np.zeros((1, 2)))
+    # 1M tracks (noise-free, two exact views): the triangulated point re-projects onto both pixels
+    rng = np.random.default_rng(5)
+    P = g["projections"]
+    n = 1_000_000
+    X = rng.normal(0, 1, (n, 3))
+    f1 = rng.integers(0, len(P), n)
+    f2 = (f1 + rng.integers(1, 6, n)) % len(P)
+    Xh = np.c_[X, np.ones(n)]
+    q1 = np.einsum("nij,nj->ni", P[f1], Xh)
+    q2 = np.einsum("nij,nj->ni", P[f2], Xh)
+    uv1, uv2 = q1[:, :2] / q1[:, 2:], q2[:, :2] / q2[:, 2:]
+    out, ms = _capi.triangulate(P, f1, f2, uv1, uv2, return_ms=True)
+    assert np.abs(out - X).max() <= 1e-7
+    assert ms > 0
