@@ -163,9 +163,11 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def algorithmic_bytes(kernel, nc, npts, nobs):
+def algorithmic_bytes(kernel, nc, npts, nobs, nnz_up=0):
     """SURVEY.md §8d / DESIGN.md: bytes one launch must move (6-parameter cameras)."""
     return {
+        # explicit reduced camera matrix: J + tile metadata in, M and M g_p per point in, y and the upper blocks out
+        "schur_build": 152 * nobs + 72 * npts + 48 * nc + 288 * nnz_up,
         "build": 184 * nobs + 96 * npts + 264 * nc,
         "schur_matvec": 152 * nobs + 48 * npts + 96 * nc,
         "schur_rhs": 152 * nobs + 72 * npts + 264 * nc,
@@ -211,8 +213,10 @@ def run_mmba(args):
     nc, npts, nobs = prob.sizes
     x0 = np.hstack((mm.frameParameters(ext), pts.reshape(-1)))
 
+    schur_mode = {"auto": _capi.SCHUR_AUTO, "implicit": _capi.SCHUR_IMPLICIT, "explicit": _capi.SCHUR_EXPLICIT}[args.schur]
     opts = mm._dist_options()
     opts.setdefault("device", local)
+    opts["schur_mode"] = schur_mode
     eng = _capi.Engine(**opts)
     t0 = time.perf_counter()
     eng.set_problem(nc, npts, K, fi, pi, uv)
@@ -246,6 +250,7 @@ def run_mmba(args):
     opts_p = mm._dist_options()          # a fresh ncclUniqueId: one id initialises one communicator
     opts_p.setdefault("device", local)
     opts_p["profile"] = 1
+    opts_p["schur_mode"] = schur_mode
     engp = _capi.Engine(**opts_p)
     engp.set_problem(nc, npts, K, fi, pi, uv)
     engp.set_x(x0)
@@ -256,11 +261,16 @@ def run_mmba(args):
     peak, peak_kind = measured_peak()
     n_obs_local, n_pts_local = shard["n_obs_local"], shard["n_points_local"]
     kernels = {}
-    for name in ("build", "schur_matvec", "schur_rhs", "backsub", "jv", "resid"):
+    explicit = prof["schur_pcg"]["launches"] > 0
+    nnz_up = nnz_full = 0
+    if explicit:
+        _, up_cols, nnz_full, _ = _capi.host_rcm_pattern(nc, npts, fi, pi)
+        nnz_up = len(up_cols)
+    for name in ("build", "schur_build", "schur_matvec", "schur_rhs", "backsub", "jv", "resid"):
         p = prof[name]
         if p["launches"]:
             avg_ms = p["ms"] / p["launches"]
-            b = algorithmic_bytes(name, nc, n_pts_local, n_obs_local)
+            b = algorithmic_bytes(name, nc, n_pts_local, n_obs_local, nnz_up)
             kernels[name] = {"launches_per_step": p["launches"], "avg_ms": avg_ms, "share_of_step": p["ms"] / rp.solve_ms,
                              "algorithmic_bytes": b, "gbs": b / (avg_ms * 1e-3) / 1e9, "frac": b / (avg_ms * 1e-3) / 1e9 / peak}
     dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
@@ -279,6 +289,18 @@ def run_mmba(args):
                 "other_classes_ms_per_step": {k: {"launches": prof[k]["launches"], "ms": prof[k]["ms"]}
                                               for k in ("vec", "allreduce", "cam_prep", "point_invert")},
                 "profiled_step_ms": rp.solve_ms}
+    if explicit:
+        # The PCG on the explicit, L2/L1-resident reduced camera matrix is one cooperative launch per outer
+        # iteration: no HBM stream, two grid barriers per PCG iteration.  It has no HBM roofline; what bounds it
+        # is the barrier + L2 round-trip latency, reported as time per PCG iteration.
+        p = prof["schur_pcg"]
+        its_p = max(int(rp.pcg_iterations), 1)
+        roofline["schur_pcg_on_chip"] = {
+            "launches_per_step": p["launches"], "ms_per_step": p["ms"], "share_of_step": p["ms"] / rp.solve_ms,
+            "pcg_iterations_per_step": int(rp.pcg_iterations), "us_per_pcg_iteration": 1e3 * p["ms"] / its_p,
+            "matrix_bytes": 288 * nnz_full, "blocks_full": nnz_full, "blocks_upper": nnz_up,
+            "l2_gbs": 288 * nnz_full * its_p / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else None,
+            "bound": "grid-barrier / L2 latency (2 barriers per iteration), not HBM"}
 
     # ---- end to end through the drop-in adjustPoints with host buffers ---------------------------
     e2e_steps = max(2, min(args.steps, 5))
@@ -310,7 +332,9 @@ def run_mmba(args):
                        "init": "hard (points sigma 0.15, tvec sigma 0.1), 0.5 px noise, windowed visibility",
                        "l2": f"working set {(18 + 2 + 2 + 1) * 8 * n_obs_local / 1e6:.0f} MB per GPU streamed per pass "
                              f"(> 126 MB L2)" if n_obs_local * 184 > 126e6 else "working set fits L2 (no flush)",
-                       "ftol": 1e-4, "pcg_rtol": eng.options.pcg_rtol},
+                       "ftol": 1e-4, "pcg_rtol": eng.options.pcg_rtol,
+                       "schur": ("explicit reduced camera matrix + one-kernel PCG" if explicit else
+                                 "implicit (one streaming pass over J per PCG iteration)")},
             "lm_iterations_per_step": nit_per_step, "lm_iterations_per_s": its / (dev_ms * 1e-3),
             "pcg_iterations_per_step": pcg / args.steps, "final_cost": final_cost,
             "wall_ms_per_step": wall_ms / args.steps, "setup_ms": setup_ms,
@@ -334,6 +358,8 @@ def main():
     ap.add_argument("--config", default="auto", choices=["auto", "C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--ref-scale", type=float, default=None, help="size of the CPU sample relative to C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--schur", default="auto", choices=["auto", "implicit", "explicit"],
+                    help="reduced camera system: explicit block-sparse matrix or implicit products (auto: library rule)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -57,7 +57,16 @@ typedef struct mmba_options {
     int32_t pcg_maxit;
     int32_t profile;      /* 1 = bracket kernels with CUDA events (mmba_get_profile) */
     uint8_t nccl_id[128]; /* ncclUniqueId bytes, same on all ranks (nranks > 1 only) */
+    int32_t schur_mode;   /* MMBA_SCHUR_*: how the PCG applies the reduced camera system (read by mmba_set_problem) */
+    int32_t reserved;
 } mmba_options;
+
+/* The reduced camera system S = U - W V'^-1 W^T of the damped Gauss-Newton step:
+ *   IMPLICIT  S p is evaluated by one streaming pass over J per PCG iteration (152 B/observation);
+ *   EXPLICIT  the block-sparse S is formed once per outer iteration (one streaming pass) and the whole PCG
+ *             runs in one cooperative kernel on the L2-resident matrix;
+ *   AUTO      EXPLICIT when S is small next to the observation stream (video-like visibility), else IMPLICIT. */
+enum { MMBA_SCHUR_AUTO = 0, MMBA_SCHUR_IMPLICIT = 1, MMBA_SCHUR_EXPLICIT = 2 };
 
 typedef struct mmba_result {
     double cost;          /* 0.5 * f.f at the returned x */
@@ -90,7 +99,9 @@ enum {
     MMBA_K_JV = 7,        /* J*v products (Cauchy step, 2-D subspace Gram) */
     MMBA_K_VEC = 8,       /* small vector kernels */
     MMBA_K_ALLREDUCE = 9,
-    MMBA_K_COUNT = 10
+    MMBA_K_SBUILD = 10,   /* explicit reduced camera matrix + Schur right-hand side (one pass over J) */
+    MMBA_K_PCG = 11,      /* the whole PCG solve on the explicit matrix (one cooperative launch) */
+    MMBA_K_COUNT = 12
 };
 
 int mmba_version(void);
@@ -154,6 +165,11 @@ int mmba_eval_blocks(mmba_handle* h, const double* x, double* U, double* V, doub
  * solves (J_h^T J_h + reg I) p = J_h^T f by Schur elimination + block-Jacobi PCG. p has n entries. */
 int mmba_eval_gn_step(mmba_handle* h, const double* x, const double* scale, double reg, double* p,
                       int64_t* pcg_iterations, double* pcg_relres);
+/* test hook of the explicit reduced camera matrix (schur_mode != IMPLICIT and the matrix was formed):
+ * S = D (J_c^T J_c - W V'^-1 W^T) D + reg I as a dense (6 n_cams)^2 row-major matrix and the right-hand side
+ * b = D (g_c - W V'^-1 g_p), with D = diag(scale) of the camera parameters; MMBA_ERR_STATE otherwise */
+int mmba_eval_reduced_system(mmba_handle* h, const double* x, const double* scale, double reg, double* S_dense,
+                             double* rhs);
 /* J * s for an n-vector s -> 2*n_obs (caller's observation order); test hook for the J*v kernel
  * (build_quadratic_1d / evaluate_quadratic, common.py:282-288, 348-361): returns ||J s||^2 */
 int mmba_eval_jnorm2(mmba_handle* h, const double* x, const double* s, double* jnorm2);
@@ -180,6 +196,14 @@ int mmba_host_update_tr_radius(double delta, double actual, double predicted, do
 /* replaces: check_termination (common.py:705-717); returns 0 for "continue", else 2/3/4 */
 int mmba_host_check_termination(double dF, double F, double dx_norm, double x_norm, double ratio,
                                 double ftol, double xtol);
+
+/* block pattern of the reduced camera matrix (which camera pairs share a point), upper triangle incl. the
+ * diagonal, CSR: sizes[0] = blocks in the upper triangle, sizes[1] = blocks of the full pattern, sizes[2] = sum
+ * over points of L (L + 1) / 2.  up_rowptr (n_cams + 1) / up_cols (capacity entries) may be NULL (sizes only);
+ * returns MMBA_ERR_NOMEM when capacity is too small. */
+int mmba_host_rcm_pattern(int64_t n_cams, int64_t n_points, int64_t n_obs, const int64_t* cam_idx,
+                          const int64_t* pt_idx, int64_t sizes[3], int32_t* up_rowptr, int32_t* up_cols,
+                          int64_t capacity);
 
 /* tile plan (observation reordering + point sharding) built on the host */
 int mmba_plan_create(mmba_plan** out, int64_t n_cams, int64_t n_points, int64_t n_obs,

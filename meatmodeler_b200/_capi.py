@@ -13,9 +13,11 @@ import numpy as np
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmmba.so")
 
 K_NAMES = ("cam_prep", "build", "resid", "point_invert", "schur_rhs", "schur_matvec", "backsub", "jv",
-           "vec", "allreduce")
-K_CAMPREP, K_BUILD, K_RESID, K_PTINV, K_RHS, K_MATVEC, K_BACKSUB, K_JV, K_VEC, K_ALLREDUCE = range(10)
-K_COUNT = 10
+           "vec", "allreduce", "schur_build", "schur_pcg")
+(K_CAMPREP, K_BUILD, K_RESID, K_PTINV, K_RHS, K_MATVEC, K_BACKSUB, K_JV, K_VEC, K_ALLREDUCE, K_SBUILD,
+ K_PCG) = range(12)
+K_COUNT = 12
+SCHUR_AUTO, SCHUR_IMPLICIT, SCHUR_EXPLICIT = 0, 1, 2
 
 ERR_NAMES = {-1: "MMBA_ERR_ARG", -2: "MMBA_ERR_CUDA", -3: "MMBA_ERR_STATE", -4: "MMBA_ERR_NONFINITE",
              -5: "MMBA_ERR_TRACK", -6: "MMBA_ERR_NCCL", -7: "MMBA_ERR_NOMEM"}
@@ -31,7 +33,7 @@ class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("verbose", C.c_int32),
                 ("ftol", C.c_double), ("xtol", C.c_double), ("gtol", C.c_double), ("max_nfev", C.c_int64),
                 ("pcg_rtol", C.c_double), ("pcg_maxit", C.c_int32), ("profile", C.c_int32),
-                ("nccl_id", C.c_uint8 * 128)]
+                ("nccl_id", C.c_uint8 * 128), ("schur_mode", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -73,6 +75,7 @@ SIGNATURES = {
     "mmba_eval_jacobian": (C.c_int, [_H, _f64, _f64, _f64]),
     "mmba_eval_blocks": (C.c_int, [_H, _f64, _f64, _f64, _f64, _f64, C.POINTER(C.c_double)]),
     "mmba_eval_gn_step": (C.c_int, [_H, _f64, _f64, C.c_double, _f64, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "mmba_eval_reduced_system": (C.c_int, [_H, _f64, _f64, C.c_double, _f64, _f64]),
     "mmba_eval_jnorm2": (C.c_int, [_H, _f64, _f64, C.POINTER(C.c_double)]),
     "mmba_bench_kernel": (C.c_int, [_H, _f64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "mmba_triangulate": (C.c_int, [C.c_int, C.c_int64, _f64, C.c_int64, _i64, _i64, _f64, _f64, _f64, C.POINTER(C.c_double)]),
@@ -83,6 +86,8 @@ SIGNATURES = {
     "mmba_host_update_tr_radius": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
                                              C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mmba_host_check_termination": (C.c_int, [C.c_double] * 7),
+    "mmba_host_rcm_pattern": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _i64, _i64, C.POINTER(C.c_int64 * 3), C.c_void_p,
+                                        C.c_void_p, C.c_int64]),
     "mmba_plan_create": (C.c_int, [C.POINTER(_H), C.c_int64, C.c_int64, C.c_int64, _i64, _i64, C.c_int, C.c_int]),
     "mmba_plan_destroy": (None, [_H]),
     "mmba_plan_sizes": (C.c_int, [_H, C.POINTER(C.c_int64 * 8)]),
@@ -150,7 +155,7 @@ class Engine:
 
     def set_options(self, **kw):
         """Change tolerances / limits of the live handle (ftol, xtol, gtol, max_nfev, pcg_rtol, pcg_maxit,
-        verbose, profile)."""
+        verbose, profile, schur_mode — the latter is read by the next set_problem; IMPLICIT applies at once)."""
         for k, v in kw.items():
             if k in ("device", "rank", "nranks", "nccl_id") or not hasattr(self.options, k):
                 raise TypeError(f"option {k} cannot be changed on a live engine")
@@ -269,6 +274,14 @@ class Engine:
                                        C.byref(rel)), self._h)
         return p, its.value, rel.value
 
+    def reduced_system(self, x, scale, reg):
+        """Dense (6 Nc)^2 reduced camera matrix and right-hand side of the explicit Schur path (test hook)."""
+        n6 = 6 * self.sizes[0]
+        S = np.zeros((n6, n6))
+        rhs = np.zeros(n6)
+        _check(lib().mmba_eval_reduced_system(self._h, self._x(x), self._x(scale), float(reg), S.reshape(-1), rhs), self._h)
+        return S, rhs
+
     def jnorm2(self, x, s):
         out = C.c_double()
         _check(lib().mmba_eval_jnorm2(self._h, self._x(x), self._x(s), C.byref(out)), self._h)
@@ -300,6 +313,19 @@ def triangulate(projections, f1, f2, uv1, uv2, device=0, return_ms=False):
 
 
 # -- host-only helpers (no GPU) -------------------------------------------------------------------
+def host_rcm_pattern(n_cams, n_points, cam_idx, pt_idx):
+    """Upper-triangle block pattern of the reduced camera matrix: (up_rowptr, up_cols, nnz_full, total_pairs)."""
+    cam_idx = _c(cam_idx, np.int64).reshape(-1)
+    pt_idx = _c(pt_idx, np.int64).reshape(-1)
+    sizes = (C.c_int64 * 3)()
+    _check(lib().mmba_host_rcm_pattern(int(n_cams), int(n_points), len(cam_idx), cam_idx, pt_idx, C.byref(sizes), None, None, 0))
+    rowptr = np.empty(int(n_cams) + 1, dtype=np.int32)
+    cols = np.empty(max(int(sizes[0]), 1), dtype=np.int32)
+    _check(lib().mmba_host_rcm_pattern(int(n_cams), int(n_points), len(cam_idx), cam_idx, pt_idx, C.byref(sizes),
+                                       rowptr.ctypes.data, cols.ctypes.data, len(cols)))
+    return rowptr, cols[:sizes[0]], int(sizes[1]), int(sizes[2])
+
+
 def host_tr2d(B, g, delta):
     Bc = (C.c_double * 3)(B[0][0], B[0][1], B[1][1])
     gc = (C.c_double * 2)(*g)

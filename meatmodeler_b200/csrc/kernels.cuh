@@ -71,7 +71,7 @@ enum Scal {
     S_COUNT = 24
 };
 
-enum Mode { M_BUILD = 0, M_RESID, M_RESID_STORE, M_MATVEC, M_RHS, M_BACKSUB, M_JV1, M_JV2, M_BUILD_FULL, M_COUNT };
+enum Mode { M_BUILD = 0, M_RESID, M_RESID_STORE, M_MATVEC, M_RHS, M_BACKSUB, M_JV1, M_JV2, M_BUILD_FULL, M_SBUILD, M_COUNT };
 __host__ __device__ constexpr bool is_build(int m) { return m == M_BUILD || m == M_BUILD_FULL; }
 __host__ __device__ constexpr bool is_project(int m) { return is_build(m) || m == M_RESID || m == M_RESID_STORE; }
 
@@ -86,18 +86,20 @@ struct Traits {
     static constexpr bool kLoadUV = !kLoadJ;
     // doubles gathered per camera into shared memory, and the (odd, conflict-free) smem stride
     static constexpr int kCamRows = is_build(MODE) ? 21 : (MODE == M_RESID || MODE == M_RESID_STORE) ? 12
-                                  : MODE == M_RHS ? 0 : MODE == M_JV2 ? 12 : 6;
+                                  : (MODE == M_RHS || MODE == M_SBUILD) ? 0 : MODE == M_JV2 ? 12 : 6;
     static constexpr int kCamStride = kCamRows | 1;
     // per-point payloads staged by the producer
-    static constexpr int kPA = (MODE == M_MATVEC || MODE == M_RHS || MODE == M_BACKSUB) ? 6 : 3;
-    static constexpr int kPB = (MODE == M_RHS || MODE == M_BACKSUB || MODE == M_JV2) ? 3 : 0;
+    static constexpr int kPA = (MODE == M_MATVEC || MODE == M_RHS || MODE == M_BACKSUB || MODE == M_SBUILD) ? 6 : 3;
+    static constexpr int kPB = (MODE == M_RHS || MODE == M_BACKSUB || MODE == M_JV2 || MODE == M_SBUILD) ? 3 : 0;
     static constexpr bool kScatter = is_build(MODE) || MODE == M_MATVEC || MODE == M_RHS;
     static constexpr int kPtAcc = (MODE == M_MATVEC || MODE == M_BACKSUB) ? 3 : 0;
     // scatter staging rows: BUILD stages 12 camera + 9 point rows + 1 row of point-run starts in its
     // own buffer.  The Schur passes stage 6 / 9 rows INSIDE the current pipeline stage's J block:
     // every consumer holds its 18 J values in registers by then, the block is dead until the stage
     // is released, and consecutive tiles use different stages (free double buffering).
-    static constexpr int kStageRows = is_build(MODE) ? 22 : 0;
+    // SBUILD keeps the J block intact for its pair phase: 6 rows stage the right-hand-side scatter, 6 rows hold
+    // Jp M per observation.
+    static constexpr int kStageRows = is_build(MODE) ? 22 : MODE == M_SBUILD ? 12 : 0;
     static constexpr int kStageBufs = 1;
 };
 
@@ -127,6 +129,9 @@ struct ModeArgs {
     double* V;             // [Np][6]                        BUILD
     double* gp;            // [Np][3]                        BUILD
     double* dp;            // [Np][3]                        BACKSUB
+    double* Tup;           // [nnz_up][36] reduced camera matrix, upper blocks, unscaled   SBUILD
+    const int* up_rowptr;  // [Nc + 1]  block pattern of Tup (rcm.h)                       SBUILD
+    const int* up_cols;    // [nnz_up]
     double* scal;          // scalar slots                   BUILD (S_COST) JV (S_JV*)
     double* cost;          // trial cost slot                RESID
     const int* done;       // PCG converged flag             MATVEC
@@ -137,7 +142,7 @@ struct ModeArgs {
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
     int off_J, off_meta, off_uv, off_camid, off_camvec, off_pa, off_pb, stage_bytes;
-    int off_stages, off_pt, off_z, off_buf, off_red, off_ids, off_ytab, total;
+    int off_stages, off_pt, off_z, off_buf, off_red, off_ids, off_ytab, off_tab, off_pstart, total;
 };
 
 __host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -175,6 +180,10 @@ __host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts, int
     o += align_up(T::kStages * max_cams * 4, 16);
     L.off_ytab = o;
     if (MODE == M_MATVEC) o += align_up(ytab_cams * 6 * 8, 16);
+    L.off_tab = o;
+    if (MODE == M_SBUILD) o += kRcmTabCap * 2;                     // (point, camera) -> slot table, u16
+    L.off_pstart = o;
+    if (MODE == M_SBUILD) o += 2 * align_up((max_pts + 2) * 4, 16);  // first slot / pair offset of every point
     L.total = o;
     return L;
 }
@@ -428,6 +437,55 @@ __device__ __forceinline__ void project_obs(const double* __restrict__ cam /* sm
 }
 
 // ---------------------------------------------------------------------------------------------
+// S-build helpers (explicit reduced camera matrix, rcm.h)
+// ---------------------------------------------------------------------------------------------
+// pr-th pair (a <= b) of the upper triangle of an n x n matrix in row-major order
+__device__ __forceinline__ void tri_decode(int pr, int n, int& a, int& b) {
+    const double t = 2.0 * n + 1.0;
+    int aa = (int)((t - sqrt(t * t - 8.0 * pr)) * 0.5);
+    aa = max(0, min(aa, n - 1));
+    while (aa > 0 && aa * n - aa * (aa - 1) / 2 > pr) --aa;
+    while (aa + 1 < n && (aa + 1) * n - (aa + 1) * aa / 2 <= pr) ++aa;
+    a = aa;
+    b = aa + (pr - (aa * n - aa * (aa - 1) / 2));
+}
+
+// index of block (ci, cj), ci <= cj, in the upper-triangle pattern (video-like visibility: a band, so the
+// first guess is usually right)
+__device__ __forceinline__ int rcm_lookup(const int* __restrict__ rowptr, const int* __restrict__ cols, int ci, int cj) {
+    int lo = __ldg(rowptr + ci), hi = __ldg(rowptr + ci + 1);
+    const int guess = lo + (cj - ci);
+    if (guess < hi && __ldg(cols + guess) == cj) return guess;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(cols + mid) <= cj) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// acc[b] += row `row` of  Jc_i^T (delta_ij I - Jp_i M Jp_j^T) Jc_j  for the observations in slots i, j of one point:
+// the (camera(i), camera(j)) block of  J_c^T J_c - W V'^-1 W^T  restricted to this point.  sJ: the tile's J block,
+// s_pm: rows k of Jp M (2x3, row-major) at stride kBufStride.
+__device__ __forceinline__ void sbuild_row(const double* __restrict__ sJ, const double* __restrict__ s_pm, int i, int j,
+                                           int row, double (&acc)[6]) {
+    double g00 = i == j ? 1.0 : 0.0, g01 = 0.0, g10 = 0.0, g11 = g00;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double pm0 = s_pm[k * kBufStride + i], pm1 = s_pm[(3 + k) * kBufStride + i];
+        const double q0 = sJ[(12 + k) * kT + j], q1 = sJ[(15 + k) * kT + j];
+        g00 -= pm0 * q0;
+        g01 -= pm0 * q1;
+        g10 -= pm1 * q0;
+        g11 -= pm1 * q1;
+    }
+    const double c0 = sJ[row * kT + i], c1 = sJ[(6 + row) * kT + i];
+    const double t0 = c0 * g00 + c1 * g10, t1 = c0 * g01 + c1 * g11;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) acc[b] += t0 * sJ[b * kT + j] + t1 * sJ[(6 + b) * kT + j];
+}
+
+// ---------------------------------------------------------------------------------------------
 // The streaming kernel.  Algorithmic bytes per observation:
 //   BUILD   184  (24 in: metadata + uv; 16 residual + 144 Jacobian out) + fused V/g_p, U/g_c, cost
 //   RESID    24  trial cost only
@@ -436,6 +494,8 @@ __device__ __forceinline__ void project_obs(const double* __restrict__ cam /* sm
 //   BACKSUB 152  dp_p = M_p (g_p - sum_{j in p} Jp_j^T Jc_j xt_c(j))
 //   JV1/JV2 152  ||J v||^2 / 2x2 Gram of J [v0 v1]   (build_quadratic_1d, J_h.dot(S): common.py:282-288,
 //                trf.py:498-499); only scalars leave the SM
+//   SBUILD  152  explicit reduced camera matrix: T_(ci,cj) += Jc_i^T (delta_ij I - Jp_i M_p Jp_j^T) Jc_j over the
+//                observation pairs of every point (upper blocks), and the Schur right-hand side y_c (as RHS)
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const TileArgs A, const ModeArgs P) {
@@ -772,6 +832,115 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
                 acc[1] += e[0][0] * e[NV - 1][0] + e[0][1] * e[NV - 1][1];
                 acc[2] += e[NV - 1][0] * e[NV - 1][0] + e[NV - 1][1] * e[NV - 1][1];
             }
+        } else if constexpr (MODE == M_SBUILD) {
+            // ---- explicit reduced camera matrix (upper blocks) + Schur right-hand side ----
+            double jc[12], jp[6];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) jc[i] = valid ? sJ[i * kT + tid] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) jp[i] = valid ? sJ[(12 + i) * kT + tid] : 0.0;
+            const int ncams = mt->ncams, pair_mode = mt->pair_mode;
+            uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + L.off_tab);
+            int* s_pstart = reinterpret_cast<int*>(smem + L.off_pstart);
+            int* s_poff = s_pstart + align_up((A.max_pts + 2) * 4, 16) / 4;
+            double* s_pm = s_buf + 6 * kBufStride;
+            {
+                const double* m = s_pa + lps * 6;
+                const double* zg = s_pb + lps * 3;
+                // y_c += Jc^T Jp (M_p g_p)
+                const double v0 = jp[0] * zg[0] + jp[1] * zg[1] + jp[2] * zg[2];
+                const double v1 = jp[3] * zg[0] + jp[4] * zg[1] + jp[5] * zg[2];
+                double cv[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) cv[k] = jc[k] * v0 + jc[6 + k] * v1;
+                // Jp M (2x3) of this observation
+                const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const double a0 = jp[r * 3], a1 = jp[r * 3 + 1], a2 = jp[r * 3 + 2];
+                    s_pm[(r * 3 + 0) * kBufStride + tid] = a0 * m0 + a1 * m1 + a2 * m2;
+                    s_pm[(r * 3 + 1) * kBufStride + tid] = a0 * m1 + a1 * m3 + a2 * m4;
+                    s_pm[(r * 3 + 2) * kBufStride + tid] = a0 * m2 + a1 * m4 + a2 * m5;
+                }
+                if (pair_mode) {
+                    for (int i = tid; i < npts * ncams; i += kConsumers) s_tab[i] = 0xFFFF;
+                } else {
+                    if (valid && (tid == 0 || mt->slot_pt[tid - 1] != lp)) s_pstart[lp] = tid;
+                    if (tid == 0) s_pstart[npts] = mt->nobs;
+                }
+                camera_scatter_round<6>(cv, s_buf, mt, s_camid, P.y, 6, 0);   // one consumer barrier inside
+            }
+            if (pair_mode) {
+                if (valid) s_tab[lp * ncams + lc] = (uint16_t)tid;
+            } else if (tid == 0) {
+                int o = 0;
+                for (int p = 0; p < npts; ++p) {
+                    s_poff[p] = o;
+                    const int len = s_pstart[p + 1] - s_pstart[p];
+                    o += len * (len + 1) / 2;
+                }
+                s_poff[npts] = o;
+            }
+            consumer_sync();
+            if (pair_mode) {
+                // unit = (camera pair a <= b of the tile, block row, point slice): register accumulation over the
+                // tile's points, then one RED per entry
+                const int npair = ncams * (ncams + 1) / 2;
+                int nslice = 1;
+                if (npair * 6 < kConsumers) nslice = max(1, min(npts, kConsumers / (npair * 6)));
+                const int units = npair * 6 * nslice;
+                for (int u = tid; u < units; u += kConsumers) {
+                    const int sl = u % nslice, rest = u / nslice;
+                    const int row = rest % 6, pr = rest / 6;
+                    int a, b;
+                    tri_decode(pr, ncams, a, b);
+                    double acc[6] = {0, 0, 0, 0, 0, 0};
+                    bool hit = false;
+                    for (int p = sl; p < npts; p += nslice) {
+                        const unsigned i = s_tab[p * ncams + a];
+                        if (i == 0xFFFFu) continue;
+                        const unsigned j = s_tab[p * ncams + b];
+                        if (j == 0xFFFFu) continue;
+                        hit = true;
+                        sbuild_row(sJ, s_pm, (int)i, (int)j, row, acc);
+                    }
+                    if (hit) {
+                        const int k = rcm_lookup(P.up_rowptr, P.up_cols, s_camid[a], s_camid[b]);
+                        double* dst = P.Tup + (int64_t)k * 36 + row * 6;
+#pragma unroll
+                        for (int bb = 0; bb < 6; ++bb) red_add(dst + bb, acc[bb]);
+                    }
+                }
+            } else {
+                // unit = (observation pair i <= j of one point, block row): cameras ascend inside a point
+                const int units = mt->npairs * 6;
+                for (int u = tid; u < units; u += kConsumers) {
+                    const int row = u % 6, q = u / 6;
+                    int lo = 0, hi = npts;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_poff[mid] <= q) lo = mid;
+                        else hi = mid;
+                    }
+                    const int start = s_pstart[lo], len = s_pstart[lo + 1] - start;
+                    int ii, jj;
+                    tri_decode(q - s_poff[lo], len, ii, jj);
+                    const int i = start + ii, j = start + jj;
+                    double acc[6] = {0, 0, 0, 0, 0, 0};
+                    sbuild_row(sJ, s_pm, i, j, row, acc);
+                    const int ci = s_camid[mt->slot_cam[i]], cj = s_camid[mt->slot_cam[j]];
+                    const int k = rcm_lookup(P.up_rowptr, P.up_cols, ci, cj);
+                    double* dst = P.Tup + (int64_t)k * 36;
+#pragma unroll
+                    for (int bb = 0; bb < 6; ++bb) red_add(dst + row * 6 + bb, acc[bb]);
+                    if (ci == cj && i != j) {
+                        // one camera observing the point twice: the mirrored pair lands in the same diagonal block
+#pragma unroll
+                        for (int bb = 0; bb < 6; ++bb) red_add(dst + bb * 6 + row, acc[bb]);
+                    }
+                }
+            }
+            consumer_sync();   // staging rows and tables are rewritten by the next tile
         } else {
             // ---- Schur passes: MATVEC / RHS / BACKSUB ----
             double jc[12], jp[6];

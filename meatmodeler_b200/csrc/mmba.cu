@@ -25,6 +25,8 @@
 #include "../../include/mmba.h"
 #include "kernels.cuh"
 #include "plan.h"
+#include "rcm.cuh"
+#include "rcm.h"
 #include "trf_host.h"
 #include "veckernels.cuh"
 
@@ -111,6 +113,10 @@ struct Dev {
     int* flags;
     double* scal;
     double* xp_full;   // all points, internal order (nranks > 1 only)
+    // explicit reduced camera matrix (rcm.h / rcm.cuh); null when the implicit product is used
+    double *Tup, *S, *rcm_b, *rcm_part;
+    int *up_rowptr, *up_cols, *rc_rowptr, *rc_cols, *rc_rows, *rc_src, *rc_diag;
+    unsigned* rcm_bar;
 };
 
 // One-shot peer all-reduce of the per-iteration Schur product (see xchg_push_kernel)
@@ -144,6 +150,9 @@ struct mmba_handle {
     ncclComm_t comm = nullptr;
     bool has_problem = false;
     Plan plan;
+    RcmPattern rcm;
+    bool rcm_ready = false;        // pattern built and device arrays carved for the current problem
+    int rcm_grid = 0, rcm_warps = 0, rcm_kmax = 0;
     int64_t Nc = 0, npl = 0, ns = 0, nt = 0, nloc = 0;
     double K[9];
     void* arena = nullptr;
@@ -322,6 +331,25 @@ void carve(mmba_handle* h, Arena& a) {
     d.flags = a.take<int>(4);
     d.scal = a.take<double>(S_COUNT);
     d.xp_full = h->opt.nranks > 1 ? a.take<double>(3 * (size_t)pl.n_points) : nullptr;
+    if (h->rcm_ready) {
+        const RcmPattern& r = h->rcm;
+        d.Tup = a.take<double>(36 * (size_t)r.nnz_up());
+        d.S = a.take<double>(36 * (size_t)r.nnz_full());
+        d.rcm_b = a.take<double>(6 * Nc);
+        d.rcm_part = a.take<double>(2 * (size_t)kRcmMaxCtas * 2);
+        d.up_rowptr = a.take<int>(Nc + 1);
+        d.up_cols = a.take<int>(r.nnz_up());
+        d.rc_rowptr = a.take<int>(Nc + 1);
+        d.rc_cols = a.take<int>(r.nnz_full());
+        d.rc_rows = a.take<int>(r.nnz_full());
+        d.rc_src = a.take<int>(r.nnz_full());
+        d.rc_diag = a.take<int>(Nc);
+        d.rcm_bar = a.take<unsigned>(4);
+    } else {
+        d.Tup = d.S = d.rcm_b = d.rcm_part = nullptr;
+        d.up_rowptr = d.up_cols = d.rc_rowptr = d.rc_cols = d.rc_rows = d.rc_src = d.rc_diag = nullptr;
+        d.rcm_bar = nullptr;
+    }
 }
 
 void xchg_release(mmba_handle* h) {
@@ -681,6 +709,79 @@ ModeArgs backsub_args(mmba_handle* h) {
 
 // damped Gauss-Newton step in scaled variables: (D J^T J D + reg I) p = D g.
 // Leaves the camera part in d.px (scaled) and the unscaled point part in d.dp.
+bool use_rcm(const mmba_handle* h) { return h->rcm_ready && h->opt.schur_mode != MMBA_SCHUR_IMPLICIT; }
+
+ModeArgs sbuild_args(mmba_handle* h) {
+    Dev& d = h->d;
+    ModeArgs P{};
+    P.J = d.J;
+    P.ptA = d.M;
+    P.ptB = d.zg;
+    P.y = d.y;
+    P.Tup = d.Tup;
+    P.up_rowptr = d.up_rowptr;
+    P.up_cols = d.up_cols;
+    return P;
+}
+
+RcmPcgArgs rcm_pcg_args(mmba_handle* h) {
+    Dev& d = h->d;
+    RcmPcgArgs A{};
+    A.S = d.S;
+    A.rowptr = d.rc_rowptr;
+    A.cols = d.rc_cols;
+    A.Pinv = d.Pinv;
+    A.b = d.rcm_b;
+    A.x = d.px;
+    A.z = d.pz;
+    A.p0 = d.pp;
+    A.p1 = d.pq;
+    A.part = d.rcm_part;
+    A.bar = d.rcm_bar;
+    A.flags = d.flags;
+    A.state = d.state;
+    A.n_cams = (int)h->Nc;
+    A.maxit = h->opt.pcg_maxit;
+    A.kmax = h->rcm_kmax;
+    A.rtol2 = h->opt.pcg_rtol * h->opt.pcg_rtol;
+    return A;
+}
+
+// S-build pass: unscaled upper blocks of the reduced camera matrix + Schur right-hand side (summed over ranks)
+int rcm_build(mmba_handle* h) {
+    Dev& d = h->d;
+    TRY(zero(h, d.y, 6 * h->Nc));
+    TRY(zero(h, d.Tup, 36 * (size_t)h->rcm.nnz_up()));
+    TRY(launch_tile<M_SBUILD>(h, MMBA_K_SBUILD, sbuild_args(h)));
+    TRY(allreduce(h, {{d.y, (size_t)(6 * h->Nc), false}, {d.Tup, 36 * (size_t)h->rcm.nnz_up(), false}}));
+    return MMBA_OK;
+}
+
+// scaled full-pattern blocks, block-Jacobi preconditioner and right-hand side
+int rcm_finalize(mmba_handle* h, double reg) {
+    Dev& d = h->d;
+    const int64_t n_entries = 36 * h->rcm.nnz_full();
+    LAUNCH(MMBA_K_VEC, rcm_finalize_kernel, cdiv(n_entries, 256), 256, 0, d.Tup, d.rc_rows, d.rc_cols, d.rc_src, d.sinv, reg, d.S,
+           n_entries);
+    LAUNCH(MMBA_K_VEC, rcm_prepare_kernel, cdiv(h->Nc, kCamBlock), kCamBlock, 0, d.S, d.rc_diag, d.g, d.y, d.sinv, d.Pinv,
+           d.rcm_b, (int)h->Nc);
+    return MMBA_OK;
+}
+
+// the whole PCG solve: one cooperative launch
+int rcm_pcg(mmba_handle* h) {
+    Dev& d = h->d;
+    CU(cudaMemsetAsync(d.rcm_bar, 0, 4 * sizeof(unsigned), h->stream));
+    CU(cudaMemsetAsync(d.flags, 0, 3 * sizeof(int), h->stream));
+    RcmPcgArgs A = rcm_pcg_args(h);
+    void* args[] = {&A};
+    prof_begin(h, MMBA_K_PCG);
+    CU(cudaLaunchCooperativeKernel((const void*)rcm_pcg_kernel, dim3(h->rcm_grid), dim3(32 * h->rcm_warps), args,
+                                   (size_t)h->rcm_warps * h->rcm_kmax * 30 * sizeof(double), h->stream));
+    prof_end(h, MMBA_K_PCG);
+    return MMBA_OK;
+}
+
 int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
     Dev& d = h->d;
     const int camblocks = cdiv(h->Nc, kCamBlock);
@@ -688,6 +789,23 @@ int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
     if (h->npl)
         LAUNCH(MMBA_K_PTINV, point_invert_kernel, cdiv(h->npl, 256), 256, 0, d.V, d.g + 6 * h->Nc, d.sinv + 6 * h->Nc, reg,
                d.M, d.zg, h->npl);
+    if (use_rcm(h)) {
+        // explicit reduced camera matrix: one streaming pass builds S, the PCG runs on-chip in one kernel
+        TRY(rcm_build(h));
+        TRY(rcm_finalize(h, reg));
+        TRY(rcm_pcg(h));
+        CU(cudaMemcpyAsync(h->h_flags, d.flags, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        double st[4] = {0, 0, 0, 0};
+        if (relres_out) CU(cudaMemcpyAsync(st, d.state, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (h->h_flags[2]) return fail(h, MMBA_ERR_CUDA, "reduced-system PCG: grid barrier timed out");
+        if (its_out) *its_out = h->h_flags[1];
+        if (relres_out) *relres_out = (h->h_flags[1] > 0 && st[1] > 0) ? std::sqrt(st[2] / st[1]) : 0.0;
+        LAUNCH(MMBA_K_VEC, unscale_kernel, cdiv(6 * h->Nc, 256), 256, 0, d.px, d.sinv, 1.0, d.pxt, 6 * h->Nc);
+        TRY(launch_tile<M_BACKSUB>(h, MMBA_K_BACKSUB, backsub_args(h)));
+        CU(cudaGetLastError());
+        return MMBA_OK;
+    }
     TRY(zero(h, d.y, 6 * h->Nc));
     TRY(zero(h, d.Sd, 21 * h->Nc));
     TRY(launch_tile<M_RHS>(h, MMBA_K_RHS, rhs_args(h)));
@@ -951,6 +1069,16 @@ int configure_kernels(mmba_handle* h) {
     TRY(configure_mode<M_JV1>(h));
     TRY(configure_mode<M_JV2>(h));
     TRY(configure_mode<M_BUILD_FULL>(h));
+    if (h->rcm_ready) {
+        TRY(configure_mode<M_SBUILD>(h));
+        // PCG grid: one warp per camera while the cameras last, at most one CTA per SM (all co-resident)
+        h->rcm_grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(h->sm_count, kRcmMaxCtas), h->Nc));
+        h->rcm_warps = (int)std::min<int64_t>(8, (h->Nc + h->rcm_grid - 1) / h->rcm_grid);
+        h->rcm_kmax = (int)((h->Nc + (int64_t)h->rcm_grid * h->rcm_warps - 1) / ((int64_t)h->rcm_grid * h->rcm_warps));
+        const size_t smem = (size_t)h->rcm_warps * h->rcm_kmax * 30 * sizeof(double);
+        if (smem > 200 * 1024) return fail(h, MMBA_ERR_NOMEM, "reduced-system PCG: too many cameras per CTA");
+        CU(cudaFuncSetAttribute(rcm_pcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     return MMBA_OK;
 }
 
@@ -1093,6 +1221,8 @@ void mmba_default_options(mmba_options* opt) {
     opt->pcg_rtol = 1e-8;
     opt->pcg_maxit = 1000;
     opt->profile = 0;
+    opt->schur_mode = MMBA_SCHUR_AUTO;
+    opt->reserved = 0;
 }
 
 int mmba_nccl_unique_id(uint8_t out[128]) {
@@ -1168,6 +1298,8 @@ int mmba_set_options(mmba_handle* h, const mmba_options* opt) {
     h->opt.pcg_rtol = opt->pcg_rtol;
     h->opt.pcg_maxit = opt->pcg_maxit;
     h->opt.profile = opt->profile;
+    if (opt->schur_mode < MMBA_SCHUR_AUTO || opt->schur_mode > MMBA_SCHUR_EXPLICIT) return fail(h, MMBA_ERR_ARG, "schur_mode out of range");
+    h->opt.schur_mode = opt->schur_mode;   // explicit / auto take effect at the next mmba_set_problem
     return MMBA_OK;
 }
 
@@ -1207,6 +1339,20 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     h->nt = pl.n_tiles;
     h->nloc = 6 * h->Nc + 3 * h->npl;
     std::memcpy(h->K, K, sizeof(h->K));
+    // Explicit reduced camera matrix (rcm.h) when it is small next to the observation stream: at most
+    // 20 000 cameras (co-visibility bitmap), blocks within ~1/2 of the J bytes a PCG iteration would stream
+    // and L2-sized, and a bounded S-build cost (pair-blocks per observation).
+    h->rcm_ready = false;
+    h->rcm = RcmPattern();
+    if (h->opt.schur_mode != MMBA_SCHUR_IMPLICIT && n_cams <= 20000) {
+        const bool forced = h->opt.schur_mode == MMBA_SCHUR_EXPLICIT;
+        const int64_t cap_full = forced ? (int64_t)8 << 20 : std::min<int64_t>(((int64_t)96 << 20) / 288, (152 * n_obs / 2) / 288);
+        const bool ok = build_rcm_pattern(h->rcm, n_cams, n_points, n_obs, cam_idx, pt_idx, std::max<int64_t>(cap_full, n_cams));
+        h->rcm_ready = ok && (forced || (h->rcm.nnz_full() <= std::max<int64_t>(cap_full, n_cams) && h->rcm.total_pairs <= 64 * n_obs));
+        if (!h->rcm_ready) h->rcm = RcmPattern();
+    }
+    if (h->opt.schur_mode == MMBA_SCHUR_EXPLICIT && !h->rcm_ready)
+        return fail(h, MMBA_ERR_ARG, "set_problem: the reduced camera matrix is too large to be formed explicitly");
 
     Arena measure;
     carve(h, measure);
@@ -1253,6 +1399,15 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
             }
         });
         TRY(upload(h, d.uv, uvs));
+        if (h->rcm_ready) {
+            TRY(upload(h, d.up_rowptr, h->rcm.up_rowptr));
+            TRY(upload(h, d.up_cols, h->rcm.up_cols));
+            TRY(upload(h, d.rc_rowptr, h->rcm.rowptr));
+            TRY(upload(h, d.rc_cols, h->rcm.cols));
+            TRY(upload(h, d.rc_rows, h->rcm.rows));
+            TRY(upload(h, d.rc_src, h->rcm.src));
+            TRY(upload(h, d.rc_diag, h->rcm.diag));
+        }
         CU(cudaStreamSynchronize(h->stream));
     }
     TileArgs& A = h->targs;
@@ -1457,6 +1612,37 @@ int mmba_eval_gn_step(mmba_handle* h, const double* x, const double* scale, doub
     return get_x(h, d.gn, p);
 }
 
+int mmba_eval_reduced_system(mmba_handle* h, const double* x, const double* scale, double reg, double* S_dense, double* rhs) {
+    TRY(need_problem(h));
+    if (!x || !scale || !S_dense || !rhs) return fail(h, MMBA_ERR_ARG, "eval_reduced_system: null argument");
+    if (!use_rcm(h)) return fail(h, MMBA_ERR_STATE, "eval_reduced_system: the reduced camera matrix is not formed explicitly");
+    Dev& d = h->d;
+    TRY(put_x(h, x, d.x));
+    TRY(linearise(h));
+    {
+        std::vector<double> si(6 * h->Nc + 3 * h->plan.n_points);
+        for (size_t i = 0; i < si.size(); ++i) si[i] = 1.0 / scale[i];
+        TRY(put_x(h, si.data(), d.sinv));
+    }
+    if (h->npl)
+        LAUNCH(MMBA_K_PTINV, point_invert_kernel, cdiv(h->npl, 256), 256, 0, d.V, d.g + 6 * h->Nc, d.sinv + 6 * h->Nc, reg,
+               d.M, d.zg, h->npl);
+    TRY(rcm_build(h));
+    TRY(rcm_finalize(h, reg));
+    const RcmPattern& r = h->rcm;
+    std::vector<double> hS(36 * (size_t)r.nnz_full());
+    CU(cudaMemcpyAsync(hS.data(), d.S, hS.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(rhs, d.rcm_b, 6 * h->Nc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    const int64_t n6 = 6 * h->Nc;
+    std::memset(S_dense, 0, (size_t)n6 * n6 * sizeof(double));
+    for (int64_t k = 0; k < r.nnz_full(); ++k)
+        for (int a = 0; a < 6; ++a)
+            for (int b = 0; b < 6; ++b) S_dense[(6 * (int64_t)r.rows[k] + a) * n6 + 6 * (int64_t)r.cols[k] + b] = hS[k * 36 + a * 6 + b];
+    return MMBA_OK;
+}
+
 int mmba_eval_jnorm2(mmba_handle* h, const double* x, const double* s, double* jnorm2) {
     TRY(need_problem(h));
     if (!x || !s || !jnorm2) return fail(h, MMBA_ERR_ARG, "eval_jnorm2: null argument");
@@ -1522,6 +1708,14 @@ int mmba_bench_kernel(mmba_handle* h, const double* x, int kernel_class, int ite
                 case 101:   // plain streaming read of Jt: the ceiling a trivial kernel reaches on these bytes
                     stream_read_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(reinterpret_cast<const double2*>(d.J),
                                                                                 (int64_t)kJRows * h->ns / 2, d.scal + S_DOT9);
+                    break;
+                case MMBA_K_SBUILD:
+                    if (!use_rcm(h)) return fail(h, MMBA_ERR_STATE, "bench_kernel: the reduced camera matrix is not formed explicitly");
+                    TRY(launch_tile<M_SBUILD>(h, MMBA_K_SBUILD, sbuild_args(h)));
+                    break;
+                case MMBA_K_PCG:
+                    if (!use_rcm(h)) return fail(h, MMBA_ERR_STATE, "bench_kernel: the reduced camera matrix is not formed explicitly");
+                    TRY(rcm_pcg(h));
                     break;
                 case MMBA_K_PTINV:
                     point_invert_kernel<<<cdiv(h->npl, 256), 256, 0, h->stream>>>(d.V, d.g + 6 * h->Nc, d.sinv + 6 * h->Nc, reg,
@@ -1605,6 +1799,27 @@ int mmba_triangulate(int device, int64_t n_frames, const double* projections, in
 }
 
 // ---- host-only functions ------------------------------------------------------------------------
+int mmba_host_rcm_pattern(int64_t n_cams, int64_t n_points, int64_t n_obs, const int64_t* cam_idx, const int64_t* pt_idx,
+                          int64_t sizes[3], int32_t* up_rowptr, int32_t* up_cols, int64_t capacity) {
+    if (n_cams <= 0 || n_points <= 0 || n_obs <= 0 || !cam_idx || !pt_idx || !sizes)
+        return fail(nullptr, MMBA_ERR_ARG, "rcm_pattern: bad argument");
+    for (int64_t i = 0; i < n_obs; ++i)
+        if (cam_idx[i] < 0 || cam_idx[i] >= n_cams || pt_idx[i] < 0 || pt_idx[i] >= n_points)
+            return fail(nullptr, MMBA_ERR_ARG, "rcm_pattern: index out of range at observation " + std::to_string(i));
+    RcmPattern r;
+    if (!build_rcm_pattern(r, n_cams, n_points, n_obs, cam_idx, pt_idx, INT32_MAX / 36))
+        return fail(nullptr, MMBA_ERR_NOMEM, "rcm_pattern: too many blocks");
+    sizes[0] = r.nnz_up();
+    sizes[1] = r.nnz_full();
+    sizes[2] = r.total_pairs;
+    if (up_rowptr) std::memcpy(up_rowptr, r.up_rowptr.data(), (n_cams + 1) * sizeof(int32_t));
+    if (up_cols) {
+        if (capacity < r.nnz_up()) return fail(nullptr, MMBA_ERR_NOMEM, "rcm_pattern: capacity too small");
+        std::memcpy(up_cols, r.up_cols.data(), r.nnz_up() * sizeof(int32_t));
+    }
+    return MMBA_OK;
+}
+
 int mmba_host_tr2d(const double B[3], const double g[2], double delta, double p[2], int* newton) {
     if (!B || !g || !p) return MMBA_ERR_ARG;
     bool nw = false;

@@ -165,7 +165,7 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
             m.nobs = n;
             max_cams = std::max(max_cams, m.ncams);
             max_pts = std::max(max_pts, m.npts);
-            m.pad[0] = m.pad[1] = m.pad[2] = 0;
+            m.pair_mode = m.npairs = m.pad = 0;
             for (int j = 0; j < kTileObs; ++j) {
                 m.slot_cam[j] = 0;
                 m.slot_pt[j] = 0xFFFF;   // empty slots carry the pad marker
@@ -174,13 +174,23 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
                 m.run_cam[j] = 0;
             }
             int i = 0;
+            int64_t npairs = 0;
+            bool dup = false;   // a camera observing the same point twice
             for (int64_t q = rg.p0; q < rg.p1; ++q) {
+                const int64_t L = start[q + 1] - start[q];
+                npairs += L * (L + 1) / 2;
                 for (int64_t o = start[q]; o < start[q + 1]; ++o, ++i) {
                     plan.slot_obs[base + i] = grouped[o];
                     m.slot_cam[i] = (uint16_t)local_of[cam_idx[grouped[o]]];
                     m.slot_pt[i] = (uint16_t)(q - rg.p0);
+                    if (o > start[q] && m.slot_cam[i] == m.slot_cam[i - 1]) dup = true;
                 }
             }
+            // S-build strategy of the tile: with few cameras every (camera pair, row) unit accumulates over the
+            // tile's points in registers and issues one RED per entry; otherwise one unit per (observation pair, row)
+            m.npairs = (int32_t)npairs;
+            const int64_t campairs = (int64_t)m.ncams * (m.ncams + 1) / 2;
+            m.pair_mode = (!dup && (int64_t)m.npts * m.ncams <= kRcmTabCap && campairs * m.npts <= 4 * npairs) ? 1 : 0;
             // stable counting sort of the slots by local camera
             const int nc = m.ncams;
             for (int c = 0; c <= nc; ++c) cnt[c] = 0;

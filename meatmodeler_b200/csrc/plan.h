@@ -16,6 +16,7 @@ constexpr int kTileObs = 256;          // observation slots per tile == threads 
 constexpr uint16_t kPadKey = 0xFFFF;   // sorted-key of an empty slot
 
 constexpr int kMaxRun = 32;            // longest camera run one thread sums (longer runs are split)
+constexpr int kRcmTabCap = 8192;       // S-build (point, camera) -> slot table entries per tile (u16)
 
 // One record per tile, bulk-copied to shared memory as a unit (2592 bytes, 16-byte multiple).
 struct TileMeta {
@@ -24,7 +25,9 @@ struct TileMeta {
     int32_t ncams;      // distinct cameras in the tile
     int32_t nobs;       // live observation slots (the rest of the 256 are padding)
     int32_t nruns;      // camera runs in the tile's camera-sorted order (each at most kMaxRun long)
-    int32_t pad[3];
+    int32_t pair_mode;  // S-build: 1 = camera-pair-major (few cameras, register accumulation), 0 = point-pair-major
+    int32_t npairs;     // sum over the tile's points of L (L + 1) / 2
+    int32_t pad;
     uint16_t slot_cam[kTileObs];   // local camera slot of the observation in its tile
     uint16_t slot_pt[kTileObs];    // local point index of the observation in its tile (0xFFFF = empty slot)
     uint16_t sort_src[kTileObs];   // j-th entry of the tile in camera-sorted order -> slot in tile

@@ -1,0 +1,35 @@
+// Block-sparsity pattern of the reduced camera matrix  S = U - W V'^-1 W^T  (host side).
+//
+// Two cameras share a block of S iff some point is observed by both.  The pattern is computed once per
+// problem from the FULL problem (identical on every rank of a sharded solve, so the block values can be
+// all-reduced), in two forms:
+//   * upper triangle (i <= j) in CSR order: the accumulation target of the S-build kernel;
+//   * full (both triangles) CSR: what the PCG kernel multiplies with; every full block names its source
+//     block in the upper triangle and whether it is read transposed.
+// Pure C++ (no CUDA): covered by the CPU test-suite through mmba_host_rcm_pattern.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mmba {
+
+struct RcmPattern {
+    int64_t n_cams = 0;
+    int64_t total_pairs = 0;            // sum over points of L (L + 1) / 2: pair-blocks one S-build evaluates
+    std::vector<int32_t> up_rowptr;     // [n_cams + 1]
+    std::vector<int32_t> up_cols;       // [nnz_up], ascending per row, the first entry of row i is the diagonal block
+    std::vector<int32_t> rowptr;        // [n_cams + 1] full pattern
+    std::vector<int32_t> cols;          // [nnz_full] ascending per row
+    std::vector<int32_t> rows;          // [nnz_full] row of each full block
+    std::vector<int32_t> src;           // [nnz_full] source block in the upper triangle; bit 31 set = transposed
+    std::vector<int32_t> diag;          // [n_cams] full-pattern index of the diagonal block
+    int64_t nnz_up() const { return (int64_t)up_cols.size(); }
+    int64_t nnz_full() const { return (int64_t)cols.size(); }
+};
+
+// max_blocks: give up (return false, pattern left empty) as soon as the upper triangle exceeds this many blocks.
+bool build_rcm_pattern(RcmPattern& out, int64_t n_cams, int64_t n_points, int64_t n_obs, const int64_t* cam_idx,
+                       const int64_t* pt_idx, int64_t max_blocks);
+
+}  // namespace mmba

@@ -32,11 +32,12 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     # sizes of the C structs as laid out by the compiler (x86-64 SysV)
-    assert ctypes.sizeof(_capi.Options) == 16 + 24 + 8 + 8 + 8 + 128
+    assert ctypes.sizeof(_capi.Options) == 16 + 24 + 8 + 8 + 8 + 128 + 8
     assert ctypes.sizeof(_capi.Result) == 24 + 24 + 8 + 8 + 8
     assert ctypes.sizeof(_capi.IterLog) == 9 * 8
     opt = _capi.default_options()
     assert (opt.ftol, opt.xtol, opt.gtol, opt.nranks, opt.max_nfev) == (1e-4, 1e-8, 1e-8, 1, 0)
+    assert opt.schur_mode == _capi.SCHUR_AUTO
 
 
 def test_no_gpu_means_loud_failure():
@@ -179,3 +180,32 @@ def test_plan_edge_cases():
     with pytest.raises(_capi.MmbaError) as e:
         _capi.plan(300, 1, np.arange(300, dtype=np.int64), np.zeros(300, dtype=np.int64))
     assert e.value.code == -5
+
+
+# ---- block pattern of the reduced camera matrix ---------------------------------------------------
+@pytest.mark.parametrize("windowed", [True, False])
+def test_rcm_pattern_is_the_covisibility_graph(windowed):
+    import scipy.sparse as sp
+    prob = synth.make_problem(40, 900, 5400, seed=3, hard=False, windowed=windowed)
+    ext, K, pts, uv, fi, pi = prob.args()
+    nc, npts = len(ext), len(pts)
+    rowptr, cols, nnz_full, pairs = _capi.host_rcm_pattern(nc, npts, fi, pi)
+    vis = sp.csr_matrix((np.ones(len(fi)), (fi, pi)), shape=(nc, npts))
+    cov = ((vis @ vis.T).toarray() > 0) | np.eye(nc, dtype=bool)
+    dense = np.zeros((nc, nc), dtype=bool)
+    for i in range(nc):
+        c = cols[rowptr[i]:rowptr[i + 1]]
+        assert c[0] == i and np.all(np.diff(c) > 0)
+        dense[i, c] = True
+    assert np.array_equal(dense, np.triu(cov))
+    assert nnz_full == cov.sum()
+    L = np.bincount(pi, minlength=npts)
+    assert pairs == int((L * (L + 1) // 2).sum())
+
+
+def test_rcm_pattern_unobserved_camera_keeps_its_diagonal():
+    fi = np.array([0, 2, 0, 2])
+    pi = np.array([0, 0, 1, 1])
+    rowptr, cols, nnz_full, pairs = _capi.host_rcm_pattern(4, 2, fi, pi)
+    assert rowptr.tolist() == [0, 2, 3, 4, 5] and cols.tolist() == [0, 2, 1, 2, 3]
+    assert nnz_full == 6 and pairs == 6

@@ -77,7 +77,8 @@ def case(request):
     x0 = problem_x0(prob)
     ext, K, pts, uv, fi, pi = prob.args()
     lin = schur_trf.Linearisation(x0, K, len(ext), len(pts), fi, pi, uv)
-    eng = engine_for(prob, pcg_rtol=1e-10)       # the oracle's PCG tolerance
+    # the oracle's PCG tolerance; implicit Schur product (the explicit matrix: test_gpu_schur_explicit.py)
+    eng = engine_for(prob, pcg_rtol=1e-10, schur_mode=_capi.SCHUR_IMPLICIT)
     yield prob, x0, lin, eng
     eng.close()
 

@@ -1,0 +1,131 @@
+"""The explicit reduced camera matrix (schur_mode = EXPLICIT): S-build pass + one-kernel PCG against a numpy
+Schur complement built from the oracle's Jacobian blocks, against the oracle's PCG / TRF, and against the
+implicit path of the same engine."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from meatmodeler_b200 import _capi, synth
+from oracle import schur_trf
+
+from conftest import problem_x0
+from test_gpu_parity import PROBLEMS, engine_for
+
+pytestmark = pytest.mark.gpu
+
+
+def _with_duplicates():
+    """A camera observing the same point twice (two slightly different pixels): legal input for the reference."""
+    prob = synth.make_problem(12, 300, 1500, seed=31, hard=True)
+    rng = np.random.default_rng(4)
+    pick = rng.choice(len(prob.uv), 200, replace=False)
+    prob.uv = np.vstack((prob.uv, prob.uv[pick] + rng.normal(0, 0.3, (200, 2))))
+    prob.cam_idx = np.concatenate((prob.cam_idx, prob.cam_idx[pick]))
+    prob.pt_idx = np.concatenate((prob.pt_idx, prob.pt_idx[pick]))
+    return prob
+
+
+CASES = dict(PROBLEMS)
+CASES["duplicates"] = _with_duplicates
+CASES["long_tracks"] = lambda: synth.make_problem(150, 60, 6000, seed=5, hard=True)   # 100 observations per point
+
+
+@pytest.fixture(scope="module", params=sorted(CASES))
+def xcase(request):
+    prob = CASES[request.param]()
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(len(prob.uv))
+    prob.uv, prob.cam_idx, prob.pt_idx = prob.uv[perm], prob.cam_idx[perm], prob.pt_idx[perm]
+    x0 = problem_x0(prob)
+    ext, K, pts, uv, fi, pi = prob.args()
+    lin = schur_trf.Linearisation(x0, K, len(ext), len(pts), fi, pi, uv)
+    eng = engine_for(prob, pcg_rtol=1e-10, schur_mode=_capi.SCHUR_EXPLICIT)
+    yield prob, x0, lin, eng
+    eng.close()
+
+
+def numpy_reduced_system(lin, d, reg):
+    """S = D_c (U - W V'^-1 W^T) D_c + reg I and b = D_c (g_c - W V'^-1 g_p), dense, from the oracle's blocks."""
+    no, nc, npt = len(lin.fi), lin.Nc, lin.Np
+    rows = np.repeat(np.arange(2 * no), 6)
+    Jc = sp.csr_matrix((lin.Jc.reshape(-1), (rows, (6 * lin.fi[:, None, None] + np.arange(6)[None, None, :] +
+                                                    np.zeros((1, 2, 1), dtype=np.int64)).reshape(-1))), shape=(2 * no, 6 * nc))
+    rows3 = np.repeat(np.arange(2 * no), 3)
+    Jp = sp.csr_matrix((lin.Jp.reshape(-1), (rows3, (3 * lin.pi[:, None, None] + np.arange(3)[None, None, :] +
+                                                     np.zeros((1, 2, 1), dtype=np.int64)).reshape(-1))), shape=(2 * no, 3 * npt))
+    dc, dp = d[:6 * nc], d[6 * nc:]
+    Jc = Jc @ sp.diags(dc)
+    Jp = Jp @ sp.diags(dp)
+    U = (Jc.T @ Jc).toarray()
+    W = (Jc.T @ Jp).tocsr()
+    V = (Jp.T @ Jp + reg * sp.identity(3 * npt)).tocsc()
+    Vinv = sp.linalg.inv(V) if npt * 3 < 4000 else None
+    g = d * lin.grad()
+    if Vinv is None:
+        lu = sp.linalg.splu(V)
+        WVi = lu.solve(W.T.toarray()).T
+    else:
+        WVi = (W @ Vinv).toarray()
+    S = U + reg * np.eye(6 * nc) - WVi @ W.T.toarray()
+    b = g[:6 * nc] - WVi @ g[6 * nc:]
+    return S, b
+
+
+@pytest.mark.parametrize("reg", [1e-2, 1e-6])
+def test_reduced_system_vs_numpy(xcase, reg):
+    prob, x0, lin, eng = xcase
+    d = 1.0 / np.where(lin.colnorm() == 0, 1.0, lin.colnorm())
+    S, b = eng.reduced_system(x0, d, reg)
+    S_ref, b_ref = numpy_reduced_system(lin, d, reg)
+    assert np.abs(S - S.T).max() <= 1e-12 * np.abs(S).max()
+    assert np.abs(S - S_ref).max() <= 1e-10 * np.abs(S_ref).max()
+    assert np.abs(b - b_ref).max() <= 1e-10 * np.abs(b_ref).max()
+
+
+@pytest.mark.parametrize("reg", [1e-2, 1e-6])
+def test_explicit_gauss_newton_step_vs_oracle(xcase, reg):
+    prob, x0, lin, eng = xcase
+    d = 1.0 / np.where(lin.colnorm() == 0, 1.0, lin.colnorm())
+    p, its, rel = eng.gn_step(x0, d, reg)
+    p_ref, its_ref, rel_ref = schur_trf.schur_pcg(lin, d, reg, 1e-10, 1000)
+    assert rel <= 1e-10 and abs(its - its_ref) <= max(3, its_ref // 5)
+    Jdp = lin.jdot(d * p)
+    nc = lin.Nc
+    JtJdp = np.hstack((schur_trf._segsum(lin.fi, np.einsum("nij,ni->nj", lin.Jc, Jdp), nc).ravel(),
+                       schur_trf._segsum(lin.pi, np.einsum("nij,ni->nj", lin.Jp, Jdp), lin.Np).ravel()))
+    rhs = d * lin.grad()
+    resid = d * JtJdp + reg * p - rhs
+    assert np.linalg.norm(resid) <= 1e-8 * np.linalg.norm(rhs)
+    assert np.linalg.norm(p - p_ref) <= 1e-5 * np.linalg.norm(p_ref)
+
+
+def test_explicit_solve_vs_oracle_and_implicit(xcase):
+    prob, x0, lin, eng = xcase
+    ext, K, pts, uv, fi, pi = prob.args()
+    rec = []
+    out = schur_trf.solve(x0, K, len(ext), len(pts), fi, pi, uv, record=rec)
+    x, r, fun = eng.solve(x0, want_fun=True)
+    costs = [row["cost"] for row in eng.log()][1:]
+    assert r.nfev == out["nfev"] and r.status == out["status"] and len(costs) == len(rec)
+    np.testing.assert_allclose(costs, rec, rtol=1e-8)
+    assert r.cost == pytest.approx(out["cost"], rel=1e-9)
+    # the same engine with the implicit product (the mode can be lowered on a live handle)
+    eng.set_options(schur_mode=_capi.SCHUR_IMPLICIT)
+    x2, r2, _ = eng.solve(x0)
+    eng.set_options(schur_mode=_capi.SCHUR_EXPLICIT)
+    assert r2.nfev == r.nfev and r2.status == r.status
+    assert r2.cost == pytest.approx(r.cost, rel=1e-9)
+    assert r.pcg_iterations > 0
+
+
+def test_auto_mode_picks_explicit_for_video_like_visibility_only():
+    dense = synth.make_problem(300, 900, 4000, seed=9, windowed=False)
+    video = synth.make_config("C1", hard=True)
+    x0 = problem_x0(video)
+    with engine_for(video) as eng:
+        d = np.ones(x0.size)
+        eng.reduced_system(x0, d, 1e-3)                     # formed: no error
+    with engine_for(dense) as eng:
+        with pytest.raises(_capi.MmbaError) as e:
+            eng.reduced_system(problem_x0(dense), np.ones(problem_x0(dense).size), 1e-3)
+        assert e.value.code == -3
