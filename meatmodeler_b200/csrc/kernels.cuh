@@ -81,7 +81,7 @@ struct Traits {
     // J-streaming tiles are 39 KB: two stages per CTA, two CTAs per SM.  The projection passes (BUILD, RESID)
     // stage only 7-13 KB per tile but gather 12-21 doubles per camera, so their per-tile latency chains need
     // more tiles (and producer warps) in flight.
-    static constexpr int kStages = is_project(MODE) ? 4 : 2;
+    static constexpr int kStages = is_project(MODE) ? 4 : MODE == M_SBUILD ? 3 : 2;   // SBUILD: one CTA per SM
     static constexpr int kThreads = kConsumers + 32 * kStages;
     static constexpr bool kLoadUV = !kLoadJ;
     // doubles gathered per camera into shared memory, and the (odd, conflict-free) smem stride
@@ -101,6 +101,7 @@ struct Traits {
     // Jp M per observation.
     static constexpr int kStageRows = is_build(MODE) ? 22 : MODE == M_SBUILD ? 12 : 0;
     static constexpr int kStageBufs = 1;
+    static constexpr int kMinBlocks = MODE == M_SBUILD ? 1 : 2;   // SBUILD: one CTA per SM, up to 204 registers per thread
 };
 
 struct TileArgs {
@@ -142,7 +143,7 @@ struct ModeArgs {
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
     int off_J, off_meta, off_uv, off_camid, off_camvec, off_pa, off_pb, stage_bytes;
-    int off_stages, off_pt, off_z, off_buf, off_red, off_ids, off_ytab, off_tab, off_pstart, total;
+    int off_stages, off_pt, off_z, off_buf, off_red, off_ids, off_ytab, off_tab, off_pstart, off_run, total;
 };
 
 __host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -184,6 +185,8 @@ __host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts, int
     if (MODE == M_SBUILD) o += kRcmTabCap * 2;                     // (point, camera) -> slot table, u16
     L.off_pstart = o;
     if (MODE == M_SBUILD) o += 2 * align_up((max_pts + 2) * 4, 16);  // first slot / pair offset of every point
+    L.off_run = o;
+    if (MODE == M_SBUILD) o += 48 * 4;                             // cameras of the current accumulation run + flag
     L.total = o;
     return L;
 }
@@ -485,6 +488,41 @@ __device__ __forceinline__ void sbuild_row(const double* __restrict__ sJ, const 
     for (int b = 0; b < 6; ++b) acc[b] += t0 * sJ[b * kT + j] + t1 * sJ[(6 + b) * kT + j];
 }
 
+// acc (6x6, row-major) += Jc_i^T (delta_ij I - Jp_i M Jp_j^T) Jc_j : the whole block of one observation pair
+__device__ __forceinline__ void sbuild_block(const double* __restrict__ sJ, const double* __restrict__ s_pm, int i, int j,
+                                             double (&acc)[36]) {
+    double g00 = i == j ? 1.0 : 0.0, g01 = 0.0, g10 = 0.0, g11 = g00;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double pm0 = s_pm[k * kBufStride + i], pm1 = s_pm[(3 + k) * kBufStride + i];
+        const double q0 = sJ[(12 + k) * kT + j], q1 = sJ[(15 + k) * kT + j];
+        g00 -= pm0 * q0;
+        g01 -= pm0 * q1;
+        g10 -= pm1 * q0;
+        g11 -= pm1 * q1;
+    }
+    double h0[6], h1[6];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        const double c0 = sJ[b * kT + j], c1 = sJ[(6 + b) * kT + j];
+        h0[b] = g00 * c0 + g01 * c1;
+        h1[b] = g10 * c0 + g11 * c1;
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        const double c0 = sJ[a * kT + i], c1 = sJ[(6 + a) * kT + i];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) acc[a * 6 + b] += c0 * h0[b] + c1 * h1[b];
+    }
+}
+
+// point slices per camera pair of the persistent S-build path: a power of two, 256 threads in all
+__device__ __forceinline__ int sbuild_slices(int npair) {
+    int s = 1;
+    while (s < 8 && 2 * s * npair <= kConsumers) s *= 2;
+    return s;
+}
+
 // ---------------------------------------------------------------------------------------------
 // The streaming kernel.  Algorithmic bytes per observation:
 //   BUILD   184  (24 in: metadata + uv; 16 residual + 144 Jacobian out) + fused V/g_p, U/g_c, cost
@@ -498,7 +536,7 @@ __device__ __forceinline__ void sbuild_row(const double* __restrict__ sJ, const 
 //                observation pairs of every point (upper blocks), and the Schur right-hand side y_c (as RHS)
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const TileArgs A, const ModeArgs P) {
+__global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBlocks) tile_kernel(const TileArgs A, const ModeArgs P) {
     using T = Traits<MODE>;
     constexpr int kStages = T::kStages;
     constexpr int kThreads = T::kThreads;
@@ -545,7 +583,8 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
         // shared memory and arrives, so a stage is almost never without a copy in flight.
         const int pw = (tid - kConsumers) >> 5, lane = tid & 31;
         constexpr int kCPL = kT / 32;   // camera ids per lane (registers)
-        constexpr int kBatch = 8;
+        // gathered values prefetched one tile ahead per lane (SBUILD stages 9 values per point: up to 1 152 per tile)
+        constexpr int kBatch = MODE == M_SBUILD ? 16 : 8;
         const int stage = pw;
         unsigned char* st = smem + L.off_stages + stage * L.stage_bytes;
         int* s_camid = reinterpret_cast<int*>(st + L.off_camid);
@@ -679,6 +718,33 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
     int round = 0;                 // staging-buffer parity of camera_scatter_round
     int par = 0;                   // per-point accumulator parity (MATVEC / BACKSUB)
     double acc[3] = {0, 0, 0};     // cost (BUILD / RESID) or Gram (JV)
+    // SBUILD: one 6x6 block of the reduced camera matrix per thread, accumulated over a run of tiles with the
+    // same camera list (video-like visibility: tens of tiles) and added to HBM once per run
+    double sacc[MODE == M_SBUILD ? 36 : 1];
+#pragma unroll
+    for (int i = 0; i < (MODE == M_SBUILD ? 36 : 1); ++i) sacc[i] = 0.0;
+    int run_ncams = 0;
+    bool run_touched = false;
+    int* s_run = reinterpret_cast<int*>(smem + L.off_run);   // [0..31] cameras of the run, [32] "list differs" flag
+    auto sbuild_flush = [&]() {
+        if constexpr (MODE == M_SBUILD) {
+            if (run_ncams) {
+                const int npair = run_ncams * (run_ncams + 1) / 2, nslice = sbuild_slices(npair);
+                const int pr = tid / nslice;
+                if (pr < npair && run_touched) {
+                    int a, b;
+                    tri_decode(pr, run_ncams, a, b);
+                    double* dst = P.Tup + (int64_t)rcm_lookup(P.up_rowptr, P.up_cols, s_run[a], s_run[b]) * 36;
+#pragma unroll
+                    for (int e = 0; e < 36; ++e) red_add(dst + e, sacc[e]);
+                }
+#pragma unroll
+                for (int e = 0; e < 36; ++e) sacc[e] = 0.0;
+                run_touched = false;
+                run_ncams = 0;
+            }
+        }
+    };
     int stage = 0;
     unsigned phase = 0;
     for (int t = t_begin; t < t_end; ++t) {
@@ -862,6 +928,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
                     s_pm[(r * 3 + 1) * kBufStride + tid] = a0 * m1 + a1 * m3 + a2 * m4;
                     s_pm[(r * 3 + 2) * kBufStride + tid] = a0 * m2 + a1 * m4 + a2 * m5;
                 }
+                if (tid == 0) s_run[32] = 0;
                 if (pair_mode) {
                     for (int i = tid; i < npts * ncams; i += kConsumers) s_tab[i] = 0xFFFF;
                 } else {
@@ -872,6 +939,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
             }
             if (pair_mode) {
                 if (valid) s_tab[lp * ncams + lc] = (uint16_t)tid;
+                if (pair_mode == 2 && tid < ncams && (ncams != run_ncams || s_camid[tid] != s_run[tid])) s_run[32] = 1;
             } else if (tid == 0) {
                 int o = 0;
                 for (int p = 0; p < npts; ++p) {
@@ -882,7 +950,34 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
                 s_poff[npts] = o;
             }
             consumer_sync();
-            if (pair_mode) {
+            if (!(pair_mode == 2 && run_ncams == ncams && s_run[32] == 0)) {
+                // this tile does not continue the current run: add the run's blocks to HBM, start a new one
+                const bool had_run = run_ncams != 0;
+                sbuild_flush();
+                if (pair_mode == 2) {
+                    if (had_run) consumer_sync();   // every thread has read the old camera list
+                    if (tid < ncams) s_run[tid] = s_camid[tid];
+                    run_ncams = ncams;
+                    consumer_sync();
+                }
+            }
+            if (pair_mode == 2) {
+                // unit = (camera pair a <= b, point slice): whole 6x6 block in registers
+                const int npair = ncams * (ncams + 1) / 2, nslice = sbuild_slices(npair);
+                const int sl = tid % nslice, pr = tid / nslice;
+                if (pr < npair) {
+                    int a, b;
+                    tri_decode(pr, ncams, a, b);
+                    for (int p = sl; p < npts; p += nslice) {
+                        const unsigned i = s_tab[p * ncams + a];
+                        if (i == 0xFFFFu) continue;
+                        const unsigned j = s_tab[p * ncams + b];
+                        if (j == 0xFFFFu) continue;
+                        run_touched = true;
+                        sbuild_block(sJ, s_pm, (int)i, (int)j, sacc);
+                    }
+                }
+            } else if (pair_mode) {
                 // unit = (camera pair a <= b of the tile, block row, point slice): register accumulation over the
                 // tile's points, then one RED per entry
                 const int npair = ncams * (ncams + 1) / 2;
@@ -1069,6 +1164,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, 2) tile_kernel(const T
             phase ^= 1;
         }
     }
+    sbuild_flush();
     if constexpr (MODE == M_MATVEC) {
         // few cameras (heavy RED contention on few addresses): the CTA's sums were kept in shared memory
         if (A.ytab_cams) {

@@ -114,9 +114,11 @@ struct Dev {
     double* scal;
     double* xp_full;   // all points, internal order (nranks > 1 only)
     // explicit reduced camera matrix (rcm.h / rcm.cuh); null when the implicit product is used
-    double *Tup, *S, *rcm_b, *rcm_part;
+    double *Tup, *S, *rcm_b;
     int *up_rowptr, *up_cols, *rc_rowptr, *rc_cols, *rc_rows, *rc_src, *rc_diag;
-    unsigned* rcm_bar;
+    int *rc_halo_ptr, *rc_halo_cols, *rc_own;
+    uint16_t* rc_lcol;
+    RcmSlot* rcm_slots;
 };
 
 // One-shot peer all-reduce of the per-iteration Schur product (see xchg_push_kernel)
@@ -151,8 +153,10 @@ struct mmba_handle {
     bool has_problem = false;
     Plan plan;
     RcmPattern rcm;
+    RcmPartition rcm_part;
     bool rcm_ready = false;        // pattern built and device arrays carved for the current problem
-    int rcm_grid = 0, rcm_warps = 0, rcm_kmax = 0;
+    int rcm_warps = 0, rcm_s_in_smem = 0;
+    size_t rcm_smem_bytes = 0;
     int64_t Nc = 0, npl = 0, ns = 0, nt = 0, nloc = 0;
     double K[9];
     void* arena = nullptr;
@@ -336,7 +340,6 @@ void carve(mmba_handle* h, Arena& a) {
         d.Tup = a.take<double>(36 * (size_t)r.nnz_up());
         d.S = a.take<double>(36 * (size_t)r.nnz_full());
         d.rcm_b = a.take<double>(6 * Nc);
-        d.rcm_part = a.take<double>(2 * (size_t)kRcmMaxCtas * 2);
         d.up_rowptr = a.take<int>(Nc + 1);
         d.up_cols = a.take<int>(r.nnz_up());
         d.rc_rowptr = a.take<int>(Nc + 1);
@@ -344,11 +347,17 @@ void carve(mmba_handle* h, Arena& a) {
         d.rc_rows = a.take<int>(r.nnz_full());
         d.rc_src = a.take<int>(r.nnz_full());
         d.rc_diag = a.take<int>(Nc);
-        d.rcm_bar = a.take<unsigned>(4);
+        d.rc_halo_ptr = a.take<int>(h->rcm_part.halo_ptr.size());
+        d.rc_halo_cols = a.take<int>(h->rcm_part.halo_cols.size());
+        d.rc_own = a.take<int>(Nc);
+        d.rc_lcol = a.take<uint16_t>(r.nnz_full());
+        d.rcm_slots = a.take<RcmSlot>(2 * (size_t)kRcmMaxCtas);
     } else {
-        d.Tup = d.S = d.rcm_b = d.rcm_part = nullptr;
+        d.Tup = d.S = d.rcm_b = nullptr;
         d.up_rowptr = d.up_cols = d.rc_rowptr = d.rc_cols = d.rc_rows = d.rc_src = d.rc_diag = nullptr;
-        d.rcm_bar = nullptr;
+        d.rc_halo_ptr = d.rc_halo_cols = d.rc_own = nullptr;
+        d.rc_lcol = nullptr;
+        d.rcm_slots = nullptr;
     }
 }
 
@@ -729,20 +738,23 @@ RcmPcgArgs rcm_pcg_args(mmba_handle* h) {
     RcmPcgArgs A{};
     A.S = d.S;
     A.rowptr = d.rc_rowptr;
-    A.cols = d.rc_cols;
+    A.lcol = d.rc_lcol;
+    A.halo_ptr = d.rc_halo_ptr;
+    A.halo_cols = d.rc_halo_cols;
+    A.own_l = d.rc_own;
     A.Pinv = d.Pinv;
     A.b = d.rcm_b;
     A.x = d.px;
     A.z = d.pz;
-    A.p0 = d.pp;
-    A.p1 = d.pq;
-    A.part = d.rcm_part;
-    A.bar = d.rcm_bar;
+    A.slots = d.rcm_slots;
     A.flags = d.flags;
     A.state = d.state;
     A.n_cams = (int)h->Nc;
     A.maxit = h->opt.pcg_maxit;
-    A.kmax = h->rcm_kmax;
+    A.cpc = h->rcm_part.cpc;
+    A.nblk_max = h->rcm_part.nblk_max;
+    A.nh_max = h->rcm_part.nh_max;
+    A.s_in_smem = h->rcm_s_in_smem;
     A.rtol2 = h->opt.pcg_rtol * h->opt.pcg_rtol;
     return A;
 }
@@ -771,13 +783,13 @@ int rcm_finalize(mmba_handle* h, double reg) {
 // the whole PCG solve: one cooperative launch
 int rcm_pcg(mmba_handle* h) {
     Dev& d = h->d;
-    CU(cudaMemsetAsync(d.rcm_bar, 0, 4 * sizeof(unsigned), h->stream));
+    CU(cudaMemsetAsync(d.rcm_slots, 0, 2 * (size_t)h->rcm_part.n_ctas * sizeof(RcmSlot), h->stream));
     CU(cudaMemsetAsync(d.flags, 0, 3 * sizeof(int), h->stream));
     RcmPcgArgs A = rcm_pcg_args(h);
     void* args[] = {&A};
     prof_begin(h, MMBA_K_PCG);
-    CU(cudaLaunchCooperativeKernel((const void*)rcm_pcg_kernel, dim3(h->rcm_grid), dim3(32 * h->rcm_warps), args,
-                                   (size_t)h->rcm_warps * h->rcm_kmax * 30 * sizeof(double), h->stream));
+    CU(cudaLaunchCooperativeKernel((const void*)rcm_pcg_kernel, dim3(h->rcm_part.n_ctas), dim3(32 * h->rcm_warps), args,
+                                   h->rcm_smem_bytes, h->stream));
     prof_end(h, MMBA_K_PCG);
     return MMBA_OK;
 }
@@ -1071,13 +1083,16 @@ int configure_kernels(mmba_handle* h) {
     TRY(configure_mode<M_BUILD_FULL>(h));
     if (h->rcm_ready) {
         TRY(configure_mode<M_SBUILD>(h));
-        // PCG grid: one warp per camera while the cameras last, at most one CTA per SM (all co-resident)
-        h->rcm_grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(h->sm_count, kRcmMaxCtas), h->Nc));
-        h->rcm_warps = (int)std::min<int64_t>(8, (h->Nc + h->rcm_grid - 1) / h->rcm_grid);
-        h->rcm_kmax = (int)((h->Nc + (int64_t)h->rcm_grid * h->rcm_warps - 1) / ((int64_t)h->rcm_grid * h->rcm_warps));
-        const size_t smem = (size_t)h->rcm_warps * h->rcm_kmax * 30 * sizeof(double);
-        if (smem > 200 * 1024) return fail(h, MMBA_ERR_NOMEM, "reduced-system PCG: too many cameras per CTA");
-        CU(cudaFuncSetAttribute(rcm_pcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // PCG grid (rcm_part): contiguous camera ranges, at most one CTA per SM (all co-resident), one warp per
+        // camera of the range.  The CTA's rows of S stay in shared memory when they fit, else they are re-read
+        // from L2 every iteration.
+        const RcmPartition& pt = h->rcm_part;
+        h->rcm_warps = std::min(kRcmPcgThreads / 32, pt.cpc);
+        h->rcm_s_in_smem = rcm_smem(pt.cpc, pt.nblk_max, pt.nh_max, 1).total <= 200 * 1024 ? 1 : 0;
+        const RcmSmem rl = rcm_smem(pt.cpc, pt.nblk_max, pt.nh_max, h->rcm_s_in_smem);
+        if (rl.total > 200 * 1024) return fail(h, MMBA_ERR_NOMEM, "reduced-system PCG: too many cameras per CTA");
+        h->rcm_smem_bytes = (size_t)rl.total;
+        CU(cudaFuncSetAttribute(rcm_pcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rl.total));
     }
     return MMBA_OK;
 }
@@ -1350,6 +1365,14 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
         const bool ok = build_rcm_pattern(h->rcm, n_cams, n_points, n_obs, cam_idx, pt_idx, std::max<int64_t>(cap_full, n_cams));
         h->rcm_ready = ok && (forced || (h->rcm.nnz_full() <= std::max<int64_t>(cap_full, n_cams) && h->rcm.total_pairs <= 64 * n_obs));
         if (!h->rcm_ready) h->rcm = RcmPattern();
+        else {
+            build_rcm_partition(h->rcm_part, h->rcm, std::min(h->sm_count, kRcmMaxCtas));
+            // the PCG kernel keeps the search direction on every CTA's halo in shared memory
+            if (rcm_smem(h->rcm_part.cpc, h->rcm_part.nblk_max, h->rcm_part.nh_max, 0).total > 200 * 1024) {
+                h->rcm_ready = false;
+                h->rcm = RcmPattern();
+            }
+        }
     }
     if (h->opt.schur_mode == MMBA_SCHUR_EXPLICIT && !h->rcm_ready)
         return fail(h, MMBA_ERR_ARG, "set_problem: the reduced camera matrix is too large to be formed explicitly");
@@ -1407,6 +1430,10 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
             TRY(upload(h, d.rc_rows, h->rcm.rows));
             TRY(upload(h, d.rc_src, h->rcm.src));
             TRY(upload(h, d.rc_diag, h->rcm.diag));
+            TRY(upload(h, d.rc_halo_ptr, h->rcm_part.halo_ptr));
+            TRY(upload(h, d.rc_halo_cols, h->rcm_part.halo_cols));
+            TRY(upload(h, d.rc_own, h->rcm_part.own_l));
+            TRY(upload(h, d.rc_lcol, h->rcm_part.lcol));
         }
         CU(cudaStreamSynchronize(h->stream));
     }

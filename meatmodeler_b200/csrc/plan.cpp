@@ -29,16 +29,27 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
     plan.rank = rank;
     plan.nranks = nranks;
 
-    // 1. per-point observation count and first (smallest) camera
+    // 1. per-point observation count and first camera.  "First" is the smallest camera id, except for tracks
+    //    that wrap around a closed camera ring (turntable video: frames N-1 and 0 are neighbours): a track spanning
+    //    more than half of the ids is keyed by its smallest camera in the upper half, so that the window
+    //    {190..199, 0..9} sorts next to {190..199} instead of mixing with {0..19} (fewer cameras per tile).
     std::vector<int32_t> count(n_points, 0), first_cam(n_points, (int32_t)n_cams);
-    for (int64_t i = 0; i < n_obs; ++i) {
-        const int64_t c = cam_idx[i], p = pt_idx[i];
-        if (c < 0 || c >= n_cams || p < 0 || p >= n_points) {
-            err = "set_problem: index out of range at observation " + std::to_string(i);
-            return MMBA_ERR_ARG;
+    {
+        std::vector<int32_t> last_cam(n_points, -1), first_hi(n_points, (int32_t)n_cams);
+        const int64_t half = n_cams / 2;
+        for (int64_t i = 0; i < n_obs; ++i) {
+            const int64_t c = cam_idx[i], p = pt_idx[i];
+            if (c < 0 || c >= n_cams || p < 0 || p >= n_points) {
+                err = "set_problem: index out of range at observation " + std::to_string(i);
+                return MMBA_ERR_ARG;
+            }
+            ++count[p];
+            if (c < first_cam[p]) first_cam[p] = (int32_t)c;
+            if (c > last_cam[p]) last_cam[p] = (int32_t)c;
+            if (c >= half && c < first_hi[p]) first_hi[p] = (int32_t)c;
         }
-        ++count[p];
-        if (c < first_cam[p]) first_cam[p] = (int32_t)c;
+        for (int64_t p = 0; p < n_points; ++p)
+            if (count[p] && last_cam[p] - first_cam[p] > half && first_hi[p] < n_cams) first_cam[p] = first_hi[p];
     }
     for (int64_t p = 0; p < n_points; ++p) {
         if (count[p] > kTileObs) {
@@ -191,6 +202,7 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
             m.npairs = (int32_t)npairs;
             const int64_t campairs = (int64_t)m.ncams * (m.ncams + 1) / 2;
             m.pair_mode = (!dup && (int64_t)m.npts * m.ncams <= kRcmTabCap && campairs * m.npts <= 4 * npairs) ? 1 : 0;
+            if (m.pair_mode == 1 && campairs <= kTileObs) m.pair_mode = 2;   // one whole 6x6 block per thread, kept across tiles
             // stable counting sort of the slots by local camera
             const int nc = m.ncams;
             for (int c = 0; c <= nc; ++c) cnt[c] = 0;

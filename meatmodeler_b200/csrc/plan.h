@@ -25,7 +25,9 @@ struct TileMeta {
     int32_t ncams;      // distinct cameras in the tile
     int32_t nobs;       // live observation slots (the rest of the 256 are padding)
     int32_t nruns;      // camera runs in the tile's camera-sorted order (each at most kMaxRun long)
-    int32_t pair_mode;  // S-build: 1 = camera-pair-major (few cameras, register accumulation), 0 = point-pair-major
+    int32_t pair_mode;  // S-build: 0 = point-pair-major; 1 = camera-pair-major (row units, flushed per tile);
+                        // 2 = camera-pair-major with <= 256 camera pairs: one 6x6 block per thread, kept in registers
+                        //     across consecutive tiles that touch the same cameras
     int32_t npairs;     // sum over the tile's points of L (L + 1) / 2
     int32_t pad;
     uint16_t slot_cam[kTileObs];   // local camera slot of the observation in its tile

@@ -113,4 +113,42 @@ bool build_rcm_pattern(RcmPattern& out, int64_t n_cams, int64_t n_points, int64_
     return true;
 }
 
+void build_rcm_partition(RcmPartition& out, const RcmPattern& pat, int max_ctas) {
+    out = RcmPartition();
+    const int64_t nc = pat.n_cams;
+    // a few cameras per CTA even for small problems: fewer CTAs make the grid barrier cheaper
+    int64_t g = std::max<int64_t>(1, std::min<int64_t>(max_ctas, (nc + 3) / 4));
+    const int64_t cpc = (nc + g - 1) / g;
+    g = (nc + cpc - 1) / cpc;
+    out.n_ctas = (int)g;
+    out.cpc = (int)cpc;
+    out.halo_ptr.assign(g + 1, 0);
+    out.lcol.resize(pat.nnz_full());
+    out.own_l.assign(nc, 0);
+    std::vector<int32_t> local_of(nc, -1), list;
+    for (int64_t b = 0; b < g; ++b) {
+        const int64_t c0 = b * cpc, c1 = std::min(nc, c0 + cpc);
+        const int32_t e0 = pat.rowptr[c0], e1 = pat.rowptr[c1];
+        list.clear();
+        for (int32_t e = e0; e < e1; ++e) {
+            const int32_t j = pat.cols[e];
+            if (local_of[j] != (int32_t)b) {
+                local_of[j] = (int32_t)b;
+                list.push_back(j);
+            }
+        }
+        std::sort(list.begin(), list.end());
+        // reuse local_of as the index table of this CTA (overwritten CTA by CTA; cameras outside `list` are never read)
+        std::vector<int32_t>& idx = local_of;
+        for (size_t i = 0; i < list.size(); ++i) idx[list[i]] = (int32_t)i;
+        for (int32_t e = e0; e < e1; ++e) out.lcol[e] = (uint16_t)idx[pat.cols[e]];
+        for (int64_t c = c0; c < c1; ++c) out.own_l[c] = idx[c];
+        for (int32_t j : list) idx[j] = -1 - (int32_t)b;   // never equal to a later CTA id
+        out.halo_ptr[b + 1] = out.halo_ptr[b] + (int32_t)list.size();
+        out.halo_cols.insert(out.halo_cols.end(), list.begin(), list.end());
+        out.nblk_max = std::max(out.nblk_max, (int)(e1 - e0));
+        out.nh_max = std::max(out.nh_max, (int)list.size());
+    }
+}
+
 }  // namespace mmba

@@ -17,7 +17,7 @@
 
 namespace mmba {
 
-constexpr int kRcmMaxCtas = 256;   // capacity of the per-CTA partial-sum slots
+constexpr int kRcmMaxCtas = 256;   // capacity of the per-CTA reduction slots
 constexpr int kRcmSlots = 5;       // lanes of a warp: 5 block slots x 6 rows (lanes 30, 31 idle)
 
 // S[k] = D_i T[src(k)]^(T) D_j (+ reg I on the diagonal); one thread per entry
@@ -61,50 +61,43 @@ __global__ void __launch_bounds__(kCamBlock) rcm_prepare_kernel(const double* __
     }
 }
 
+// One slot per CTA and reduction parity, 1 KB apart: every CTA polls every slot, so the slots must sit on
+// different L2 slices (address bits 8 and 10.. select the slice) or a handful of slices serves G^2 requests.
+struct RcmSlot {
+    double v0, v1;              // this CTA's partial sums of one reduction
+    unsigned long long seq;     // reduction number they belong to (written last, with release semantics)
+    unsigned long long pad[125];
+};
+static_assert(sizeof(RcmSlot) == 1024, "RcmSlot stride");
+
 struct RcmPcgArgs {
-    const double* S;        // [nnz_full][36]
-    const int* rowptr;      // [Nc + 1]
-    const int* cols;        // [nnz_full]
-    const double* Pinv;     // [Nc][21]
-    const double* b;        // [Nc][6]
-    double* x;              // [Nc][6]  result (scaled step)
-    double* z;              // [Nc][6]  preconditioned residual, shared through L2
-    double* p0;             // [Nc][6]  search direction, two parities
-    double* p1;
-    double* part;           // [2][kRcmMaxCtas][2] per-CTA partial sums
-    unsigned* bar;          // grid-barrier counter, zero at launch
-    int* flags;             // [0] stop code (0 = maxit reached, 1 = converged, 2 = breakdown), [1] iterations,
-                            // [2] set when a grid barrier timed out
-    double* state;          // [1] ||b||^2, [2] ||r||^2
-    int n_cams, maxit, kmax;
+    const double* S;            // [nnz_full][36]
+    const int* rowptr;          // [Nc + 1]
+    const uint16_t* lcol;       // [nnz_full] column of each block as an index into its CTA's halo list
+    const int* halo_ptr;        // [G + 1]
+    const int* halo_cols;       // global camera ids of every CTA's halo
+    const int* own_l;           // [Nc] index of camera c in its CTA's halo list
+    const double* Pinv;         // [Nc][21]
+    const double* b;            // [Nc][6]
+    double* x;                  // [Nc][6]  result (scaled step)
+    double* z;                  // [Nc][6]  preconditioned residual, the one vector exchanged through L2
+    RcmSlot* slots;             // [2][G] partial sums + arrival sequence numbers, zero at launch
+    int* flags;                 // [0] stop code (0 = maxit reached, 1 = converged, 2 = breakdown), [1] iterations,
+                                // [2] set when a grid-wide reduction timed out
+    double* state;              // [1] ||b||^2, [2] ||r||^2
+    int n_cams, maxit, cpc, nblk_max, nh_max, s_in_smem;
     double rtol2;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-
-// All CTAs of the (co-resident, cooperatively launched) grid.  Returns false when the other CTAs did not
-// arrive within ~1 s (never expected; the kernel then gives up instead of hanging the device).
-__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned target, int* s_dead) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
-        const long long t0 = clock64();
-        while (ld_acquire_gpu_u32(bar) < target) {
-            if (clock64() - t0 > (1ll << 31)) {
-                *s_dead = 1;
-                break;
-            }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-    return *s_dead == 0;
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 __device__ __forceinline__ double warp_sum_all(double v) {
 #pragma unroll
@@ -112,28 +105,83 @@ __device__ __forceinline__ double warp_sum_all(double v) {
     return v;
 }
 
+constexpr int kRcmPcgThreads = 256;
+
+// shared-memory carve-up of rcm_pcg_kernel (same arithmetic on the host)
+struct RcmSmem {
+    int off_S, off_pinv, off_vec, off_ph, off_hcols, off_rowptr, off_own, off_lcol, total;
+};
+__host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, int s_in_smem) {
+    RcmSmem L{};
+    int o = 0;
+    L.off_S = o;
+    if (s_in_smem) o += nblk_max * 36 * 8;
+    L.off_pinv = o;
+    o += cpc * 21 * 8;
+    L.off_vec = o;
+    o += cpc * 18 * 8;                       // x, r, q of the CTA's cameras
+    L.off_ph = o;
+    o += nh_max * 6 * 8;                     // search direction on the CTA's halo
+    L.off_hcols = o;
+    o += nh_max * 4;
+    L.off_rowptr = o;
+    o += (cpc + 1) * 4;
+    L.off_own = o;
+    o += cpc * 4;
+    L.off_lcol = o;
+    o += (nblk_max * 2 + 15) / 16 * 16;
+    L.total = o;
+    return L;
+}
+
 // Preconditioned conjugate gradients on S x = b, zero initial guess, block-Jacobi preconditioner, relative
-// residual stop (the same recurrences and stopping rules as pcg_update_kernel).  One warp per camera (strided):
-// lane = (block slot 0..4, row 0..5); lanes 0..5 own the camera's x, r, p, z, q entries (kept in shared memory).
-// Two grid barriers per iteration: after q = S p (for p.q) and after z = Pinv r (for r.z, ||r||^2).  The
-// search direction of OTHER cameras is never waited for: p_j = z_j + beta p_j(old) is recomputed by the reader
-// from the two published vectors with the same fma the owner uses.
-// Every reduction is a fixed-order sum evaluated identically by all warps of all CTAs (and of all ranks of a
-// sharded solve: S and b are all-reduced, the PCG itself is replicated), so all take the same decisions.
-__global__ void __launch_bounds__(256, 1) rcm_pcg_kernel(const RcmPcgArgs A) {
-    extern __shared__ double s_vec[];   // [warp][k][x r p z q][6]
-    __shared__ double s_part[8][2];
+// residual stop (the recurrences and stopping rules of pcg_update_kernel).  CTA `b` owns `cpc` consecutive
+// cameras: its rows of S, their preconditioner blocks and x, r, q live in shared memory for the whole solve;
+// one warp per camera (strided), lane = (block slot 0..4, row 0..5).
+// Only z = Pinv r travels through L2.  Every CTA keeps its own copy of the search direction on its halo (the
+// columns its rows touch) and advances it with the owner's recurrence p_j = z_j + beta p_j, so the new
+// direction is never waited for: an iteration has two grid-wide reductions (p.q, then r.z and ||r||^2) and
+// nothing else crosses CTAs.  A reduction is one release store per CTA (partials + sequence number) and an
+// acquire-poll of all CTAs' slots by warp 0; partials are added in CTA order by every CTA, so all CTAs (and all
+// ranks of a sharded solve: S and b are all-reduced, the PCG is replicated) take identical decisions.
+__global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcgArgs A) {
+    extern __shared__ __align__(16) unsigned char rsm[];
+    __shared__ double s_part[kRcmPcgThreads / 32][2];
+    __shared__ double s_tot[2];
     __shared__ int s_dead;
-    if (threadIdx.x == 0) s_dead = 0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int G = gridDim.x, wtot = G * nwarps, gw = blockIdx.x * nwarps + warp;
+    const RcmSmem L = rcm_smem(A.cpc, A.nblk_max, A.nh_max, A.s_in_smem);
+    double* S_s = reinterpret_cast<double*>(rsm + L.off_S);
+    double* pinv_s = reinterpret_cast<double*>(rsm + L.off_pinv);
+    double* vec = reinterpret_cast<double*>(rsm + L.off_vec);
+    double* ph = reinterpret_cast<double*>(rsm + L.off_ph);
+    int* hcols_s = reinterpret_cast<int*>(rsm + L.off_hcols);
+    int* rowptr_s = reinterpret_cast<int*>(rsm + L.off_rowptr);
+    int* own_s = reinterpret_cast<int*>(rsm + L.off_own);
+    uint16_t* lcol_s = reinterpret_cast<uint16_t*>(rsm + L.off_lcol);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int G = gridDim.x;
     const int a = lane % 6, slot = lane / 6;
     const bool rowlane = lane < 6;
-    double* my = s_vec + (size_t)warp * A.kmax * 30;
-    const int n = A.n_cams;
-    unsigned nbar = 0;
+    const int c0 = blockIdx.x * A.cpc, ncam = min(A.cpc, A.n_cams - c0);
+    const int e0 = A.rowptr[c0], nblk = A.rowptr[c0 + ncam] - e0;
+    const int h0 = A.halo_ptr[blockIdx.x], nh = A.halo_ptr[blockIdx.x + 1] - h0;
+    if (tid == 0) s_dead = 0;
+    if (A.s_in_smem)
+        for (int i = tid; i < nblk * 36; i += blockDim.x) S_s[i] = A.S[(int64_t)e0 * 36 + i];
+    for (int i = tid; i < nblk; i += blockDim.x) lcol_s[i] = A.lcol[e0 + i];
+    for (int i = tid; i < nh; i += blockDim.x) hcols_s[i] = A.halo_cols[h0 + i];
+    for (int i = tid; i < nh * 6; i += blockDim.x) ph[i] = 0.0;
+    for (int i = tid; i < ncam * 21; i += blockDim.x) pinv_s[i] = A.Pinv[(int64_t)c0 * 21 + i];
+    for (int i = tid; i <= ncam; i += blockDim.x) rowptr_s[i] = A.rowptr[c0 + i] - e0;
+    for (int i = tid; i < ncam; i += blockDim.x) own_s[i] = A.own_l[c0 + i];
+    const double* S_rows = A.s_in_smem ? S_s : A.S + (int64_t)e0 * 36;
+    __syncthreads();
+    unsigned long long nbar = 0;
 
-    auto reduce2 = [&](double v0, double v1, int phase, double& o0, double& o1) -> bool {
+    // grid-wide sums of (v0, v1); false when the other CTAs did not arrive within ~1 s (never expected: the
+    // kernel then gives up instead of hanging the device)
+    auto reduce2 = [&](double v0, double v1, double& o0, double& o1) -> bool {
         v0 = warp_sum_all(v0);
         v1 = warp_sum_all(v1);
         if (lane == 0) {
@@ -141,92 +189,108 @@ __global__ void __launch_bounds__(256, 1) rcm_pcg_kernel(const RcmPcgArgs A) {
             s_part[warp][1] = v1;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            double t0 = 0, t1 = 0;
-            for (int w = 0; w < nwarps; ++w) {
-                t0 += s_part[w][0];
-                t1 += s_part[w][1];
-            }
-            double* dst = A.part + ((size_t)phase * kRcmMaxCtas + blockIdx.x) * 2;
-            dst[0] = t0;
-            dst[1] = t1;
-        }
         ++nbar;
-        if (!grid_barrier(A.bar, nbar * (unsigned)G, &s_dead)) {
-            if (threadIdx.x == 0) A.flags[2] = 1;
+        RcmSlot* base = A.slots + (nbar & 1) * G;
+        if (warp == 0) {
+            if (lane == 0) {
+                double t0 = 0, t1 = 0;
+                for (int w = 0; w < nwarps; ++w) {
+                    t0 += s_part[w][0];
+                    t1 += s_part[w][1];
+                }
+                RcmSlot* mine = base + blockIdx.x;
+                mine->v0 = t0;
+                mine->v1 = t1;
+                st_release_gpu_u64(&mine->seq, nbar);   // also publishes this CTA's z (bar.sync + cumulativity)
+            }
+            const long long t_start = clock64();
+            bool pending = true;
+            while (pending) {
+                pending = false;
+                for (int c = lane; c < G; c += 32)
+                    if (ld_relaxed_gpu_u64(&base[c].seq) != nbar) pending = true;
+                if (pending && clock64() - t_start > (1ll << 31)) {
+                    s_dead = 1;
+                    break;
+                }
+            }
+            fence_acq_rel_gpu();
+            double s0 = 0, s1 = 0;
+            for (int c = lane; c < G; c += 32) {
+                s0 += __ldcg(&base[c].v0);
+                s1 += __ldcg(&base[c].v1);
+            }
+            s0 = warp_sum_all(s0);
+            s1 = warp_sum_all(s1);
+            if (lane == 0) {
+                s_tot[0] = s0;
+                s_tot[1] = s1;
+            }
+        }
+        __syncthreads();
+        if (s_dead) {
+            if (tid == 0) A.flags[2] = 1;
             return false;
         }
-        double s0 = 0, s1 = 0;
-        for (int c = lane; c < G; c += 32) {
-            s0 += __ldcg(A.part + ((size_t)phase * kRcmMaxCtas + c) * 2);
-            s1 += __ldcg(A.part + ((size_t)phase * kRcmMaxCtas + c) * 2 + 1);
-        }
-        o0 = warp_sum_all(s0);
-        o1 = warp_sum_all(s1);
+        o0 = s_tot[0];
+        o1 = s_tot[1];
         return true;
     };
-    // z = Pinv_c r for the camera of this warp (r in lanes 0..5); valid in lanes 0..5
-    auto precond = [&](int c, double r_a) {
+    // z = Pinv_k r for camera k of this CTA (r in lanes 0..5); valid in lanes 0..5
+    auto precond = [&](int k, double r_a) {
         double z = 0;
-        const double* pin = A.Pinv + (int64_t)c * 21;
+        const double* pin = pinv_s + k * 21;
 #pragma unroll
         for (int bb = 0; bb < 6; ++bb) {
             const double rb = __shfl_sync(0xffffffffu, r_a, bb);
-            z += __ldg(pin + (a <= bb ? tri6(a, bb) : tri6(bb, a))) * rb;
+            z += pin[a <= bb ? tri6(a, bb) : tri6(bb, a)] * rb;
         }
         return z;
     };
 
     // x = 0, r = b, z = Pinv r
     double rz = 0, rr = 0;
-    for (int k = 0; k < A.kmax; ++k) {
-        const int c = gw + k * wtot;
-        if (c >= n) break;
-        double* v = my + k * 30;
+    for (int k = warp; k < ncam; k += nwarps) {
+        const int c = c0 + k;
         const double r_a = rowlane ? A.b[c * 6 + a] : 0.0;
-        const double z = precond(c, r_a);
+        const double z = precond(k, r_a);
         if (rowlane) {
-            v[a] = 0.0;
-            v[6 + a] = r_a;
-            v[12 + a] = 0.0;
-            v[18 + a] = z;
+            vec[k * 18 + a] = 0.0;
+            vec[k * 18 + 6 + a] = r_a;
             A.z[c * 6 + a] = z;
             rz += r_a * z;
             rr += r_a * r_a;
         }
     }
     double rho, b2;
-    if (!reduce2(rz, rr, 1, rho, b2)) return;
+    if (!reduce2(rz, rr, rho, b2)) return;
     int its = 0, done = 0;
     double beta = 0.0, rr_last = b2;
     if (!(b2 > 0.0)) {
         done = 1;
     } else {
         for (int it = 0; it < A.maxit; ++it) {
-            const double* pold = (it & 1) ? A.p0 : A.p1;
-            double* pnew = (it & 1) ? A.p1 : A.p0;
+            // p = z + beta p on the halo: one round of independent L2 loads
+            for (int i = tid; i < nh * 6; i += blockDim.x) {
+                const int j = i / 6;
+                const double zj = __ldcg(A.z + (int64_t)hcols_s[j] * 6 + (i - j * 6));
+                ph[i] = it == 0 ? zj : fma(beta, ph[i], zj);
+            }
+            __syncthreads();
             double pq = 0;
-            for (int k = 0; k < A.kmax; ++k) {
-                const int c = gw + k * wtot;
-                if (c >= n) break;
-                double* v = my + k * 30;
-                double pown = 0;
-                if (rowlane) {
-                    pown = it == 0 ? v[18 + a] : fma(beta, v[12 + a], v[18 + a]);
-                    v[12 + a] = pown;
-                    pnew[c * 6 + a] = pown;
-                }
+            for (int k = warp; k < ncam; k += nwarps) {
                 double acc = 0;
                 if (slot < kRcmSlots) {
-                    const int e1 = __ldg(A.rowptr + c + 1);
-                    for (int e = __ldg(A.rowptr + c) + slot; e < e1; e += kRcmSlots) {
-                        const int j = __ldg(A.cols + e);
-                        const double* srow = A.S + (int64_t)e * 36 + a * 6;
+                    const int e1 = rowptr_s[k + 1];
+                    for (int e = rowptr_s[k] + slot; e < e1; e += kRcmSlots) {
+                        const double* srow = S_rows + e * 36 + a * 6;
+                        const double* pj = ph + lcol_s[e] * 6;
+                        if (A.s_in_smem) {
 #pragma unroll
-                        for (int bb = 0; bb < 6; ++bb) {
-                            const double zj = __ldcg(A.z + j * 6 + bb);
-                            const double pj = it == 0 ? zj : fma(beta, __ldcg(pold + j * 6 + bb), zj);
-                            acc += __ldg(srow + bb) * pj;
+                            for (int bb = 0; bb < 6; ++bb) acc += srow[bb] * pj[bb];
+                        } else {
+#pragma unroll
+                            for (int bb = 0; bb < 6; ++bb) acc += __ldg(srow + bb) * pj[bb];
                         }
                     }
                 }
@@ -236,35 +300,32 @@ __global__ void __launch_bounds__(256, 1) rcm_pcg_kernel(const RcmPcgArgs A) {
                 q += __shfl_down_sync(0xffffffffu, acc, 18);
                 q += __shfl_down_sync(0xffffffffu, acc, 24);
                 if (rowlane) {
-                    v[24 + a] = q;
-                    pq += pown * q;
+                    vec[k * 18 + 12 + a] = q;
+                    pq += ph[own_s[k] * 6 + a] * q;
                 }
             }
             double pq_tot, unused;
-            if (!reduce2(pq, 0.0, 0, pq_tot, unused)) return;
+            if (!reduce2(pq, 0.0, pq_tot, unused)) return;
             const double alpha = rho / pq_tot;
             rz = 0;
             rr = 0;
-            for (int k = 0; k < A.kmax; ++k) {
-                const int c = gw + k * wtot;
-                if (c >= n) break;
-                double* v = my + k * 30;
+            for (int k = warp; k < ncam; k += nwarps) {
+                double* v = vec + k * 18;
                 double r_a = 0;
                 if (rowlane) {
-                    v[a] += alpha * v[12 + a];
-                    r_a = v[6 + a] - alpha * v[24 + a];
+                    v[a] += alpha * ph[own_s[k] * 6 + a];
+                    r_a = v[6 + a] - alpha * v[12 + a];
                     v[6 + a] = r_a;
                 }
-                const double z = precond(c, r_a);
+                const double z = precond(k, r_a);
                 if (rowlane) {
-                    v[18 + a] = z;
-                    A.z[c * 6 + a] = z;
+                    A.z[(c0 + k) * 6 + a] = z;
                     rz += r_a * z;
                     rr += r_a * r_a;
                 }
             }
             double rz_tot, rr_tot;
-            if (!reduce2(rz, rr, 1, rz_tot, rr_tot)) return;
+            if (!reduce2(rz, rr, rz_tot, rr_tot)) return;
             its = it + 1;
             rr_last = rr_tot;
             if (rr_tot <= A.rtol2 * b2) {
@@ -279,12 +340,9 @@ __global__ void __launch_bounds__(256, 1) rcm_pcg_kernel(const RcmPcgArgs A) {
             rho = rz_tot;
         }
     }
-    for (int k = 0; k < A.kmax; ++k) {
-        const int c = gw + k * wtot;
-        if (c >= n) break;
-        if (rowlane) A.x[c * 6 + a] = my[k * 30 + a];
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int k = warp; k < ncam; k += nwarps)
+        if (rowlane) A.x[(c0 + k) * 6 + a] = vec[k * 18 + a];
+    if (blockIdx.x == 0 && tid == 0) {
         A.flags[0] = done;
         A.flags[1] = its;
         A.state[1] = b2;

@@ -28,6 +28,18 @@ struct RcmPattern {
     int64_t nnz_full() const { return (int64_t)cols.size(); }
 };
 
+// Partition of the cameras over the CTAs of the PCG kernel (contiguous ranges of `cpc` cameras) with, per CTA, the
+// sorted union of the columns its rows touch (its "halo": the entries of the search direction it needs).
+struct RcmPartition {
+    int n_ctas = 0, cpc = 0;            // CTAs, cameras per CTA
+    int nblk_max = 0, nh_max = 0;       // largest number of blocks / halo columns of one CTA
+    std::vector<int32_t> halo_ptr;      // [n_ctas + 1]
+    std::vector<int32_t> halo_cols;     // global camera ids, ascending per CTA
+    std::vector<uint16_t> lcol;         // [nnz_full] column of each block as an index into its CTA's halo list
+    std::vector<int32_t> own_l;         // [n_cams] index of camera c in its CTA's halo list
+};
+void build_rcm_partition(RcmPartition& out, const RcmPattern& pat, int max_ctas);
+
 // max_blocks: give up (return false, pattern left empty) as soon as the upper triangle exceeds this many blocks.
 bool build_rcm_pattern(RcmPattern& out, int64_t n_cams, int64_t n_points, int64_t n_obs, const int64_t* cam_idx,
                        const int64_t* pt_idx, int64_t max_blocks);

@@ -19,7 +19,8 @@ from meatmodeler_b200 import _capi, synth  # noqa: E402
 from meatmodeler_b200 import bundleAdjuster as mm  # noqa: E402
 
 CLASSES = {"build": _capi.K_BUILD, "resid": _capi.K_RESID, "schur_rhs": _capi.K_RHS, "schur_matvec": _capi.K_MATVEC,
-           "backsub": _capi.K_BACKSUB, "jv": _capi.K_JV, "jv1": 100, "stream_read_J": 101}
+           "backsub": _capi.K_BACKSUB, "jv": _capi.K_JV, "jv1": 100, "stream_read_J": 101,
+           "schur_build": _capi.K_SBUILD, "schur_pcg": _capi.K_PCG}
 
 
 def main():
@@ -39,7 +40,7 @@ def main():
         for name in args.kernels.split(","):
             ms = eng.bench_kernel(x0, CLASSES[name], args.iters)
             b = (algorithmic_bytes("jv", nc, npts, nobs) if name == "jv1" else 144 * 256 * eng.shard()["n_tiles"]
-                 if name == "stream_read_J" else algorithmic_bytes(name, nc, npts, nobs))
+                 if name == "stream_read_J" else 0 if name == "schur_pcg" else algorithmic_bytes(name, nc, npts, nobs))
             print(json.dumps({"kernel": name, "config": args.config, "avg_ms": ms, "algorithmic_bytes": b,
                               "gbs": b / ms / 1e6, "frac_of_%s_peak" % kind: b / ms / 1e6 / peak}))
 
