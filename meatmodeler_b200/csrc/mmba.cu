@@ -119,6 +119,7 @@ struct Dev {
     int *rc_halo_ptr, *rc_halo_cols, *rc_own;
     uint16_t* rc_lcol;
     RcmSlot* rcm_slots;
+    LLLine* rcm_z;
 };
 
 // One-shot peer all-reduce of the per-iteration Schur product (see xchg_push_kernel)
@@ -351,13 +352,15 @@ void carve(mmba_handle* h, Arena& a) {
         d.rc_halo_cols = a.take<int>(h->rcm_part.halo_cols.size());
         d.rc_own = a.take<int>(Nc);
         d.rc_lcol = a.take<uint16_t>(r.nnz_full());
-        d.rcm_slots = a.take<RcmSlot>(2 * (size_t)kRcmMaxCtas);
+        d.rcm_slots = a.take<RcmSlot>((size_t)kRcmMaxCtas);
+        d.rcm_z = a.take<LLLine>(6 * Nc);
     } else {
         d.Tup = d.S = d.rcm_b = nullptr;
         d.up_rowptr = d.up_cols = d.rc_rowptr = d.rc_cols = d.rc_rows = d.rc_src = d.rc_diag = nullptr;
         d.rc_halo_ptr = d.rc_halo_cols = d.rc_own = nullptr;
         d.rc_lcol = nullptr;
         d.rcm_slots = nullptr;
+        d.rcm_z = nullptr;
     }
 }
 
@@ -745,7 +748,7 @@ RcmPcgArgs rcm_pcg_args(mmba_handle* h) {
     A.Pinv = d.Pinv;
     A.b = d.rcm_b;
     A.x = d.px;
-    A.z = d.pz;
+    A.z = d.rcm_z;
     A.slots = d.rcm_slots;
     A.flags = d.flags;
     A.state = d.state;
@@ -783,7 +786,8 @@ int rcm_finalize(mmba_handle* h, double reg) {
 // the whole PCG solve: one cooperative launch
 int rcm_pcg(mmba_handle* h) {
     Dev& d = h->d;
-    CU(cudaMemsetAsync(d.rcm_slots, 0, 2 * (size_t)h->rcm_part.n_ctas * sizeof(RcmSlot), h->stream));
+    CU(cudaMemsetAsync(d.rcm_slots, 0, (size_t)h->rcm_part.n_ctas * sizeof(RcmSlot), h->stream));
+    CU(cudaMemsetAsync(d.rcm_z, 0, 6 * (size_t)h->Nc * sizeof(LLLine), h->stream));
     CU(cudaMemsetAsync(d.flags, 0, 3 * sizeof(int), h->stream));
     RcmPcgArgs A = rcm_pcg_args(h);
     void* args[] = {&A};

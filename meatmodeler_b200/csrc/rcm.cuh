@@ -61,12 +61,31 @@ __global__ void __launch_bounds__(kCamBlock) rcm_prepare_kernel(const double* __
     }
 }
 
-// One slot per CTA and reduction parity, 1 KB apart: every CTA polls every slot, so the slots must sit on
-// different L2 slices (address bits 8 and 10.. select the slice) or a handful of slices serves G^2 requests.
+// ---- flag-in-data exchange (the "LL" protocol of NCCL) ---------------------------------------------------
+// A double travels as one 16-byte line {lo, seq, hi, seq}: each 8-byte half is written atomically and carries
+// the sequence number of the exchange, so a reader that sees both flags equal to the expected number holds a
+// valid value.  No fence, no separate flag, no second round trip: the datum validates itself.
+struct __align__(16) LLLine {
+    unsigned lo, f1, hi, f2;
+};
+__device__ __forceinline__ void ll_store(LLLine* line, double v, unsigned seq) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"((unsigned)__double2loint(v)), "r"(seq),
+                 "r"((unsigned)__double2hiint(v)), "r"(seq)
+                 : "memory");
+}
+__device__ __forceinline__ bool ll_try_load(const LLLine* line, unsigned seq, double& v) {
+    unsigned lo, f1, hi, f2;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(line) : "memory");
+    v = __hiloint2double((int)hi, (int)lo);
+    return f1 == seq && f2 == seq;
+}
+
+// One reduction slot per CTA, 1 KB apart: every CTA polls every slot, so the slots must sit on different L2
+// slices (address bits 8 and 10.. select the slice) or a handful of slices serves G^2 requests.
 struct RcmSlot {
-    double v0, v1;              // this CTA's partial sums of one reduction
-    unsigned long long seq;     // reduction number they belong to (written last, with release semantics)
-    unsigned long long pad[125];
+    LLLine pq;                  // reduction 1 of an iteration: p.q
+    LLLine rz, rr;              // reduction 2: r.z, ||r||^2
+    LLLine pad[61];
 };
 static_assert(sizeof(RcmSlot) == 1024, "RcmSlot stride");
 
@@ -80,24 +99,14 @@ struct RcmPcgArgs {
     const double* Pinv;         // [Nc][21]
     const double* b;            // [Nc][6]
     double* x;                  // [Nc][6]  result (scaled step)
-    double* z;                  // [Nc][6]  preconditioned residual, the one vector exchanged through L2
-    RcmSlot* slots;             // [2][G] partial sums + arrival sequence numbers, zero at launch
+    LLLine* z;                  // [Nc][6]  preconditioned residual, the one vector exchanged through L2; zero at launch
+    RcmSlot* slots;             // [G] partial sums of the grid-wide reductions; zero at launch
     int* flags;                 // [0] stop code (0 = maxit reached, 1 = converged, 2 = breakdown), [1] iterations,
-                                // [2] set when a grid-wide reduction timed out
+                                // [2] set when an exchange timed out
     double* state;              // [1] ||b||^2, [2] ||r||^2
     int n_cams, maxit, cpc, nblk_max, nh_max, s_in_smem;
     double rtol2;
 };
-
-__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 __device__ __forceinline__ double warp_sum_all(double v) {
 #pragma unroll
@@ -141,9 +150,12 @@ __host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, i
 // Only z = Pinv r travels through L2.  Every CTA keeps its own copy of the search direction on its halo (the
 // columns its rows touch) and advances it with the owner's recurrence p_j = z_j + beta p_j, so the new
 // direction is never waited for: an iteration has two grid-wide reductions (p.q, then r.z and ||r||^2) and
-// nothing else crosses CTAs.  A reduction is one release store per CTA (partials + sequence number) and an
-// acquire-poll of all CTAs' slots by warp 0; partials are added in CTA order by every CTA, so all CTAs (and all
-// ranks of a sharded solve: S and b are all-reduced, the PCG is replicated) take identical decisions.
+// nothing else crosses CTAs.  Both the z entries and the partial sums travel as self-validating LL lines
+// (see ll_store): a reduction is one 16-byte store per CTA and value, polled by warp 0 of every CTA; no fences.
+// Partials are added in CTA order by every CTA, so all CTAs (and all ranks of a sharded solve: S and b are
+// all-reduced, the PCG is replicated) take identical decisions.
+// Buffer reuse is safe without extra synchronisation: a CTA rewrites its z lines / slot only after it has passed
+// the next reduction, which every other CTA joins only after it has consumed the previous values.
 __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcgArgs A) {
     extern __shared__ __align__(16) unsigned char rsm[];
     __shared__ double s_part[kRcmPcgThreads / 32][2];
@@ -167,8 +179,21 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
     const int e0 = A.rowptr[c0], nblk = A.rowptr[c0 + ncam] - e0;
     const int h0 = A.halo_ptr[blockIdx.x], nh = A.halo_ptr[blockIdx.x + 1] - h0;
     if (tid == 0) s_dead = 0;
-    if (A.s_in_smem)
-        for (int i = tid; i < nblk * 36; i += blockDim.x) S_s[i] = A.S[(int64_t)e0 * 36 + i];
+    if (A.s_in_smem) {
+        // blocks are 288 bytes: 16-byte loads, four in flight per thread
+        const double2* src = reinterpret_cast<const double2*>(A.S + (int64_t)e0 * 36);
+        double2* dst = reinterpret_cast<double2*>(S_s);
+        const int n2 = nblk * 18;
+        for (int i = tid; i < n2; i += 4 * blockDim.x) {
+            double2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u * blockDim.x < n2) v[u] = __ldg(src + i + u * blockDim.x);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u * blockDim.x < n2) dst[i + u * blockDim.x] = v[u];
+        }
+    }
     for (int i = tid; i < nblk; i += blockDim.x) lcol_s[i] = A.lcol[e0 + i];
     for (int i = tid; i < nh; i += blockDim.x) hcols_s[i] = A.halo_cols[h0 + i];
     for (int i = tid; i < nh * 6; i += blockDim.x) ph[i] = 0.0;
@@ -177,20 +202,18 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
     for (int i = tid; i < ncam; i += blockDim.x) own_s[i] = A.own_l[c0 + i];
     const double* S_rows = A.s_in_smem ? S_s : A.S + (int64_t)e0 * 36;
     __syncthreads();
-    unsigned long long nbar = 0;
+    constexpr long long kSpinLimit = 1ll << 31;   // ~1 s: give up instead of hanging the device
 
-    // grid-wide sums of (v0, v1); false when the other CTAs did not arrive within ~1 s (never expected: the
-    // kernel then gives up instead of hanging the device)
-    auto reduce2 = [&](double v0, double v1, double& o0, double& o1) -> bool {
+    // grid-wide sums: `which` = 0 -> slot.pq (v0 only), 1 -> slot.rz / slot.rr.  false when the other CTAs did
+    // not arrive within ~1 s (never expected)
+    auto reduce2 = [&](double v0, double v1, int which, unsigned seq, double& o0, double& o1) -> bool {
         v0 = warp_sum_all(v0);
-        v1 = warp_sum_all(v1);
+        if (which) v1 = warp_sum_all(v1);
         if (lane == 0) {
             s_part[warp][0] = v0;
             s_part[warp][1] = v1;
         }
         __syncthreads();
-        ++nbar;
-        RcmSlot* base = A.slots + (nbar & 1) * G;
         if (warp == 0) {
             if (lane == 0) {
                 double t0 = 0, t1 = 0;
@@ -198,27 +221,48 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                     t0 += s_part[w][0];
                     t1 += s_part[w][1];
                 }
-                RcmSlot* mine = base + blockIdx.x;
-                mine->v0 = t0;
-                mine->v1 = t1;
-                st_release_gpu_u64(&mine->seq, nbar);   // also publishes this CTA's z (bar.sync + cumulativity)
+                RcmSlot* mine = A.slots + blockIdx.x;
+                if (which) {
+                    ll_store(&mine->rz, t0, seq);
+                    ll_store(&mine->rr, t1, seq);
+                } else {
+                    ll_store(&mine->pq, t0, seq);
+                }
+            }
+            // lane l polls the slots of CTAs l, l + 32, ...: all of them in flight at once
+            constexpr int kPer = kRcmMaxCtas / 32;
+            double a0[kPer], a1[kPer];
+            unsigned pend = 0;
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                a0[u] = a1[u] = 0.0;
+                if (lane + 32 * u < G) pend |= 1u << u;
             }
             const long long t_start = clock64();
-            bool pending = true;
-            while (pending) {
-                pending = false;
-                for (int c = lane; c < G; c += 32)
-                    if (ld_relaxed_gpu_u64(&base[c].seq) != nbar) pending = true;
-                if (pending && clock64() - t_start > (1ll << 31)) {
+            while (pend) {
+                bool ok[kPer];
+#pragma unroll
+                for (int u = 0; u < kPer; ++u) {
+                    ok[u] = false;
+                    if (pend >> u & 1) {
+                        const RcmSlot* sl = A.slots + lane + 32 * u;
+                        ok[u] = which ? (ll_try_load(&sl->rz, seq, a0[u]) & ll_try_load(&sl->rr, seq, a1[u]))
+                                      : ll_try_load(&sl->pq, seq, a0[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kPer; ++u)
+                    if (ok[u]) pend &= ~(1u << u);
+                if (pend && clock64() - t_start > kSpinLimit) {
                     s_dead = 1;
                     break;
                 }
             }
-            fence_acq_rel_gpu();
             double s0 = 0, s1 = 0;
-            for (int c = lane; c < G; c += 32) {
-                s0 += __ldcg(&base[c].v0);
-                s1 += __ldcg(&base[c].v1);
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                s0 += a0[u];
+                s1 += a1[u];
             }
             s0 = warp_sum_all(s0);
             s1 = warp_sum_all(s1);
@@ -257,24 +301,52 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
         if (rowlane) {
             vec[k * 18 + a] = 0.0;
             vec[k * 18 + 6 + a] = r_a;
-            A.z[c * 6 + a] = z;
+            ll_store(A.z + c * 6 + a, z, 1u);
             rz += r_a * z;
             rr += r_a * r_a;
         }
     }
     double rho, b2;
-    if (!reduce2(rz, rr, rho, b2)) return;
+    if (!reduce2(rz, rr, 1, 1u, rho, b2)) return;
     int its = 0, done = 0;
     double beta = 0.0, rr_last = b2;
     if (!(b2 > 0.0)) {
         done = 1;
     } else {
         for (int it = 0; it < A.maxit; ++it) {
-            // p = z + beta p on the halo: one round of independent L2 loads
-            for (int i = tid; i < nh * 6; i += blockDim.x) {
-                const int j = i / 6;
-                const double zj = __ldcg(A.z + (int64_t)hcols_s[j] * 6 + (i - j * 6));
-                ph[i] = it == 0 ? zj : fma(beta, ph[i], zj);
+            // p = z + beta p on the halo: one round of independent L2 loads (lines of iteration `it` carry it + 1)
+            {
+                const long long t_start = clock64();
+                const int n6 = nh * 6;
+                const unsigned seq = (unsigned)it + 1u;
+                for (int base = tid; base < n6; base += 4 * blockDim.x) {
+                    double zv[4];
+                    bool ok[4];
+                    const LLLine* line[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = base + u * blockDim.x;
+                        ok[u] = true;
+                        zv[u] = 0.0;
+                        if (i < n6) {
+                            const int j = i / 6;
+                            line[u] = A.z + (int64_t)hcols_s[j] * 6 + (i - j * 6);
+                            ok[u] = ll_try_load(line[u], seq, zv[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        while (!ok[u]) {
+                            ok[u] = ll_try_load(line[u], seq, zv[u]);
+                            if (!ok[u] && clock64() - t_start > kSpinLimit) {
+                                s_dead = 1;
+                                break;
+                            }
+                        }
+                        const int i = base + u * blockDim.x;
+                        if (i < n6) ph[i] = it == 0 ? zv[u] : fma(beta, ph[i], zv[u]);
+                    }
+                }
             }
             __syncthreads();
             double pq = 0;
@@ -305,7 +377,7 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                 }
             }
             double pq_tot, unused;
-            if (!reduce2(pq, 0.0, pq_tot, unused)) return;
+            if (!reduce2(pq, 0.0, 0, (unsigned)it + 1u, pq_tot, unused)) return;
             const double alpha = rho / pq_tot;
             rz = 0;
             rr = 0;
@@ -319,13 +391,13 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                 }
                 const double z = precond(k, r_a);
                 if (rowlane) {
-                    A.z[(c0 + k) * 6 + a] = z;
+                    ll_store(A.z + (c0 + k) * 6 + a, z, (unsigned)it + 2u);
                     rz += r_a * z;
                     rr += r_a * r_a;
                 }
             }
             double rz_tot, rr_tot;
-            if (!reduce2(rz, rr, rz_tot, rr_tot)) return;
+            if (!reduce2(rz, rr, 1, (unsigned)it + 2u, rz_tot, rr_tot)) return;
             its = it + 1;
             rr_last = rr_tot;
             if (rr_tot <= A.rtol2 * b2) {
