@@ -61,23 +61,25 @@ __global__ void __launch_bounds__(kCamBlock) rcm_prepare_kernel(const double* __
     }
 }
 
-// ---- flag-in-data exchange (the "LL" protocol of NCCL) ---------------------------------------------------
-// A double travels as one 16-byte line {lo, seq, hi, seq}: each 8-byte half is written atomically and carries
-// the sequence number of the exchange, so a reader that sees both flags equal to the expected number holds a
-// valid value.  No fence, no separate flag, no second round trip: the datum validates itself.
+// ---- flag-in-data exchange (the idea of NCCL's LL protocol) --------------------------------------------------
+// A double travels as one 16-byte line of two 64-bit words {lo | seq << 32, hi | seq << 32}: each word is a
+// naturally aligned scalar of the vector access (single-copy atomic) and carries the sequence number of the
+// exchange, so a reader that finds the expected number in both words holds a valid value.  No fence, no
+// separate flag, no second round trip: the datum validates itself.
 struct __align__(16) LLLine {
-    unsigned lo, f1, hi, f2;
+    unsigned long long w0, w1;
 };
 __device__ __forceinline__ void ll_store(LLLine* line, double v, unsigned seq) {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"((unsigned)__double2loint(v)), "r"(seq),
-                 "r"((unsigned)__double2hiint(v)), "r"(seq)
+    const unsigned long long tag = (unsigned long long)seq << 32;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(line), "l"(tag | (unsigned)__double2loint(v)),
+                 "l"(tag | (unsigned)__double2hiint(v))
                  : "memory");
 }
 __device__ __forceinline__ bool ll_try_load(const LLLine* line, unsigned seq, double& v) {
-    unsigned lo, f1, hi, f2;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(line) : "memory");
-    v = __hiloint2double((int)hi, (int)lo);
-    return f1 == seq && f2 == seq;
+    unsigned long long w0, w1;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(line) : "memory");
+    v = __hiloint2double((int)(unsigned)w1, (int)(unsigned)w0);
+    return (unsigned)(w0 >> 32) == seq && (unsigned)(w1 >> 32) == seq;
 }
 
 // One reduction slot per CTA, 1 KB apart: every CTA polls every slot, so the slots must sit on different L2
@@ -118,7 +120,7 @@ constexpr int kRcmPcgThreads = 256;
 
 // shared-memory carve-up of rcm_pcg_kernel (same arithmetic on the host)
 struct RcmSmem {
-    int off_S, off_pinv, off_vec, off_ph, off_hcols, off_rowptr, off_own, off_lcol, total;
+    int off_S, off_pinv, off_vec, off_ph, off_zh, off_hcols, off_rowptr, off_own, off_lcol, total;
 };
 __host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, int s_in_smem) {
     RcmSmem L{};
@@ -131,6 +133,8 @@ __host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, i
     o += cpc * 18 * 8;                       // x, r, q of the CTA's cameras
     L.off_ph = o;
     o += nh_max * 6 * 8;                     // search direction on the CTA's halo
+    L.off_zh = o;
+    o += nh_max * 6 * 8;                     // z on the halo, as gathered
     L.off_hcols = o;
     o += nh_max * 4;
     L.off_rowptr = o;
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
     double* pinv_s = reinterpret_cast<double*>(rsm + L.off_pinv);
     double* vec = reinterpret_cast<double*>(rsm + L.off_vec);
     double* ph = reinterpret_cast<double*>(rsm + L.off_ph);
+    double* zh = reinterpret_cast<double*>(rsm + L.off_zh);
     int* hcols_s = reinterpret_cast<int*>(rsm + L.off_hcols);
     int* rowptr_s = reinterpret_cast<int*>(rsm + L.off_rowptr);
     int* own_s = reinterpret_cast<int*>(rsm + L.off_own);
@@ -206,7 +211,9 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
 
     // grid-wide sums: `which` = 0 -> slot.pq (v0 only), 1 -> slot.rz / slot.rr.  false when the other CTAs did
     // not arrive within ~1 s (never expected)
-    auto reduce2 = [&](double v0, double v1, int which, unsigned seq, double& o0, double& o1) -> bool {
+    // gather_z: while warp 0 polls the partial sums, the other warps fetch the z lines of the same sequence number
+    // on the CTA's halo into zh (both were published together, so the two waits overlap)
+    auto reduce2 = [&](double v0, double v1, int which, unsigned seq, bool gather_z, double& o0, double& o1) -> bool {
         v0 = warp_sum_all(v0);
         if (which) v1 = warp_sum_all(v1);
         if (lane == 0) {
@@ -271,6 +278,39 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                 s_tot[1] = s1;
             }
         }
+        if (gather_z && (warp > 0 || nwarps == 1)) {
+            const int first = nwarps == 1 ? tid : tid - 32, step = nwarps == 1 ? 32 : (int)blockDim.x - 32;
+            const long long t_start = clock64();
+            const int n6 = nh * 6;
+            for (int base = first; base < n6; base += 4 * step) {
+                double zv[4];
+                bool ok[4];
+                const LLLine* line[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * step;
+                    ok[u] = true;
+                    zv[u] = 0.0;
+                    if (i < n6) {
+                        const int j = i / 6;
+                        line[u] = A.z + (int64_t)hcols_s[j] * 6 + (i - j * 6);
+                        ok[u] = ll_try_load(line[u], seq, zv[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    while (!ok[u]) {
+                        ok[u] = ll_try_load(line[u], seq, zv[u]);
+                        if (!ok[u] && clock64() - t_start > kSpinLimit) {
+                            s_dead = 1;
+                            break;
+                        }
+                    }
+                    const int i = base + u * step;
+                    if (i < n6) zh[i] = zv[u];
+                }
+            }
+        }
         __syncthreads();
         if (s_dead) {
             if (tid == 0) A.flags[2] = 1;
@@ -307,47 +347,15 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
         }
     }
     double rho, b2;
-    if (!reduce2(rz, rr, 1, 1u, rho, b2)) return;
+    if (!reduce2(rz, rr, 1, 1u, true, rho, b2)) return;
     int its = 0, done = 0;
     double beta = 0.0, rr_last = b2;
     if (!(b2 > 0.0)) {
         done = 1;
     } else {
         for (int it = 0; it < A.maxit; ++it) {
-            // p = z + beta p on the halo: one round of independent L2 loads (lines of iteration `it` carry it + 1)
-            {
-                const long long t_start = clock64();
-                const int n6 = nh * 6;
-                const unsigned seq = (unsigned)it + 1u;
-                for (int base = tid; base < n6; base += 4 * blockDim.x) {
-                    double zv[4];
-                    bool ok[4];
-                    const LLLine* line[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = base + u * blockDim.x;
-                        ok[u] = true;
-                        zv[u] = 0.0;
-                        if (i < n6) {
-                            const int j = i / 6;
-                            line[u] = A.z + (int64_t)hcols_s[j] * 6 + (i - j * 6);
-                            ok[u] = ll_try_load(line[u], seq, zv[u]);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        while (!ok[u]) {
-                            ok[u] = ll_try_load(line[u], seq, zv[u]);
-                            if (!ok[u] && clock64() - t_start > kSpinLimit) {
-                                s_dead = 1;
-                                break;
-                            }
-                        }
-                        const int i = base + u * blockDim.x;
-                        if (i < n6) ph[i] = it == 0 ? zv[u] : fma(beta, ph[i], zv[u]);
-                    }
-                }
-            }
+            // p = z + beta p on the halo (z of this iteration was gathered together with the last reduction)
+            for (int i = tid; i < nh * 6; i += blockDim.x) ph[i] = it == 0 ? zh[i] : fma(beta, ph[i], zh[i]);
             __syncthreads();
             double pq = 0;
             for (int k = warp; k < ncam; k += nwarps) {
@@ -377,7 +385,7 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                 }
             }
             double pq_tot, unused;
-            if (!reduce2(pq, 0.0, 0, (unsigned)it + 1u, pq_tot, unused)) return;
+            if (!reduce2(pq, 0.0, 0, (unsigned)it + 1u, false, pq_tot, unused)) return;
             const double alpha = rho / pq_tot;
             rz = 0;
             rr = 0;
@@ -397,7 +405,7 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                 }
             }
             double rz_tot, rr_tot;
-            if (!reduce2(rz, rr, 1, (unsigned)it + 2u, rz_tot, rr_tot)) return;
+            if (!reduce2(rz, rr, 1, (unsigned)it + 2u, true, rz_tot, rr_tot)) return;
             its = it + 1;
             rr_last = rr_tot;
             if (rr_tot <= A.rtol2 * b2) {
