@@ -1366,7 +1366,8 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     if (h->opt.schur_mode != MMBA_SCHUR_IMPLICIT && n_cams <= 20000) {
         const bool forced = h->opt.schur_mode == MMBA_SCHUR_EXPLICIT;
         const int64_t cap_full = forced ? (int64_t)8 << 20 : std::min<int64_t>(((int64_t)96 << 20) / 288, (152 * n_obs / 2) / 288);
-        const bool ok = build_rcm_pattern(h->rcm, n_cams, n_points, n_obs, cam_idx, pt_idx, std::max<int64_t>(cap_full, n_cams));
+        const bool ok = build_rcm_pattern(h->rcm, n_cams, n_points, n_obs, cam_idx, pt_idx, std::max<int64_t>(cap_full, n_cams),
+                                          h->plan.point_perm.data());
         h->rcm_ready = ok && (forced || (h->rcm.nnz_full() <= std::max<int64_t>(cap_full, n_cams) && h->rcm.total_pairs <= 64 * n_obs));
         if (!h->rcm_ready) h->rcm = RcmPattern();
         else {
@@ -1838,7 +1839,11 @@ int mmba_host_rcm_pattern(int64_t n_cams, int64_t n_points, int64_t n_obs, const
         if (cam_idx[i] < 0 || cam_idx[i] >= n_cams || pt_idx[i] < 0 || pt_idx[i] >= n_points)
             return fail(nullptr, MMBA_ERR_ARG, "rcm_pattern: index out of range at observation " + std::to_string(i));
     RcmPattern r;
-    if (!build_rcm_pattern(r, n_cams, n_points, n_obs, cam_idx, pt_idx, INT32_MAX / 36))
+    // the same call mmba_set_problem makes: marking in the plan's internal point order
+    Plan plan;
+    std::string perr;
+    const bool have_plan = build_plan(plan, n_cams, n_points, n_obs, cam_idx, pt_idx, 0, 1, perr) == MMBA_OK;
+    if (!build_rcm_pattern(r, n_cams, n_points, n_obs, cam_idx, pt_idx, INT32_MAX / 36, have_plan ? plan.point_perm.data() : nullptr))
         return fail(nullptr, MMBA_ERR_NOMEM, "rcm_pattern: too many blocks");
     sizes[0] = r.nnz_up();
     sizes[1] = r.nnz_full();

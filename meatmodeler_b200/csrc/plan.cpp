@@ -3,6 +3,9 @@
 
 #include <algorithm>
 #include <numeric>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include "../../include/mmba.h"
 
@@ -22,6 +25,8 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
         err = "set_problem: problem too large for 32-bit device indices";
         return MMBA_ERR_ARG;
     }
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (getenv("MMBA_PLAN_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "plan %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count()); T0 = t; } };
     plan = Plan();
     plan.n_cams = n_cams;
     plan.n_points = n_points;
@@ -59,6 +64,7 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
         }
     }
 
+    lap("1 count");
     // 2. internal point order: counting sort by first camera (stable -> ties by caller index);
     //    unobserved points (first_cam == n_cams) go last
     plan.point_perm.resize(n_points);
@@ -71,6 +77,7 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
     std::vector<int32_t> point_inv(n_points);
     for (int64_t q = 0; q < n_points; ++q) point_inv[plan.point_perm[q]] = (int32_t)q;
 
+    lap("2 order");
     // 3. shard cuts: contiguous internal point ranges balanced by observation count
     plan.shard_begin.assign(nranks + 1, n_points);
     plan.shard_begin[0] = 0;
@@ -94,6 +101,7 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
     for (int64_t q = 0; q < npl; ++q) start[q + 1] = start[q] + count[plan.point_perm[plan.pt_begin + q]];
     plan.n_obs_local = start[npl];
     std::vector<int64_t> grouped(plan.n_obs_local);
+    std::vector<int32_t> gcam(plan.n_obs_local);
     {
         std::vector<int64_t> fill(start.begin(), start.end() - 1);
         for (int64_t i = 0; i < n_obs; ++i) {
@@ -102,23 +110,29 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
         }
         parallel_ranges(npl, 4096, [&](int64_t q0, int64_t q1, int) {
             for (int64_t q = q0; q < q1; ++q) {
-                // tracks are short: insertion sort (stable), usually already ascending
+                // tracks are short: insertion sort (stable), usually already ascending.  The camera of every
+                // grouped observation is kept (gcam) so that the tile pass below reads it sequentially.
                 int64_t* g = grouped.data() + start[q];
+                int32_t* gc = gcam.data() + start[q];
                 const int64_t L = start[q + 1] - start[q];
+                for (int64_t a = 0; a < L; ++a) gc[a] = (int32_t)cam_idx[g[a]];
                 for (int64_t a = 1; a < L; ++a) {
                     const int64_t v = g[a];
-                    const int64_t cv = cam_idx[v];
+                    const int32_t cv = gc[a];
                     int64_t b = a;
-                    while (b > 0 && cam_idx[g[b - 1]] > cv) {
+                    while (b > 0 && gc[b - 1] > cv) {
                         g[b] = g[b - 1];
+                        gc[b] = gc[b - 1];
                         --b;
                     }
                     g[b] = v;
+                    gc[b] = cv;
                 }
             }
         });
     }
 
+    lap("4 group");
     // 5. greedy point-aligned tiles
     struct Range { int64_t p0, p1; };
     std::vector<Range> ranges;
@@ -146,11 +160,17 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
     plan.meta.resize(plan.n_tiles);
     plan.slot_obs.assign(plan.n_slots, -1);
 
+    lap("5 ranges+alloc");
     // 6. per tile: local camera table, local slots, camera-sorted order (tiles are independent)
-    std::vector<std::vector<int32_t>> cams_of(plan.n_tiles);
+    // camera lists: appended to one pool per worker (no per-tile allocation), copied to tile_cams afterwards
+    std::vector<int32_t> pool[8];
+    std::vector<int64_t> cams_at(plan.n_tiles);      // offset of tile t's list in its worker's pool
+    std::vector<int8_t> cams_worker(plan.n_tiles);
     int max_cams_w[8] = {0}, max_pts_w[8] = {0};
     parallel_ranges(plan.n_tiles, 256, [&](int64_t t0, int64_t t1, int worker) {
         std::vector<int32_t> stamp(n_cams, -1), local_of(n_cams, 0);
+        std::vector<int32_t>& mypool = pool[worker];
+        mypool.reserve((size_t)(t1 - t0) * 32);
         std::vector<uint16_t> idx(kTileObs);
         uint16_t cnt[kTileObs + 1];
         int max_cams = 0, max_pts = 0;
@@ -159,20 +179,24 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
             const int64_t o0 = start[rg.p0], o1 = start[rg.p1];
             const int n = (int)(o1 - o0);
             const int64_t base = t * kTileObs;
-            std::vector<int32_t>& cams = cams_of[t];
+            const size_t at = mypool.size();
+            cams_at[t] = (int64_t)at;
+            cams_worker[t] = (int8_t)worker;
             for (int i = 0; i < n; ++i) {
-                const int32_t c = (int32_t)cam_idx[grouped[o0 + i]];
+                const int32_t c = gcam[o0 + i];
                 if (stamp[c] != (int32_t)t) {
                     stamp[c] = (int32_t)t;
-                    cams.push_back(c);
+                    mypool.push_back(c);
                 }
             }
-            std::sort(cams.begin(), cams.end());
-            for (size_t s = 0; s < cams.size(); ++s) local_of[cams[s]] = (int32_t)s;
+            std::sort(mypool.begin() + at, mypool.end());
+            const int32_t* cams = mypool.data() + at;
+            const size_t ncams_t = mypool.size() - at;
+            for (size_t s = 0; s < ncams_t; ++s) local_of[cams[s]] = (int32_t)s;
             TileMeta& m = plan.meta[t];
             m.pt0 = (int32_t)rg.p0;
             m.npts = (int32_t)(rg.p1 - rg.p0);
-            m.ncams = (int32_t)cams.size();
+            m.ncams = (int32_t)ncams_t;
             m.nobs = n;
             max_cams = std::max(max_cams, m.ncams);
             max_pts = std::max(max_pts, m.npts);
@@ -192,7 +216,7 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
                 npairs += L * (L + 1) / 2;
                 for (int64_t o = start[q]; o < start[q + 1]; ++o, ++i) {
                     plan.slot_obs[base + i] = grouped[o];
-                    m.slot_cam[i] = (uint16_t)local_of[cam_idx[grouped[o]]];
+                    m.slot_cam[i] = (uint16_t)local_of[gcam[o]];
                     m.slot_pt[i] = (uint16_t)(q - rg.p0);
                     if (o > start[q] && m.slot_cam[i] == m.slot_cam[i - 1]) dup = true;
                 }
@@ -224,14 +248,18 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
         max_cams_w[worker] = max_cams;
         max_pts_w[worker] = max_pts;
     });
+    lap("6 tiles");
     for (int w = 0; w < 8; ++w) {
         plan.max_tile_cams = std::max(plan.max_tile_cams, max_cams_w[w]);
         plan.max_tile_pts = std::max(plan.max_tile_pts, max_pts_w[w]);
     }
     plan.cam_stride = std::max(4, (plan.max_tile_cams + 3) / 4 * 4);
     plan.tile_cams.assign((size_t)plan.n_tiles * plan.cam_stride, -1);
-    for (int64_t t = 0; t < plan.n_tiles; ++t)
-        std::copy(cams_of[t].begin(), cams_of[t].end(), plan.tile_cams.begin() + t * plan.cam_stride);
+    for (int64_t t = 0; t < plan.n_tiles; ++t) {
+        const int32_t* src = pool[cams_worker[t]].data() + cams_at[t];
+        std::copy(src, src + plan.meta[t].ncams, plan.tile_cams.begin() + t * plan.cam_stride);
+    }
+    lap("7 tile_cams");
     return MMBA_OK;
 }
 

@@ -2,6 +2,9 @@
 #include "rcm.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "plan.h"
@@ -9,10 +12,12 @@
 namespace mmba {
 
 bool build_rcm_pattern(RcmPattern& out, int64_t n_cams, int64_t n_points, int64_t n_obs, const int64_t* cam_idx,
-                       const int64_t* pt_idx, int64_t max_blocks) {
+                       const int64_t* pt_idx, int64_t max_blocks, const int32_t* point_order) {
     out = RcmPattern();
     out.n_cams = n_cams;
     if (n_cams <= 0 || n_points <= 0 || n_obs <= 0) return false;
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (getenv("MMBA_PLAN_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "rcm %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count()); T0 = t; } };
     // cameras of every point (caller's point order), CSR
     std::vector<int64_t> start(n_points + 1, 0);
     for (int64_t i = 0; i < n_obs; ++i) ++start[pt_idx[i] + 1];
@@ -27,29 +32,50 @@ bool build_rcm_pattern(RcmPattern& out, int64_t n_cams, int64_t n_points, int64_
     {
         std::vector<int64_t> fill(start.begin(), start.end() - 1);
         for (int64_t i = 0; i < n_obs; ++i) cams[fill[pt_idx[i]]++] = (int32_t)cam_idx[i];
+        // canonical (ascending) camera lists, so that equal sets compare equal below
+        parallel_ranges(n_points, 8192, [&](int64_t p0, int64_t p1, int) {
+            for (int64_t p = p0; p < p1; ++p) {
+                int32_t* g = cams.data() + start[p];
+                const int64_t L = start[p + 1] - start[p];
+                for (int64_t a = 1; a < L; ++a) {
+                    const int32_t v = g[a];
+                    int64_t b = a;
+                    while (b > 0 && g[b - 1] > v) {
+                        g[b] = g[b - 1];
+                        --b;
+                    }
+                    g[b] = v;
+                }
+            }
+        });
     }
+    lap("csr");
     // co-visibility bitmap, upper triangle: bit (i, j), i <= j.  Video-like tracks repeat the same camera
     // list point after point: a point whose list equals its predecessor's is skipped, and a set bit is only
     // tested, so the marking is close to one pass over the observations.
     const int64_t W = (n_cams + 63) / 64;
     std::vector<uint64_t> bits((size_t)n_cams * W, 0);
-    parallel_ranges(n_points, 8192, [&](int64_t p0, int64_t p1, int) {
-        for (int64_t p = p0; p < p1; ++p) {
+    // point_order (the plan's internal order: points sorted by first camera) brings equal lists together
+    parallel_ranges(n_points, 8192, [&](int64_t q0, int64_t q1, int) {
+        int64_t prev = -1;
+        for (int64_t q = q0; q < q1; ++q) {
+            const int64_t p = point_order ? point_order[q] : q;
             const int64_t b = start[p], L = start[p + 1] - b;
             if (L == 0) continue;
-            if (p > p0 && start[p] - start[p - 1] == L &&
-                std::memcmp(&cams[b], &cams[start[p - 1]], (size_t)L * sizeof(int32_t)) == 0)
-                continue;
+            const bool same = prev >= 0 && start[prev + 1] - start[prev] == L &&
+                              std::memcmp(&cams[b], &cams[start[prev]], (size_t)L * sizeof(int32_t)) == 0;
+            prev = p;
+            if (same) continue;
             for (int64_t a = 0; a < L; ++a)
                 for (int64_t c = a; c < L; ++c) {
-                    int32_t i = cams[b + a], j = cams[b + c];
-                    if (i > j) std::swap(i, j);
+                    const int32_t i = cams[b + a], j = cams[b + c];
                     uint64_t* w = &bits[(size_t)i * W + (j >> 6)];
                     const uint64_t m = 1ull << (j & 63);
                     if (!(__atomic_load_n(w, __ATOMIC_RELAXED) & m)) __atomic_fetch_or(w, m, __ATOMIC_RELAXED);
                 }
         }
     });
+    lap("mark");
     // every camera owns its diagonal block (an unobserved camera keeps S_cc = reg I)
     for (int64_t i = 0; i < n_cams; ++i) bits[(size_t)i * W + (i >> 6)] |= 1ull << (i & 63);
     // upper CSR
@@ -78,6 +104,7 @@ bool build_rcm_pattern(RcmPattern& out, int64_t n_cams, int64_t n_points, int64_
             }
         }
     });
+    lap("upper");
     // full CSR: row i = { k < i : (k, i) set } (transposed sources, ascending k) then { j >= i : (i, j) set }
     std::vector<int32_t> cnt(n_cams, 0);
     for (int64_t i = 0; i < n_cams; ++i) {
@@ -110,6 +137,7 @@ bool build_rcm_pattern(RcmPattern& out, int64_t n_cams, int64_t n_points, int64_
             out.src[q] = e;
             if (out.up_cols[e] == i) out.diag[i] = q;
         }
+    lap("full");
     return true;
 }
 

@@ -41,7 +41,9 @@ struct RcmPartition {
 void build_rcm_partition(RcmPartition& out, const RcmPattern& pat, int max_ctas);
 
 // max_blocks: give up (return false, pattern left empty) as soon as the upper triangle exceeds this many blocks.
+// point_order (optional, n_points entries): a permutation of the points that places equal camera lists next to each
+// other (the plan's internal order); only speeds the marking up.
 bool build_rcm_pattern(RcmPattern& out, int64_t n_cams, int64_t n_points, int64_t n_obs, const int64_t* cam_idx,
-                       const int64_t* pt_idx, int64_t max_blocks);
+                       const int64_t* pt_idx, int64_t max_blocks, const int32_t* point_order = nullptr);
 
 }  // namespace mmba
