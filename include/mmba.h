@@ -59,6 +59,10 @@ typedef struct mmba_options {
     uint8_t nccl_id[128]; /* ncclUniqueId bytes, same on all ranks (nranks > 1 only) */
     int32_t schur_mode;   /* MMBA_SCHUR_*: how the PCG applies the reduced camera system (read by mmba_set_problem) */
     int32_t reserved;
+    double pcg_atol;      /* counterpart of LSMR's stopping test 2 (lsmr.py:430-459: ||A^T res|| <= atol ||A|| ||res||,
+                             which ends scipy's inner solves) on the reduced system, where A^T res is the PCG residual:
+                             stop when ||r|| <= pcg_atol ||f||.  0 = relative rule only.  Default 1e-7 (calibrated on
+                             the reference's LSMR iteration counts, see oracle/schur_trf.py). */
 } mmba_options;
 
 /* The reduced camera system S = U - W V'^-1 W^T of the damped Gauss-Newton step:

@@ -33,7 +33,8 @@ class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("verbose", C.c_int32),
                 ("ftol", C.c_double), ("xtol", C.c_double), ("gtol", C.c_double), ("max_nfev", C.c_int64),
                 ("pcg_rtol", C.c_double), ("pcg_maxit", C.c_int32), ("profile", C.c_int32),
-                ("nccl_id", C.c_uint8 * 128), ("schur_mode", C.c_int32), ("reserved", C.c_int32)]
+                ("nccl_id", C.c_uint8 * 128), ("schur_mode", C.c_int32), ("reserved", C.c_int32),
+                ("pcg_atol", C.c_double)]
 
 
 class Result(C.Structure):

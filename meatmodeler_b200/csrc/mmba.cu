@@ -156,7 +156,7 @@ struct mmba_handle {
     RcmPattern rcm;
     RcmPartition rcm_part;
     bool rcm_ready = false;        // pattern built and device arrays carved for the current problem
-    int rcm_warps = 0, rcm_s_in_smem = 0;
+    int rcm_warps = 0, rcm_s_in_smem = 0, rcm_nsub = 1;
     size_t rcm_smem_bytes = 0;
     int64_t Nc = 0, npl = 0, ns = 0, nt = 0, nloc = 0;
     double K[9];
@@ -736,7 +736,7 @@ ModeArgs sbuild_args(mmba_handle* h) {
     return P;
 }
 
-RcmPcgArgs rcm_pcg_args(mmba_handle* h) {
+RcmPcgArgs rcm_pcg_args(mmba_handle* h, double f2) {
     Dev& d = h->d;
     RcmPcgArgs A{};
     A.S = d.S;
@@ -758,7 +758,9 @@ RcmPcgArgs rcm_pcg_args(mmba_handle* h) {
     A.nblk_max = h->rcm_part.nblk_max;
     A.nh_max = h->rcm_part.nh_max;
     A.s_in_smem = h->rcm_s_in_smem;
+    A.nsub = h->rcm_nsub;
     A.rtol2 = h->opt.pcg_rtol * h->opt.pcg_rtol;
+    A.atol2f = h->opt.pcg_atol * h->opt.pcg_atol * f2;
     return A;
 }
 
@@ -784,12 +786,12 @@ int rcm_finalize(mmba_handle* h, double reg) {
 }
 
 // the whole PCG solve: one cooperative launch
-int rcm_pcg(mmba_handle* h) {
+int rcm_pcg(mmba_handle* h, double f2) {
     Dev& d = h->d;
     CU(cudaMemsetAsync(d.rcm_slots, 0, (size_t)h->rcm_part.n_ctas * sizeof(RcmSlot), h->stream));
     CU(cudaMemsetAsync(d.rcm_z, 0, 6 * (size_t)h->Nc * sizeof(LLLine), h->stream));
     CU(cudaMemsetAsync(d.flags, 0, 3 * sizeof(int), h->stream));
-    RcmPcgArgs A = rcm_pcg_args(h);
+    RcmPcgArgs A = rcm_pcg_args(h, f2);
     void* args[] = {&A};
     prof_begin(h, MMBA_K_PCG);
     CU(cudaLaunchCooperativeKernel((const void*)rcm_pcg_kernel, dim3(h->rcm_part.n_ctas), dim3(32 * h->rcm_warps), args,
@@ -798,7 +800,8 @@ int rcm_pcg(mmba_handle* h) {
     return MMBA_OK;
 }
 
-int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
+// f2 = ||f||^2 at the linearisation point (0 switches the LSMR-like absolute stopping rule off)
+int gn_step(mmba_handle* h, double reg, double f2, int64_t* its_out, double* relres_out) {
     Dev& d = h->d;
     const int camblocks = cdiv(h->Nc, kCamBlock);
     PcgVecs P = pcg_vecs(h);
@@ -809,7 +812,7 @@ int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
         // explicit reduced camera matrix: one streaming pass builds S, the PCG runs on-chip in one kernel
         TRY(rcm_build(h));
         TRY(rcm_finalize(h, reg));
-        TRY(rcm_pcg(h));
+        TRY(rcm_pcg(h, f2));
         CU(cudaMemcpyAsync(h->h_flags, d.flags, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         double st[4] = {0, 0, 0, 0};
         if (relres_out) CU(cudaMemcpyAsync(st, d.state, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -829,6 +832,7 @@ int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
     LAUNCH(MMBA_K_VEC, pcg_init_kernel, camblocks, kCamBlock, 0, P, reg);
 
     const double rtol2 = h->opt.pcg_rtol * h->opt.pcg_rtol;
+    const double atol2f = h->opt.pcg_atol * h->opt.pcg_atol * f2;
     const int maxit = h->opt.pcg_maxit;
     int it = 0, done = 0;
     int chunk = 8;
@@ -862,7 +866,7 @@ int gn_step(mmba_handle* h, double reg, int64_t* its_out, double* relres_out) {
                 cfg.attrs = attr;
                 cfg.numAttrs = h->opt.profile ? 1 : 2;   // profile mode brackets launches with events: no overlap
                 prof_begin(h, MMBA_K_VEC);
-                CU(cudaLaunchKernelEx(&cfg, pcg_update_kernel, P, reg, it, rtol2, camblocks, parity, seq));
+                CU(cudaLaunchKernelEx(&cfg, pcg_update_kernel, P, reg, it, rtol2, atol2f, camblocks, parity, seq));
                 prof_end(h, MMBA_K_VEC);
             }
         }
@@ -960,7 +964,7 @@ int run_trf(mmba_handle* h, mmba_result* out) {
 
         // damped Gauss-Newton direction (replaces lsmr(J_h, f, damp=sqrt(reg)), trf.py:494-495)
         int64_t its = 0;
-        TRY(gn_step(h, reg, &its, nullptr));
+        TRY(gn_step(h, reg, 2.0 * cost, &its, nullptr));
         pcg_total += its;
         h->log.back().reg = reg;
         h->log.back().pcg_iterations = its;
@@ -1091,7 +1095,8 @@ int configure_kernels(mmba_handle* h) {
         // camera of the range.  The CTA's rows of S stay in shared memory when they fit, else they are re-read
         // from L2 every iteration.
         const RcmPartition& pt = h->rcm_part;
-        h->rcm_warps = std::min(kRcmPcgThreads / 32, pt.cpc);
+        h->rcm_nsub = std::max(1, (kRcmPcgThreads / 32) / pt.cpc);
+        h->rcm_warps = std::min(kRcmPcgThreads / 32, pt.cpc * h->rcm_nsub);
         h->rcm_s_in_smem = rcm_smem(pt.cpc, pt.nblk_max, pt.nh_max, 1).total <= 200 * 1024 ? 1 : 0;
         const RcmSmem rl = rcm_smem(pt.cpc, pt.nblk_max, pt.nh_max, h->rcm_s_in_smem);
         if (rl.total > 200 * 1024) return fail(h, MMBA_ERR_NOMEM, "reduced-system PCG: too many cameras per CTA");
@@ -1242,6 +1247,7 @@ void mmba_default_options(mmba_options* opt) {
     opt->profile = 0;
     opt->schur_mode = MMBA_SCHUR_AUTO;
     opt->reserved = 0;
+    opt->pcg_atol = 1e-7;
 }
 
 int mmba_nccl_unique_id(uint8_t out[128]) {
@@ -1318,6 +1324,8 @@ int mmba_set_options(mmba_handle* h, const mmba_options* opt) {
     h->opt.pcg_maxit = opt->pcg_maxit;
     h->opt.profile = opt->profile;
     if (opt->schur_mode < MMBA_SCHUR_AUTO || opt->schur_mode > MMBA_SCHUR_EXPLICIT) return fail(h, MMBA_ERR_ARG, "schur_mode out of range");
+    if (!(opt->pcg_atol >= 0)) return fail(h, MMBA_ERR_ARG, "pcg_atol must be >= 0");
+    h->opt.pcg_atol = opt->pcg_atol;
     h->opt.schur_mode = opt->schur_mode;   // explicit / auto take effect at the next mmba_set_problem
     return MMBA_OK;
 }
@@ -1632,7 +1640,7 @@ int mmba_eval_gn_step(mmba_handle* h, const double* x, const double* scale, doub
         for (size_t i = 0; i < si.size(); ++i) si[i] = 1.0 / scale[i];
         TRY(put_x(h, si.data(), d.sinv));
     }
-    TRY(gn_step(h, reg, pcg_iterations, pcg_relres));
+    TRY(gn_step(h, reg, 0.0, pcg_iterations, pcg_relres));
     // p = [px | dp * sinv_p]
     const int64_t ncam = 6 * h->Nc, npt = 3 * h->npl;
     TRY(zero(h, d.scal + S_DOT0, 2));
@@ -1699,7 +1707,7 @@ int mmba_bench_kernel(mmba_handle* h, const double* x, int kernel_class, int ite
     int64_t its;
     const int saved_maxit = h->opt.pcg_maxit;
     h->opt.pcg_maxit = 2;
-    int rc = gn_step(h, reg, &its, nullptr);
+    int rc = gn_step(h, reg, 0.0, &its, nullptr);
     h->opt.pcg_maxit = saved_maxit;
     TRY(rc);
     CU(cudaMemsetAsync(d.flags, 0, 2 * sizeof(int), h->stream));
@@ -1747,7 +1755,7 @@ int mmba_bench_kernel(mmba_handle* h, const double* x, int kernel_class, int ite
                     break;
                 case MMBA_K_PCG:
                     if (!use_rcm(h)) return fail(h, MMBA_ERR_STATE, "bench_kernel: the reduced camera matrix is not formed explicitly");
-                    TRY(rcm_pcg(h));
+                    TRY(rcm_pcg(h, 0.0));
                     break;
                 case MMBA_K_PTINV:
                     point_invert_kernel<<<cdiv(h->npl, 256), 256, 0, h->stream>>>(d.V, d.g + 6 * h->Nc, d.sinv + 6 * h->Nc, reg,

@@ -107,7 +107,9 @@ struct RcmPcgArgs {
                                 // [2] set when an exchange timed out
     double* state;              // [1] ||b||^2, [2] ||r||^2
     int n_cams, maxit, cpc, nblk_max, nh_max, s_in_smem;
+    int nsub;                   // warps that share one camera row in the product q = S p
     double rtol2;
+    double atol2f;              // pcg_atol^2 ||f||^2: LSMR-like absolute rule, ||r||^2 <= atol2f
 };
 
 __device__ __forceinline__ double warp_sum_all(double v) {
@@ -120,7 +122,7 @@ constexpr int kRcmPcgThreads = 256;
 
 // shared-memory carve-up of rcm_pcg_kernel (same arithmetic on the host)
 struct RcmSmem {
-    int off_S, off_pinv, off_vec, off_ph, off_zh, off_hcols, off_rowptr, off_own, off_lcol, total;
+    int off_S, off_pinv, off_vec, off_ph, off_zh, off_qp, off_hcols, off_rowptr, off_own, off_lcol, total;
 };
 __host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, int s_in_smem) {
     RcmSmem L{};
@@ -135,6 +137,8 @@ __host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, i
     o += nh_max * 6 * 8;                     // search direction on the CTA's halo
     L.off_zh = o;
     o += nh_max * 6 * 8;                     // z on the halo, as gathered
+    L.off_qp = o;
+    o += (cpc + 8) * 6 * 8;                  // partial products [camera x sub-warp][6]: at most max(cpc, 8) items
     L.off_hcols = o;
     o += nh_max * 4;
     L.off_rowptr = o;
@@ -171,6 +175,7 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
     double* vec = reinterpret_cast<double*>(rsm + L.off_vec);
     double* ph = reinterpret_cast<double*>(rsm + L.off_ph);
     double* zh = reinterpret_cast<double*>(rsm + L.off_zh);
+    double* qp = reinterpret_cast<double*>(rsm + L.off_qp);
     int* hcols_s = reinterpret_cast<int*>(rsm + L.off_hcols);
     int* rowptr_s = reinterpret_cast<int*>(rsm + L.off_rowptr);
     int* own_s = reinterpret_cast<int*>(rsm + L.off_own);
@@ -357,29 +362,48 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
             // p = z + beta p on the halo (z of this iteration was gathered together with the last reduction)
             for (int i = tid; i < nh * 6; i += blockDim.x) ph[i] = it == 0 ? zh[i] : fma(beta, ph[i], zh[i]);
             __syncthreads();
-            double pq = 0;
-            for (int k = warp; k < ncam; k += nwarps) {
-                double acc = 0;
+            // q = S p: nsub warps share a camera row (blocks dealt round-robin to nsub x 5 lane groups); two
+            // accumulators per lane keep the dependent DFMA chains short
+            const int nsub = A.nsub;
+            for (int item = warp; item < ncam * nsub; item += nwarps) {
+                const int k = item / nsub, sub = item - k * nsub;
+                double acc0 = 0, acc1 = 0;
                 if (slot < kRcmSlots) {
                     const int e1 = rowptr_s[k + 1];
-                    for (int e = rowptr_s[k] + slot; e < e1; e += kRcmSlots) {
+                    for (int e = rowptr_s[k] + slot + kRcmSlots * sub; e < e1; e += kRcmSlots * nsub) {
                         const double* srow = S_rows + e * 36 + a * 6;
                         const double* pj = ph + lcol_s[e] * 6;
                         if (A.s_in_smem) {
-#pragma unroll
-                            for (int bb = 0; bb < 6; ++bb) acc += srow[bb] * pj[bb];
+                            acc0 += srow[0] * pj[0];
+                            acc1 += srow[1] * pj[1];
+                            acc0 += srow[2] * pj[2];
+                            acc1 += srow[3] * pj[3];
+                            acc0 += srow[4] * pj[4];
+                            acc1 += srow[5] * pj[5];
                         } else {
-#pragma unroll
-                            for (int bb = 0; bb < 6; ++bb) acc += __ldg(srow + bb) * pj[bb];
+                            acc0 += __ldg(srow + 0) * pj[0];
+                            acc1 += __ldg(srow + 1) * pj[1];
+                            acc0 += __ldg(srow + 2) * pj[2];
+                            acc1 += __ldg(srow + 3) * pj[3];
+                            acc0 += __ldg(srow + 4) * pj[4];
+                            acc1 += __ldg(srow + 5) * pj[5];
                         }
                     }
                 }
+                const double acc = acc0 + acc1;
                 double q = acc;
                 q += __shfl_down_sync(0xffffffffu, acc, 6);
                 q += __shfl_down_sync(0xffffffffu, acc, 12);
                 q += __shfl_down_sync(0xffffffffu, acc, 18);
                 q += __shfl_down_sync(0xffffffffu, acc, 24);
+                if (rowlane) qp[item * 6 + a] = q;
+            }
+            __syncthreads();
+            double pq = 0;
+            for (int k = warp; k < ncam; k += nwarps) {
                 if (rowlane) {
+                    double q = 0;
+                    for (int sub = 0; sub < nsub; ++sub) q += qp[(k * nsub + sub) * 6 + a];
                     vec[k * 18 + 12 + a] = q;
                     pq += ph[own_s[k] * 6 + a] * q;
                 }
@@ -408,7 +432,7 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
             if (!reduce2(rz, rr, 1, (unsigned)it + 2u, true, rz_tot, rr_tot)) return;
             its = it + 1;
             rr_last = rr_tot;
-            if (rr_tot <= A.rtol2 * b2) {
+            if (rr_tot <= A.rtol2 * b2 || rr_tot <= A.atol2f) {
                 done = 1;
                 break;
             }

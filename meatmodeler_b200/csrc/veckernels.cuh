@@ -242,13 +242,13 @@ __device__ __forceinline__ void cluster_sum_det(cg::cluster_group& cluster, doub
 // One PCG iteration's camera-vector work in ONE launch of one thread-block cluster, so that every
 // reduction is a fixed-order sum (LSMR's vector updates, lsmr.py:373-377):
 //   q = S p = d o y + reg p ; alpha = rho / p.q ; x += alpha p ; r -= alpha q ; z = Pinv r ;
-//   stop if ||r|| <= rtol ||b|| ; beta = r.z / rho ; p = z + beta p ; xt = d o p ; y <- 0
+//   stop if ||r|| <= rtol ||b|| or ||r|| <= atol ||f|| (atol2f) ; beta = r.z / rho ; p = z + beta p ; xt = d o p ; y <- 0
 // y holds this iteration's sum_i Jc_i^T (Jc_i xt - Jp_i z_p) from the MATVEC pass (all-reduced over ranks).
 // Launched as ONE thread-block cluster: 1 CTA for <= 256 cameras, else kPcgCluster CTAs (runtime cluster
 // dimension).  Up to cluster*kPcgThreads cameras: one camera per thread, every operand loaded up front (one
 // memory round trip); more cameras: a strided loop with q and z kept in global memory.
 __global__ void __launch_bounds__(kPcgThreads)
-pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int parity, unsigned long long seq) {
+pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, double atol2f, int nb_init, int parity, unsigned long long seq) {
     // Programmatic dependent launch (see launch_tile): this grid may be scheduled while the MATVEC pass still
     // drains.  Everything written by the PREVIOUS update (flags, p, r, x, state) or earlier (sinv, Pinv) is
     // complete by then and may be read at once; y and every store wait for griddepcontrol.wait below.
@@ -365,7 +365,7 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int 
         }
         cluster_sum_det<2>(cluster, s2, s_red, s_xb);
         const double rr = s2[0], rz = s2[1];
-        if (rr <= rtol2 * b2) done = 1;
+        if (rr <= rtol2 * b2 || rr <= atol2f) done = 1;
         else if (!(pq > 0.0) || !isfinite(rr) || !(rz > 0.0)) done = 2;
         if (lead) {
             P.state[0] = rz;
@@ -436,7 +436,7 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, int nb_init, int 
         }
         cluster_sum_det<2>(cluster, s2, s_red, s_xb);
         const double rr = s2[0], rz = s2[1];
-        if (rr <= rtol2 * b2) done = 1;
+        if (rr <= rtol2 * b2 || rr <= atol2f) done = 1;
         else if (!(pq > 0.0) || !isfinite(rr) || !(rz > 0.0)) done = 2;
         if (lead) {
             P.state[0] = rz;

@@ -194,6 +194,29 @@ def test_solve_vs_reference_golden_trajectory(name, golden_c1, golden_mid):
     assert rms == pytest.approx(float(g["ref_rms"]), rel=1e-6)
 
 
+@pytest.mark.parametrize("name", ["C2", "C4"])
+def test_full_size_solve_vs_reference_golden(name):
+    """BASELINE configs[1] / configs[3] at full size against the trajectory of the unmodified reference
+    (tests/golden/make_golden_full.py): same nfev / status, per-iteration costs within LSMR's own tolerance,
+    final cost and RMS within 1e-6 relative (the north-star bar)."""
+    import os
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, name.lower() + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    g = np.load(path)
+    prob = synth.make_config(name, hard=True)
+    assert abs(problem_x0(prob).sum() - float(g["x0_checksum"])) < 1e-6
+    res = _solve(prob)
+    costs = np.array([row["cost"] for row in res.log])
+    ref = g["ref_costs"]
+    assert res.nfev == int(g["ref_nfev"]) and res.status == int(g["ref_status"]) and len(costs) == len(ref)
+    np.testing.assert_allclose(costs, ref, rtol=1e-4)
+    assert res.cost == pytest.approx(float(g["ref_cost"]), rel=1e-6)
+    rms = np.sqrt(np.mean(np.sum(res.fun.reshape(-1, 2) ** 2, axis=1)))
+    assert rms == pytest.approx(float(g["ref_rms"]), rel=1e-6)
+
+
 def test_solve_vs_oracle_trf(case):
     """Same algorithm on both sides (analytic J, Schur PCG, TRF rules): per-iteration costs agree
     to 1e-9, i.e. far inside the 1e-6 bar; the reference comparison is the golden test above."""
