@@ -16,6 +16,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -1355,10 +1356,20 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     if (!K || !uv) return fail(h, MMBA_ERR_ARG, "set_problem: null K or uv");
     CU(cudaSetDevice(h->opt.device));
     release_problem(h);
+    // MMBA_PLAN_TIMING=1: host-side phase times of this call on stderr (diagnostics)
+    auto T0 = std::chrono::steady_clock::now();
+    const bool timing = getenv("MMBA_PLAN_TIMING") != nullptr;
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "set_problem %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count());
+        T0 = t;
+    };
     std::string err;
     int rc = build_plan(h->plan, n_cams, n_points, n_obs, cam_idx, pt_idx, h->opt.rank, h->opt.nranks, err);
     if (rc != MMBA_OK) return fail(h, rc, err);
     if (n_cams > (int64_t)kMaxCamBlocks * kCamBlock) return fail(h, MMBA_ERR_ARG, "set_problem: too many cameras");
+    lap("plan");
     const Plan& pl = h->plan;
     h->Nc = n_cams;
     h->npl = pl.n_points_local();
@@ -1390,6 +1401,7 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     if (h->opt.schur_mode == MMBA_SCHUR_EXPLICIT && !h->rcm_ready)
         return fail(h, MMBA_ERR_ARG, "set_problem: the reduced camera matrix is too large to be formed explicitly");
 
+    lap("rcm pattern");
     Arena measure;
     carve(h, measure);
     const size_t need = measure.off + 256;
@@ -1419,6 +1431,7 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     }
 
     Dev& d = h->d;
+    lap("arena");
     CU(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
     {
         TRY(upload(h, d.meta, pl.meta));
@@ -1434,6 +1447,7 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
                 }
             }
         });
+        lap("uv reorder");
         TRY(upload(h, d.uv, uvs));
         if (h->rcm_ready) {
             TRY(upload(h, d.up_rowptr, h->rcm.up_rowptr));
@@ -1450,6 +1464,7 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
         }
         CU(cudaStreamSynchronize(h->stream));
     }
+    lap("uploads");
     TileArgs& A = h->targs;
     A.meta = d.meta;
     A.tile_cams = d.tile_cams;
@@ -1462,7 +1477,9 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     A.ytab_cams = h->Nc <= 340 ? (int)h->Nc : 0;   // <= 16 KB of shared memory
     std::memcpy(A.K, K, sizeof(A.K));
     TRY(configure_kernels(h));
+    lap("configure kernels");
     TRY(xchg_setup(h));
+    lap("peer exchange setup");
     h->has_problem = true;
     return MMBA_OK;
 }

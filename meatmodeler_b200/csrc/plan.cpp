@@ -42,16 +42,38 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
     {
         std::vector<int32_t> last_cam(n_points, -1), first_hi(n_points, (int32_t)n_cams);
         const int64_t half = n_cams / 2;
-        for (int64_t i = 0; i < n_obs; ++i) {
-            const int64_t c = cam_idx[i], p = pt_idx[i];
-            if (c < 0 || c >= n_cams || p < 0 || p >= n_points) {
-                err = "set_problem: index out of range at observation " + std::to_string(i);
-                return MMBA_ERR_ARG;
+        // observation chunks in parallel: relaxed atomic count / min / max per point (the results do not depend
+        // on the order)
+        auto amin = [](int32_t* a, int32_t v) {
+            int32_t cur = __atomic_load_n(a, __ATOMIC_RELAXED);
+            while (v < cur && !__atomic_compare_exchange_n(a, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
             }
-            ++count[p];
-            if (c < first_cam[p]) first_cam[p] = (int32_t)c;
-            if (c > last_cam[p]) last_cam[p] = (int32_t)c;
-            if (c >= half && c < first_hi[p]) first_hi[p] = (int32_t)c;
+        };
+        auto amax = [](int32_t* a, int32_t v) {
+            int32_t cur = __atomic_load_n(a, __ATOMIC_RELAXED);
+            while (v > cur && !__atomic_compare_exchange_n(a, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+            }
+        };
+        int64_t bad[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+        parallel_ranges(n_obs, 65536, [&](int64_t i0, int64_t i1, int worker) {
+            for (int64_t i = i0; i < i1; ++i) {
+                const int64_t c = cam_idx[i], p = pt_idx[i];
+                if (c < 0 || c >= n_cams || p < 0 || p >= n_points) {
+                    if (bad[worker] < 0) bad[worker] = i;
+                    continue;
+                }
+                __atomic_fetch_add(&count[p], 1, __ATOMIC_RELAXED);
+                amin(&first_cam[p], (int32_t)c);
+                amax(&last_cam[p], (int32_t)c);
+                if (c >= half) amin(&first_hi[p], (int32_t)c);
+            }
+        });
+        int64_t first_bad = -1;
+        for (int w = 0; w < 8; ++w)
+            if (bad[w] >= 0 && (first_bad < 0 || bad[w] < first_bad)) first_bad = bad[w];
+        if (first_bad >= 0) {
+            err = "set_problem: index out of range at observation " + std::to_string(first_bad);
+            return MMBA_ERR_ARG;
         }
         for (int64_t p = 0; p < n_points; ++p)
             if (count[p] && last_cam[p] - first_cam[p] > half && first_hi[p] < n_cams) first_cam[p] = first_hi[p];
@@ -104,10 +126,14 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
     std::vector<int32_t> gcam(plan.n_obs_local);
     {
         std::vector<int64_t> fill(start.begin(), start.end() - 1);
-        for (int64_t i = 0; i < n_obs; ++i) {
-            const int64_t q = (int64_t)point_inv[pt_idx[i]] - plan.pt_begin;
-            if (q >= 0 && q < npl) grouped[fill[q]++] = i;
-        }
+        // scatter in parallel (atomic slot counters); the per-point sort below orders by (camera, observation),
+        // so the result does not depend on the arrival order
+        parallel_ranges(n_obs, 65536, [&](int64_t i0, int64_t i1, int) {
+            for (int64_t i = i0; i < i1; ++i) {
+                const int64_t q = (int64_t)point_inv[pt_idx[i]] - plan.pt_begin;
+                if (q >= 0 && q < npl) grouped[__atomic_fetch_add(&fill[q], 1, __ATOMIC_RELAXED)] = i;
+            }
+        });
         parallel_ranges(npl, 4096, [&](int64_t q0, int64_t q1, int) {
             for (int64_t q = q0; q < q1; ++q) {
                 // tracks are short: insertion sort (stable), usually already ascending.  The camera of every
@@ -120,7 +146,7 @@ int build_plan(Plan& plan, int64_t n_cams, int64_t n_points, int64_t n_obs, cons
                     const int64_t v = g[a];
                     const int32_t cv = gc[a];
                     int64_t b = a;
-                    while (b > 0 && gc[b - 1] > cv) {
+                    while (b > 0 && (gc[b - 1] > cv || (gc[b - 1] == cv && g[b - 1] > v))) {
                         g[b] = g[b - 1];
                         gc[b] = gc[b - 1];
                         --b;
