@@ -1,17 +1,76 @@
-"""Drop-in for the two ``processor.py`` steps either side of the bundle-adjustment hot path:
+"""Drop-in for the ``processor.py`` steps either side of the bundle-adjustment hot path:
 
+* ``pointTracking(tracks, prev_keyframe_ID, feature_points, keyframe_ID, correspondents)`` (processor.py:190-243) —
+  the O(matches x tracks) scan becomes one hash join (first track per previous-keyframe pixel);
 * ``triangulatePoints(tracks, projections)``  (processor.py:246-261) — the per-track
   ``cv2.triangulatePoints`` loop becomes ONE launch of ``triangulate_kernel`` (libmmba.so) over all tracks;
 * ``managePoints(tracks)``                    (processor.py:264-291) — the observation lists
   (points, coordinates, frame indices, point indices) that feed ``bundleAdjuster.adjustPoints``.
 
-Same names, argument meaning and side effects as the reference (``track.setPoint`` receives a (1, 3) array, as
-processor.py:259-260 produces).  ``tracks`` are duck-typed: any object with the methods of the reference's
-``track.Track`` (track.py:1-41).  No CPU fallback: the triangulation fails loudly without libmmba.so / a B200.
+Same names, argument meaning, return values and side effects as the reference (``track.setPoint`` receives a (1, 3)
+array, as processor.py:259-260 produces).  ``tracks`` are duck-typed: any object with the methods of the reference's
+``track.Track`` (track.py:1-41); new tracks are built with the caller's own ``Track`` class (``install`` takes it from
+the patched module).  No CPU fallback: the triangulation fails loudly without libmmba.so / a B200.
+
+    import processor, meatmodeler_b200.processor as mp
+    mp.install(processor)        # processor.pointTracking / triangulatePoints / managePoints now resolve here
 """
 import numpy as np
 
 from . import _capi
+
+_track_class = None
+
+
+def install(module, track_class=None):
+    """Rebind the three functions of an imported ``processor`` module (the reference's, unmodified) to this module."""
+    global _track_class
+    _track_class = track_class if track_class is not None else getattr(module, "Track", None)
+    module.pointTracking = pointTracking
+    module.triangulatePoints = triangulatePoints
+    module.managePoints = managePoints
+    return module
+
+
+def pointTracking(tracks, prev_keyframe_ID, feature_points, keyframe_ID, correspondents, track_class=None):
+    """processor.py:190-243.  A match continues the FIRST track (list order) whose pixel in the previous keyframe
+    equals the match's feature point, otherwise it starts a new track; tracks that received no match are popped.
+    Returns (popped_tracks, updated_tracks + new_tracks), both in the reference's order."""
+    make = track_class or _track_class
+    if make is None:
+        raise TypeError("pointTracking needs the Track class: pass track_class= or call install(processor) first")
+    first = {}
+    for track in tracks:
+        prior = track.getCoordinate(prev_keyframe_ID)
+        if prior is not None:
+            first.setdefault(_pixel_key(prior), track)
+    new_tracks = []
+    for feature_point, correspondent in zip(feature_points, correspondents):
+        feature_point = (feature_point[0], feature_point[1])
+        correspondent = (correspondent[0], correspondent[1])
+        track = first.get(_pixel_key(feature_point))
+        if track is not None:
+            track.update(keyframe_ID, correspondent)
+        else:
+            new_tracks.append(make(prev_keyframe_ID, feature_point, keyframe_ID, correspondent))
+    updated_tracks = []
+    popped_tracks = []
+    for track in tracks:
+        if track.wasUpdated():
+            track.reset()
+            updated_tracks.append(track)
+        else:
+            popped_tracks.append(track)
+    updated_tracks += new_tracks
+    return popped_tracks, updated_tracks
+
+
+def _pixel_key(p):
+    # tuple equality of the reference (processor.py:218): == on both coordinates; -0.0 == 0.0, nan never matches
+    x, y = float(p[0]), float(p[1])
+    if x != x or y != y:
+        return object()
+    return (x + 0.0, y + 0.0)
 
 
 def triangulationArrays(tracks):

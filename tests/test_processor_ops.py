@@ -18,9 +18,25 @@ def golden_tri():
 class _Track:
     """The reference's track.Track interface (track.py:1-41), re-stated for the tests."""
 
-    def __init__(self, coords):
+    def __init__(self, coords, *rest):
+        if rest:     # Track(prev_frame_ID, feature, frame_ID, correspondent), track.py:2
+            coords = {coords: rest[0], rest[1]: rest[2]}
         self.coordinates = dict(coords)
         self.point = None
+        self.updated = False
+
+    def update(self, frame_ID, correspondent):
+        self.coordinates[frame_ID] = correspondent
+        self.updated = True
+
+    def reset(self):
+        self.updated = False
+
+    def wasUpdated(self):
+        return self.updated
+
+    def getCoordinate(self, frame_ID):
+        return self.coordinates.get(frame_ID)
 
     def getTriangulationData(self):
         frames = list(self.coordinates.keys())
@@ -52,6 +68,66 @@ def test_manage_points_matches_reference_order():
     assert coordinates == [(1.0, 2.0), (3.0, 4.0), (9.0, 9.5), (5.0, 6.0), (7.0, 8.0)]
     assert frame_indices == [3, 5, 4, 0, 1]
     assert point_indices == [0, 0, 0, 1, 1]
+
+
+def _reference_point_tracking(tracks, prev_keyframe_ID, feature_points, keyframe_ID, correspondents):
+    """The reference's quadratic scan (processor.py:209-243), restated for the comparison."""
+    new_tracks, updated_tracks, popped_tracks = [], [], []
+    for feature_point, correspondent in zip(feature_points, correspondents):
+        feature_point = (feature_point[0], feature_point[1])
+        correspondent = (correspondent[0], correspondent[1])
+        is_new_track = True
+        for track in tracks:
+            if feature_point == track.getCoordinate(prev_keyframe_ID):
+                track.update(keyframe_ID, correspondent)
+                is_new_track = False
+                break
+        if is_new_track:
+            new_tracks.append(_Track(prev_keyframe_ID, feature_point, keyframe_ID, correspondent))
+    for track in tracks:
+        if track.wasUpdated():
+            track.reset()
+            updated_tracks.append(track)
+        else:
+            popped_tracks.append(track)
+    return popped_tracks, updated_tracks + new_tracks
+
+
+def test_point_tracking_matches_the_reference_scan():
+    rng = np.random.default_rng(9)
+
+    def scenario():
+        tracks = []
+        for i in range(300):
+            a = (float(rng.integers(0, 60)), float(rng.integers(0, 40)))      # few pixels: duplicates on purpose
+            tracks.append(_Track({3: (1.0, 1.0), 4: a} if i % 3 else {2: a, 3: (5.0, 5.0)}))
+        feats = np.array([[rng.integers(0, 60), rng.integers(0, 40)] for _ in range(400)], dtype=np.float32)
+        feats[7] = feats[3]                                                    # two matches on one feature
+        corr = rng.normal(100, 30, (400, 2)).astype(np.float32)
+        return tracks, feats, corr
+
+    state = rng.bit_generator.state
+    t_ref, feats, corr = scenario()
+    rng.bit_generator.state = state
+    t_new, feats2, corr2 = scenario()
+    assert np.array_equal(feats, feats2)
+    popped_ref, upd_ref = _reference_point_tracking(t_ref, 4, feats, 5, corr)
+    popped_new, upd_new = mp.pointTracking(t_new, 4, feats2, 5, corr2, track_class=_Track)
+    assert [t_ref.index(t) for t in popped_ref] == [t_new.index(t) for t in popped_new]
+    assert len(upd_ref) == len(upd_new)
+    for a, b in zip(upd_ref, upd_new):
+        assert a.getCoordinates() == b.getCoordinates() and a.wasUpdated() == b.wasUpdated()
+    assert any(len(t.getCoordinates()) == 3 for t in upd_new) and len(popped_new) > 0
+
+
+def test_install_rebinds_a_processor_module():
+    import types
+    fake = types.ModuleType("processor")
+    fake.Track = _Track
+    mp.install(fake)
+    assert fake.pointTracking is mp.pointTracking and fake.managePoints is mp.managePoints
+    popped, kept = fake.pointTracking([], 0, np.array([[1.0, 2.0]]), 1, np.array([[3.0, 4.0]]))
+    assert popped == [] and len(kept) == 1 and kept[0].getCoordinates() == {0: (1.0, 2.0), 1: (3.0, 4.0)}
 
 
 def test_triangulation_arrays_take_first_and_last_frame():
