@@ -262,9 +262,9 @@ def run_mmba(args):
     n_obs_local, n_pts_local = shard["n_obs_local"], shard["n_points_local"]
     kernels = {}
     explicit = prof["schur_pcg"]["launches"] > 0
-    nnz_up = nnz_full = 0
+    nnz_up = nnz_full = total_pairs = 0
     if explicit:
-        _, up_cols, nnz_full, _ = _capi.host_rcm_pattern(nc, npts, fi, pi)
+        _, up_cols, nnz_full, total_pairs = _capi.host_rcm_pattern(nc, npts, fi, pi)
         nnz_up = len(up_cols)
     for name in ("build", "schur_build", "schur_matvec", "schur_rhs", "backsub", "jv", "resid"):
         p = prof[name]
@@ -289,6 +289,17 @@ def run_mmba(args):
                 "other_classes_ms_per_step": {k: {"launches": prof[k]["launches"], "ms": prof[k]["ms"]}
                                               for k in ("vec", "allreduce", "cam_prep", "point_invert")},
                 "profiled_step_ms": rp.solve_ms}
+    if explicit and "schur_build" in kernels:
+        # The S-build pass streams J once (HBM figure above) but is bound by FP64 issue: 108 DFMA per observation pair
+        # of a point (sum over points of L (L + 1) / 2 pairs; this rank's share for a sharded solve).
+        kb = kernels["schur_build"]
+        flops = 2.0 * 108.0 * total_pairs * (n_obs_local / max(nobs, 1))
+        kb["fp64"] = {"algorithmic_dfma": flops / 2, "achieved_tflops": flops / (kb["avg_ms"] * 1e-3) / 1e12,
+                      "nominal_peak_tflops": 37.2, "frac_of_nominal": flops / (kb["avg_ms"] * 1e-3) / 1e12 / 37.2,
+                      "peak_source": "148 SMs x 64 DFMA/clk x 2 x 1.965 GHz (vector FP64, nominal)"}
+        if dom == "schur_build":
+            roofline["note"] = ("the dominant streaming kernel (S-build) is FP64-issue bound, not HBM bound: see "
+                                "kernels.schur_build.fp64; the HBM-bound passes are build / backsub / jv / resid")
     if explicit:
         # The PCG on the explicit, L2/L1-resident reduced camera matrix is one cooperative launch per outer
         # iteration: no HBM stream, two grid barriers per PCG iteration.  It has no HBM roofline; what bounds it
@@ -352,7 +363,7 @@ def run_mmba(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mmba", choices=["mmba", "reference"])
     ap.add_argument("--config", default="auto", choices=["auto", "C1", "C2", "C3", "C4", "C5"])
