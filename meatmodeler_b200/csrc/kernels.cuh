@@ -68,6 +68,7 @@ enum Scal {
     S_COST_NEW,      // sum r^2 (trial)
     S_JV00, S_JV01, S_JV11,   // Gram of J*v products
     S_DOT0, S_DOT1, S_DOT2, S_DOT3, S_DOT4, S_DOT5, S_DOT6, S_DOT7, S_DOT8, S_DOT9,   // subspace dots
+    S_PEER_ERR = 23,  // set by peer_allreduce_small_kernel when a rank did not arrive
     S_COUNT = 24
 };
 

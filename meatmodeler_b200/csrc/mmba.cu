@@ -134,6 +134,10 @@ struct Xchg {
     unsigned long long** d_peer_flags = nullptr;
     int n6 = 0;       // slot length in doubles (capacity: the buffers are kept across problems)
     unsigned long long seq = 0;
+    // small all-reduce (peer_allreduce_small_kernel): LL lines [2 parities][nranks][kPeerSmallMax] in every rank's buffer
+    LLLine* ll = nullptr;                 // this rank's area
+    LLLine** d_peer_ll = nullptr;         // device array: every rank's area as mapped here
+    unsigned llseq = 0;
 };
 
 struct Profile {
@@ -263,6 +267,23 @@ struct Red {
 // Sum (or max) the listed device arrays over ranks, in place, as one NCCL group.
 int allreduce(mmba_handle* h, std::initializer_list<Red> items) {
     if (h->opt.nranks <= 1) return MMBA_OK;
+    // a handful of scalars: one-shot exchange of self-validating lines over NVLink peer memory instead of NCCL
+    // (≈30 us per call at 8 GPUs); every rank adds the partials in rank order -> identical results everywhere
+    if (h->xchg.on && items.size() <= 2 && h->opt.nranks <= 8) {
+        size_t total = 0;
+        for (const Red& r : items) total += r.n;
+        if (total <= (size_t)kPeerSmallMax) {
+            const Red* it = items.begin();
+            const Red a = it[0], b = items.size() > 1 ? it[1] : Red{nullptr, 0, false};
+            const unsigned seq = ++h->xchg.llseq;
+            prof_begin(h, MMBA_K_ALLREDUCE);
+            peer_allreduce_small_kernel<<<1, 32 * ((kPeerSmallMax * h->opt.nranks + 31) / 32), 0, h->stream>>>(
+                a.p, (int)a.n, a.is_max ? 1 : 0, b.p, (int)b.n, b.is_max ? 1 : 0, h->xchg.d_peer_ll, h->xchg.ll, h->opt.rank,
+                h->opt.nranks, seq, h->d.scal + S_PEER_ERR);
+            prof_end(h, MMBA_K_ALLREDUCE);
+            return MMBA_OK;
+        }
+    }
     prof_begin(h, MMBA_K_ALLREDUCE);
     NC(g_nccl.GroupStart());
     for (const Red& r : items) {
@@ -281,6 +302,7 @@ int allreduce(mmba_handle* h, std::initializer_list<Red> items) {
 int read_scalars(mmba_handle* h) {
     CU(cudaMemcpyAsync(h->h_scal, h->d.scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (h->h_scal[S_PEER_ERR] != 0.0) return fail(h, MMBA_ERR_NCCL, "peer all-reduce timed out: a rank stopped participating");
     return MMBA_OK;
 }
 
@@ -373,6 +395,7 @@ void xchg_release(mmba_handle* h) {
     if (x.base) cudaFree(x.base);
     if (x.d_peer_slots) cudaFree(x.d_peer_slots);
     if (x.d_peer_flags) cudaFree(x.d_peer_flags);
+    if (x.d_peer_ll) cudaFree(x.d_peer_ll);
     x = Xchg();
 }
 
@@ -387,11 +410,13 @@ int xchg_setup(mmba_handle* h) {
     xchg_release(h);
     x.n6 = (int)std::max<int64_t>(6 * h->Nc, 8192);
     const size_t flag_bytes = 256 * ((2 * nr * sizeof(unsigned long long) + 255) / 256);
-    const size_t bytes = flag_bytes + 2 * (size_t)nr * x.n6 * sizeof(double);
+    const size_t ll_bytes = 256 * ((2 * (size_t)nr * kPeerSmallMax * sizeof(LLLine) + 255) / 256);
+    const size_t bytes = flag_bytes + ll_bytes + 2 * (size_t)nr * x.n6 * sizeof(double);
     CU(cudaMalloc(&x.base, bytes));
     CU(cudaMemsetAsync(x.base, 0, bytes, h->stream));
     x.flags = static_cast<unsigned long long*>(x.base);
-    x.slots = reinterpret_cast<double*>(static_cast<char*>(x.base) + flag_bytes);
+    x.ll = reinterpret_cast<LLLine*>(static_cast<char*>(x.base) + flag_bytes);
+    x.slots = reinterpret_cast<double*>(static_cast<char*>(x.base) + flag_bytes + ll_bytes);
     cudaIpcMemHandle_t mine;
     CU(cudaIpcGetMemHandle(&mine, x.base));
     char *d_send = nullptr, *d_recv = nullptr;
@@ -407,6 +432,7 @@ int xchg_setup(mmba_handle* h) {
     x.peers.assign(nr, nullptr);
     std::vector<double*> ps(nr);
     std::vector<unsigned long long*> pf(nr);
+    std::vector<LLLine*> pl(nr);
     bool ok = true;
     for (int r = 0; r < nr; ++r) {
         void* p = x.base;
@@ -420,7 +446,8 @@ int xchg_setup(mmba_handle* h) {
             }
         }
         pf[r] = static_cast<unsigned long long*>(p);
-        ps[r] = reinterpret_cast<double*>(static_cast<char*>(p) + flag_bytes);
+        pl[r] = reinterpret_cast<LLLine*>(static_cast<char*>(p) + flag_bytes);
+        ps[r] = reinterpret_cast<double*>(static_cast<char*>(p) + flag_bytes + ll_bytes);
     }
     // every rank must take the same path: agree on success
     double* d_ok = nullptr;
@@ -440,7 +467,10 @@ int xchg_setup(mmba_handle* h) {
     CU(cudaMalloc(&x.d_peer_flags, nr * sizeof(unsigned long long*)));
     CU(cudaMemcpyAsync(x.d_peer_slots, ps.data(), nr * sizeof(double*), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(x.d_peer_flags, pf.data(), nr * sizeof(unsigned long long*), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMalloc(&x.d_peer_ll, nr * sizeof(LLLine*)));
+    CU(cudaMemcpyAsync(x.d_peer_ll, pl.data(), nr * sizeof(LLLine*), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    x.llseq = 0;
     x.seq = 0;
     x.on = true;
     return MMBA_OK;

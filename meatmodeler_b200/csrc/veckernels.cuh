@@ -10,6 +10,7 @@
 #include <cooperative_groups.h>
 
 #include "kernels.cuh"
+#include "rcm.cuh"
 
 namespace mmba {
 
@@ -729,6 +730,70 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const double* __restri
     out[3 * i] = x[0] * iw;
     out[3 * i + 1] = x[1] * iw;
     out[3 * i + 2] = x[2] * iw;
+}
+
+// ---------------------------------------------------------------------------------------------
+// All-reduce of a handful of scalars across the ranks of a sharded solve (the sums the TRF logic reads back:
+// ||J v||^2, dot products of the 2-D subspace, trial cost, ||g||_inf) as ONE tiny kernel over NVLink peer memory,
+// instead of a ~30 us ncclAllReduce each.  Every value travels as a self-validating 16-byte line (ll_store /
+// ll_try_load with system scope): rank r stores its values into row [parity][r] of EVERY rank's area (plain
+// stores to peer-mapped addresses), then polls the rows of its own area and combines them in rank order, so all
+// ranks obtain bit-identical results.  Two parities make reuse safe: a rank can write exchange s + 2 only after it
+// has completed exchange s + 1, which every peer joins only after it has finished reading exchange s.
+// Up to two segments (p0[n0], p1[n1]); a segment is summed as doubles or max-reduced as the bit patterns of
+// non-negative doubles.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPeerSmallMax = 16;
+
+__device__ __forceinline__ void ll_store_sys(LLLine* line, unsigned long long bits, unsigned seq) {
+    const unsigned long long tag = (unsigned long long)seq << 32;
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(line), "l"(tag | (bits & 0xffffffffull)), "l"(tag | (bits >> 32))
+                 : "memory");
+}
+__device__ __forceinline__ bool ll_try_load_sys(const LLLine* line, unsigned seq, unsigned long long& bits) {
+    unsigned long long w0, w1;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(line) : "memory");
+    bits = (w0 & 0xffffffffull) | (w1 << 32);
+    return (unsigned)(w0 >> 32) == seq && (unsigned)(w1 >> 32) == seq;
+}
+
+__global__ void peer_allreduce_small_kernel(double* p0, int n0, int max0, double* p1, int n1, int max1, LLLine* const* peer_ll,
+                                            const LLLine* my_ll, int rank, int nranks, unsigned seq, double* err) {
+    __shared__ unsigned long long s_val[8 * kPeerSmallMax];   // [rank][value], nranks <= 8 per node
+    const int n = n0 + n1, tid = threadIdx.x;
+    const int parity = (int)(seq & 1u);
+    if (tid < n * nranks) {
+        const int q = tid / n, i = tid - q * n;
+        const double v = i < n0 ? p0[i] : p1[i - n0];
+        ll_store_sys(peer_ll[q] + ((size_t)parity * nranks + rank) * kPeerSmallMax + i, (unsigned long long)__double_as_longlong(v), seq);
+    }
+    if (tid < n * nranks) {
+        const int r = tid / n, i = tid - r * n;
+        const LLLine* line = my_ll + ((size_t)parity * nranks + r) * kPeerSmallMax + i;
+        unsigned long long bits = 0;
+        const long long t0 = clock64();
+        while (!ll_try_load_sys(line, seq, bits)) {
+            if (clock64() - t0 > (1ll << 32)) {   // ~2 s: a peer died; report instead of hanging
+                *err = 1.0;
+                break;
+            }
+        }
+        s_val[r * kPeerSmallMax + i] = bits;
+    }
+    __syncthreads();
+    if (tid < n) {
+        const bool is_max = tid < n0 ? max0 != 0 : max1 != 0;
+        double* dst = tid < n0 ? p0 + tid : p1 + (tid - n0);
+        if (is_max) {
+            unsigned long long best = 0;
+            for (int r = 0; r < nranks; ++r) best = max(best, s_val[r * kPeerSmallMax + tid]);
+            *dst = __longlong_as_double((long long)best);
+        } else {
+            double acc = 0.0;
+            for (int r = 0; r < nranks; ++r) acc += __longlong_as_double((long long)s_val[r * kPeerSmallMax + tid]);
+            *dst = acc;
+        }
+    }
 }
 
 // Reference point for the roofline: a plain grid-stride LDG.128 read of n doubles (what a trivial
