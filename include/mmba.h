@@ -223,6 +223,11 @@ int mmba_plan_sizes(const mmba_plan* p, int64_t sizes[8]);
 int mmba_plan_export(const mmba_plan* p, int64_t* obs_perm, int64_t* point_perm,
                      int32_t* slot_cam_global, int32_t* slot_point_local);
 
+/* per tile (n_tiles entries each, any pointer may be NULL): distinct cameras, points, the S-build strategy the
+ * plan chose (0 = point-pair-major, 1 = camera-pair-major flushed per tile, 2 = one 6x6 block per thread kept
+ * across tiles) and the number of observation pairs sum L (L + 1) / 2 */
+int mmba_plan_tile_stats(const mmba_plan* p, int32_t* n_cams, int32_t* n_points, int32_t* pair_mode, int32_t* n_pairs);
+
 #ifdef __cplusplus
 }
 #endif

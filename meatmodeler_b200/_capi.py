@@ -93,6 +93,7 @@ SIGNATURES = {
     "mmba_plan_destroy": (None, [_H]),
     "mmba_plan_sizes": (C.c_int, [_H, C.POINTER(C.c_int64 * 8)]),
     "mmba_plan_export": (C.c_int, [_H, _i64, _i64, _i32, _i32]),
+    "mmba_plan_tile_stats": (C.c_int, [_H, _i32, _i32, _i32, _i32]),
 }
 
 _lib = None

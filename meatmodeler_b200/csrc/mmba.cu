@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mmba.h"
@@ -1412,7 +1413,23 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     // and L2-sized, and a bounded S-build cost (pair-blocks per observation).
     h->rcm_ready = false;
     h->rcm = RcmPattern();
-    if (h->opt.schur_mode != MMBA_SCHUR_IMPLICIT && n_cams <= 20000) {
+    // tile-major copy of the observed pixels: host-only work that runs on this thread while the pattern is built
+    std::vector<double> uvs;
+    auto reorder_uv = [&]() {
+        uvs.assign(2 * (size_t)h->ns, 0.0);
+        parallel_ranges(h->ns, 65536, [&](int64_t s0, int64_t s1, int) {
+            for (int64_t s = s0; s < s1; ++s) {
+                const int64_t ob = pl.slot_obs[s];
+                if (ob >= 0) {
+                    const int64_t t = s / kT, j = s % kT;
+                    uvs[(t * 2) * kT + j] = uv[2 * ob];
+                    uvs[(t * 2 + 1) * kT + j] = uv[2 * ob + 1];
+                }
+            }
+        });
+    };
+    std::thread pattern_thread;
+    auto build_pattern = [&]() {
         const bool forced = h->opt.schur_mode == MMBA_SCHUR_EXPLICIT;
         const int64_t cap_full = forced ? (int64_t)8 << 20 : std::min<int64_t>(((int64_t)96 << 20) / 288, (152 * n_obs / 2) / 288);
         const bool ok = build_rcm_pattern(h->rcm, n_cams, n_points, n_obs, cam_idx, pt_idx, std::max<int64_t>(cap_full, n_cams),
@@ -1427,11 +1444,14 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
                 h->rcm = RcmPattern();
             }
         }
-    }
+    };
+    if (h->opt.schur_mode != MMBA_SCHUR_IMPLICIT && n_cams <= 20000) pattern_thread = std::thread(build_pattern);
+    reorder_uv();
+    if (pattern_thread.joinable()) pattern_thread.join();
     if (h->opt.schur_mode == MMBA_SCHUR_EXPLICIT && !h->rcm_ready)
         return fail(h, MMBA_ERR_ARG, "set_problem: the reduced camera matrix is too large to be formed explicitly");
 
-    lap("rcm pattern");
+    lap("rcm pattern | uv reorder");
     Arena measure;
     carve(h, measure);
     const size_t need = measure.off + 256;
@@ -1466,18 +1486,6 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     {
         TRY(upload(h, d.meta, pl.meta));
         TRY(upload(h, d.tile_cams, pl.tile_cams));
-        std::vector<double> uvs(2 * (size_t)h->ns, 0.0);
-        parallel_ranges(h->ns, 65536, [&](int64_t s0, int64_t s1, int) {
-            for (int64_t s = s0; s < s1; ++s) {
-                const int64_t ob = pl.slot_obs[s];
-                if (ob >= 0) {
-                    const int64_t t = s / kT, j = s % kT;
-                    uvs[(t * 2) * kT + j] = uv[2 * ob];
-                    uvs[(t * 2 + 1) * kT + j] = uv[2 * ob + 1];
-                }
-            }
-        });
-        lap("uv reorder");
         TRY(upload(h, d.uv, uvs));
         if (h->rcm_ready) {
             TRY(upload(h, d.up_rowptr, h->rcm.up_rowptr));
@@ -1981,6 +1989,18 @@ int mmba_plan_export(const mmba_plan* p, int64_t* obs_perm, int64_t* point_perm,
             if (slot_cam_global) slot_cam_global[s] = live ? pl.tile_cams[t * pl.cam_stride + pl.meta[t].slot_cam[j]] : -1;
             if (slot_point_local) slot_point_local[s] = live ? pl.meta[t].pt0 + pl.meta[t].slot_pt[j] : -1;
         }
+    }
+    return MMBA_OK;
+}
+
+int mmba_plan_tile_stats(const mmba_plan* p, int32_t* n_cams, int32_t* n_points, int32_t* pair_mode, int32_t* n_pairs) {
+    if (!p) return MMBA_ERR_ARG;
+    const Plan& pl = p->plan;
+    for (int64_t t = 0; t < pl.n_tiles; ++t) {
+        if (n_cams) n_cams[t] = pl.meta[t].ncams;
+        if (n_points) n_points[t] = pl.meta[t].npts;
+        if (pair_mode) pair_mode[t] = pl.meta[t].pair_mode;
+        if (n_pairs) n_pairs[t] = pl.meta[t].npairs;
     }
     return MMBA_OK;
 }

@@ -209,3 +209,41 @@ def test_rcm_pattern_unobserved_camera_keeps_its_diagonal():
     rowptr, cols, nnz_full, pairs = _capi.host_rcm_pattern(4, 2, fi, pi)
     assert rowptr.tolist() == [0, 2, 3, 4, 5] and cols.tolist() == [0, 2, 1, 2, 3]
     assert nnz_full == 6 and pairs == 6
+
+
+# ---- tile strategies of the S-build pass / ring-aware point order --------------------------------
+def _tile_stats(prob):
+    ext, K, pts, uv, fi, pi = prob.args()
+    fi = np.ascontiguousarray(fi, np.int64)
+    pi = np.ascontiguousarray(pi, np.int64)
+    h = _capi._H()
+    _capi._check(_capi.lib().mmba_plan_create(ctypes.byref(h), len(ext), len(pts), len(fi), fi, pi, 0, 1))
+    sizes = (ctypes.c_int64 * 8)()
+    _capi.lib().mmba_plan_sizes(h, ctypes.byref(sizes))
+    n = int(sizes[0])
+    out = [np.zeros(n, dtype=np.int32) for _ in range(4)]
+    _capi._check(_capi.lib().mmba_plan_tile_stats(h, *out))
+    _capi.lib().mmba_plan_destroy(h)
+    return out
+
+
+def test_turntable_tiles_stay_narrow_and_register_resident():
+    """Tracks that wrap around the camera ring are keyed by their first camera in the upper half: every tile of the
+    video-like shape sees about one window of cameras and takes the register-resident S-build strategy."""
+    prob = synth.make_config("C2", hard=True, scale=0.05)          # 200 cameras, windows of 20, ring closed
+    ncams, npts, mode, npairs = _tile_stats(prob)
+    assert ncams.max() <= 24 and np.all(mode == 2)
+    L = np.bincount(prob.pt_idx)
+    assert npairs.sum() == int((L * (L + 1) // 2).sum())
+
+
+def test_random_visibility_and_duplicates_take_the_general_strategy():
+    prob = synth.make_problem(300, 900, 4000, seed=9, windowed=False)
+    ncams, npts, mode, npairs = _tile_stats(prob)
+    assert ncams.max() > 100 and np.all(mode == 0)
+    dup = synth.make_problem(12, 300, 1500, seed=31)
+    dup.cam_idx = np.concatenate((dup.cam_idx, dup.cam_idx[:50]))
+    dup.pt_idx = np.concatenate((dup.pt_idx, dup.pt_idx[:50]))
+    dup.uv = np.vstack((dup.uv, dup.uv[:50]))
+    _, _, mode, _ = _tile_stats(dup)
+    assert (mode == 0).any()                                       # tiles holding a duplicated observation
