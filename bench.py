@@ -302,8 +302,8 @@ def run_mmba(args):
                                 "kernels.schur_build.fp64; the HBM-bound passes are build / backsub / jv / resid")
     if explicit:
         # The PCG on the explicit, L2/L1-resident reduced camera matrix is one cooperative launch per outer
-        # iteration: no HBM stream, two grid barriers per PCG iteration.  It has no HBM roofline; what bounds it
-        # is the barrier + L2 round-trip latency, reported as time per PCG iteration.
+        # iteration: no HBM stream, two grid-wide exchanges (self-validating lines through L2) per PCG iteration.  It
+        # has no HBM roofline; what bounds it is the L2 round-trip latency, reported as time per PCG iteration.
         p = prof["schur_pcg"]
         its_p = max(int(rp.pcg_iterations), 1)
         roofline["schur_pcg_on_chip"] = {
@@ -311,7 +311,7 @@ def run_mmba(args):
             "pcg_iterations_per_step": int(rp.pcg_iterations), "us_per_pcg_iteration": 1e3 * p["ms"] / its_p,
             "matrix_bytes": 288 * nnz_full, "blocks_full": nnz_full, "blocks_upper": nnz_up,
             "l2_gbs": 288 * nnz_full * its_p / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else None,
-            "bound": "grid-barrier / L2 latency (2 barriers per iteration), not HBM"}
+            "bound": "latency of two grid-wide exchanges through L2 per iteration, not HBM"}
 
     # ---- end to end through the drop-in adjustPoints with host buffers ---------------------------
     e2e_steps = max(2, min(args.steps, 5))

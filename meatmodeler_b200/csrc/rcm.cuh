@@ -1,13 +1,13 @@
 // Explicit reduced camera matrix: scaling / mirroring of the accumulated blocks, block-Jacobi preconditioner,
-// and the whole PCG solve in ONE cooperative kernel (grid barriers instead of 2 launches + a streaming pass
-// over J per iteration).
+// and the whole PCG solve in ONE cooperative kernel (instead of 2 launches + a streaming pass over J per iteration).
 //
 //   S = D (J_c^T J_c - W V'^-1 W^T) D + reg I      (D = diag(1 / scale_inv) of the camera parameters)
 //
 // The S-build pass (tile_kernel<M_SBUILD>, kernels.cuh) accumulates the unscaled upper blocks; here they are
 // scaled and expanded to the full block-CSR pattern (rcm.h) the PCG multiplies with.  S is a few MB (C2: 2.2 MB,
-// C4: 6.6 MB): it stays in L1/L2 for the whole solve, so a PCG iteration costs two grid barriers plus an
-// L1-resident block-sparse product instead of 152 B/observation of HBM traffic.
+// C4: 5.6 MB): every PCG CTA keeps its rows in shared memory for the whole solve, so a PCG iteration costs two
+// grid-wide exchanges of self-validating 16-byte lines through L2 plus a shared-memory block-sparse product instead
+// of 152 B/observation of HBM traffic.
 // Replaces: lsmr(J_h, f, damp=sqrt(reg)) (trf.py:494-495) together with kernels.cuh's MATVEC pass.
 #pragma once
 #include <cuda_runtime.h>
