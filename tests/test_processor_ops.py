@@ -7,6 +7,7 @@ import pytest
 from conftest import GOLDEN
 from meatmodeler_b200 import _capi
 from meatmodeler_b200 import processor as mp
+from oracle import processor_oracle as po       # checker only
 from oracle import triangulate_oracle as tri   # checker only
 
 
@@ -64,33 +65,11 @@ def test_manage_points_matches_reference_order():
     tracks[0].setPoint(np.array([[1.0, 2.0, 3.0]]))
     tracks[1].setPoint(np.array([[4.0, 5.0, 6.0]]))
     points, coordinates, frame_indices, point_indices = mp.managePoints(tracks)
+    assert (points, coordinates, frame_indices, point_indices) == po.manage_points(tracks)
     assert [p.tolist() for p in points] == [[[1.0, 2.0, 3.0]], [[4.0, 5.0, 6.0]]]
     assert coordinates == [(1.0, 2.0), (3.0, 4.0), (9.0, 9.5), (5.0, 6.0), (7.0, 8.0)]
     assert frame_indices == [3, 5, 4, 0, 1]
     assert point_indices == [0, 0, 0, 1, 1]
-
-
-def _reference_point_tracking(tracks, prev_keyframe_ID, feature_points, keyframe_ID, correspondents):
-    """The reference's quadratic scan (processor.py:209-243), restated for the comparison."""
-    new_tracks, updated_tracks, popped_tracks = [], [], []
-    for feature_point, correspondent in zip(feature_points, correspondents):
-        feature_point = (feature_point[0], feature_point[1])
-        correspondent = (correspondent[0], correspondent[1])
-        is_new_track = True
-        for track in tracks:
-            if feature_point == track.getCoordinate(prev_keyframe_ID):
-                track.update(keyframe_ID, correspondent)
-                is_new_track = False
-                break
-        if is_new_track:
-            new_tracks.append(_Track(prev_keyframe_ID, feature_point, keyframe_ID, correspondent))
-    for track in tracks:
-        if track.wasUpdated():
-            track.reset()
-            updated_tracks.append(track)
-        else:
-            popped_tracks.append(track)
-    return popped_tracks, updated_tracks + new_tracks
 
 
 def test_point_tracking_matches_the_reference_scan():
@@ -111,7 +90,7 @@ def test_point_tracking_matches_the_reference_scan():
     rng.bit_generator.state = state
     t_new, feats2, corr2 = scenario()
     assert np.array_equal(feats, feats2)
-    popped_ref, upd_ref = _reference_point_tracking(t_ref, 4, feats, 5, corr)
+    popped_ref, upd_ref = po.point_tracking(t_ref, 4, feats, 5, corr, _Track)
     popped_new, upd_new = mp.pointTracking(t_new, 4, feats2, 5, corr2, track_class=_Track)
     assert [t_ref.index(t) for t in popped_ref] == [t_new.index(t) for t in popped_new]
     assert len(upd_ref) == len(upd_new)
