@@ -247,3 +247,12 @@ def test_random_visibility_and_duplicates_take_the_general_strategy():
     dup.uv = np.vstack((dup.uv, dup.uv[:50]))
     _, _, mode, _ = _tile_stats(dup)
     assert (mode == 0).any()                                       # tiles holding a duplicated observation
+
+
+def test_rcm_pattern_does_not_depend_on_the_observation_order():
+    prob = synth.make_problem(50, 1200, 6000, seed=4)
+    ext, K, pts, uv, fi, pi = prob.args()
+    a = _capi.host_rcm_pattern(len(ext), len(pts), fi, pi)
+    perm = np.random.default_rng(1).permutation(len(fi))
+    b = _capi.host_rcm_pattern(len(ext), len(pts), fi[perm], pi[perm])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2:] == b[2:]
