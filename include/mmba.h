@@ -55,7 +55,8 @@ typedef struct mmba_options {
     int64_t max_nfev;     /* 0 = scipy default 100*n (trf.py:452-453) */
     double pcg_rtol;      /* relative residual stop of the reduced-system PCG */
     int32_t pcg_maxit;
-    int32_t profile;      /* 1 = bracket kernels with CUDA events (mmba_get_profile) */
+    int32_t profile;      /* bit 0: bracket kernels with CUDA events (mmba_get_profile); bit 1: keep the residual history
+                             of every reduced-system PCG solve (mmba_get_pcg_history; read by mmba_set_problem) */
     uint8_t nccl_id[128]; /* ncclUniqueId bytes, same on all ranks (nranks > 1 only) */
     int32_t schur_mode;   /* MMBA_SCHUR_*: how the PCG applies the reduced camera system (read by mmba_set_problem) */
     int32_t reserved;
@@ -63,6 +64,11 @@ typedef struct mmba_options {
                              which ends scipy's inner solves) on the reduced system, where A^T res is the PCG residual:
                              stop when ||r|| <= pcg_atol ||f||.  0 = relative rule only.  Default 1e-7 (calibrated on
                              the reference's LSMR iteration counts, see oracle/schur_trf.py). */
+    double pcg_ktol;      /* LSMR's test 2 with its growing norm estimate (lsmr.py:430-459: ||A^T res|| <= atol ||A||_est
+                             ||res||, ||A||_est ~ sqrt(k) for unit-norm columns) on the reduced system.  LSMR is a
+                             minimal-residual method on the normal equations; the minimal-residual norm of the PCG
+                             process is nu_k, 1 / nu_k^2 = sum_{j<=k} 1 / ||r_j||^2: stop when
+                             nu_k <= pcg_ktol sqrt(k) ||f||.  0 = off. */
 } mmba_options;
 
 /* The reduced camera system S = U - W V'^-1 W^T of the damped Gauss-Newton step:
@@ -151,6 +157,11 @@ int mmba_get_x(mmba_handle* h, double* x);
 
 int mmba_get_log(const mmba_handle* h, mmba_iter_log* out, int capacity); /* returns row count */
 int mmba_get_profile(const mmba_handle* h, int64_t launches[MMBA_K_COUNT], double ms[MMBA_K_COUNT]);
+/* residual history of the reduced-system PCG solves of the last mmba_solve* call (explicit Schur path, handles whose
+ * options had profile bit 1 set at mmba_set_problem): outer_iteration < 0 returns the number of inner solves recorded;
+ * otherwise the pairs (||r_k||^2, r_k . Pinv r_k), k = 0 .. iterations, are copied to out (capacity doubles) and
+ * their count (2 (iterations + 1)) is returned */
+int mmba_get_pcg_history(const mmba_handle* h, int outer_iteration, double* out, int capacity);
 /* observations / points held by this rank and number of tiles (after set_problem) */
 int mmba_get_shard(const mmba_handle* h, int64_t* n_obs_local, int64_t* n_points_local,
                    int64_t* n_tiles);

@@ -34,7 +34,7 @@ class Options(C.Structure):
                 ("ftol", C.c_double), ("xtol", C.c_double), ("gtol", C.c_double), ("max_nfev", C.c_int64),
                 ("pcg_rtol", C.c_double), ("pcg_maxit", C.c_int32), ("profile", C.c_int32),
                 ("nccl_id", C.c_uint8 * 128), ("schur_mode", C.c_int32), ("reserved", C.c_int32),
-                ("pcg_atol", C.c_double)]
+                ("pcg_atol", C.c_double), ("pcg_ktol", C.c_double)]
 
 
 class Result(C.Structure):
@@ -71,6 +71,7 @@ SIGNATURES = {
     "mmba_get_x": (C.c_int, [_H, _f64]),
     "mmba_get_log": (C.c_int, [_H, C.POINTER(IterLog), C.c_int]),
     "mmba_get_profile": (C.c_int, [_H, C.POINTER(C.c_int64 * K_COUNT), C.POINTER(C.c_double * K_COUNT)]),
+    "mmba_get_pcg_history": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int]),
     "mmba_get_shard": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mmba_eval_residual": (C.c_int, [_H, _f64, _f64]),
     "mmba_eval_jacobian": (C.c_int, [_H, _f64, _f64, _f64]),
@@ -236,6 +237,17 @@ class Engine:
         rows = (IterLog * max(n, 1))()
         lib().mmba_get_log(self._h, rows, n)
         return [{f: getattr(rows[i], f) for f, _ in IterLog._fields_} for i in range(n)]
+
+    def pcg_history(self):
+        """Per inner solve of the last solve: array (iterations + 1, 2) of (||r_k||^2, r_k . Pinv r_k).  Needs an
+        engine created with ``profile=2`` (or 3) and the explicit Schur path."""
+        out = []
+        for i in range(lib().mmba_get_pcg_history(self._h, -1, None, 0)):
+            n = lib().mmba_get_pcg_history(self._h, i, None, 0)
+            buf = np.empty(max(n, 2))
+            lib().mmba_get_pcg_history(self._h, i, buf.ctypes.data, n)
+            out.append(buf[:n].reshape(-1, 2))
+        return out
 
     def profile(self):
         launches, ms = (C.c_int64 * K_COUNT)(), (C.c_double * K_COUNT)()

@@ -146,7 +146,7 @@ def _dist_options():
 
 
 _ENGINES = {}          # (device, rank, nranks) -> live engine: one stream / NCCL communicator per process
-_TUNABLE = ("ftol", "xtol", "gtol", "max_nfev", "pcg_rtol", "pcg_maxit", "verbose", "profile", "schur_mode", "pcg_atol")
+_TUNABLE = ("ftol", "xtol", "gtol", "max_nfev", "pcg_rtol", "pcg_maxit", "verbose", "profile", "schur_mode", "pcg_atol", "pcg_ktol")
 
 
 def _engine(camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D, **options):

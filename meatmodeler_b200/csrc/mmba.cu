@@ -122,6 +122,7 @@ struct Dev {
     uint16_t* rc_lcol;
     RcmSlot* rcm_slots;
     LLLine* rcm_z;
+    double* rcm_hist;   // (||r||^2, r.z) of every PCG iterate of the last inner solve (profile & 2)
 };
 
 // One-shot peer all-reduce of the per-iteration Schur product (see xchg_push_kernel)
@@ -163,6 +164,9 @@ struct mmba_handle {
     RcmPartition rcm_part;
     bool rcm_ready = false;        // pattern built and device arrays carved for the current problem
     int rcm_warps = 0, rcm_s_in_smem = 0, rcm_nsub = 1;
+    unsigned rcm_seq = 0;          // sequence numbers handed to the PCG launches of this problem (never reused)
+    int hist_cap = 0;              // iterations the history buffer holds (pcg_maxit at set_problem time)
+    std::vector<std::vector<double>> pcg_hist;   // per outer iteration: (||r_k||^2, r_k.z_k), k = 0 .. its
     size_t rcm_smem_bytes = 0;
     int64_t Nc = 0, npl = 0, ns = 0, nt = 0, nloc = 0;
     double K[9];
@@ -219,7 +223,7 @@ inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // ---- profiling -------------------------------------------------------------------------------
 void prof_begin(mmba_handle* h, int cls) {
     h->prof.launches[cls]++;
-    if (!h->opt.profile) return;
+    if (!(h->opt.profile & 1)) return;
     Profile& p = h->prof;
     if (p.used * 2 + 2 > p.pool.size()) {
         if (p.pool.size() >= 2 * 65536) return;
@@ -234,7 +238,7 @@ void prof_begin(mmba_handle* h, int cls) {
     cudaEventRecord(p.pool[2 * p.used], h->stream);
 }
 void prof_end(mmba_handle* h, int) {
-    if (!h->opt.profile) return;
+    if (!(h->opt.profile & 1)) return;
     Profile& p = h->prof;
     if (p.used * 2 + 2 > p.pool.size()) return;
     cudaEventRecord(p.pool[2 * p.used + 1], h->stream);
@@ -242,7 +246,7 @@ void prof_end(mmba_handle* h, int) {
 }
 void prof_collect(mmba_handle* h) {
     Profile& p = h->prof;
-    if (!h->opt.profile) return;
+    if (!(h->opt.profile & 1)) return;
     cudaStreamSynchronize(h->stream);
     for (size_t i = 0; i < p.used; ++i) {
         float ms = 0;
@@ -376,8 +380,9 @@ void carve(mmba_handle* h, Arena& a) {
         d.rc_halo_cols = a.take<int>(h->rcm_part.halo_cols.size());
         d.rc_own = a.take<int>(Nc);
         d.rc_lcol = a.take<uint16_t>(r.nnz_full());
-        d.rcm_slots = a.take<RcmSlot>((size_t)kRcmMaxCtas);
-        d.rcm_z = a.take<LLLine>(6 * Nc);
+        d.rcm_slots = a.take<RcmSlot>(2 * (size_t)kRcmMaxCtas);
+        d.rcm_z = a.take<LLLine>(2 * 6 * Nc);
+        d.rcm_hist = (h->opt.profile & 2) ? a.take<double>(2 * ((size_t)h->opt.pcg_maxit + 1)) : nullptr;
     } else {
         d.Tup = d.S = d.rcm_b = nullptr;
         d.up_rowptr = d.up_cols = d.rc_rowptr = d.rc_cols = d.rc_rows = d.rc_src = d.rc_diag = nullptr;
@@ -385,6 +390,7 @@ void carve(mmba_handle* h, Arena& a) {
         d.rc_lcol = nullptr;
         d.rcm_slots = nullptr;
         d.rcm_z = nullptr;
+        d.rcm_hist = nullptr;
     }
 }
 
@@ -724,7 +730,7 @@ ModeArgs matvec_args(mmba_handle* h) {
 
 int schur_matvec(mmba_handle* h) {
     Dev& d = h->d;
-    TRY(launch_tile<M_MATVEC>(h, MMBA_K_MATVEC, matvec_args(h), !h->opt.profile));
+    TRY(launch_tile<M_MATVEC>(h, MMBA_K_MATVEC, matvec_args(h), !(h->opt.profile & 1)));
     TRY(allreduce(h, {{d.y, (size_t)(6 * h->Nc), false}}));
     return MMBA_OK;
 }
@@ -793,6 +799,10 @@ RcmPcgArgs rcm_pcg_args(mmba_handle* h, double f2) {
     A.nsub = h->rcm_nsub;
     A.rtol2 = h->opt.pcg_rtol * h->opt.pcg_rtol;
     A.atol2f = h->opt.pcg_atol * h->opt.pcg_atol * f2;
+    A.ktol2f = h->opt.pcg_ktol * h->opt.pcg_ktol * f2;
+    A.hist = (d.rcm_hist && h->opt.pcg_maxit <= h->hist_cap) ? d.rcm_hist : nullptr;
+    A.seq0 = h->rcm_seq;
+    h->rcm_seq += (unsigned)h->opt.pcg_maxit + 2u;
     return A;
 }
 
@@ -820,14 +830,14 @@ int rcm_finalize(mmba_handle* h, double reg) {
 // the whole PCG solve: one cooperative launch
 int rcm_pcg(mmba_handle* h, double f2) {
     Dev& d = h->d;
-    CU(cudaMemsetAsync(d.rcm_slots, 0, (size_t)h->rcm_part.n_ctas * sizeof(RcmSlot), h->stream));
-    CU(cudaMemsetAsync(d.rcm_z, 0, 6 * (size_t)h->Nc * sizeof(LLLine), h->stream));
+    // neither the exchange lines nor the slots are cleared: every launch uses fresh sequence numbers (seq0)
     CU(cudaMemsetAsync(d.flags, 0, 3 * sizeof(int), h->stream));
     RcmPcgArgs A = rcm_pcg_args(h, f2);
     void* args[] = {&A};
+    static const bool classic = getenv("MMBA_PCG_CLASSIC") && getenv("MMBA_PCG_CLASSIC")[0] == '1';
     prof_begin(h, MMBA_K_PCG);
-    CU(cudaLaunchCooperativeKernel((const void*)rcm_pcg_kernel, dim3(h->rcm_part.n_ctas), dim3(32 * h->rcm_warps), args,
-                                   h->rcm_smem_bytes, h->stream));
+    CU(cudaLaunchCooperativeKernel(classic ? (const void*)rcm_pcg_classic_kernel : (const void*)rcm_pcg_kernel,
+                                   dim3(h->rcm_part.n_ctas), dim3(32 * h->rcm_warps), args, h->rcm_smem_bytes, h->stream));
     prof_end(h, MMBA_K_PCG);
     return MMBA_OK;
 }
@@ -852,6 +862,12 @@ int gn_step(mmba_handle* h, double reg, double f2, int64_t* its_out, double* rel
         if (h->h_flags[2]) return fail(h, MMBA_ERR_CUDA, "reduced-system PCG: grid barrier timed out");
         if (its_out) *its_out = h->h_flags[1];
         if (relres_out) *relres_out = (h->h_flags[1] > 0 && st[1] > 0) ? std::sqrt(st[2] / st[1]) : 0.0;
+        if (d.rcm_hist && h->opt.pcg_maxit <= h->hist_cap) {
+            std::vector<double> hist(2 * ((size_t)h->h_flags[1] + 1));
+            CU(cudaMemcpyAsync(hist.data(), d.rcm_hist, hist.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            h->pcg_hist.push_back(std::move(hist));
+        }
         LAUNCH(MMBA_K_VEC, unscale_kernel, cdiv(6 * h->Nc, 256), 256, 0, d.px, d.sinv, 1.0, d.pxt, 6 * h->Nc);
         TRY(launch_tile<M_BACKSUB>(h, MMBA_K_BACKSUB, backsub_args(h)));
         CU(cudaGetLastError());
@@ -865,6 +881,7 @@ int gn_step(mmba_handle* h, double reg, double f2, int64_t* its_out, double* rel
 
     const double rtol2 = h->opt.pcg_rtol * h->opt.pcg_rtol;
     const double atol2f = h->opt.pcg_atol * h->opt.pcg_atol * f2;
+    const double ktol2f = h->opt.pcg_ktol * h->opt.pcg_ktol * f2;
     const int maxit = h->opt.pcg_maxit;
     int it = 0, done = 0;
     int chunk = 8;
@@ -875,7 +892,7 @@ int gn_step(mmba_handle* h, double reg, double f2, int64_t* its_out, double* rel
             unsigned long long seq = 0;
             if (h->xchg.on) {
                 // MATVEC + peer push; the all-reduce completes inside pcg_update
-                TRY(launch_tile<M_MATVEC>(h, MMBA_K_MATVEC, matvec_args(h), !h->opt.profile));
+                TRY(launch_tile<M_MATVEC>(h, MMBA_K_MATVEC, matvec_args(h), !(h->opt.profile & 1)));
                 seq = ++h->xchg.seq;
                 parity = (int)(seq & 1);
             } else {
@@ -896,9 +913,9 @@ int gn_step(mmba_handle* h, double reg, double f2, int64_t* its_out, double* rel
                 attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
                 attr[1].val.programmaticStreamSerializationAllowed = 1;
                 cfg.attrs = attr;
-                cfg.numAttrs = h->opt.profile ? 1 : 2;   // profile mode brackets launches with events: no overlap
+                cfg.numAttrs = (h->opt.profile & 1) ? 1 : 2;   // profile mode brackets launches with events: no overlap
                 prof_begin(h, MMBA_K_VEC);
-                CU(cudaLaunchKernelEx(&cfg, pcg_update_kernel, P, reg, it, rtol2, atol2f, camblocks, parity, seq));
+                CU(cudaLaunchKernelEx(&cfg, pcg_update_kernel, P, reg, it, rtol2, atol2f, ktol2f, camblocks, parity, seq));
                 prof_end(h, MMBA_K_VEC);
             }
         }
@@ -952,6 +969,7 @@ int run_trf(mmba_handle* h, mmba_result* out) {
     const int64_t nloc = h->nloc, ncam = 6 * h->Nc, npt = 3 * h->npl;
     const int gv = cdiv(nloc, 256), gc_ = cdiv(ncam, 256), gp_ = std::max(1, cdiv(npt, 256));
     h->log.clear();
+    h->pcg_hist.clear();
 
     TRY(linearise(h));
     TRY(scale_and_grad(h, true));
@@ -1129,11 +1147,12 @@ int configure_kernels(mmba_handle* h) {
         const RcmPartition& pt = h->rcm_part;
         h->rcm_nsub = std::max(1, (kRcmPcgThreads / 32) / pt.cpc);
         h->rcm_warps = std::min(kRcmPcgThreads / 32, pt.cpc * h->rcm_nsub);
-        h->rcm_s_in_smem = rcm_smem(pt.cpc, pt.nblk_max, pt.nh_max, 1).total <= 200 * 1024 ? 1 : 0;
-        const RcmSmem rl = rcm_smem(pt.cpc, pt.nblk_max, pt.nh_max, h->rcm_s_in_smem);
+        h->rcm_s_in_smem = rcm_smem(pt.cpc, pt.nblk_max, pt.nh_max, 1, pt.n_ctas).total <= 200 * 1024 ? 1 : 0;
+        const RcmSmem rl = rcm_smem(pt.cpc, pt.nblk_max, pt.nh_max, h->rcm_s_in_smem, pt.n_ctas);
         if (rl.total > 200 * 1024) return fail(h, MMBA_ERR_NOMEM, "reduced-system PCG: too many cameras per CTA");
         h->rcm_smem_bytes = (size_t)rl.total;
         CU(cudaFuncSetAttribute(rcm_pcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rl.total));
+        CU(cudaFuncSetAttribute(rcm_pcg_classic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rl.total));
     }
     return MMBA_OK;
 }
@@ -1280,6 +1299,7 @@ void mmba_default_options(mmba_options* opt) {
     opt->schur_mode = MMBA_SCHUR_AUTO;
     opt->reserved = 0;
     opt->pcg_atol = 1e-7;
+    opt->pcg_ktol = 3e-7;
 }
 
 int mmba_nccl_unique_id(uint8_t out[128]) {
@@ -1358,6 +1378,8 @@ int mmba_set_options(mmba_handle* h, const mmba_options* opt) {
     if (opt->schur_mode < MMBA_SCHUR_AUTO || opt->schur_mode > MMBA_SCHUR_EXPLICIT) return fail(h, MMBA_ERR_ARG, "schur_mode out of range");
     if (!(opt->pcg_atol >= 0)) return fail(h, MMBA_ERR_ARG, "pcg_atol must be >= 0");
     h->opt.pcg_atol = opt->pcg_atol;
+    if (!(opt->pcg_ktol >= 0)) return fail(h, MMBA_ERR_ARG, "pcg_ktol must be >= 0");
+    h->opt.pcg_ktol = opt->pcg_ktol;
     h->opt.schur_mode = opt->schur_mode;   // explicit / auto take effect at the next mmba_set_problem
     return MMBA_OK;
 }
@@ -1439,7 +1461,7 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
         else {
             build_rcm_partition(h->rcm_part, h->rcm, std::min(h->sm_count, kRcmMaxCtas));
             // the PCG kernel keeps the search direction on every CTA's halo in shared memory
-            if (rcm_smem(h->rcm_part.cpc, h->rcm_part.nblk_max, h->rcm_part.nh_max, 0).total > 200 * 1024) {
+            if (rcm_smem(h->rcm_part.cpc, h->rcm_part.nblk_max, h->rcm_part.nh_max, 0, h->rcm_part.n_ctas).total > 200 * 1024) {
                 h->rcm_ready = false;
                 h->rcm = RcmPattern();
             }
@@ -1451,6 +1473,7 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     if (h->opt.schur_mode == MMBA_SCHUR_EXPLICIT && !h->rcm_ready)
         return fail(h, MMBA_ERR_ARG, "set_problem: the reduced camera matrix is too large to be formed explicitly");
 
+    h->hist_cap = (h->rcm_ready && (h->opt.profile & 2)) ? h->opt.pcg_maxit : 0;
     lap("rcm pattern | uv reorder");
     Arena measure;
     carve(h, measure);
@@ -1598,6 +1621,16 @@ int mmba_get_log(const mmba_handle* h, mmba_iter_log* out, int capacity) {
     if (out)
         for (int i = 0; i < n && i < capacity; ++i) out[i] = h->log[i];
     return n;
+}
+
+int mmba_get_pcg_history(const mmba_handle* h, int outer_iteration, double* out, int capacity) {
+    if (!h) return MMBA_ERR_ARG;
+    if (outer_iteration < 0) return (int)h->pcg_hist.size();
+    if ((size_t)outer_iteration >= h->pcg_hist.size()) return MMBA_ERR_ARG;
+    const std::vector<double>& v = h->pcg_hist[outer_iteration];
+    if (out)
+        for (int i = 0; i < (int)v.size() && i < capacity; ++i) out[i] = v[i];
+    return (int)v.size();
 }
 
 int mmba_get_profile(const mmba_handle* h, int64_t launches[MMBA_K_COUNT], double ms[MMBA_K_COUNT]) {

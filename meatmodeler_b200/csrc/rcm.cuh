@@ -84,10 +84,10 @@ __device__ __forceinline__ bool ll_try_load(const LLLine* line, unsigned seq, do
 
 // One reduction slot per CTA, 1 KB apart: every CTA polls every slot, so the slots must sit on different L2
 // slices (address bits 8 and 10.. select the slice) or a handful of slices serves G^2 requests.
+constexpr int kRcmSums = 7;      // partial sums of one PCG iteration: p.q, q.z, q.zq, r.q, q.q, r.z, r.r
 struct RcmSlot {
-    LLLine pq;                  // reduction 1 of an iteration: p.q
-    LLLine rz, rr;              // reduction 2: r.z, ||r||^2
-    LLLine pad[61];
+    LLLine v[kRcmSums];
+    LLLine pad[64 - kRcmSums];
 };
 static_assert(sizeof(RcmSlot) == 1024, "RcmSlot stride");
 
@@ -101,15 +101,19 @@ struct RcmPcgArgs {
     const double* Pinv;         // [Nc][21]
     const double* b;            // [Nc][6]
     double* x;                  // [Nc][6]  result (scaled step)
-    LLLine* z;                  // [Nc][6]  preconditioned residual, the one vector exchanged through L2; zero at launch
-    RcmSlot* slots;             // [G] partial sums of the grid-wide reductions; zero at launch
+    LLLine* z;                  // [2 parities][Nc][6]  the one vector exchanged through L2 (Pinv q; classic kernel: z)
+    RcmSlot* slots;             // [2 parities][kRcmMaxCtas] partial sums of the grid-wide reductions
     int* flags;                 // [0] stop code (0 = maxit reached, 1 = converged, 2 = breakdown), [1] iterations,
                                 // [2] set when an exchange timed out
     double* state;              // [1] ||b||^2, [2] ||r||^2
+    double* hist;               // optional [2 (maxit + 1)]: (||r_k||^2, r_k.z_k) of every iterate, k = 0 first
     int n_cams, maxit, cpc, nblk_max, nh_max, s_in_smem;
     int nsub;                   // warps that share one camera row in the product q = S p
+    unsigned seq0;              // sequence numbers of this launch are seq0 + 1 ...: lines of earlier launches never match,
+                                // so neither z nor slots are cleared between launches
     double rtol2;
-    double atol2f;              // pcg_atol^2 ||f||^2: LSMR-like absolute rule, ||r||^2 <= atol2f
+    double atol2f;              // pcg_atol^2 ||f||^2: absolute rule, ||r||^2 <= atol2f
+    double ktol2f;              // pcg_ktol^2 ||f||^2: LSMR-like rule on the smoothed residual, nu_k^2 <= ktol2f k
 };
 
 __device__ __forceinline__ double warp_sum_all(double v) {
@@ -122,9 +126,9 @@ constexpr int kRcmPcgThreads = 256;
 
 // shared-memory carve-up of rcm_pcg_kernel (same arithmetic on the host)
 struct RcmSmem {
-    int off_S, off_pinv, off_vec, off_ph, off_zh, off_qp, off_hcols, off_rowptr, off_own, off_lcol, total;
+    int off_S, off_pinv, off_vec, off_ph, off_zh, off_zqh, off_sums, off_qp, off_hcols, off_rowptr, off_own, off_lcol, total;
 };
-__host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, int s_in_smem) {
+__host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, int s_in_smem, int n_ctas) {
     RcmSmem L{};
     int o = 0;
     L.off_S = o;
@@ -136,7 +140,11 @@ __host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, i
     L.off_ph = o;
     o += nh_max * 6 * 8;                     // search direction on the CTA's halo
     L.off_zh = o;
-    o += nh_max * 6 * 8;                     // z on the halo, as gathered
+    o += nh_max * 6 * 8;                     // z on the halo
+    L.off_zqh = o;
+    o += nh_max * 6 * 8;                     // Pinv q on the halo, as gathered
+    L.off_sums = o;
+    o += n_ctas * kRcmSums * 8;              // every CTA's partial sums, as polled
     L.off_qp = o;
     o += (cpc + 8) * 6 * 8;                  // partial products [camera x sub-warp][6]: at most max(cpc, 8) items
     L.off_hcols = o;
@@ -151,6 +159,7 @@ __host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, i
     return L;
 }
 
+// CLASSIC two-exchange variant, kept for A/B measurements (MMBA_PCG_CLASSIC=1); the solve uses rcm_pcg_kernel below.
 // Preconditioned conjugate gradients on S x = b, zero initial guess, block-Jacobi preconditioner, relative
 // residual stop (the recurrences and stopping rules of pcg_update_kernel).  CTA `b` owns `cpc` consecutive
 // cameras: its rows of S, their preconditioner blocks and x, r, q live in shared memory for the whole solve;
@@ -164,12 +173,12 @@ __host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, i
 // all-reduced, the PCG is replicated) take identical decisions.
 // Buffer reuse is safe without extra synchronisation: a CTA rewrites its z lines / slot only after it has passed
 // the next reduction, which every other CTA joins only after it has consumed the previous values.
-__global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcgArgs A) {
+__global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_classic_kernel(const RcmPcgArgs A) {
     extern __shared__ __align__(16) unsigned char rsm[];
     __shared__ double s_part[kRcmPcgThreads / 32][2];
     __shared__ double s_tot[2];
     __shared__ int s_dead;
-    const RcmSmem L = rcm_smem(A.cpc, A.nblk_max, A.nh_max, A.s_in_smem);
+    const RcmSmem L = rcm_smem(A.cpc, A.nblk_max, A.nh_max, A.s_in_smem, (int)gridDim.x);
     double* S_s = reinterpret_cast<double*>(rsm + L.off_S);
     double* pinv_s = reinterpret_cast<double*>(rsm + L.off_pinv);
     double* vec = reinterpret_cast<double*>(rsm + L.off_vec);
@@ -235,10 +244,10 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                 }
                 RcmSlot* mine = A.slots + blockIdx.x;
                 if (which) {
-                    ll_store(&mine->rz, t0, seq);
-                    ll_store(&mine->rr, t1, seq);
+                    ll_store(&mine->v[1], t0, seq);
+                    ll_store(&mine->v[2], t1, seq);
                 } else {
-                    ll_store(&mine->pq, t0, seq);
+                    ll_store(&mine->v[0], t0, seq);
                 }
             }
             // lane l polls the slots of CTAs l, l + 32, ...: all of them in flight at once
@@ -258,8 +267,8 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                     ok[u] = false;
                     if (pend >> u & 1) {
                         const RcmSlot* sl = A.slots + lane + 32 * u;
-                        ok[u] = which ? (ll_try_load(&sl->rz, seq, a0[u]) & ll_try_load(&sl->rr, seq, a1[u]))
-                                      : ll_try_load(&sl->pq, seq, a0[u]);
+                        ok[u] = which ? (ll_try_load(&sl->v[1], seq, a0[u]) & ll_try_load(&sl->v[2], seq, a1[u]))
+                                      : ll_try_load(&sl->v[0], seq, a0[u]);
                     }
                 }
 #pragma unroll
@@ -346,13 +355,13 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
         if (rowlane) {
             vec[k * 18 + a] = 0.0;
             vec[k * 18 + 6 + a] = r_a;
-            ll_store(A.z + c * 6 + a, z, 1u);
+            ll_store(A.z + c * 6 + a, z, A.seq0 + 1u);
             rz += r_a * z;
             rr += r_a * r_a;
         }
     }
     double rho, b2;
-    if (!reduce2(rz, rr, 1, 1u, true, rho, b2)) return;
+    if (!reduce2(rz, rr, 1, A.seq0 + 1u, true, rho, b2)) return;
     int its = 0, done = 0;
     double beta = 0.0, rr_last = b2;
     if (!(b2 > 0.0)) {
@@ -409,7 +418,7 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                 }
             }
             double pq_tot, unused;
-            if (!reduce2(pq, 0.0, 0, (unsigned)it + 1u, false, pq_tot, unused)) return;
+            if (!reduce2(pq, 0.0, 0, A.seq0 + (unsigned)it + 1u, false, pq_tot, unused)) return;
             const double alpha = rho / pq_tot;
             rz = 0;
             rr = 0;
@@ -423,13 +432,13 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                 }
                 const double z = precond(k, r_a);
                 if (rowlane) {
-                    ll_store(A.z + (c0 + k) * 6 + a, z, (unsigned)it + 2u);
+                    ll_store(A.z + (c0 + k) * 6 + a, z, A.seq0 + (unsigned)it + 2u);
                     rz += r_a * z;
                     rr += r_a * r_a;
                 }
             }
             double rz_tot, rr_tot;
-            if (!reduce2(rz, rr, 1, (unsigned)it + 2u, true, rz_tot, rr_tot)) return;
+            if (!reduce2(rz, rr, 1, A.seq0 + (unsigned)it + 2u, true, rz_tot, rr_tot)) return;
             its = it + 1;
             rr_last = rr_tot;
             if (rr_tot <= A.rtol2 * b2 || rr_tot <= A.atol2f) {
@@ -444,6 +453,314 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
             rho = rz_tot;
         }
     }
+    for (int k = warp; k < ncam; k += nwarps)
+        if (rowlane) A.x[(c0 + k) * 6 + a] = vec[k * 18 + a];
+    if (blockIdx.x == 0 && tid == 0) {
+        A.flags[0] = done;
+        A.flags[1] = its;
+        A.state[1] = b2;
+        A.state[2] = rr_last;
+    }
+}
+
+
+// ---- the PCG kernel of the solve: ONE grid-wide exchange per iteration -------------------------------------------
+// Same method (preconditioned CG, zero initial guess, block-Jacobi), reorganised so that everything that crosses
+// CTAs in an iteration travels in one round trip through L2:
+//     q = S p                       own rows, p on the CTA's halo in shared memory
+//     w = Pinv q                    own rows                                   -> published (LL lines)
+//     partial sums over the own rows of  p.q, q.z, q.w, r.q, q.q, r.z, r.r      -> published (one 112-byte slot)
+//     ---- exchange: poll every CTA's slot, gather w on the halo ----
+//     alpha = (r.z) / (p.q)
+//     x += alpha p ;  r -= alpha q ;  z -= alpha w            (z = Pinv r by recurrence, on the whole halo)
+//     rho' = r.z - 2 alpha q.z + alpha^2 q.w ,  ||r'||^2 = r.r - 2 alpha r.q + alpha^2 q.q
+//     beta = rho' / (r.z) ;  p = z + beta p                  (on the whole halo: no second exchange)
+// The inner products of the NEXT residual follow from this iteration's sums (r' = r - alpha q, z' = z - alpha w), so
+// beta needs no second reduction; they are one-step predictions from exactly reduced values — r.z and r.r of the
+// current iterate ride in the same exchange — so nothing accumulates.  Both the slots and the w lines have two
+// parities: a CTA rewrites parity s only after it has passed exchange s + 1, which every other CTA joins only
+// after it has consumed exchange s.
+// Stopping rules on ||r'||: relative (rtol), absolute (atol ||f||), and the counterpart of LSMR's test 2
+// (lsmr.py:430-459: ||A^T res|| <= atol ||A|| ||res|| with the running Frobenius estimate ||A|| ~ sqrt(k)): LSMR is
+// a minimal-residual method on the normal equations, and the minimal-residual norm of a CG process is the smoothed
+// norm 1 / nu_k^2 = sum_{j<=k} 1 / ||r_j||^2, hence  nu_k <= pcg_ktol sqrt(k) ||f||.
+// Breakdown (p.q <= 0 or a non-finite sum): the update is NOT applied; x keeps the last finite iterate, flags[0] = 2.
+__global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcgArgs A) {
+    extern __shared__ __align__(16) unsigned char rsm[];
+    __shared__ double s_part[kRcmPcgThreads / 32][kRcmSums];
+    __shared__ double s_tot[kRcmSums];
+    __shared__ int s_dead;
+    const int G = gridDim.x;
+    const RcmSmem L = rcm_smem(A.cpc, A.nblk_max, A.nh_max, A.s_in_smem, G);
+    double* S_s = reinterpret_cast<double*>(rsm + L.off_S);
+    double* pinv_s = reinterpret_cast<double*>(rsm + L.off_pinv);
+    double* vec = reinterpret_cast<double*>(rsm + L.off_vec);      // [camera][x 6 | r 6 | q 6]
+    double* ph = reinterpret_cast<double*>(rsm + L.off_ph);
+    double* zh = reinterpret_cast<double*>(rsm + L.off_zh);
+    double* wh = reinterpret_cast<double*>(rsm + L.off_zqh);
+    double* sums_s = reinterpret_cast<double*>(rsm + L.off_sums);
+    double* qp = reinterpret_cast<double*>(rsm + L.off_qp);
+    int* hcols_s = reinterpret_cast<int*>(rsm + L.off_hcols);
+    int* rowptr_s = reinterpret_cast<int*>(rsm + L.off_rowptr);
+    int* own_s = reinterpret_cast<int*>(rsm + L.off_own);
+    uint16_t* lcol_s = reinterpret_cast<uint16_t*>(rsm + L.off_lcol);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int a = lane % 6, slot = lane / 6;
+    const bool rowlane = lane < 6;
+    const int c0 = blockIdx.x * A.cpc, ncam = min(A.cpc, A.n_cams - c0);
+    const int e0 = A.rowptr[c0], nblk = A.rowptr[c0 + ncam] - e0;
+    const int h0 = A.halo_ptr[blockIdx.x], nh = A.halo_ptr[blockIdx.x + 1] - h0;
+    if (tid == 0) s_dead = 0;
+    if (A.s_in_smem) {
+        const double2* src = reinterpret_cast<const double2*>(A.S + (int64_t)e0 * 36);
+        double2* dst = reinterpret_cast<double2*>(S_s);
+        const int n2 = nblk * 18;
+        for (int i = tid; i < n2; i += 4 * blockDim.x) {
+            double2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u * blockDim.x < n2) v[u] = __ldg(src + i + u * blockDim.x);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u * blockDim.x < n2) dst[i + u * blockDim.x] = v[u];
+        }
+    }
+    for (int i = tid; i < nblk; i += blockDim.x) lcol_s[i] = A.lcol[e0 + i];
+    for (int i = tid; i < nh; i += blockDim.x) hcols_s[i] = A.halo_cols[h0 + i];
+    for (int i = tid; i < ncam * 21; i += blockDim.x) pinv_s[i] = A.Pinv[(int64_t)c0 * 21 + i];
+    for (int i = tid; i <= ncam; i += blockDim.x) rowptr_s[i] = A.rowptr[c0 + i] - e0;
+    for (int i = tid; i < ncam; i += blockDim.x) own_s[i] = A.own_l[c0 + i];
+    const double* S_rows = A.s_in_smem ? S_s : A.S + (int64_t)e0 * 36;
+    __syncthreads();
+    const int own0 = own_s[0];      // the CTA's own cameras are consecutive entries of its (ascending) halo list
+    constexpr long long kSpinLimit = 1ll << 31;   // ~1 s: give up instead of hanging the device
+
+    // One exchange: the per-thread partial sums v[0..nv) are reduced over the grid (every CTA adds the published
+    // CTA totals in CTA order: identical bits everywhere) and the lines of sequence number `seq` on the CTA's halo
+    // are gathered into `gather`.  All threads share the polling: item i < G nv is a partial sum, the rest are
+    // halo lines; eight polls in flight per thread.
+    auto exchange = [&](const double (&v)[kRcmSums], int nv, unsigned seq, double* gather, double (&tot)[kRcmSums]) -> bool {
+        const int par = (int)(seq & 1u);
+#pragma unroll
+        for (int i = 0; i < kRcmSums; ++i)
+            if (i < nv) {
+                const double w = warp_sum_all(v[i]);
+                if (lane == 0) s_part[warp][i] = w;
+            }
+        __syncthreads();
+        RcmSlot* slots = A.slots + par * kRcmMaxCtas;
+        if (tid < nv) {
+            double t = 0;
+            for (int w = 0; w < nwarps; ++w) t += s_part[w][tid];
+            ll_store(&slots[blockIdx.x].v[tid], t, seq);
+        }
+        const LLLine* zl = A.z + (int64_t)par * 6 * A.n_cams;
+        const int n_sum = G * nv, n_items = n_sum + nh * 6;
+        const long long t_start = clock64();
+        constexpr int kFly = 8;      // polls in flight per thread: G nv + 6 nh <= 8 x 256 items go out in one batch
+        for (int base = tid; base < n_items; base += kFly * (int)blockDim.x) {
+            const LLLine* line[kFly];
+            double val[kFly];
+            bool ok[kFly];
+#pragma unroll
+            for (int u = 0; u < kFly; ++u) {
+                const int i = base + u * (int)blockDim.x;
+                ok[u] = true;
+                val[u] = 0.0;
+                line[u] = nullptr;
+                if (i < n_items) {
+                    if (i < n_sum) {
+                        const int cta = i / nv;
+                        line[u] = &slots[cta].v[i - cta * nv];
+                    } else {
+                        const int j = (i - n_sum) / 6;
+                        line[u] = zl + (int64_t)hcols_s[j] * 6 + (i - n_sum - j * 6);
+                    }
+                    ok[u] = ll_try_load(line[u], seq, val[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kFly; ++u) {
+                while (!ok[u]) {
+                    ok[u] = ll_try_load(line[u], seq, val[u]);
+                    if (!ok[u] && clock64() - t_start > kSpinLimit) {
+                        s_dead = 1;
+                        break;
+                    }
+                }
+                const int i = base + u * (int)blockDim.x;
+                if (i < n_items) {
+                    if (i < n_sum) sums_s[i] = val[u];
+                    else gather[i - n_sum] = val[u];
+                }
+            }
+        }
+        __syncthreads();
+        if (s_dead) {
+            if (tid == 0) A.flags[2] = 1;
+            return false;
+        }
+        for (int vi = warp; vi < nv; vi += nwarps) {
+            double s = 0;
+            for (int c = lane; c < G; c += 32) s += sums_s[c * nv + vi];
+            s = warp_sum_all(s);
+            if (lane == 0) s_tot[vi] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kRcmSums; ++i) tot[i] = i < nv ? s_tot[i] : 0.0;
+        return true;
+    };
+    // Pinv_k v for camera k of this CTA (v in lanes 0..5); valid in lanes 0..5
+    auto precond = [&](int k, double v_a) {
+        double z = 0;
+        const double* pin = pinv_s + k * 21;
+#pragma unroll
+        for (int bb = 0; bb < 6; ++bb) {
+            const double vb = __shfl_sync(0xffffffffu, v_a, bb);
+            z += pin[a <= bb ? tri6(a, bb) : tri6(bb, a)] * vb;
+        }
+        return z;
+    };
+
+    // x = 0, r = b, z = Pinv r (published with sequence number seq0 + 1 and gathered on the halo), p = z
+    double v[kRcmSums], tot[kRcmSums];
+#pragma unroll
+    for (int i = 0; i < kRcmSums; ++i) v[i] = 0.0;
+    {
+        const unsigned seq = A.seq0 + 1u;
+        LLLine* zl = A.z + (int64_t)(seq & 1u) * 6 * A.n_cams;
+        for (int k = warp; k < ncam; k += nwarps) {
+            const int c = c0 + k;
+            const double r_a = rowlane ? A.b[c * 6 + a] : 0.0;
+            const double z = precond(k, r_a);
+            if (rowlane) {
+                vec[k * 18 + a] = 0.0;
+                vec[k * 18 + 6 + a] = r_a;
+                ll_store(zl + c * 6 + a, z, seq);
+                v[0] += r_a * z;
+                v[1] += r_a * r_a;
+            }
+        }
+        if (!exchange(v, 2, seq, zh, tot)) return;
+    }
+    const double rho0 = tot[0], b2 = tot[1];
+    int its = 0, done = 0;
+    double rr_last = b2;
+    double inv_nu2 = b2 > 0.0 ? 1.0 / b2 : 0.0;     // smoothed (minimal-residual) norm: 1 / nu^2 = sum 1 / ||r_j||^2
+    if (A.hist && blockIdx.x == 0 && tid == 0) {
+        A.hist[0] = b2;
+        A.hist[1] = rho0;
+    }
+    if (!(b2 > 0.0) || !isfinite(rho0)) {
+        done = 1;      // zero (or non-finite) right-hand side: x = 0
+    } else {
+        for (int i = tid; i < nh * 6; i += blockDim.x) ph[i] = zh[i];
+        __syncthreads();
+        const int nsub = A.nsub;
+        for (int it = 0; it < A.maxit; ++it) {
+            const unsigned seq = A.seq0 + (unsigned)it + 2u;
+            // q = S p: nsub warps share a camera row (blocks dealt round-robin to nsub x 5 lane groups)
+            for (int item = warp; item < ncam * nsub; item += nwarps) {
+                const int k = item / nsub, sub = item - k * nsub;
+                double acc0 = 0, acc1 = 0;
+                if (slot < kRcmSlots) {
+                    const int e1 = rowptr_s[k + 1];
+                    for (int e = rowptr_s[k] + slot + kRcmSlots * sub; e < e1; e += kRcmSlots * nsub) {
+                        const double* srow = S_rows + e * 36 + a * 6;
+                        const double* pj = ph + lcol_s[e] * 6;
+                        if (A.s_in_smem) {
+                            acc0 += srow[0] * pj[0];
+                            acc1 += srow[1] * pj[1];
+                            acc0 += srow[2] * pj[2];
+                            acc1 += srow[3] * pj[3];
+                            acc0 += srow[4] * pj[4];
+                            acc1 += srow[5] * pj[5];
+                        } else {
+                            acc0 += __ldg(srow + 0) * pj[0];
+                            acc1 += __ldg(srow + 1) * pj[1];
+                            acc0 += __ldg(srow + 2) * pj[2];
+                            acc1 += __ldg(srow + 3) * pj[3];
+                            acc0 += __ldg(srow + 4) * pj[4];
+                            acc1 += __ldg(srow + 5) * pj[5];
+                        }
+                    }
+                }
+                const double acc = acc0 + acc1;
+                double q = acc;
+                q += __shfl_down_sync(0xffffffffu, acc, 6);
+                q += __shfl_down_sync(0xffffffffu, acc, 12);
+                q += __shfl_down_sync(0xffffffffu, acc, 18);
+                q += __shfl_down_sync(0xffffffffu, acc, 24);
+                if (rowlane) qp[item * 6 + a] = q;
+            }
+            __syncthreads();
+            // w = Pinv q on the own rows (published), and the seven partial sums
+#pragma unroll
+            for (int i = 0; i < kRcmSums; ++i) v[i] = 0.0;
+            LLLine* wl = A.z + (int64_t)(seq & 1u) * 6 * A.n_cams;
+            for (int k = warp; k < ncam; k += nwarps) {
+                double q = 0, pk = 0, zk = 0, rk = 0;
+                if (rowlane) {
+                    for (int sub = 0; sub < nsub; ++sub) q += qp[(k * nsub + sub) * 6 + a];
+                    vec[k * 18 + 12 + a] = q;
+                    pk = ph[(own0 + k) * 6 + a];
+                    zk = zh[(own0 + k) * 6 + a];
+                    rk = vec[k * 18 + 6 + a];
+                }
+                const double w = precond(k, q);
+                if (rowlane) {
+                    ll_store(wl + (c0 + k) * 6 + a, w, seq);
+                    v[0] += pk * q;
+                    v[1] += q * zk;
+                    v[2] += q * w;
+                    v[3] += rk * q;
+                    v[4] += q * q;
+                    v[5] += rk * zk;
+                    v[6] += rk * rk;
+                }
+            }
+            if (!exchange(v, kRcmSums, seq, wh, tot)) return;
+            const double pq = tot[0], rho = tot[5];
+            const double alpha = rho / pq;
+            const double rho_n = fma(alpha, fma(alpha, tot[2], -2.0 * tot[1]), rho);
+            double rr_n = fma(alpha, fma(alpha, tot[4], -2.0 * tot[3]), tot[6]);
+            if (!(pq > 0.0) || !(rho > 0.0) || !isfinite(alpha) || !isfinite(rho_n) || !isfinite(rr_n)) {
+                done = 2;      // breakdown: keep the last finite iterate
+                break;
+            }
+            if (rr_n < 0.0) rr_n = 0.0;
+            const double beta = rho_n > 0.0 ? rho_n / rho : 0.0;
+            // x += alpha p, r -= alpha q (own rows); z -= alpha w, p = z + beta p (whole halo)
+            for (int i = tid; i < nh * 6; i += blockDim.x) {
+                const int j = i / 6;
+                const double p_old = ph[i];
+                const double z_new = fma(-alpha, wh[i], zh[i]);
+                zh[i] = z_new;
+                ph[i] = fma(beta, p_old, z_new);
+                const int k = j - own0;
+                if (k >= 0 && k < ncam) {
+                    double* vk = vec + k * 18 + (i - j * 6);
+                    vk[0] = fma(alpha, p_old, vk[0]);
+                    vk[6] = fma(-alpha, vk[12], vk[6]);
+                }
+            }
+            its = it + 1;
+            rr_last = rr_n;
+            if (A.hist && blockIdx.x == 0 && tid == 0) {
+                A.hist[2 * its] = rr_n;
+                A.hist[2 * its + 1] = rho_n;
+            }
+            inv_nu2 += rr_n > 0.0 ? 1.0 / rr_n : INFINITY;
+            if (rr_n <= A.rtol2 * b2 || rr_n <= A.atol2f || 1.0 <= inv_nu2 * A.ktol2f * (double)its) {
+                done = 1;
+                break;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
     for (int k = warp; k < ncam; k += nwarps)
         if (rowlane) A.x[(c0 + k) * 6 + a] = vec[k * 18 + a];
     if (blockIdx.x == 0 && tid == 0) {

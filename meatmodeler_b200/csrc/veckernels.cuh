@@ -249,7 +249,7 @@ __device__ __forceinline__ void cluster_sum_det(cg::cluster_group& cluster, doub
 // dimension).  Up to cluster*kPcgThreads cameras: one camera per thread, every operand loaded up front (one
 // memory round trip); more cameras: a strided loop with q and z kept in global memory.
 __global__ void __launch_bounds__(kPcgThreads)
-pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, double atol2f, int nb_init, int parity, unsigned long long seq) {
+pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, double atol2f, double ktol2f, int nb_init, int parity, unsigned long long seq) {
     // Programmatic dependent launch (see launch_tile): this grid may be scheduled while the MATVEC pass still
     // drains.  Everything written by the PREVIOUS update (flags, p, r, x, state) or earlier (sinv, Pinv) is
     // complete by then and may be read at once; y and every store wait for griddepcontrol.wait below.
@@ -366,12 +366,15 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, double atol2f, in
         }
         cluster_sum_det<2>(cluster, s2, s_red, s_xb);
         const double rr = s2[0], rz = s2[1];
-        if (rr <= rtol2 * b2 || rr <= atol2f) done = 1;
+        // smoothed (minimal-residual) norm of the CG process, see rcm_pcg_kernel: 1 / nu^2 = sum 1 / ||r_j||^2
+        const double inv_nu2 = (it == 0 ? 1.0 / b2 : P.state[3]) + (rr > 0.0 ? 1.0 / rr : INFINITY);
+        if (rr <= rtol2 * b2 || rr <= atol2f || 1.0 <= inv_nu2 * ktol2f * (double)(it + 1)) done = 1;
         else if (!(pq > 0.0) || !isfinite(rr) || !(rz > 0.0)) done = 2;
         if (lead) {
             P.state[0] = rz;
             P.state[1] = b2;
             P.state[2] = rr;
+            P.state[3] = inv_nu2;
             if (done) {
                 P.flags[1] = it + 1;
                 __threadfence();
@@ -437,12 +440,15 @@ pcg_update_kernel(PcgVecs P, double reg, int it, double rtol2, double atol2f, in
         }
         cluster_sum_det<2>(cluster, s2, s_red, s_xb);
         const double rr = s2[0], rz = s2[1];
-        if (rr <= rtol2 * b2 || rr <= atol2f) done = 1;
+        // smoothed (minimal-residual) norm of the CG process, see rcm_pcg_kernel: 1 / nu^2 = sum 1 / ||r_j||^2
+        const double inv_nu2 = (it == 0 ? 1.0 / b2 : P.state[3]) + (rr > 0.0 ? 1.0 / rr : INFINITY);
+        if (rr <= rtol2 * b2 || rr <= atol2f || 1.0 <= inv_nu2 * ktol2f * (double)(it + 1)) done = 1;
         else if (!(pq > 0.0) || !isfinite(rr) || !(rz > 0.0)) done = 2;
         if (lead) {
             P.state[0] = rz;
             P.state[1] = b2;
             P.state[2] = rr;
+            P.state[3] = inv_nu2;
             if (done) {
                 P.flags[1] = it + 1;
                 __threadfence();

@@ -32,12 +32,12 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     # sizes of the C structs as laid out by the compiler (x86-64 SysV)
-    assert ctypes.sizeof(_capi.Options) == 16 + 24 + 8 + 8 + 8 + 128 + 8 + 8
+    assert ctypes.sizeof(_capi.Options) == 16 + 24 + 8 + 8 + 8 + 128 + 8 + 8 + 8
     assert ctypes.sizeof(_capi.Result) == 24 + 24 + 8 + 8 + 8
     assert ctypes.sizeof(_capi.IterLog) == 9 * 8
     opt = _capi.default_options()
     assert (opt.ftol, opt.xtol, opt.gtol, opt.nranks, opt.max_nfev) == (1e-4, 1e-8, 1e-8, 1, 0)
-    assert opt.schur_mode == _capi.SCHUR_AUTO and opt.pcg_atol == 1e-7
+    assert opt.schur_mode == _capi.SCHUR_AUTO and opt.pcg_atol == 1e-7 and opt.pcg_ktol == 3e-7
 
 
 def test_no_gpu_means_loud_failure():

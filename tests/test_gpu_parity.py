@@ -80,7 +80,7 @@ def case(request):
     # the oracle's PCG tolerance; implicit Schur product (the explicit matrix: test_gpu_schur_explicit.py)
     # pcg_atol = 0: the absolute (LSMR-like) stop is a threshold decision; identity of the two implementations is
     # checked with fully converged inner solves, the default rule against the reference's golden trajectories
-    eng = engine_for(prob, pcg_rtol=1e-10, pcg_atol=0.0, schur_mode=_capi.SCHUR_IMPLICIT)
+    eng = engine_for(prob, pcg_rtol=1e-10, pcg_atol=0.0, pcg_ktol=0.0, schur_mode=_capi.SCHUR_IMPLICIT)
     yield prob, x0, lin, eng
     eng.close()
 
@@ -237,7 +237,7 @@ def test_solve_vs_oracle_trf(case):
     prob, x0, lin, eng = case
     ext, K, pts, uv, fi, pi = prob.args()
     rec = []
-    out = schur_trf.solve(x0, K, len(ext), len(pts), fi, pi, uv, record=rec, pcg_atol=0.0)
+    out = schur_trf.solve(x0, K, len(ext), len(pts), fi, pi, uv, record=rec, pcg_atol=0.0, pcg_ktol=0.0)
     x, r, fun = eng.solve(x0, want_fun=True)
     costs = [row["cost"] for row in eng.log()][1:]
     assert r.nfev == out["nfev"] and r.status == out["status"] and len(costs) == len(rec)

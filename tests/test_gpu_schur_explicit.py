@@ -39,7 +39,7 @@ def xcase(request):
     x0 = problem_x0(prob)
     ext, K, pts, uv, fi, pi = prob.args()
     lin = schur_trf.Linearisation(x0, K, len(ext), len(pts), fi, pi, uv)
-    eng = engine_for(prob, pcg_rtol=1e-10, pcg_atol=0.0, schur_mode=_capi.SCHUR_EXPLICIT)
+    eng = engine_for(prob, pcg_rtol=1e-10, pcg_atol=0.0, pcg_ktol=0.0, schur_mode=_capi.SCHUR_EXPLICIT)
     yield prob, x0, lin, eng
     eng.close()
 
@@ -105,7 +105,7 @@ def test_explicit_solve_vs_oracle_and_implicit(xcase):
     prob, x0, lin, eng = xcase
     ext, K, pts, uv, fi, pi = prob.args()
     rec = []
-    out = schur_trf.solve(x0, K, len(ext), len(pts), fi, pi, uv, record=rec, pcg_atol=0.0)
+    out = schur_trf.solve(x0, K, len(ext), len(pts), fi, pi, uv, record=rec, pcg_atol=0.0, pcg_ktol=0.0)
     x, r, fun = eng.solve(x0, want_fun=True)
     costs = [row["cost"] for row in eng.log()][1:]
     assert r.nfev == out["nfev"] and r.status == out["status"] and len(costs) == len(rec)
