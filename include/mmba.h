@@ -130,9 +130,12 @@ void mmba_destroy(mmba_handle* h);
 int mmba_set_options(mmba_handle* h, const mmba_options* opt);
 
 /* replaces: pointAdjustmentSparsity (bundleAdjuster.py:55-78, 179) — the block structure is implied
- * by the two index arrays.  Copies the problem to the device, narrows indices to int32, reorders
- * observations into point-aligned tiles and (nranks > 1) keeps only this rank's point range.
- * All ranks pass the full, identical problem. */
+ * by the two index arrays.  Indices are narrowed to int32 and range-checked while they are staged to
+ * the device; the tile plan (point order, point-aligned tiles, per-tile camera tables) and the block
+ * pattern of the reduced camera matrix are built by device kernels (csrc/devplan.cu).
+ * nranks > 1: all ranks pass the full, identical problem; rank r READS only observations
+ * [n_obs r / nranks, n_obs (r + 1) / nranks) of the arrays, and one all-to-all over NVLink moves every
+ * observation to the rank that owns its point. */
 int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n_obs,
                      const double K[9], const int64_t* cam_idx, const int64_t* pt_idx,
                      const double* uv /* n_obs x 2 row-major */);
@@ -165,6 +168,15 @@ int mmba_get_pcg_history(const mmba_handle* h, int outer_iteration, double* out,
 /* observations / points held by this rank and number of tiles (after set_problem) */
 int mmba_get_shard(const mmba_handle* h, int64_t* n_obs_local, int64_t* n_points_local,
                    int64_t* n_tiles);
+
+/* The plan mmba_set_problem built ON THE DEVICE (csrc/devplan.cu), downloaded in the formats of the host builder's
+ * exports so that tests can compare the two bit for bit: sizes as mmba_plan_sizes; meta / tile_cams as mmba_plan_raw;
+ * obs_perm (n_slots) / point_perm (n_points) as mmba_plan_export.  Any pointer may be NULL. */
+int mmba_get_plan_sizes(mmba_handle* h, int64_t sizes[8]);
+int mmba_get_plan_raw(mmba_handle* h, void* meta, int32_t* tile_cams, int64_t* obs_perm, int64_t* point_perm);
+/* the device-built block pattern of the reduced camera matrix: sizes[0..6] = upper blocks, full blocks, sum L (L + 1) / 2,
+ * PCG CTAs, cameras per CTA, max blocks per CTA, max halo columns per CTA; up_rowptr / up_cols as mmba_host_rcm_pattern */
+int mmba_get_rcm_pattern(mmba_handle* h, int64_t sizes[8], int32_t* up_rowptr, int32_t* up_cols, int64_t capacity);
 
 /* ---- evaluation hooks (parity tests; same device code as the solve) ------------------------ */
 /* replaces: pointFun(x, ...) (bundleAdjuster.py:81-102) */
@@ -233,6 +245,10 @@ int mmba_plan_sizes(const mmba_plan* p, int64_t sizes[8]);
  * (-1 for empty slots); the tile of a slot is slot / tile_obs */
 int mmba_plan_export(const mmba_plan* p, int64_t* obs_perm, int64_t* point_perm,
                      int32_t* slot_cam_global, int32_t* slot_point_local);
+
+/* the raw tile records (n_tiles x 2592 bytes: header + slot tables, csrc/plan.h TileMeta) and camera lists
+ * (n_tiles x 256 global camera ids, -1 padded) of a host-built plan */
+int mmba_plan_raw(const mmba_plan* p, void* meta, int32_t* tile_cams);
 
 /* per tile (n_tiles entries each, any pointer may be NULL): distinct cameras, points, the S-build strategy the
  * plan chose (0 = point-pair-major, 1 = camera-pair-major flushed per tile, 2 = one 6x6 block per thread kept

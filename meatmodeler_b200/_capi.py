@@ -18,6 +18,7 @@ K_NAMES = ("cam_prep", "build", "resid", "point_invert", "schur_rhs", "schur_mat
  K_PCG) = range(12)
 K_COUNT = 12
 SCHUR_AUTO, SCHUR_IMPLICIT, SCHUR_EXPLICIT = 0, 1, 2
+TILE_META_BYTES = 2592      # sizeof(TileMeta), csrc/plan.h
 
 ERR_NAMES = {-1: "MMBA_ERR_ARG", -2: "MMBA_ERR_CUDA", -3: "MMBA_ERR_STATE", -4: "MMBA_ERR_NONFINITE",
              -5: "MMBA_ERR_TRACK", -6: "MMBA_ERR_NCCL", -7: "MMBA_ERR_NOMEM"}
@@ -95,6 +96,10 @@ SIGNATURES = {
     "mmba_plan_sizes": (C.c_int, [_H, C.POINTER(C.c_int64 * 8)]),
     "mmba_plan_export": (C.c_int, [_H, _i64, _i64, _i32, _i32]),
     "mmba_plan_tile_stats": (C.c_int, [_H, _i32, _i32, _i32, _i32]),
+    "mmba_plan_raw": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "mmba_get_plan_sizes": (C.c_int, [_H, C.POINTER(C.c_int64 * 8)]),
+    "mmba_get_plan_raw": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmba_get_rcm_pattern": (C.c_int, [_H, C.POINTER(C.c_int64 * 8), C.c_void_p, C.c_void_p, C.c_int64]),
 }
 
 _lib = None
@@ -197,6 +202,32 @@ class Engine:
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         _check(lib().mmba_get_shard(self._h, C.byref(a), C.byref(b), C.byref(c)), self._h)
         return dict(n_obs_local=a.value, n_points_local=b.value, n_tiles=c.value)
+
+    def plan(self):
+        """The tile plan built on the device, in the format of ``_capi.plan`` (host builder) plus the raw records."""
+        sizes = (C.c_int64 * 8)()
+        _check(lib().mmba_get_plan_sizes(self._h, C.byref(sizes)), self._h)
+        keys = ("n_tiles", "n_obs_local", "n_points_local", "point_begin", "point_end", "tile_obs", "max_tile_cams", "n_slots")
+        out = dict(zip(keys, list(sizes)))
+        nt, ns = out["n_tiles"], out["n_slots"]
+        meta = np.zeros((max(nt, 1), TILE_META_BYTES), dtype=np.uint8)
+        tile_cams = np.full((max(nt, 1), 256), -1, dtype=np.int32)
+        obs_perm = np.full(max(ns, 1), -1, dtype=np.int64)
+        point_perm = np.zeros(self.sizes[1], dtype=np.int64)
+        _check(lib().mmba_get_plan_raw(self._h, meta.ctypes.data, tile_cams.ctypes.data, obs_perm.ctypes.data,
+                                       point_perm.ctypes.data), self._h)
+        out.update(meta=meta[:nt], tile_cams=tile_cams[:nt], obs_perm=obs_perm[:ns], point_perm=point_perm)
+        return out
+
+    def rcm_pattern(self):
+        """Device-built block pattern: dict(up_rowptr, up_cols, nnz_full, total_pairs, n_ctas, cpc, nblk_max, nh_max)."""
+        sizes = (C.c_int64 * 8)()
+        _check(lib().mmba_get_rcm_pattern(self._h, C.byref(sizes), None, None, 0), self._h)
+        rowptr = np.empty(self.sizes[0] + 1, dtype=np.int32)
+        cols = np.empty(max(int(sizes[0]), 1), dtype=np.int32)
+        _check(lib().mmba_get_rcm_pattern(self._h, C.byref(sizes), rowptr.ctypes.data, cols.ctypes.data, len(cols)), self._h)
+        return dict(up_rowptr=rowptr, up_cols=cols[:sizes[0]], nnz_full=int(sizes[1]), total_pairs=int(sizes[2]),
+                    n_ctas=int(sizes[3]), cpc=int(sizes[4]), nblk_max=int(sizes[5]), nh_max=int(sizes[6]))
 
     # -- solve --------------------------------------------------------------------------------
     def solve(self, x0, want_fun=False):
@@ -387,6 +418,11 @@ def plan(n_cams, n_points, cam_idx, pt_idx, rank=0, nranks=1):
         _check(lib().mmba_plan_export(h, obs_perm, point_perm, slot_cam, slot_pt))
         out.update(obs_perm=obs_perm[:out["n_slots"]], point_perm=point_perm, slot_cam=slot_cam[:out["n_slots"]],
                    slot_point=slot_pt[:out["n_slots"]])
+        nt = out["n_tiles"]
+        meta = np.zeros((max(nt, 1), TILE_META_BYTES), dtype=np.uint8)
+        tile_cams = np.full((max(nt, 1), 256), -1, dtype=np.int32)
+        _check(lib().mmba_plan_raw(h, meta.ctypes.data, tile_cams.ctypes.data))
+        out.update(meta=meta[:nt], tile_cams=tile_cams[:nt])
         return out
     finally:
         lib().mmba_plan_destroy(h)

@@ -716,7 +716,6 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
     double* s_pt = reinterpret_cast<double*>(smem + L.off_pt);
     double* s_buf = reinterpret_cast<double*>(smem + L.off_buf);
     double* s_red = reinterpret_cast<double*>(smem + L.off_red);
-    int round = 0;                 // staging-buffer parity of camera_scatter_round
     int par = 0;                   // per-point accumulator parity (MATVEC / BACKSUB)
     double acc[3] = {0, 0, 0};     // cost (BUILD / RESID) or Gram (JV)
     // SBUILD: one 6x6 block of the reduced camera matrix per thread, accumulated over a run of tiles with the

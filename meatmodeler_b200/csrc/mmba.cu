@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/mmba.h"
+#include "devplan.h"
 #include "kernels.cuh"
 #include "plan.h"
 #include "rcm.cuh"
@@ -46,6 +47,8 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -75,6 +78,8 @@ bool load_nccl(std::string& err) {
     MMBA_SYM(CommDestroy)
     MMBA_SYM(AllReduce)
     MMBA_SYM(AllGather)
+    MMBA_SYM(Send)
+    MMBA_SYM(Recv)
     MMBA_SYM(GroupStart)
     MMBA_SYM(GroupEnd)
     MMBA_SYM(GetErrorString)
@@ -114,7 +119,7 @@ struct Dev {
     double *pose_lam, *pose_suf, *pose_V, *pose_w;   // pose-only adjustment (per-camera eigen data)
     int* flags;
     double* scal;
-    double* xp_full;   // all points, internal order (nranks > 1 only)
+    double* x_io;      // [6 Nc + 3 Np] parameters in the caller's layout (upload / download staging on the device)
     // explicit reduced camera matrix (rcm.h / rcm.cuh); null when the implicit product is used
     double *Tup, *S, *rcm_b;
     int *up_rowptr, *up_cols, *rc_rowptr, *rc_cols, *rc_rows, *rc_src, *rc_diag;
@@ -152,6 +157,9 @@ struct Profile {
 
 }  // namespace
 
+constexpr int kStageSlots = 3;
+constexpr size_t kStageSlotBytes = (size_t)24 << 20;
+
 struct mmba_handle {
     mmba_options opt;
     std::string err;
@@ -159,9 +167,9 @@ struct mmba_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ncclComm_t comm = nullptr;
     bool has_problem = false;
-    Plan plan;
-    RcmPattern rcm;
-    RcmPartition rcm_part;
+    DevPlanner planner;            // device-side plan builder (devplan.h) and its buffers
+    DevPlan dp;                    // the current problem's plan: sizes on the host, tables on the device
+    std::vector<int32_t> h_point_perm, h_rc_rows, h_rc_cols;   // host copies for the evaluation hooks (downloaded on demand)
     bool rcm_ready = false;        // pattern built and device arrays carved for the current problem
     int rcm_warps = 0, rcm_s_in_smem = 0, rcm_nsub = 1;
     unsigned rcm_seq = 0;          // sequence numbers handed to the PCG launches of this problem (never reused)
@@ -177,8 +185,12 @@ struct mmba_handle {
     int sm_count = 148;
     size_t smem[M_COUNT] = {0};     // dynamic shared memory of tile_kernel<MODE>
     int grid[M_COUNT] = {0};        // persistent grid of tile_kernel<MODE>: min(tiles, SMs x resident CTAs)
-    double* h_stage = nullptr;   // pinned, max(nloc, 2*ns ...) doubles
-    size_t h_stage_n = 0;
+    // pinned staging ring between pageable caller buffers and the device: several host threads fill a slot while
+    // the copy engine drains the previous one
+    char* stage_buf = nullptr;
+    cudaEvent_t stage_ev[kStageSlots] = {nullptr, nullptr, nullptr};
+    bool stage_busy[kStageSlots] = {false, false, false};
+    int stage_next = 0;
     double* h_scal = nullptr;    // pinned S_COUNT
     int* h_flags = nullptr;      // pinned 4
     std::vector<mmba_iter_log> log;
@@ -317,13 +329,15 @@ int zero(mmba_handle* h, double* p, size_t n) {
 }
 
 // ---- memory layout ----------------------------------------------------------------------------
+// The plan's tables (tile metadata, camera lists, tile-major pixels, block pattern) live in the planner's buffers;
+// the arena holds everything the solve reads and writes.
 void carve(mmba_handle* h, Arena& a) {
-    const Plan& pl = h->plan;
+    const DevPlan& dp = h->dp;
     Dev& d = h->d;
     const size_t Nc = h->Nc, npl = std::max<int64_t>(h->npl, 1), ns = std::max<int64_t>(h->ns, 1), nloc = 6 * Nc + 3 * npl;
-    d.meta = a.take<TileMeta>(std::max<size_t>(pl.meta.size(), 1));
-    d.tile_cams = a.take<int32_t>(std::max<size_t>(pl.tile_cams.size(), 4));
-    d.uv = a.take<double>(2 * ns);
+    d.meta = dp.meta;
+    d.tile_cams = dp.tile_cams;
+    d.uv = dp.uvt;
     d.J = a.take<double>(18 * ns);
     d.res = a.take<double>(2 * ns);
     d.x = a.take<double>(nloc);
@@ -363,23 +377,22 @@ void carve(mmba_handle* h, Arena& a) {
     d.pose_w = a.take<double>(6 * Nc);
     d.flags = a.take<int>(4);
     d.scal = a.take<double>(S_COUNT);
-    d.xp_full = h->opt.nranks > 1 ? a.take<double>(3 * (size_t)pl.n_points) : nullptr;
+    d.x_io = a.take<double>(6 * Nc + 3 * (size_t)dp.n_points);
     if (h->rcm_ready) {
-        const RcmPattern& r = h->rcm;
-        d.Tup = a.take<double>(36 * (size_t)r.nnz_up());
-        d.S = a.take<double>(36 * (size_t)r.nnz_full());
+        d.Tup = a.take<double>(36 * (size_t)dp.nnz_up);
+        d.S = a.take<double>(36 * (size_t)dp.nnz_full);
         d.rcm_b = a.take<double>(6 * Nc);
-        d.up_rowptr = a.take<int>(Nc + 1);
-        d.up_cols = a.take<int>(r.nnz_up());
-        d.rc_rowptr = a.take<int>(Nc + 1);
-        d.rc_cols = a.take<int>(r.nnz_full());
-        d.rc_rows = a.take<int>(r.nnz_full());
-        d.rc_src = a.take<int>(r.nnz_full());
-        d.rc_diag = a.take<int>(Nc);
-        d.rc_halo_ptr = a.take<int>(h->rcm_part.halo_ptr.size());
-        d.rc_halo_cols = a.take<int>(h->rcm_part.halo_cols.size());
-        d.rc_own = a.take<int>(Nc);
-        d.rc_lcol = a.take<uint16_t>(r.nnz_full());
+        d.up_rowptr = dp.up_rowptr;
+        d.up_cols = dp.up_cols;
+        d.rc_rowptr = dp.rowptr;
+        d.rc_cols = dp.cols;
+        d.rc_rows = dp.rows;
+        d.rc_src = dp.src;
+        d.rc_diag = dp.diag;
+        d.rc_halo_ptr = dp.halo_ptr;
+        d.rc_halo_cols = dp.halo_cols;
+        d.rc_own = dp.own_l;
+        d.rc_lcol = dp.lcol;
         d.rcm_slots = a.take<RcmSlot>(2 * (size_t)kRcmMaxCtas);
         d.rcm_z = a.take<LLLine>(2 * 6 * Nc);
         d.rcm_hist = (h->opt.profile & 2) ? a.take<double>(2 * ((size_t)h->opt.pcg_maxit + 1)) : nullptr;
@@ -392,6 +405,76 @@ void carve(mmba_handle* h, Arena& a) {
         d.rcm_z = nullptr;
         d.rcm_hist = nullptr;
     }
+}
+
+// ---- host <-> device transfers through the pinned staging ring ------------------------------------
+int stage_init(mmba_handle* h) {
+    if (h->stage_buf) return MMBA_OK;
+    CU(cudaMallocHost(&h->stage_buf, kStageSlots * kStageSlotBytes));
+    for (int i = 0; i < kStageSlots; ++i) CU(cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming));
+    return MMBA_OK;
+}
+// next slot of the ring, free to be written by the host
+int stage_acquire(mmba_handle* h, int* idx, char** ptr) {
+    TRY(stage_init(h));
+    const int i = h->stage_next;
+    h->stage_next = (i + 1) % kStageSlots;
+    if (h->stage_busy[i]) {
+        CU(cudaEventSynchronize(h->stage_ev[i]));
+        h->stage_busy[i] = false;
+    }
+    *idx = i;
+    *ptr = h->stage_buf + (size_t)i * kStageSlotBytes;
+    return MMBA_OK;
+}
+int stage_commit(mmba_handle* h, int idx) {
+    CU(cudaEventRecord(h->stage_ev[idx], h->stream));
+    h->stage_busy[idx] = true;
+    return MMBA_OK;
+}
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    parallel_ranges((int64_t)bytes, (int64_t)1 << 20, [&](int64_t b, int64_t e, int) {
+        std::memcpy(static_cast<char*>(dst) + b, static_cast<const char*>(src) + b, (size_t)(e - b));
+    });
+}
+// pageable host -> device; the caller's buffer is fully consumed on return
+int h2d(mmba_handle* h, void* dst, const void* src, size_t bytes) {
+    for (size_t off = 0; off < bytes; off += kStageSlotBytes) {
+        const size_t n = std::min(kStageSlotBytes, bytes - off);
+        int idx;
+        char* slot;
+        TRY(stage_acquire(h, &idx, &slot));
+        parallel_memcpy(slot, static_cast<const char*>(src) + off, n);
+        CU(cudaMemcpyAsync(static_cast<char*>(dst) + off, slot, n, cudaMemcpyHostToDevice, h->stream));
+        TRY(stage_commit(h, idx));
+    }
+    return MMBA_OK;
+}
+// device -> pageable host; complete on return
+int d2h(mmba_handle* h, void* dst, const void* src, size_t bytes) {
+    struct Pending { int idx; char* slot; size_t off, n; } pend[kStageSlots] = {};
+    int npend = 0;
+    auto drain_one = [&]() -> int {
+        const Pending q = pend[0];
+        CU(cudaEventSynchronize(h->stage_ev[q.idx]));
+        h->stage_busy[q.idx] = false;
+        parallel_memcpy(static_cast<char*>(dst) + q.off, q.slot, q.n);
+        for (int i = 1; i < npend; ++i) pend[i - 1] = pend[i];
+        --npend;
+        return MMBA_OK;
+    };
+    for (size_t off = 0; off < bytes; off += kStageSlotBytes) {
+        if (npend == kStageSlots - 1) TRY(drain_one());
+        const size_t n = std::min(kStageSlotBytes, bytes - off);
+        int idx;
+        char* slot;
+        TRY(stage_acquire(h, &idx, &slot));
+        CU(cudaMemcpyAsync(slot, static_cast<const char*>(src) + off, n, cudaMemcpyDeviceToHost, h->stream));
+        TRY(stage_commit(h, idx));
+        pend[npend++] = Pending{idx, slot, off, n};
+    }
+    while (npend) TRY(drain_one());
+    return MMBA_OK;
 }
 
 void xchg_release(mmba_handle* h) {
@@ -489,96 +572,50 @@ void release_problem(mmba_handle* h) {
     h->has_problem = false;
 }
 
-template <typename T>
-int upload(mmba_handle* h, T* dst, const std::vector<T>& src) {
-    if (!src.empty()) CU(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    return MMBA_OK;
-}
-
 // caller's x (cameras | points in caller order) -> device x (cameras | local points, internal order)
 int put_x(mmba_handle* h, const double* x, double* dst) {
-    const Plan& pl = h->plan;
-    double* s = h->h_stage;
-    std::memcpy(s, x, 6 * h->Nc * sizeof(double));
-    const double* xp = x + 6 * h->Nc;
-    double* o = s + 6 * h->Nc;
-    for (int64_t q = 0; q < h->npl; ++q) {
-        const int64_t p = pl.point_perm[pl.pt_begin + q];
-        o[3 * q] = xp[3 * p];
-        o[3 * q + 1] = xp[3 * p + 1];
-        o[3 * q + 2] = xp[3 * p + 2];
-    }
-    CU(cudaMemcpyAsync(dst, s, h->nloc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));   // the staging buffer is reused
+    const DevPlan& dp = h->dp;
+    TRY(h2d(h, h->d.x_io, x, (size_t)(6 * h->Nc + 3 * dp.n_points) * sizeof(double)));
+    devplan_gather_x(h->d.x_io, dst, dp.point_perm, h->Nc, dp.pt_begin, h->npl, h->stream);
     return MMBA_OK;
 }
 
 // device n-vector -> caller's layout.  With nranks > 1 the point part is completed over ranks.
 int get_x(mmba_handle* h, const double* src, double* x) {
-    const Plan& pl = h->plan;
-    double* s = h->h_stage;
-    if (h->opt.nranks > 1) {
-        CU(cudaMemsetAsync(h->d.xp_full, 0, 3 * pl.n_points * sizeof(double), h->stream));
-        if (h->npl)
-            CU(cudaMemcpyAsync(h->d.xp_full + 3 * pl.pt_begin, src + 6 * h->Nc, 3 * h->npl * sizeof(double),
-                               cudaMemcpyDeviceToDevice, h->stream));
-        TRY(allreduce(h, {{h->d.xp_full, (size_t)(3 * pl.n_points), false}}));
-        CU(cudaMemcpyAsync(s, src, 6 * h->Nc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaMemcpyAsync(s + 6 * h->Nc, h->d.xp_full, 3 * pl.n_points * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        std::memcpy(x, s, 6 * h->Nc * sizeof(double));
-        const double* o = s + 6 * h->Nc;
-        double* xp = x + 6 * h->Nc;
-        for (int64_t q = 0; q < pl.n_points; ++q) {
-            const int64_t p = pl.point_perm[q];
-            xp[3 * p] = o[3 * q];
-            xp[3 * p + 1] = o[3 * q + 1];
-            xp[3 * p + 2] = o[3 * q + 2];
-        }
-        return MMBA_OK;
-    }
-    CU(cudaMemcpyAsync(s, src, h->nloc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    std::memcpy(x, s, 6 * h->Nc * sizeof(double));
-    const double* o = s + 6 * h->Nc;
-    double* xp = x + 6 * h->Nc;
-    for (int64_t q = 0; q < h->npl; ++q) {
-        const int64_t p = pl.point_perm[pl.pt_begin + q];
-        xp[3 * p] = o[3 * q];
-        xp[3 * p + 1] = o[3 * q + 1];
-        xp[3 * p + 2] = o[3 * q + 2];
-    }
-    return MMBA_OK;
+    const DevPlan& dp = h->dp;
+    const size_t n_total = (size_t)(6 * h->Nc + 3 * dp.n_points);
+    if (h->opt.nranks > 1) CU(cudaMemsetAsync(h->d.x_io + 6 * h->Nc, 0, 3 * (size_t)dp.n_points * sizeof(double), h->stream));
+    devplan_scatter_x(src, h->d.x_io, dp.point_perm, h->Nc, dp.pt_begin, h->npl, true, h->stream);
+    if (h->opt.nranks > 1) TRY(allreduce(h, {{h->d.x_io + 6 * h->Nc, (size_t)(3 * dp.n_points), false}}));
+    return d2h(h, x, h->d.x_io, n_total * sizeof(double));
 }
 
-// tile-major [tile][rows][256] on the device -> caller-ordered (n_obs, rows) row-major; local entries only
-int get_slots(mmba_handle* h, const double* src, int rows, double* out, int out_stride, int out_off) {
-    const Plan& pl = h->plan;
-    std::vector<double> tmp((size_t)rows * h->ns);
-    CU(cudaMemcpyAsync(tmp.data(), src, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    for (int64_t s = 0; s < h->ns; ++s) {
-        const int64_t o = pl.slot_obs[s];
-        if (o < 0) continue;
-        const int64_t t = s / kT, j = s % kT;
-        for (int r = 0; r < rows; ++r) out[o * out_stride + out_off + r] = tmp[((size_t)t * rows + r) * kT + j];
-    }
-    return MMBA_OK;
+// tile-major rows [row0, row0 + rows) of src ([tile][src_rows][256]) -> caller-ordered (n_obs, rows) row-major;
+// entries of observations held by other ranks are zero
+int get_slots(mmba_handle* h, const double* src, int src_rows, int row0, int rows, double* out) {
+    const DevPlan& dp = h->dp;
+    const size_t n = (size_t)dp.n_obs * rows;
+    double* tmp = nullptr;
+    CU(cudaMalloc(&tmp, std::max<size_t>(n, 1) * sizeof(double)));
+    cudaMemsetAsync(tmp, 0, n * sizeof(double), h->stream);
+    devplan_scatter_slots(src, src_rows, row0, rows, dp.slot_obs, h->ns, tmp, h->stream);
+    int rc = d2h(h, out, tmp, n * sizeof(double));
+    cudaFree(tmp);
+    return rc;
 }
 
-// Jt [tile][18][256] -> caller-ordered Jc (n_obs,2,6) and Jp (n_obs,2,3); local entries only
+// Jt [tile][18][256] -> caller-ordered Jc (n_obs,2,6) and Jp (n_obs,2,3)
 int get_jacobian_slots(mmba_handle* h, double* Jc, double* Jp) {
-    const Plan& pl = h->plan;
-    std::vector<double> tmp((size_t)kJRows * h->ns);
-    CU(cudaMemcpyAsync(tmp.data(), h->d.J, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    TRY(get_slots(h, h->d.J, kJRows, 0, 12, Jc));
+    return get_slots(h, h->d.J, kJRows, 12, 6, Jp);
+}
+
+// host copy of the internal point order (evaluation hooks only)
+int host_point_perm(mmba_handle* h) {
+    if ((int64_t)h->h_point_perm.size() == h->dp.n_points) return MMBA_OK;
+    h->h_point_perm.resize(h->dp.n_points);
+    CU(cudaMemcpyAsync(h->h_point_perm.data(), h->dp.point_perm, h->dp.n_points * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    for (int64_t s = 0; s < h->ns; ++s) {
-        const int64_t o = pl.slot_obs[s];
-        if (o < 0) continue;
-        const int64_t t = s / kT, j = s % kT;
-        for (int r = 0; r < 12; ++r) Jc[o * 12 + r] = tmp[((size_t)t * kJRows + r) * kT + j];
-        for (int r = 0; r < 6; ++r) Jp[o * 6 + r] = tmp[((size_t)t * kJRows + 12 + r) * kT + j];
-    }
     return MMBA_OK;
 }
 
@@ -792,9 +829,9 @@ RcmPcgArgs rcm_pcg_args(mmba_handle* h, double f2) {
     A.state = d.state;
     A.n_cams = (int)h->Nc;
     A.maxit = h->opt.pcg_maxit;
-    A.cpc = h->rcm_part.cpc;
-    A.nblk_max = h->rcm_part.nblk_max;
-    A.nh_max = h->rcm_part.nh_max;
+    A.cpc = h->dp.cpc;
+    A.nblk_max = h->dp.nblk_max;
+    A.nh_max = h->dp.nh_max;
     A.s_in_smem = h->rcm_s_in_smem;
     A.nsub = h->rcm_nsub;
     A.rtol2 = h->opt.pcg_rtol * h->opt.pcg_rtol;
@@ -810,16 +847,16 @@ RcmPcgArgs rcm_pcg_args(mmba_handle* h, double f2) {
 int rcm_build(mmba_handle* h) {
     Dev& d = h->d;
     TRY(zero(h, d.y, 6 * h->Nc));
-    TRY(zero(h, d.Tup, 36 * (size_t)h->rcm.nnz_up()));
+    TRY(zero(h, d.Tup, 36 * (size_t)h->dp.nnz_up));
     TRY(launch_tile<M_SBUILD>(h, MMBA_K_SBUILD, sbuild_args(h)));
-    TRY(allreduce(h, {{d.y, (size_t)(6 * h->Nc), false}, {d.Tup, 36 * (size_t)h->rcm.nnz_up(), false}}));
+    TRY(allreduce(h, {{d.y, (size_t)(6 * h->Nc), false}, {d.Tup, 36 * (size_t)h->dp.nnz_up, false}}));
     return MMBA_OK;
 }
 
 // scaled full-pattern blocks, block-Jacobi preconditioner and right-hand side
 int rcm_finalize(mmba_handle* h, double reg) {
     Dev& d = h->d;
-    const int64_t n_entries = 36 * h->rcm.nnz_full();
+    const int64_t n_entries = 36 * h->dp.nnz_full;
     LAUNCH(MMBA_K_VEC, rcm_finalize_kernel, cdiv(n_entries, 256), 256, 0, d.Tup, d.rc_rows, d.rc_cols, d.rc_src, d.sinv, reg, d.S,
            n_entries);
     LAUNCH(MMBA_K_VEC, rcm_prepare_kernel, cdiv(h->Nc, kCamBlock), kCamBlock, 0, d.S, d.rc_diag, d.g, d.y, d.sinv, d.Pinv,
@@ -837,7 +874,7 @@ int rcm_pcg(mmba_handle* h, double f2) {
     static const bool classic = getenv("MMBA_PCG_CLASSIC") && getenv("MMBA_PCG_CLASSIC")[0] == '1';
     prof_begin(h, MMBA_K_PCG);
     CU(cudaLaunchCooperativeKernel(classic ? (const void*)rcm_pcg_classic_kernel : (const void*)rcm_pcg_kernel,
-                                   dim3(h->rcm_part.n_ctas), dim3(32 * h->rcm_warps), args, h->rcm_smem_bytes, h->stream));
+                                   dim3(h->dp.n_ctas), dim3(32 * h->rcm_warps), args, h->rcm_smem_bytes, h->stream));
     prof_end(h, MMBA_K_PCG);
     return MMBA_OK;
 }
@@ -964,7 +1001,7 @@ int run_trf(mmba_handle* h, mmba_result* out) {
     Dev& d = h->d;
     const mmba_options& o = h->opt;
     const int lead = o.rank == 0;
-    const int64_t n_total = 6 * h->Nc + 3 * h->plan.n_points;
+    const int64_t n_total = 6 * h->Nc + 3 * h->dp.n_points;
     const int64_t max_nfev = o.max_nfev > 0 ? o.max_nfev : 100 * n_total;
     const int64_t nloc = h->nloc, ncam = 6 * h->Nc, npt = 3 * h->npl;
     const int gv = cdiv(nloc, 256), gc_ = cdiv(ncam, 256), gp_ = std::max(1, cdiv(npt, 256));
@@ -1144,7 +1181,7 @@ int configure_kernels(mmba_handle* h) {
         // PCG grid (rcm_part): contiguous camera ranges, at most one CTA per SM (all co-resident), one warp per
         // camera of the range.  The CTA's rows of S stay in shared memory when they fit, else they are re-read
         // from L2 every iteration.
-        const RcmPartition& pt = h->rcm_part;
+        const DevPlan& pt = h->dp;
         h->rcm_nsub = std::max(1, (kRcmPcgThreads / 32) / pt.cpc);
         h->rcm_warps = std::min(kRcmPcgThreads / 32, pt.cpc * h->rcm_nsub);
         h->rcm_s_in_smem = rcm_smem(pt.cpc, pt.nblk_max, pt.nh_max, 1, pt.n_ctas).total <= 200 * 1024 ? 1 : 0;
@@ -1166,7 +1203,7 @@ int run_trf_pose(mmba_handle* h, mmba_result* out) {
     const mmba_options& o = h->opt;
     const int64_t ncam = 6 * h->Nc, nloc = h->nloc;
     const int64_t max_nfev = o.max_nfev > 0 ? o.max_nfev : 100 * ncam;
-    const double m_rows = 2.0 * (double)h->plan.n_obs;
+    const double m_rows = 2.0 * (double)h->dp.n_obs;
     h->log.clear();
     auto sg_cam = scale_grad_kernel<6, false>;
 
@@ -1392,7 +1429,10 @@ void mmba_destroy(mmba_handle* h) {
     if (h->arena) cudaFree(h->arena);
     h->arena = nullptr;
     xchg_release(h);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
+    h->planner.release();
+    if (h->stage_buf) cudaFreeHost(h->stage_buf);
+    for (int i = 0; i < kStageSlots; ++i)
+        if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
     if (h->comm) g_nccl.CommDestroy(h->comm);
     for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1403,78 +1443,227 @@ void mmba_destroy(mmba_handle* h) {
     delete h;
 }
 
+// Sharded set-up: the observations a rank staged (a contiguous chunk of the caller's arrays) travel to the ranks that
+// own their points.  One all-gather of the per-destination counts, then one grouped send / receive per peer over NVLink.
+// Chunks arrive in rank order and keep their order, so every rank ends up with its observations in ascending caller
+// order: the plan below is the one a single GPU would build for these points.
+static int exchange_observations(mmba_handle* h, int64_t o0) {
+    DevPlanner& P = h->planner;
+    const int nr = h->opt.nranks, me = h->opt.rank;
+    std::string err;
+    int rc = devplan_dispatch_pack(P, h->dp, o0, h->stream, err);
+    if (rc != MMBA_OK) return fail(h, rc, err);
+    int* d_all = P.d_counts + 16;
+    NC(g_nccl.AllGather(P.d_counts, d_all, (size_t)nr, ncclInt32, h->comm, h->stream));
+    std::vector<int> all((size_t)nr * nr);
+    CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int64_t n_recv = 0;
+    for (int r = 0; r < nr; ++r) n_recv += all[(size_t)r * nr + me];
+    const int32_t *cam_s = P.cam_s, *pt_s = P.pt_s, *gidx_s = P.gidx_s;
+    const double* uv_s = P.uv_s;
+    rc = devplan_dispatch_recv(P, n_recv, err);
+    if (rc != MMBA_OK) return fail(h, rc, err);
+    prof_begin(h, MMBA_K_ALLREDUCE);
+    NC(g_nccl.GroupStart());
+    int64_t soff = 0, roff = 0;
+    for (int r = 0; r < nr; ++r) {
+        const size_t sc = (size_t)all[(size_t)me * nr + r], rcn = (size_t)all[(size_t)r * nr + me];
+        if (sc) {
+            NC(g_nccl.Send(cam_s + soff, sc, ncclInt32, r, h->comm, h->stream));
+            NC(g_nccl.Send(pt_s + soff, sc, ncclInt32, r, h->comm, h->stream));
+            NC(g_nccl.Send(gidx_s + soff, sc, ncclInt32, r, h->comm, h->stream));
+            NC(g_nccl.Send(uv_s + 2 * soff, 2 * sc, ncclDouble, r, h->comm, h->stream));
+        }
+        if (rcn) {
+            NC(g_nccl.Recv(P.cam_r + roff, rcn, ncclInt32, r, h->comm, h->stream));
+            NC(g_nccl.Recv(P.pt_r + roff, rcn, ncclInt32, r, h->comm, h->stream));
+            NC(g_nccl.Recv(P.gidx_r + roff, rcn, ncclInt32, r, h->comm, h->stream));
+            NC(g_nccl.Recv(P.uv_r + 2 * roff, 2 * rcn, ncclDouble, r, h->comm, h->stream));
+        }
+        soff += (int64_t)sc;
+        roff += (int64_t)rcn;
+    }
+    NC(g_nccl.GroupEnd());
+    prof_end(h, MMBA_K_ALLREDUCE);
+    return MMBA_OK;
+}
+
+// Sharded set-up: every rank marked the camera pairs of its own points; the block pattern is their union.
+static int or_bitmaps(mmba_handle* h) {
+    DevPlanner& P = h->planner;
+    unsigned long long* bits;
+    size_t n_words;
+    devplan_bitmap(P, h->dp, &bits, &n_words);
+    const int nr = h->opt.nranks;
+    cudaError_t e = P.tmp.ensure((size_t)nr * n_words * sizeof(unsigned long long));
+    if (e != cudaSuccess) return fail(h, MMBA_ERR_NOMEM, std::string("set_problem: bitmap exchange buffer: ") + cudaGetErrorString(e));
+    NC(g_nccl.AllGather(bits, P.tmp.p, n_words, ncclUint64, h->comm, h->stream));
+    devplan_or_bitmaps(bits, reinterpret_cast<unsigned long long*>(P.tmp.p), n_words, nr, h->stream);
+    return MMBA_OK;
+}
+
+// Stage observations [o0, o1) of the caller's arrays through the pinned ring into the planner's input buffers:
+// indices narrowed to int32 and range-checked on the way (several host threads per slot), pixels copied as they are.
+static int upload_observations(mmba_handle* h, int64_t n_cams, int64_t n_points, const int64_t* cam_idx, const int64_t* pt_idx,
+                               const double* uv, int64_t o0, int64_t o1) {
+    DevPlanner& P = h->planner;
+    const int64_t n = o1 - o0;
+    const bool sharded = h->opt.nranks > 1;
+    for (int pass = 0; pass < 2; ++pass) {
+        Carver c;
+        c.base = pass ? P.in.p : nullptr;
+        P.cam = c.take<int32_t>((size_t)std::max<int64_t>(n, 1));
+        P.pt = c.take<int32_t>((size_t)std::max<int64_t>(n, 1));
+        P.uv = c.take<double>(2 * (size_t)std::max<int64_t>(n, 1));
+        if (sharded) {   // the same observations grouped by destination rank (devplan_dispatch_pack)
+            P.cam_s = c.take<int32_t>((size_t)std::max<int64_t>(n, 1));
+            P.pt_s = c.take<int32_t>((size_t)std::max<int64_t>(n, 1));
+            P.gidx_s = c.take<int32_t>((size_t)std::max<int64_t>(n, 1));
+            P.uv_s = c.take<double>(2 * (size_t)std::max<int64_t>(n, 1));
+        }
+        if (!pass) {
+            cudaError_t e = P.in.ensure(c.off + 256);
+            if (e != cudaSuccess) return fail(h, MMBA_ERR_NOMEM, std::string("set_problem: input buffers: ") + cudaGetErrorString(e));
+        }
+    }
+    P.gidx = nullptr;
+    P.n_in = n;
+    const int64_t chunk = (int64_t)(kStageSlotBytes / 24);   // 4 + 4 + 16 bytes per observation
+    int64_t first_bad = -1;
+    for (int64_t b = o0; b < o1; b += chunk) {
+        const int64_t m = std::min(chunk, o1 - b);
+        int idx;
+        char* slot;
+        TRY(stage_acquire(h, &idx, &slot));
+        int32_t* s_cam = reinterpret_cast<int32_t*>(slot);
+        int32_t* s_pt = s_cam + m;
+        double* s_uv = reinterpret_cast<double*>(slot + 8 * (size_t)((m + 1) / 2 * 2));
+        int64_t bad[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+        parallel_ranges(m, 32768, [&](int64_t i0, int64_t i1, int worker) {
+            for (int64_t i = i0; i < i1; ++i) {
+                const int64_t c = cam_idx[b + i], p = pt_idx[b + i];
+                if ((uint64_t)c >= (uint64_t)n_cams || (uint64_t)p >= (uint64_t)n_points) {
+                    if (bad[worker] < 0) bad[worker] = b + i;
+                    s_cam[i] = 0;
+                    s_pt[i] = 0;
+                } else {
+                    s_cam[i] = (int32_t)c;
+                    s_pt[i] = (int32_t)p;
+                }
+            }
+            std::memcpy(s_uv + 2 * i0, uv + 2 * (b + i0), (size_t)(i1 - i0) * 16);
+        });
+        for (int w = 0; w < 8; ++w)
+            if (bad[w] >= 0 && (first_bad < 0 || bad[w] < first_bad)) first_bad = bad[w];
+        CU(cudaMemcpyAsync(P.cam + (b - o0), s_cam, (size_t)m * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(P.pt + (b - o0), s_pt, (size_t)m * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(P.uv + 2 * (b - o0), s_uv, (size_t)m * 16, cudaMemcpyHostToDevice, h->stream));
+        TRY(stage_commit(h, idx));
+        if (first_bad >= 0) break;
+    }
+    if (first_bad >= 0) {
+        CU(cudaStreamSynchronize(h->stream));
+        return fail(h, MMBA_ERR_ARG, "set_problem: index out of range at observation " + std::to_string(first_bad));
+    }
+    return MMBA_OK;
+}
+
 int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n_obs, const double K[9],
                      const int64_t* cam_idx, const int64_t* pt_idx, const double* uv) {
     if (!h) return fail(nullptr, MMBA_ERR_ARG, "null handle");
     if (!K || !uv) return fail(h, MMBA_ERR_ARG, "set_problem: null K or uv");
+    if (n_cams <= 0 || n_points <= 0 || n_obs <= 0 || !cam_idx || !pt_idx)
+        return fail(h, MMBA_ERR_ARG, "set_problem: sizes must be positive and index arrays non-null");
+    if (n_cams > (int64_t)kMaxCamBlocks * kCamBlock) return fail(h, MMBA_ERR_ARG, "set_problem: too many cameras");
     CU(cudaSetDevice(h->opt.device));
     release_problem(h);
-    // MMBA_PLAN_TIMING=1: host-side phase times of this call on stderr (diagnostics)
+    // MMBA_PLAN_TIMING=1: host-side phase times of this call on stderr (diagnostics; synchronises after every phase)
     auto T0 = std::chrono::steady_clock::now();
     const bool timing = getenv("MMBA_PLAN_TIMING") != nullptr;
     auto lap = [&](const char* what) {
         if (!timing) return;
+        cudaStreamSynchronize(h->stream);
         auto t = std::chrono::steady_clock::now();
         fprintf(stderr, "set_problem %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count());
         T0 = t;
     };
     std::string err;
-    int rc = build_plan(h->plan, n_cams, n_points, n_obs, cam_idx, pt_idx, h->opt.rank, h->opt.nranks, err);
+    DevPlanner& P = h->planner;
+    DevPlan& D = h->dp;
+    D = DevPlan();
+    D.n_cams = n_cams;
+    D.n_points = n_points;
+    D.n_obs = n_obs;
+    D.rank = h->opt.rank;
+    D.nranks = h->opt.nranks;
+    h->h_point_perm.clear();
+    const int nr = h->opt.nranks;
+    // 1. this rank's share of the caller's arrays goes to the device (rank r stages observations
+    //    [n_obs r / nranks, n_obs (r + 1) / nranks): no rank reads the whole problem)
+    const int64_t o0 = n_obs * h->opt.rank / nr, o1 = n_obs * (h->opt.rank + 1) / nr;
+    TRY(upload_observations(h, n_cams, n_points, cam_idx, pt_idx, uv, o0, o1));
+    lap("stage + upload");
+    // 2. per-point statistics (summed over ranks), internal point order, shard cuts
+    int rc = devplan_stats(P, D, h->stream, err);
     if (rc != MMBA_OK) return fail(h, rc, err);
-    if (n_cams > (int64_t)kMaxCamBlocks * kCamBlock) return fail(h, MMBA_ERR_ARG, "set_problem: too many cameras");
-    lap("plan");
-    const Plan& pl = h->plan;
+    if (nr > 1) {
+        int *cnt, *first, *last, *first_hi;
+        devplan_stat_arrays(P, D, &cnt, &first, &last, &first_hi);
+        prof_begin(h, MMBA_K_ALLREDUCE);
+        NC(g_nccl.GroupStart());
+        NC(g_nccl.AllReduce(cnt, cnt, (size_t)n_points, ncclInt32, ncclSum, h->comm, h->stream));
+        NC(g_nccl.AllReduce(first, first, (size_t)n_points, ncclInt32, ncclMin, h->comm, h->stream));
+        NC(g_nccl.AllReduce(last, last, (size_t)n_points, ncclInt32, ncclMax, h->comm, h->stream));
+        NC(g_nccl.AllReduce(first_hi, first_hi, (size_t)n_points, ncclInt32, ncclMin, h->comm, h->stream));
+        NC(g_nccl.GroupEnd());
+        prof_end(h, MMBA_K_ALLREDUCE);
+    }
+    rc = devplan_order(P, D, h->stream, err);
+    if (rc != MMBA_OK) return fail(h, rc, err);
+    lap("point order");
+    // 3. (sharded) every observation travels to the rank that owns its point: one all-to-all over NVLink
+    if (nr > 1) TRY(exchange_observations(h, o0));
+    // 4. observation grouping, tiles, per-tile tables, co-visibility bitmap
+    const bool want_pattern = h->opt.schur_mode != MMBA_SCHUR_IMPLICIT && n_cams <= 20000;
+    rc = devplan_tiles(P, D, want_pattern, h->stream, err);
+    if (rc != MMBA_OK) return fail(h, rc, err);
+    if (want_pattern) {
+        if (nr > 1) TRY(or_bitmaps(h));
+        rc = devplan_pattern_sizes(P, D, h->stream, err);
+        if (rc != MMBA_OK) return fail(h, rc, err);
+    }
+    rc = devplan_sync_sizes(P, D, h->stream, err);
+    if (rc != MMBA_OK) return fail(h, rc, err);
+    lap("tiles + pattern bitmap");
     h->Nc = n_cams;
-    h->npl = pl.n_points_local();
-    h->ns = pl.n_slots;
-    h->nt = pl.n_tiles;
+    h->npl = D.pt_end - D.pt_begin;
+    h->ns = D.n_slots;
+    h->nt = D.n_tiles;
     h->nloc = 6 * h->Nc + 3 * h->npl;
     std::memcpy(h->K, K, sizeof(h->K));
     // Explicit reduced camera matrix (rcm.h) when it is small next to the observation stream: at most
     // 20 000 cameras (co-visibility bitmap), blocks within ~1/2 of the J bytes a PCG iteration would stream
     // and L2-sized, and a bounded S-build cost (pair-blocks per observation).
     h->rcm_ready = false;
-    h->rcm = RcmPattern();
-    // tile-major copy of the observed pixels: host-only work that runs on this thread while the pattern is built
-    std::vector<double> uvs;
-    auto reorder_uv = [&]() {
-        uvs.assign(2 * (size_t)h->ns, 0.0);
-        parallel_ranges(h->ns, 65536, [&](int64_t s0, int64_t s1, int) {
-            for (int64_t s = s0; s < s1; ++s) {
-                const int64_t ob = pl.slot_obs[s];
-                if (ob >= 0) {
-                    const int64_t t = s / kT, j = s % kT;
-                    uvs[(t * 2) * kT + j] = uv[2 * ob];
-                    uvs[(t * 2 + 1) * kT + j] = uv[2 * ob + 1];
-                }
-            }
-        });
-    };
-    std::thread pattern_thread;
-    auto build_pattern = [&]() {
+    if (want_pattern) {
         const bool forced = h->opt.schur_mode == MMBA_SCHUR_EXPLICIT;
         const int64_t cap_full = forced ? (int64_t)8 << 20 : std::min<int64_t>(((int64_t)96 << 20) / 288, (152 * n_obs / 2) / 288);
-        const bool ok = build_rcm_pattern(h->rcm, n_cams, n_points, n_obs, cam_idx, pt_idx, std::max<int64_t>(cap_full, n_cams),
-                                          h->plan.point_perm.data());
-        h->rcm_ready = ok && (forced || (h->rcm.nnz_full() <= std::max<int64_t>(cap_full, n_cams) && h->rcm.total_pairs <= 64 * n_obs));
-        if (!h->rcm_ready) h->rcm = RcmPattern();
-        else {
-            build_rcm_partition(h->rcm_part, h->rcm, std::min(h->sm_count, kRcmMaxCtas));
+        const int64_t cap = std::max<int64_t>(cap_full, n_cams);
+        // (the host builder bounds the upper triangle by the same cap while counting)
+        h->rcm_ready = D.nnz_up <= cap && (forced || (D.nnz_full <= cap && D.total_pairs <= 64 * n_obs));
+        if (h->rcm_ready) {
+            rc = devplan_pattern_fill(P, D, std::min(h->sm_count, kRcmMaxCtas), h->stream, err);
+            if (rc != MMBA_OK) return fail(h, rc, err);
             // the PCG kernel keeps the search direction on every CTA's halo in shared memory
-            if (rcm_smem(h->rcm_part.cpc, h->rcm_part.nblk_max, h->rcm_part.nh_max, 0, h->rcm_part.n_ctas).total > 200 * 1024) {
-                h->rcm_ready = false;
-                h->rcm = RcmPattern();
-            }
+            if (rcm_smem(D.cpc, D.nblk_max, D.nh_max, 0, D.n_ctas).total > 200 * 1024) h->rcm_ready = false;
         }
-    };
-    if (h->opt.schur_mode != MMBA_SCHUR_IMPLICIT && n_cams <= 20000) pattern_thread = std::thread(build_pattern);
-    reorder_uv();
-    if (pattern_thread.joinable()) pattern_thread.join();
+    }
+    D.rcm_ok = h->rcm_ready;
     if (h->opt.schur_mode == MMBA_SCHUR_EXPLICIT && !h->rcm_ready)
         return fail(h, MMBA_ERR_ARG, "set_problem: the reduced camera matrix is too large to be formed explicitly");
-
     h->hist_cap = (h->rcm_ready && (h->opt.profile & 2)) ? h->opt.pcg_maxit : 0;
-    lap("rcm pattern | uv reorder");
+    lap("pattern CSR + partition");
     Arena measure;
     carve(h, measure);
     const size_t need = measure.off + 256;
@@ -1494,46 +1683,17 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     Arena a;
     a.base = static_cast<char*>(h->arena);
     carve(h, a);
-    const size_t stage_n = (size_t)std::max<int64_t>(6 * h->Nc + 3 * pl.n_points, 64);
-    if (stage_n > h->h_stage_n) {   // pinned staging buffer: grown, never shrunk, freed with the handle
-        if (h->h_stage) cudaFreeHost(h->h_stage);
-        h->h_stage = nullptr;
-        h->h_stage_n = 0;
-        CU(cudaMallocHost(&h->h_stage, stage_n * sizeof(double)));
-        h->h_stage_n = stage_n;
-    }
-
     Dev& d = h->d;
-    lap("arena");
     CU(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
-    {
-        TRY(upload(h, d.meta, pl.meta));
-        TRY(upload(h, d.tile_cams, pl.tile_cams));
-        TRY(upload(h, d.uv, uvs));
-        if (h->rcm_ready) {
-            TRY(upload(h, d.up_rowptr, h->rcm.up_rowptr));
-            TRY(upload(h, d.up_cols, h->rcm.up_cols));
-            TRY(upload(h, d.rc_rowptr, h->rcm.rowptr));
-            TRY(upload(h, d.rc_cols, h->rcm.cols));
-            TRY(upload(h, d.rc_rows, h->rcm.rows));
-            TRY(upload(h, d.rc_src, h->rcm.src));
-            TRY(upload(h, d.rc_diag, h->rcm.diag));
-            TRY(upload(h, d.rc_halo_ptr, h->rcm_part.halo_ptr));
-            TRY(upload(h, d.rc_halo_cols, h->rcm_part.halo_cols));
-            TRY(upload(h, d.rc_own, h->rcm_part.own_l));
-            TRY(upload(h, d.rc_lcol, h->rcm_part.lcol));
-        }
-        CU(cudaStreamSynchronize(h->stream));
-    }
-    lap("uploads");
+    lap("arena");
     TileArgs& A = h->targs;
     A.meta = d.meta;
     A.tile_cams = d.tile_cams;
     A.uv = d.uv;
     A.n_tiles = (int)h->nt;
-    A.cam_stride = pl.cam_stride;
-    A.max_cams = std::max(pl.max_tile_cams, 1);
-    A.max_pts = std::max(pl.max_tile_pts, 1);
+    A.cam_stride = D.cam_stride;
+    A.max_cams = std::max(D.max_tile_cams, 1);
+    A.max_pts = std::max(D.max_tile_pts, 1);
     A.n_cams = (int)h->Nc;
     A.ytab_cams = h->Nc <= 340 ? (int)h->Nc : 0;   // <= 16 KB of shared memory
     std::memcpy(A.K, K, sizeof(A.K));
@@ -1567,10 +1727,7 @@ int mmba_solve(mmba_handle* h, double* x, mmba_result* result, double* fun_out) 
     TRY(put_x(h, x, h->d.x));
     TRY(solve_on_device(h, result));
     TRY(get_x(h, h->d.x, x));
-    if (fun_out) {
-        if (h->opt.nranks > 1) std::memset(fun_out, 0, 2 * h->plan.n_obs * sizeof(double));
-        TRY(get_slots(h, h->d.res, 2, fun_out, 2, 0));
-    }
+    if (fun_out) TRY(get_slots(h, h->d.res, 2, 0, 2, fun_out));
     return MMBA_OK;
 }
 
@@ -1592,7 +1749,7 @@ int mmba_solve_pose(mmba_handle* h, double* x, mmba_result* result, double* fun_
     prof_collect(h);
     if (rc != MMBA_OK) return rc;
     TRY(get_x(h, h->d.x, x));
-    if (fun_out) TRY(get_slots(h, h->d.res, 2, fun_out, 2, 0));
+    if (fun_out) TRY(get_slots(h, h->d.res, 2, 0, 2, fun_out));
     return MMBA_OK;
 }
 
@@ -1644,7 +1801,7 @@ int mmba_get_profile(const mmba_handle* h, int64_t launches[MMBA_K_COUNT], doubl
 
 int mmba_get_shard(const mmba_handle* h, int64_t* n_obs_local, int64_t* n_points_local, int64_t* n_tiles) {
     if (!h || !h->has_problem) return MMBA_ERR_STATE;
-    if (n_obs_local) *n_obs_local = h->plan.n_obs_local;
+    if (n_obs_local) *n_obs_local = h->dp.n_obs_local;
     if (n_points_local) *n_points_local = h->npl;
     if (n_tiles) *n_tiles = h->nt;
     return MMBA_OK;
@@ -1667,8 +1824,7 @@ int mmba_eval_residual(mmba_handle* h, const double* x, double* f) {
         TRY(launch_tile<M_RESID_STORE>(h, MMBA_K_RESID, P));
     }
     CU(cudaGetLastError());
-    if (h->opt.nranks > 1) std::memset(f, 0, 2 * h->plan.n_obs * sizeof(double));
-    return get_slots(h, d.res, 2, f, 2, 0);
+    return get_slots(h, d.res, 2, 0, 2, f);
 }
 
 int mmba_eval_jacobian(mmba_handle* h, const double* x, double* Jc, double* Jp) {
@@ -1677,10 +1833,6 @@ int mmba_eval_jacobian(mmba_handle* h, const double* x, double* Jc, double* Jp) 
     Dev& d = h->d;
     TRY(put_x(h, x, d.x));
     TRY(linearise(h));
-    if (h->opt.nranks > 1) {
-        std::memset(Jc, 0, 12 * h->plan.n_obs * sizeof(double));
-        std::memset(Jp, 0, 6 * h->plan.n_obs * sizeof(double));
-    }
     return get_jacobian_slots(h, Jc, Jp);
 }
 
@@ -1688,9 +1840,10 @@ int mmba_eval_blocks(mmba_handle* h, const double* x, double* U, double* V, doub
     TRY(need_problem(h));
     if (!x) return fail(h, MMBA_ERR_ARG, "eval_blocks: null x");
     Dev& d = h->d;
-    const Plan& pl = h->plan;
+    const DevPlan& pl = h->dp;
     TRY(put_x(h, x, d.x));
     TRY(linearise(h, true));
+    TRY(host_point_perm(h));
     std::vector<double> hU(21 * h->Nc), hg(h->nloc), hV(6 * std::max<int64_t>(h->npl, 1));
     CU(cudaMemcpyAsync(hU.data(), d.U, hU.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(hg.data(), d.g, hg.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1705,7 +1858,7 @@ int mmba_eval_blocks(mmba_handle* h, const double* x, double* U, double* V, doub
     if (V && h->opt.nranks > 1) std::memset(V, 0, 9 * pl.n_points * sizeof(double));
     if (gp && h->opt.nranks > 1) std::memset(gp, 0, 3 * pl.n_points * sizeof(double));
     for (int64_t q = 0; q < h->npl; ++q) {
-        const int64_t p = pl.point_perm[pl.pt_begin + q];
+        const int64_t p = h->h_point_perm[pl.pt_begin + q];
         if (V)
             for (int a = 0; a < 3; ++a)
                 for (int b = 0; b < 3; ++b) V[p * 9 + a * 3 + b] = hV[q * 6 + (a <= b ? tri3(a, b) : tri3(b, a))];
@@ -1724,7 +1877,7 @@ int mmba_eval_gn_step(mmba_handle* h, const double* x, const double* scale, doub
     TRY(linearise(h));
     // scale_inv = 1 / scale in the internal layout
     {
-        std::vector<double> si(6 * h->Nc + 3 * h->plan.n_points);
+        std::vector<double> si(6 * h->Nc + 3 * h->dp.n_points);
         for (size_t i = 0; i < si.size(); ++i) si[i] = 1.0 / scale[i];
         TRY(put_x(h, si.data(), d.sinv));
     }
@@ -1748,7 +1901,7 @@ int mmba_eval_reduced_system(mmba_handle* h, const double* x, const double* scal
     TRY(put_x(h, x, d.x));
     TRY(linearise(h));
     {
-        std::vector<double> si(6 * h->Nc + 3 * h->plan.n_points);
+        std::vector<double> si(6 * h->Nc + 3 * h->dp.n_points);
         for (size_t i = 0; i < si.size(); ++i) si[i] = 1.0 / scale[i];
         TRY(put_x(h, si.data(), d.sinv));
     }
@@ -1757,17 +1910,22 @@ int mmba_eval_reduced_system(mmba_handle* h, const double* x, const double* scal
                d.M, d.zg, h->npl);
     TRY(rcm_build(h));
     TRY(rcm_finalize(h, reg));
-    const RcmPattern& r = h->rcm;
-    std::vector<double> hS(36 * (size_t)r.nnz_full());
+    const int64_t nnz = h->dp.nnz_full;
+    h->h_rc_rows.resize(nnz);
+    h->h_rc_cols.resize(nnz);
+    CU(cudaMemcpyAsync(h->h_rc_rows.data(), h->dp.rows, nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_rc_cols.data(), h->dp.cols, nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<double> hS(36 * (size_t)nnz);
     CU(cudaMemcpyAsync(hS.data(), d.S, hS.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(rhs, d.rcm_b, 6 * h->Nc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     const int64_t n6 = 6 * h->Nc;
     std::memset(S_dense, 0, (size_t)n6 * n6 * sizeof(double));
-    for (int64_t k = 0; k < r.nnz_full(); ++k)
+    for (int64_t k = 0; k < nnz; ++k)
         for (int a = 0; a < 6; ++a)
-            for (int b = 0; b < 6; ++b) S_dense[(6 * (int64_t)r.rows[k] + a) * n6 + 6 * (int64_t)r.cols[k] + b] = hS[k * 36 + a * 6 + b];
+            for (int b = 0; b < 6; ++b)
+                S_dense[(6 * (int64_t)h->h_rc_rows[k] + a) * n6 + 6 * (int64_t)h->h_rc_cols[k] + b] = hS[k * 36 + a * 6 + b];
     return MMBA_OK;
 }
 
@@ -2023,6 +2181,82 @@ int mmba_plan_export(const mmba_plan* p, int64_t* obs_perm, int64_t* point_perm,
             if (slot_point_local) slot_point_local[s] = live ? pl.meta[t].pt0 + pl.meta[t].slot_pt[j] : -1;
         }
     }
+    return MMBA_OK;
+}
+
+int mmba_plan_raw(const mmba_plan* p, void* meta, int32_t* tile_cams) {
+    if (!p) return MMBA_ERR_ARG;
+    const Plan& pl = p->plan;
+    if (meta && pl.n_tiles) std::memcpy(meta, pl.meta.data(), (size_t)pl.n_tiles * sizeof(TileMeta));
+    if (tile_cams)
+        for (int64_t t = 0; t < pl.n_tiles; ++t)
+            for (int c = 0; c < kTileObs; ++c)
+                tile_cams[t * kTileObs + c] = c < pl.meta[t].ncams ? pl.tile_cams[t * pl.cam_stride + c] : -1;
+    return MMBA_OK;
+}
+
+int mmba_get_plan_sizes(mmba_handle* h, int64_t sizes[8]) {
+    TRY(need_problem(h));
+    if (!sizes) return fail(h, MMBA_ERR_ARG, "get_plan_sizes: null argument");
+    const DevPlan& D = h->dp;
+    sizes[0] = D.n_tiles;
+    sizes[1] = D.n_obs_local;
+    sizes[2] = D.pt_end - D.pt_begin;
+    sizes[3] = D.pt_begin;
+    sizes[4] = D.pt_end;
+    sizes[5] = kTileObs;
+    sizes[6] = D.max_tile_cams;
+    sizes[7] = D.n_slots;
+    return MMBA_OK;
+}
+
+int mmba_get_plan_raw(mmba_handle* h, void* meta, int32_t* tile_cams, int64_t* obs_perm, int64_t* point_perm) {
+    TRY(need_problem(h));
+    const DevPlan& D = h->dp;
+    if (meta && D.n_tiles) CU(cudaMemcpyAsync(meta, D.meta, (size_t)D.n_tiles * sizeof(TileMeta), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int32_t> tc, so, pp;
+    if (tile_cams) {
+        tc.resize((size_t)D.n_tiles * D.cam_stride + 1);
+        CU(cudaMemcpyAsync(tc.data(), D.tile_cams, (size_t)D.n_tiles * D.cam_stride * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (obs_perm) {
+        so.resize((size_t)D.n_slots + 1);
+        CU(cudaMemcpyAsync(so.data(), D.slot_obs, (size_t)D.n_slots * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (point_perm) {
+        pp.resize((size_t)D.n_points);
+        CU(cudaMemcpyAsync(pp.data(), D.point_perm, (size_t)D.n_points * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (tile_cams)
+        for (int64_t t = 0; t < D.n_tiles; ++t)
+            for (int c = 0; c < kTileObs; ++c) tile_cams[t * kTileObs + c] = c < D.cam_stride ? tc[t * D.cam_stride + c] : -1;
+    if (obs_perm)
+        for (int64_t i = 0; i < D.n_slots; ++i) obs_perm[i] = so[i];
+    if (point_perm)
+        for (int64_t i = 0; i < D.n_points; ++i) point_perm[i] = pp[i];
+    return MMBA_OK;
+}
+
+int mmba_get_rcm_pattern(mmba_handle* h, int64_t sizes[8], int32_t* up_rowptr, int32_t* up_cols, int64_t capacity) {
+    TRY(need_problem(h));
+    if (!sizes) return fail(h, MMBA_ERR_ARG, "get_rcm_pattern: null argument");
+    if (!h->rcm_ready) return fail(h, MMBA_ERR_STATE, "get_rcm_pattern: the reduced camera matrix is not formed explicitly");
+    const DevPlan& D = h->dp;
+    sizes[0] = D.nnz_up;
+    sizes[1] = D.nnz_full;
+    sizes[2] = D.total_pairs;
+    sizes[3] = D.n_ctas;
+    sizes[4] = D.cpc;
+    sizes[5] = D.nblk_max;
+    sizes[6] = D.nh_max;
+    sizes[7] = 0;
+    if (up_rowptr) CU(cudaMemcpyAsync(up_rowptr, D.up_rowptr, (size_t)(h->Nc + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (up_cols) {
+        if (capacity < D.nnz_up) return fail(h, MMBA_ERR_NOMEM, "get_rcm_pattern: capacity too small");
+        CU(cudaMemcpyAsync(up_cols, D.up_cols, (size_t)D.nnz_up * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
     return MMBA_OK;
 }
 

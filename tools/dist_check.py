@@ -32,6 +32,16 @@ def main():
         x0 = np.hstack((mm.frameParameters(ext), np.asarray(pts).reshape(-1)))
         res = mm.solve(x0, K, nc, npts, fi, pi, uv, want_fun=True)       # sharded (torch.distributed is initialised)
         costs = np.array([r["cost"] for r in res.log])
+        # every rank: the shard plan built on the device (chunked upload + all-to-all) == the host plan of this rank
+        eng_s = next(iter(mm._ENGINES.values()))
+        dev, host = eng_s.plan(), _capi.plan(nc, npts, fi, pi, rank, world)
+        plan_ok = all(dev[k] == host[k] for k in ("n_tiles", "n_obs_local", "point_begin", "point_end")) and all(
+            np.array_equal(dev[k], host[k]) for k in ("point_perm", "obs_perm", "meta", "tile_cams"))
+        t_ok = torch.tensor([1 if plan_ok else 0], device="cuda")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"{name}: world={world} shard plans device == host -> {'OK' if t_ok.item() else 'MISMATCH'}", flush=True)
+            ok = ok and bool(t_ok.item())
         if rank == 0:
             with _capi.Engine(device=local) as eng:                        # single GPU
                 eng.set_problem(nc, npts, K, fi, pi, uv)
