@@ -1562,6 +1562,16 @@ static int upload_observations(mmba_handle* h, int64_t n_cams, int64_t n_points,
         TRY(stage_commit(h, idx));
         if (first_bad >= 0) break;
     }
+    if (sharded) {   // every rank checked its own chunk: agree on the first bad observation, fail together
+        if (!P.d_counts) CU(cudaMalloc(&P.d_counts, (16 + 16 * 16) * sizeof(int)));
+        long long v = first_bad < 0 ? INT64_MAX : first_bad;
+        long long* d_v = reinterpret_cast<long long*>(P.d_counts);
+        CU(cudaMemcpyAsync(d_v, &v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
+        NC(g_nccl.AllReduce(d_v, d_v, 1, ncclInt64, ncclMin, h->comm, h->stream));
+        CU(cudaMemcpyAsync(&v, d_v, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        first_bad = v == INT64_MAX ? -1 : (int64_t)v;
+    }
     if (first_bad >= 0) {
         CU(cudaStreamSynchronize(h->stream));
         return fail(h, MMBA_ERR_ARG, "set_problem: index out of range at observation " + std::to_string(first_bad));
@@ -1633,6 +1643,8 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
         rc = devplan_pattern_sizes(P, D, h->stream, err);
         if (rc != MMBA_OK) return fail(h, rc, err);
     }
+    // (sharded: a too-long track is seen by the rank that owns the point only; all ranks must fail together)
+    if (nr > 1) NC(g_nccl.AllReduce(&P.d_info->err_track, &P.d_info->err_track, 1, ncclInt32, ncclMax, h->comm, h->stream));
     rc = devplan_sync_sizes(P, D, h->stream, err);
     if (rc != MMBA_OK) return fail(h, rc, err);
     lap("tiles + pattern bitmap");

@@ -1,37 +1,31 @@
-"""Where does the end-to-end adjustPoints call spend its time? (host-side breakdown)"""
-import cProfile, io, os, pstats, sys, time, contextlib
+"""Where an adjustPoints call spends its time (host + device phases), per config.
+    MMBA_PLAN_TIMING=1 python tools/e2e_profile.py [C2] [C4]"""
+import contextlib, io, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from meatmodeler_b200 import synth, _capi
+from meatmodeler_b200 import _capi, synth
 from meatmodeler_b200 import bundleAdjuster as mm
 
-prob = synth.make_config(sys.argv[1] if len(sys.argv) > 1 else "C2", hard=True)
-ext, K, pts, uv, fi, pi = prob.args()
-sink = io.StringIO()
-with contextlib.redirect_stdout(sink):
-    mm.adjustPoints(ext, K, pts, uv, fi, pi)
-for rep in range(3):
-    t0 = time.perf_counter()
-    with contextlib.redirect_stdout(sink):
-        mm.adjustPoints(ext, K, pts, uv, fi, pi)
-    print("adjustPoints wall", round(1e3 * (time.perf_counter() - t0), 2), "ms; solve_ms", round(mm.last_result.solve_ms, 2))
-# pieces
-nc, npts, nobs = prob.sizes
-eng = mm._ENGINES[(0, 0, 1)]
-for rep in range(3):
-    t0 = time.perf_counter(); eng.set_problem(nc, npts, K, fi, pi, uv); t1 = time.perf_counter()
-    x0 = np.hstack((mm.frameParameters(ext), pts.reshape(-1))); t2 = time.perf_counter()
-    x, r, _ = eng.solve(x0); t3 = time.perf_counter()
-    log = eng.log(); t4 = time.perf_counter()
-    class R: pass
-    rr = R(); rr.x = x
-    mm.reformatPointResult(rr, nc, npts); t5 = time.perf_counter()
-    print("set_problem %.2f pack %.2f solve(call) %.2f [device %.2f] log %.2f reformat %.2f ms" % tuple(1e3 * v for v in (t1 - t0, t2 - t1, t3 - t2, r.solve_ms / 1e3, t4 - t3, t5 - t4)))
-lib = _capi.lib()
-import ctypes as C
-for rep in range(3):
-    h = _capi._H(); t0 = time.perf_counter()
-    lib.mmba_plan_create(C.byref(h), nc, npts, nobs, np.ascontiguousarray(fi), np.ascontiguousarray(pi), 0, 1)
-    print("plan_create %.2f ms (OMP threads default; cpu_count %d)" % (1e3 * (time.perf_counter() - t0), os.cpu_count()))
-    lib.mmba_plan_destroy(h)
+for name in sys.argv[1:] or ["C2"]:
+    prob = synth.make_config(name, hard=True)
+    ext, K, pts, uv, fi, pi = prob.args()
+    nc, npts, nobs = prob.sizes
+    sink = io.StringIO()
+    for rep in range(3):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(sink):
+            mm.adjustPoints(ext, K, pts, uv, fi, pi)
+        t1 = time.perf_counter()
+        print(f"{name} adjustPoints call {rep}: {1e3 * (t1 - t0):.2f} ms (solve {mm.last_result.solve_ms:.2f} ms, nit {mm.last_result.nit}, "
+              f"pcg {mm.last_result.pcg_iterations}, cost {mm.last_result.cost:.6f})", flush=True)
+    # phases of the Python wrapper
+    t = time.perf_counter()
+    x0 = np.hstack((mm.frameParameters(np.asarray(ext, dtype=np.float64)), np.asarray(pts, dtype=np.float64).reshape(-1)))
+    t_pack = time.perf_counter() - t
+    eng = next(iter(mm._ENGINES.values()))
+    t = time.perf_counter(); eng.set_problem(nc, npts, K, fi, pi, uv); t_set = time.perf_counter() - t
+    t = time.perf_counter(); x, r, _ = eng.solve(x0); t_solve = time.perf_counter() - t
+    t = time.perf_counter(); out = mm.reformatPointResult(mm.SolveResult(x=x), nc, npts); t_unpack = time.perf_counter() - t
+    print(f"{name} phases: pack {1e3 * t_pack:.2f} ms | set_problem {1e3 * t_set:.2f} ms | Engine.solve {1e3 * t_solve:.2f} ms "
+          f"(device {r.solve_ms:.2f}) | unpack {1e3 * t_unpack:.2f} ms", flush=True)
