@@ -2,21 +2,26 @@
 """Benchmark of the bundle-adjustment hot path (BASELINE.json metric: BA observations/s, one LM
 iteration = residual + Jacobian + Schur/PCG solve + step selection).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mmba|reference] [--config auto|C1..C5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mmba|reference] [--config auto|C1..C5] [--weak]
 
 A "step" is one complete solve (the work of one ``adjustPoints`` call) from the same synthetic
 starting point; ``value`` = observations x LM iterations of the K timed steps / device time, with
 the problem resident in HBM; ``e2e`` = the same metric through the drop-in
-``bundleAdjuster.adjustPoints`` call with host (numpy) buffers, i.e. including the host-side plan,
-every host->device copy and the device->host read of the result.
+``bundleAdjuster.adjustPoints`` call with host (numpy) buffers, i.e. including the staged upload of the
+index / pixel arrays, the device-side plan, every host->device copy and the device->host read of the result.
 
-Workloads: N=1 -> BASELINE configs[1] (200 cameras, 50k points, 1M observations).  N>1 -> the same
-shape per GPU (200 cameras replicated, N x 50k points, N x 1M observations sharded by point):
-"scaling": "weak".  ``--config C4`` runs the 5M-observation Venice-sized problem at any N (strong).
+Workload (``--config auto``, every N): BASELINE configs[3], the Venice-sized problem the metric is quoted on
+"at 1/2/4/8 GPUs" (1 778 cameras, 993 k points, 5 M observations), sharded by point over the N GPUs:
+"scaling": "strong".  At N = 1 the line also carries BASELINE configs[1] (C2, the food-video shape) under
+``also.C2``.  ``--weak`` runs the round-1 weak-scaling workload (C2 shape per GPU) instead.
+At N > 1 rank 0 additionally solves the whole problem on its own GPU and the line records that the sharded
+solve reproduces it (``sharded_vs_single``); a mismatch fails the run.
 
-``--impl reference`` times the reference's CPU path (scipy least_squares with the reference's
-arguments, restated in oracle/ba_oracle.py because the reference is a Python module that cannot be
-compiled into oracle/_ref) on a bounded sample of the same workload, on rank 0 only.
+``--impl reference`` times the reference's CPU path on a bounded sample of the same workload on rank 0:
+the UNMODIFIED reference module (/root/reference/bundleAdjuster.py) when it is present, else its restatement
+(oracle/ba_oracle.py: the same scipy call with the same arguments; the GPU box has no /root/reference).
+The full-size wall time of the unmodified reference, measured once in the build container, rides along
+(``cpu_baseline.full_size``, from tests/golden/c4.npz / c2.npz).
 """
 from __future__ import annotations
 
@@ -47,17 +52,19 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def workload(name, n_gpus):
+def workload(name, n_gpus, weak=False):
     from meatmodeler_b200 import synth
-    if name == "auto":
+    if weak:
         nc, npts, nobs = synth.CONFIGS["C2"]
         prob = synth.make_problem(nc, npts * n_gpus, nobs * n_gpus, seed=synth.CONFIG_SEEDS["C2"], hard=True)
         label = "C2 food-video shape: 200 cameras, 50k points, 1M observations" + (
             f" per GPU x {n_gpus} (points and observations scaled, cameras replicated)" if n_gpus > 1 else "")
-        return prob, label, "weak"
+        return prob, label, "weak", "C2"
+    if name == "auto":
+        name = "C4"
     prob = synth.make_config(name, hard=True)
     nc, npts, nobs = prob.sizes
-    return prob, f"{name}: {nc} cameras, {npts} points, {nobs} observations", "strong"
+    return prob, f"{name} (BASELINE configs[{int(name[1]) - 1}]): {nc} cameras, {npts} points, {nobs} observations", "strong", name
 
 
 class ClockSampler:
@@ -108,57 +115,101 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_sample(scale=None):
-    """The reference's CPU path on a bounded sample: C2 scaled down (all 200 cameras kept, points
-    and observations x scale), full solve with the reference's least_squares arguments."""
+REF_SAMPLE_SCALE = {"C1": 1.0, "C2": 0.03, "C3": 0.05, "C4": 0.006, "C5": 0.0015}
+REF_SAMPLE_ARC = {"C1": False, "C2": False, "C3": True, "C4": True, "C5": True}
+
+
+def full_size_reference(cfg):
+    """Wall time of the UNMODIFIED reference at full size, measured once in the build container
+    (tests/golden/make_golden_full.py) and committed with the golden trajectory."""
+    path = os.path.join(ROOT, "tests", "golden", cfg.lower() + ".npz")
+    try:
+        g = np.load(path)
+        nobs, nit, wall = int(g["sizes"][2]), len(g["ref_costs"]) - 1, float(g["ref_wall_s"])
+        return {"config": cfg, "wall_s": wall, "lm_iterations": nit, "value": nobs * nit / wall, "unit": UNIT,
+                "source": f"tests/golden/{cfg.lower()}.npz (unmodified /root/reference/bundleAdjuster.adjustPoints, build-container CPU)"}
+    except Exception:
+        return None
+
+
+def cpu_reference_sample(cfg="C4", scale=None):
+    """The reference's CPU path on a bounded sample of the workload: the config scaled down (all cameras kept,
+    points and observations x scale), full solve with the reference's least_squares arguments.  Runs the unmodified
+    reference module when /root/reference is present (build container), else its restatement in oracle/."""
     from threadpoolctl import threadpool_info
     from meatmodeler_b200 import synth
-    from oracle import ba_oracle as ba        # CPU baseline leg: the one place bench.py runs oracle/
 
-    scale = 0.03 if scale is None else scale
-    prob = synth.make_config("C2", hard=True, scale=scale)
+    scale = REF_SAMPLE_SCALE[cfg] if scale is None else scale
+    prob = synth.make_config(cfg, hard=True, scale=scale, arc=REF_SAMPLE_ARC[cfg])
     ext, K, pts, uv, fi, pi = prob.args()
-    rec = []
-    t0 = time.perf_counter()
-    res = ba.solve_reference_path(ext, K, pts, uv, fi, pi, record=rec)
-    wall = time.perf_counter() - t0
-    nit = len(rec)
+    ref_dir = "/root/reference"
+    kind = "port"
+    if os.path.exists(os.path.join(ref_dir, "bundleAdjuster.py")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_reference_bundleAdjuster", os.path.join(ref_dir, "bundleAdjuster.py"))
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        kind = "reference"
+        sink = io.StringIO()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(sink):
+            ref.adjustPoints(ext, K, pts, uv, fi, pi)
+        wall = time.perf_counter() - t0
+        rows = [ln for ln in sink.getvalue().splitlines() if ln.strip() and ln.split()[0].isdigit()]
+        nit = max(len(rows) - 1, 1)                      # scipy's verbose=2 table: one row per iterate
+        nfev = int(rows[-1].split()[1]) if rows else -1
+        cost = float(rows[-1].split()[2]) if rows else float("nan")
+    else:
+        from oracle import ba_oracle as ba        # CPU baseline leg: the one place bench.py runs oracle/
+        rec = []
+        t0 = time.perf_counter()
+        res = ba.solve_reference_path(ext, K, pts, uv, fi, pi, record=rec)
+        wall = time.perf_counter() - t0
+        nit, nfev, cost = len(rec), int(res.nfev), float(res.cost)
     threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    return {"value": len(uv) * nit / wall, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"C2 scaled x{scale}: {prob.sizes[0]} cameras, {prob.sizes[1]} points, {prob.sizes[2]} observations, "
-                      f"{nit} LM iterations (nfev {res.nfev}) in {wall:.2f} s; scipy TRF+LSMR with 2-point sparse finite "
-                      f"differences, numpy/scipy effectively single-threaded (BLAS threads available: {threads}, "
-                      f"host cpus: {os.cpu_count()})",
-            "wall_s": wall, "lm_iterations": nit, "cost": float(res.cost), "n_obs": len(uv)}
+    out = {"value": len(uv) * nit / wall, "unit": UNIT, "cores": 1, "kind": kind,
+           "sample": f"{cfg} scaled x{scale}" + (" (an arc of the camera ring, the config's observations per camera)"
+                                                   if REF_SAMPLE_ARC[cfg] else " (all cameras kept)") +
+                     f": {prob.sizes[0]} cameras, {prob.sizes[1]} points, {prob.sizes[2]} observations, "
+                     f"{nit} LM iterations (nfev {nfev}) in {wall:.2f} s; scipy TRF+LSMR with 2-point sparse finite differences; "
+                     f"numpy elementwise + scipy sparse are single-threaded: 1 effective core (BLAS threads available: {threads}, "
+                     f"host cpus: {os.cpu_count()})",
+           "wall_s": wall, "lm_iterations": nit, "cost": cost, "n_obs": len(uv)}
+    full = full_size_reference(cfg)
+    if full:
+        out["full_size"] = full
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    prob, label, scaling = workload(args.config, args.gpus) if args.config != "auto" else (None, None, "weak")
-    if label is None:
-        label = "C2 food-video shape: 200 cameras, 50k points, 1M observations" + (
-            f" per GPU x {args.gpus} (points and observations scaled, cameras replicated)" if args.gpus > 1 else "")
-    del prob
+    from meatmodeler_b200 import synth
+    cfg = "C2" if args.weak else ("C4" if args.config == "auto" else args.config)
+    nc, npts, nobs = synth.CONFIGS[cfg]
+    label = (f"{cfg} (BASELINE configs[{int(cfg[1]) - 1}]): {nc} cameras, {npts} points, {nobs} observations" if not args.weak else
+             "C2 food-video shape: 200 cameras, 50k points, 1M observations" + (
+                 f" per GPU x {args.gpus} (points and observations scaled, cameras replicated)" if args.gpus > 1 else ""))
     samples = []
     for i in range(args.warmup + args.steps):
-        s = cpu_reference_sample(scale=args.ref_scale)
+        s = cpu_reference_sample(cfg, scale=args.ref_scale)
         if i >= args.warmup:
             samples.append(s)
     wall = sum(s["wall_s"] for s in samples)
     its = sum(s["lm_iterations"] for s in samples)
-    nobs = samples[0]["n_obs"]
-    value = nobs * its / wall
+    nobs_s = samples[0]["n_obs"]
+    value = nobs_s * its / wall
     base = dict(samples[-1])
     base["value"] = value
     for k in ("wall_s", "lm_iterations", "cost", "n_obs"):
         base.pop(k, None)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * wall / len(samples), "higher_is_better": True, "scaling": scaling,
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": label, "timed_on": "bounded CPU sample of the workload, see cpu_baseline.sample"},
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / len(samples), "higher_is_better": True,
+        "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": label, "timed_on": "bounded CPU sample of the workload (cpu_baseline.sample); the full-size wall "
+                                                  "time of the unmodified reference is cpu_baseline.full_size"},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -177,12 +228,196 @@ def algorithmic_bytes(kernel, nc, npts, nobs, nnz_up=0):
     }[kernel]
 
 
-def run_mmba(args):
+def measure(args, ctx, prob, label, scaling, cfg, clocks=None):
+    """Device-resident timing, per-kernel profile and end-to-end timing of one workload; returns the fields of the
+    JSON line that depend on the workload."""
     import torch
-    import torch.distributed as dist
 
     from meatmodeler_b200 import _capi
     from meatmodeler_b200 import bundleAdjuster as mm
+
+    rank, world, local = ctx["rank"], ctx["world"], ctx["local"]
+    barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
+    ext, K, pts, uv, fi, pi = prob.args()
+    nc, npts, nobs = prob.sizes
+    x0 = np.hstack((mm.frameParameters(ext), pts.reshape(-1)))
+    schur_mode = {"auto": _capi.SCHUR_AUTO, "implicit": _capi.SCHUR_IMPLICIT, "explicit": _capi.SCHUR_EXPLICIT}[args.schur]
+    opts = mm._dist_options()
+    opts.setdefault("device", local)
+    opts["schur_mode"] = schur_mode
+    eng = _capi.Engine(**opts)
+    eng.set_problem(nc, npts, K, fi, pi, uv)          # first call: buffers are allocated
+    barrier()
+    t0 = time.perf_counter()
+    eng.set_problem(nc, npts, K, fi, pi, uv)          # steady state: staged upload + device plan
+    setup_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    shard = eng.shard()
+    eng.set_x(x0)
+
+    # ---- device-resident timing: W warm-up + K timed solves -----------------------------------
+    for _ in range(args.warmup):
+        eng.solve_resident()
+    barrier()
+    dev_ms, its, pcg, launches = 0.0, 0, 0, 0
+    with (clocks if clocks is not None else contextlib.nullcontext()):
+        wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = eng.solve_resident()
+            dev_ms += r.solve_ms
+            its += r.nit
+            pcg += r.pcg_iterations
+            launches += sum(v["launches"] for k, v in eng.profile().items() if k != "allreduce")
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - wall0)
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+    value = nobs * its / (dev_ms * 1e-3)
+    final_cost, nit_per_step, nfev = r.cost, r.nit, r.nfev
+    pcg_rtol, pcg_atol, pcg_ktol = eng.options.pcg_rtol, eng.options.pcg_atol, eng.options.pcg_ktol
+
+    # ---- sharded solve == single-GPU solve (rank 0 solves the whole problem on its own GPU) ------------------
+    sharded_vs_single = None
+    if world > 1:
+        ok = 1
+        if rank == 0:
+            with _capi.Engine(device=local, schur_mode=schur_mode) as e1:
+                e1.set_problem(nc, npts, K, fi, pi, uv)
+                e1.set_x(x0)
+                r1 = e1.solve_resident()
+            rel = abs(r1.cost - final_cost) / r1.cost
+            sharded_vs_single = {"single_gpu_cost": r1.cost, "sharded_cost": final_cost, "rel_cost_diff": rel,
+                                 "nfev": [int(nfev), int(r1.nfev)], "status": [int(r.status), int(r1.status)],
+                                 "single_gpu_ms": r1.solve_ms, "bar": 1e-6}
+            ok = int(rel <= 1e-6 and nfev == r1.nfev and r.status == r1.status)
+        t = torch.tensor([ok], device="cuda")
+        torch.distributed.broadcast(t, src=0)
+        if not t.item():
+            raise SystemExit(f"sharded solve does not reproduce the single-GPU solve: {sharded_vs_single}")
+
+    # ---- per-kernel durations: one extra step with every launch bracketed by CUDA events --------
+    eng.close()
+    opts_p = mm._dist_options()          # a fresh ncclUniqueId: one id initialises one communicator
+    opts_p.setdefault("device", local)
+    opts_p["profile"] = 1
+    opts_p["schur_mode"] = schur_mode
+    engp = _capi.Engine(**opts_p)
+    engp.set_problem(nc, npts, K, fi, pi, uv)
+    engp.set_x(x0)
+    engp.solve_resident()
+    rp = engp.solve_resident()
+    prof = engp.profile()
+    explicit = prof["schur_pcg"]["launches"] > 0
+    pat = engp.rcm_pattern() if explicit else None
+    ll_rtt_us = engp.bench_kernel(x0, 102, 2000) * 1e3 if explicit else None     # LL-line round trip between two far CTAs
+    engp.close()
+    peak, peak_kind = measured_peak()
+    n_obs_local, n_pts_local = shard["n_obs_local"], shard["n_points_local"]
+    kernels = {}
+    nnz_up = len(pat["up_cols"]) if pat else 0
+    nnz_full = pat["nnz_full"] if pat else 0
+    total_pairs = pat["total_pairs"] if pat else 0
+    for name in ("build", "schur_build", "schur_matvec", "schur_rhs", "backsub", "jv", "resid"):
+        p = prof[name]
+        if p["launches"]:
+            avg_ms = p["ms"] / p["launches"]
+            b = algorithmic_bytes(name, nc, n_pts_local, n_obs_local, nnz_up)
+            kernels[name] = {"launches_per_step": p["launches"], "avg_ms": avg_ms, "share_of_step": p["ms"] / rp.solve_ms,
+                             "algorithmic_bytes": b, "gbs": b / (avg_ms * 1e-3) / 1e9, "frac": b / (avg_ms * 1e-3) / 1e9 / peak}
+    if explicit:
+        # The PCG on the explicit, shared-memory / L2-resident reduced camera matrix: one cooperative launch per outer
+        # iteration.  Its HBM traffic is the matrix once per launch (the figure below, a tiny fraction of peak by
+        # construction); what bounds it is the latency of ONE grid-wide exchange of self-validating lines through L2
+        # per PCG iteration: latency_model = half a measured LL round trip between two far CTAs + the block-sparse
+        # product at the nominal FP64 rate.
+        p = prof["schur_pcg"]
+        its_p = max(int(rp.pcg_iterations), 1)
+        avg_ms = p["ms"] / p["launches"]
+        b = 288 * nnz_full + 2 * 48 * nc + 168 * nc
+        us_it = 1e3 * p["ms"] / its_p
+        product_us = 36.0 * nnz_full / max(pat["n_ctas"], 1) / 64.0 / 1965.0
+        model_us = 0.5 * ll_rtt_us + product_us
+        kernels["schur_pcg"] = {"launches_per_step": p["launches"], "avg_ms": avg_ms, "share_of_step": p["ms"] / rp.solve_ms,
+                                "algorithmic_bytes": b, "gbs": b / (avg_ms * 1e-3) / 1e9, "frac": b / (avg_ms * 1e-3) / 1e9 / peak,
+                                "pcg_iterations_per_step": int(rp.pcg_iterations), "us_per_pcg_iteration": us_it,
+                                "matrix_bytes": 288 * nnz_full, "blocks_full": nnz_full, "blocks_upper": nnz_up,
+                                "ctas": pat["n_ctas"], "cameras_per_cta": pat["cpc"],
+                                "latency_model": {"ll_round_trip_us": ll_rtt_us, "product_us_at_nominal_fp64": product_us,
+                                                  "model_us_per_iteration": model_us, "achieved_us_per_iteration": us_it,
+                                                  "frac": model_us / us_it,
+                                                  "bound": "one grid-wide exchange through L2 per PCG iteration (latency), not HBM"}}
+    dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{dom}:{cfg}:{args.gpus}")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"], "avg_launch_ms": kernels[dom]["avg_ms"],
+                "share_of_step": kernels[dom]["share_of_step"],
+                "how": "CUDA events around every launch on the engine's stream during one extra, identical step "
+                       "(profile=1); the timed steps carry no per-launch events; the dominant kernel is the class with the "
+                       "largest share of the step, the PCG kernel included",
+                "kernels": kernels,
+                "other_classes_ms_per_step": {k: {"launches": prof[k]["launches"], "ms": prof[k]["ms"]}
+                                              for k in ("vec", "allreduce", "cam_prep", "point_invert")},
+                "profiled_step_ms": rp.solve_ms}
+    if dom == "schur_pcg":
+        roofline["note"] = ("the dominant kernel is the on-chip PCG: latency-bound, see kernels.schur_pcg.latency_model; its HBM "
+                            "figure (the matrix read once per launch) is a tiny fraction of peak by construction")
+    if explicit and "schur_build" in kernels:
+        # The S-build pass streams J once (HBM figure above) and evaluates 108 DFMA per observation pair of a point
+        kb = kernels["schur_build"]
+        flops = 2.0 * 108.0 * total_pairs * (n_obs_local / max(nobs, 1))
+        kb["fp64"] = {"algorithmic_dfma": flops / 2, "achieved_tflops": flops / (kb["avg_ms"] * 1e-3) / 1e12,
+                      "nominal_peak_tflops": 37.2, "frac_of_nominal": flops / (kb["avg_ms"] * 1e-3) / 1e12 / 37.2,
+                      "peak_source": "148 SMs x 64 DFMA/clk x 2 x 1.965 GHz (vector FP64, nominal)"}
+
+    # ---- end to end through the drop-in adjustPoints with host buffers ---------------------------
+    e2e_steps = max(2, min(args.steps, 5))
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        mm.adjustPoints(ext, K, pts, uv, fi, pi)        # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    e2e_its = 0
+    for _ in range(e2e_steps):
+        with contextlib.redirect_stdout(sink):
+            out_pts, out_ext = mm.adjustPoints(ext, K, pts, uv, fi, pi)
+        e2e_its += mm.last_result.nit
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    mm.release()
+    n_total = 6 * nc + 3 * npts
+    chunk = nobs * (rank + 1) // world - nobs * rank // world
+    h2d = 24 * chunk + 8 * n_total          # int32 camera + point index and the f64 pixel of this rank's chunk; x
+    d2h = 8 * n_total
+    e2e = {"value": nobs * e2e_its / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+           "includes": "frameParameters + packing, staged upload of this rank's chunk of the index / pixel arrays, device-side "
+                       "tile plan and block pattern" + (", all-to-all of the observations over NVLink" if world > 1 else "") +
+                       ", H2D of x, solve, D2H of x, reformatPointResult"}
+    return {
+        "value": value, "ms_per_step": dev_ms / args.steps, "scaling": scaling,
+        "config": {"workload": label, "cameras": nc, "points": npts, "observations": nobs,
+                   "init": "hard (points sigma 0.15, tvec sigma 0.1), 0.5 px noise, windowed visibility",
+                   "l2": f"working set {(18 + 2 + 2 + 1) * 8 * n_obs_local / 1e6:.0f} MB per GPU streamed per pass "
+                         f"(> 126 MB L2)" if n_obs_local * 184 > 126e6 else "working set fits L2 (no flush)",
+                   "ftol": 1e-4, "pcg_rtol": pcg_rtol, "pcg_atol": pcg_atol, "pcg_ktol": pcg_ktol,
+                   "schur": ("explicit reduced camera matrix + one-kernel PCG" if explicit else
+                             "implicit (one streaming pass over J per PCG iteration)")},
+        "lm_iterations_per_step": nit_per_step, "lm_iterations_per_s": its / (dev_ms * 1e-3),
+        "pcg_iterations_per_step": pcg / args.steps, "final_cost": final_cost,
+        "wall_ms_per_step": wall_ms / args.steps, "setup_ms": setup_ms,
+        "gpu_launches": launches, "e2e": e2e, "roofline": roofline,
+        **({"sharded_vs_single": sharded_vs_single} if sharded_vs_single else {}),
+    }
+
+
+def run_mmba(args):
+    import torch
+    import torch.distributed as dist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,151 +443,38 @@ def run_mmba(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    prob, label, scaling = workload(args.config, args.gpus)
-    ext, K, pts, uv, fi, pi = prob.args()
-    nc, npts, nobs = prob.sizes
-    x0 = np.hstack((mm.frameParameters(ext), pts.reshape(-1)))
-
-    schur_mode = {"auto": _capi.SCHUR_AUTO, "implicit": _capi.SCHUR_IMPLICIT, "explicit": _capi.SCHUR_EXPLICIT}[args.schur]
-    opts = mm._dist_options()
-    opts.setdefault("device", local)
-    opts["schur_mode"] = schur_mode
-    eng = _capi.Engine(**opts)
-    t0 = time.perf_counter()
-    eng.set_problem(nc, npts, K, fi, pi, uv)
-    setup_ms = 1e3 * (time.perf_counter() - t0)
-    shard = eng.shard()
-    eng.set_x(x0)
-
-    # ---- device-resident timing: W warm-up + K timed solves -----------------------------------
-    for _ in range(args.warmup):
-        eng.solve_resident()
-    barrier()
-    dev_ms, its, pcg, launches = 0.0, 0, 0, 0
-    with ClockSampler(local) as clocks:
-        wall0 = time.perf_counter()
-        for _ in range(args.steps):
-            r = eng.solve_resident()
-            dev_ms += r.solve_ms
-            its += r.nit
-            pcg += r.pcg_iterations
-            launches += sum(v["launches"] for k, v in eng.profile().items() if k != "allreduce")
-        barrier()
-        wall_ms = 1e3 * (time.perf_counter() - wall0)
-    dev_ms = max_over_ranks(dev_ms)
-    wall_ms = max_over_ranks(wall_ms)
-    value = nobs * its / (dev_ms * 1e-3)
-    log = eng.log()
-    final_cost, nit_per_step = r.cost, r.nit
-
-    # ---- per-kernel durations: one extra step with every launch bracketed by CUDA events --------
-    eng.close()
-    opts_p = mm._dist_options()          # a fresh ncclUniqueId: one id initialises one communicator
-    opts_p.setdefault("device", local)
-    opts_p["profile"] = 1
-    opts_p["schur_mode"] = schur_mode
-    engp = _capi.Engine(**opts_p)
-    engp.set_problem(nc, npts, K, fi, pi, uv)
-    engp.set_x(x0)
-    engp.solve_resident()
-    rp = engp.solve_resident()
-    prof = engp.profile()
-    engp.close()
-    peak, peak_kind = measured_peak()
-    n_obs_local, n_pts_local = shard["n_obs_local"], shard["n_points_local"]
-    kernels = {}
-    explicit = prof["schur_pcg"]["launches"] > 0
-    nnz_up = nnz_full = total_pairs = 0
-    if explicit:
-        _, up_cols, nnz_full, total_pairs = _capi.host_rcm_pattern(nc, npts, fi, pi)
-        nnz_up = len(up_cols)
-    for name in ("build", "schur_build", "schur_matvec", "schur_rhs", "backsub", "jv", "resid"):
-        p = prof[name]
-        if p["launches"]:
-            avg_ms = p["ms"] / p["launches"]
-            b = algorithmic_bytes(name, nc, n_pts_local, n_obs_local, nnz_up)
-            kernels[name] = {"launches_per_step": p["launches"], "avg_ms": avg_ms, "share_of_step": p["ms"] / rp.solve_ms,
-                             "algorithmic_bytes": b, "gbs": b / (avg_ms * 1e-3) / 1e9, "frac": b / (avg_ms * 1e-3) / 1e9 / peak}
-    dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"{dom}:{args.config}:{args.gpus}")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
-                "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"], "avg_launch_ms": kernels[dom]["avg_ms"],
-                "how": "CUDA events around every launch on the engine's stream during one extra, identical step "
-                       "(profile=1); the timed steps carry no per-launch events",
-                "kernels": kernels,
-                "other_classes_ms_per_step": {k: {"launches": prof[k]["launches"], "ms": prof[k]["ms"]}
-                                              for k in ("vec", "allreduce", "cam_prep", "point_invert")},
-                "profiled_step_ms": rp.solve_ms}
-    if explicit and "schur_build" in kernels:
-        # The S-build pass streams J once (HBM figure above) but is bound by FP64 issue: 108 DFMA per observation pair
-        # of a point (sum over points of L (L + 1) / 2 pairs; this rank's share for a sharded solve).
-        kb = kernels["schur_build"]
-        flops = 2.0 * 108.0 * total_pairs * (n_obs_local / max(nobs, 1))
-        kb["fp64"] = {"algorithmic_dfma": flops / 2, "achieved_tflops": flops / (kb["avg_ms"] * 1e-3) / 1e12,
-                      "nominal_peak_tflops": 37.2, "frac_of_nominal": flops / (kb["avg_ms"] * 1e-3) / 1e12 / 37.2,
-                      "peak_source": "148 SMs x 64 DFMA/clk x 2 x 1.965 GHz (vector FP64, nominal)"}
-        if dom == "schur_build":
-            roofline["note"] = ("the dominant streaming kernel (S-build) is FP64-issue bound, not HBM bound: see "
-                                "kernels.schur_build.fp64; the HBM-bound passes are build / backsub / jv / resid")
-    if explicit:
-        # The PCG on the explicit, L2/L1-resident reduced camera matrix is one cooperative launch per outer
-        # iteration: no HBM stream, two grid-wide exchanges (self-validating lines through L2) per PCG iteration.  It
-        # has no HBM roofline; what bounds it is the L2 round-trip latency, reported as time per PCG iteration.
-        p = prof["schur_pcg"]
-        its_p = max(int(rp.pcg_iterations), 1)
-        roofline["schur_pcg_on_chip"] = {
-            "launches_per_step": p["launches"], "ms_per_step": p["ms"], "share_of_step": p["ms"] / rp.solve_ms,
-            "pcg_iterations_per_step": int(rp.pcg_iterations), "us_per_pcg_iteration": 1e3 * p["ms"] / its_p,
-            "matrix_bytes": 288 * nnz_full, "blocks_full": nnz_full, "blocks_upper": nnz_up,
-            "l2_gbs": 288 * nnz_full * its_p / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else None,
-            "bound": "latency of two grid-wide exchanges through L2 per iteration, not HBM"}
-
-    # ---- end to end through the drop-in adjustPoints with host buffers ---------------------------
-    e2e_steps = max(2, min(args.steps, 5))
-    sink = io.StringIO()
-    with contextlib.redirect_stdout(sink):
-        mm.adjustPoints(ext, K, pts, uv, fi, pi)        # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    e2e_its = 0
-    for _ in range(e2e_steps):
-        with contextlib.redirect_stdout(sink):
-            out_pts, out_ext = mm.adjustPoints(ext, K, pts, uv, fi, pi)
-        e2e_its += mm.last_result.nit
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    ns = shard["n_tiles"] * 256
-    h2d = 16 * ns + 8 * ns + 16 * shard["n_tiles"] + 8 * (6 * nc + 3 * n_pts_local)
-    d2h = 8 * (6 * nc + 3 * n_pts_local)
-    e2e = {"value": nobs * e2e_its / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
-           "includes": "frameParameters, tile plan (host), all H2D copies, solve, D2H of x, reformatPointResult"}
-
+    ctx = dict(rank=rank, world=world, local=local, barrier=barrier, max_over_ranks=max_over_ranks)
+    prob, label, scaling, cfg = workload(args.config, args.gpus, args.weak)
+    clocks = ClockSampler(local)
+    m = measure(args, ctx, prob, label, scaling, cfg, clocks)
+    del prob
+    also = {}
+    if world == 1 and args.config == "auto" and not args.weak and not args.no_also:
+        # BASELINE configs[1] beside the headline workload (same code path, same measurements)
+        prob2, label2, scaling2, cfg2 = workload("C2", 1)
+        m2 = measure(args, ctx, prob2, label2, scaling2, cfg2)
+        also["C2"] = {k: m2[k] for k in ("value", "ms_per_step", "config", "lm_iterations_per_step", "pcg_iterations_per_step",
+                                         "final_cost", "setup_ms", "gpu_launches", "e2e")}
+        also["C2"]["roofline"] = {k: m2["roofline"][k] for k in ("kernel", "achieved", "peak", "frac", "share_of_step", "kernels")}
+        del prob2
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": label, "cameras": nc, "points": npts, "observations": nobs,
-                       "init": "hard (points sigma 0.15, tvec sigma 0.1), 0.5 px noise, windowed visibility",
-                       "l2": f"working set {(18 + 2 + 2 + 1) * 8 * n_obs_local / 1e6:.0f} MB per GPU streamed per pass "
-                             f"(> 126 MB L2)" if n_obs_local * 184 > 126e6 else "working set fits L2 (no flush)",
-                       "ftol": 1e-4, "pcg_rtol": eng.options.pcg_rtol,
-                       "schur": ("explicit reduced camera matrix + one-kernel PCG" if explicit else
-                                 "implicit (one streaming pass over J per PCG iteration)")},
-            "lm_iterations_per_step": nit_per_step, "lm_iterations_per_s": its / (dev_ms * 1e-3),
-            "pcg_iterations_per_step": pcg / args.steps, "final_cost": final_cost,
-            "wall_ms_per_step": wall_ms / args.steps, "setup_ms": setup_ms,
-            "gpu_launches": launches, "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": m["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": m["config"],
         }
+        for k in ("lm_iterations_per_step", "lm_iterations_per_s", "pcg_iterations_per_step", "final_cost", "wall_ms_per_step",
+                  "setup_ms", "gpu_launches"):
+            line[k] = m[k]
+        line["clocks"] = clocks.summary()
+        line["e2e"] = m["e2e"]
+        line["roofline"] = m["roofline"]
+        if "sharded_vs_single" in m:
+            line["sharded_vs_single"] = m["sharded_vs_single"]
+        if also:
+            line["also"] = also
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = {k: v for k, v in cpu_reference_sample(scale=args.ref_scale).items()
+            line["cpu_baseline"] = {k: v for k, v in cpu_reference_sample(cfg, scale=args.ref_scale).items()
                                     if k not in ("wall_s", "lm_iterations", "cost", "n_obs")}
         print(json.dumps(line))
     if world > 1:
@@ -363,12 +485,14 @@ def run_mmba(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mmba", choices=["mmba", "reference"])
     ap.add_argument("--config", default="auto", choices=["auto", "C1", "C2", "C3", "C4", "C5"])
-    ap.add_argument("--ref-scale", type=float, default=None, help="size of the CPU sample relative to C2")
+    ap.add_argument("--ref-scale", type=float, default=None, help="size of the CPU sample relative to the config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the second (C2) workload of the default N=1 run")
+    ap.add_argument("--weak", action="store_true", help="round-1 workload: C2 shape per GPU (weak scaling)")
     ap.add_argument("--schur", default="auto", choices=["auto", "implicit", "explicit"],
                     help="reduced camera system: explicit block-sparse matrix or implicit products (auto: library rule)")
     args = ap.parse_args()

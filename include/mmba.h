@@ -212,6 +212,14 @@ int mmba_bench_kernel(mmba_handle* h, const double* x, int kernel_class, int ite
 int mmba_triangulate(int device, int64_t n_frames, const double* projections, int64_t n, const int64_t* f1,
                      const int64_t* f2, const double* uv1, const double* uv2, double* points, double* kernel_ms);
 
+/* ---- rotate / project ---------------------------------------------------------------------------
+ * replaces: rotate(points, rot_vecs) (bundleAdjuster.py:7-28: Rodrigues rotation of row i by rot_vecs[i]; theta = 0 leaves
+ * the point unchanged) and project(points, frame_params, camera_matrix) (bundleAdjuster.py:31-52: rotate, translate by
+ * frame_params[i, 3:6], multiply by K, divide by depth).  n rows; frame_params has param_stride >= 6 doubles per row. */
+int mmba_rotate(int device, int64_t n, const double* points, const double* rot_vecs, double* out /* n x 3 */);
+int mmba_project(int device, int64_t n, const double* points, const double* frame_params, int64_t param_stride,
+                 const double K[9], double* out /* n x 2 */);
+
 /* ---- host-only functions (no GPU needed; covered by the CPU test-suite) --------------------- */
 /* replaces: solve_trust_region_2d (common.py:171-219); B = [b00, b01, b11] */
 int mmba_host_tr2d(const double B[3], const double g[2], double delta, double p[2], int* newton);

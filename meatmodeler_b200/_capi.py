@@ -82,6 +82,8 @@ SIGNATURES = {
     "mmba_eval_jnorm2": (C.c_int, [_H, _f64, _f64, C.POINTER(C.c_double)]),
     "mmba_bench_kernel": (C.c_int, [_H, _f64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "mmba_triangulate": (C.c_int, [C.c_int, C.c_int64, _f64, C.c_int64, _i64, _i64, _f64, _f64, _f64, C.POINTER(C.c_double)]),
+    "mmba_rotate": (C.c_int, [C.c_int, C.c_int64, _f64, _f64, _f64]),
+    "mmba_project": (C.c_int, [C.c_int, C.c_int64, _f64, _f64, C.c_int64, _f64, _f64]),
     "mmba_host_tr2d": (C.c_int, [C.POINTER(C.c_double * 3), C.POINTER(C.c_double * 2), C.c_double,
                                  C.POINTER(C.c_double * 2), C.POINTER(C.c_int)]),
     "mmba_host_min_quadratic_1d": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_double,
@@ -355,6 +357,32 @@ def triangulate(projections, f1, f2, uv1, uv2, device=0, return_ms=False):
                                   uv2.reshape(-1) if n else np.zeros(2), out.reshape(-1), C.byref(ms)))
     out = out[:n]
     return (out, ms.value) if return_ms else out
+
+
+def rotate(points, rot_vecs, device=0):
+    """Row-wise Rodrigues rotation on the GPU (bundleAdjuster.py:7-28)."""
+    pts = _c(points, np.float64).reshape(-1, 3)
+    rv = _c(rot_vecs, np.float64).reshape(-1, 3)
+    if len(pts) != len(rv):
+        raise ValueError("points and rot_vecs must have one row per point")
+    out = np.empty((max(len(pts), 1), 3))
+    _check(lib().mmba_rotate(int(device), len(pts), pts.reshape(-1) if len(pts) else np.zeros(3),
+                             rv.reshape(-1) if len(pts) else np.zeros(3), out.reshape(-1)))
+    return out[:len(pts)]
+
+
+def project(points, frame_params, camera_matrix, device=0):
+    """Row-wise projection on the GPU (bundleAdjuster.py:31-52)."""
+    pts = _c(points, np.float64).reshape(-1, 3)
+    fp = _c(frame_params, np.float64)
+    fp = fp.reshape(len(pts), -1) if len(pts) else fp.reshape(0, 6)
+    if fp.shape[1] < 6:
+        raise ValueError("frame_params needs at least 6 columns (rvec | tvec)")
+    K = _c(camera_matrix, np.float64).reshape(9)
+    out = np.empty((max(len(pts), 1), 2))
+    _check(lib().mmba_project(int(device), len(pts), pts.reshape(-1) if len(pts) else np.zeros(3),
+                              fp.reshape(-1) if len(pts) else np.zeros(6), fp.shape[1], K, out.reshape(-1)))
+    return out[:len(pts)]
 
 
 # -- host-only helpers (no GPU) -------------------------------------------------------------------

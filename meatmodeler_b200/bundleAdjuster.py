@@ -45,8 +45,37 @@ _STATUS_MESSAGES = {
 
 
 class SolveResult(dict):
-    """Attribute-style result, the fields scipy's ``OptimizeResult`` carries for this call."""
-    __getattr__ = dict.__getitem__
+    """Attribute-style result, the fields scipy's ``OptimizeResult`` carries for this call (missing attributes raise
+    AttributeError, as OptimizeResult does, so that hasattr / getattr-with-default / copy / pickle behave)."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError as e:
+            raise AttributeError(name) from e
+
+    __setattr__ = dict.__setitem__
+    __delattr__ = dict.__delitem__
+
+    def __dir__(self):
+        return list(self.keys())
+
+
+def rotate(points, rot_vecs):
+    """Rodrigues rotation of ``points[i]`` by ``rot_vecs[i]`` (bundleAdjuster.py:7-28), on the GPU."""
+    return _capi.rotate(points, rot_vecs, device=_current_device())
+
+
+def project(points, frame_params, camera_matrix):
+    """Re-projection of ``points[i]`` with the parameters ``frame_params[i]`` (bundleAdjuster.py:31-52), on the GPU."""
+    return _capi.project(points, frame_params, camera_matrix, device=_current_device())
+
+
+def _current_device():
+    if _is_distributed():
+        import torch
+        return torch.cuda.current_device()
+    return 0
 
 
 # --------------------------------------------------------------------------------------------------
@@ -158,6 +187,10 @@ def _engine(camera_matrix, n_frames, n_points, frame_indices, point_indices, poi
     if unknown:
         raise TypeError(f"unknown option(s) {unknown}")
     key = None
+    if fixed:
+        # explicitly configured engines are cached too (one per configuration), so that repeated calls do not leak a
+        # device arena each; release() closes them
+        key = ("explicit", fixed.get("device", 0), fixed.get("rank", 0), fixed.get("nranks", 1), bytes(fixed.get("nccl_id", b"")))
     if single and not fixed:
         # pose-only problems are tiny: every rank solves them whole on its own GPU
         dev = 0
@@ -166,7 +199,7 @@ def _engine(camera_matrix, n_frames, n_points, frame_indices, point_indices, poi
             dev = torch.cuda.current_device()
         key = (dev, 0, 1)
         fixed = dict(device=dev) if key not in _ENGINES else {}
-    elif not fixed:
+    elif key is None:
         if _is_distributed():
             import torch
             key = (torch.cuda.current_device(), torch.distributed.get_rank(), torch.distributed.get_world_size())

@@ -1991,6 +1991,25 @@ int mmba_bench_kernel(mmba_handle* h, const double* x, int kernel_class, int ite
     Pj.cam1 = d.gh;
     Pj.ptB = d.gh + 6 * h->Nc;
     Pj.scal = d.scal;
+    if (kernel_class == 102) {
+        // LL-line round trip between the first and the last CTA of a device-filling grid (all CTAs co-resident)
+        if (!use_rcm(h)) return fail(h, MMBA_ERR_STATE, "bench_kernel: the reduced camera matrix is not formed explicitly");
+        LLLine* a = d.rcm_z;
+        LLLine* b = d.rcm_z + 64;
+        for (int pass = 0; pass < 2; ++pass) {
+            const int n = pass == 0 ? 16 : iters;
+            if (pass == 1) CU(cudaEventRecord(h->ev0, h->stream));
+            ll_pingpong_kernel<<<h->sm_count, 32, 0, h->stream>>>(a, b, n, h->rcm_seq);
+            h->rcm_seq += (unsigned)n + 2u;
+            if (pass == 1) CU(cudaEventRecord(h->ev1, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            CU(cudaGetLastError());
+        }
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *avg_ms = ms / iters;
+        return MMBA_OK;
+    }
     for (int pass = 0; pass < 2; ++pass) {
         const int n = pass == 0 ? 2 : iters;
         if (pass == 1) CU(cudaEventRecord(h->ev0, h->stream));
@@ -2094,6 +2113,54 @@ int mmba_triangulate(int device, int64_t n_frames, const double* projections, in
 #undef TRI
     cleanup();
     return MMBA_OK;
+}
+
+// ---- rotate / project (no handle: free functions on one device) ------------------------------------
+static int rows_op(int device, int64_t n, const double* pts, const double* params, int stride, const double* K, double* out, int out_cols) {
+    mmba_handle* h = nullptr;
+    if (n < 0 || (n > 0 && (!pts || !params || !out))) return fail(h, MMBA_ERR_ARG, "rotate/project: bad argument");
+    if (n == 0) return MMBA_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(h, MMBA_ERR_CUDA, "no CUDA device (libmmba has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    double *d_p = nullptr, *d_q = nullptr, *d_o = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_p);
+        cudaFree(d_q);
+        cudaFree(d_o);
+    };
+#define ROW(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            cleanup();                                                                             \
+            return fail(h, MMBA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+        }                                                                                          \
+    } while (0)
+    ROW(cudaMalloc(&d_p, n * 3 * sizeof(double)));
+    ROW(cudaMalloc(&d_q, n * stride * sizeof(double)));
+    ROW(cudaMalloc(&d_o, n * out_cols * sizeof(double)));
+    ROW(cudaMemcpy(d_p, pts, n * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    ROW(cudaMemcpy(d_q, params, n * stride * sizeof(double), cudaMemcpyHostToDevice));
+    if (K)
+        project_rows_kernel<<<cdiv(n, 256), 256>>>(d_p, d_q, stride, K[0], K[1], K[2], K[3], K[4], K[5], K[6], K[7], K[8], d_o, n);
+    else
+        rotate_rows_kernel<<<cdiv(n, 256), 256>>>(d_p, d_q, d_o, n);
+    ROW(cudaGetLastError());
+    ROW(cudaMemcpy(out, d_o, n * out_cols * sizeof(double), cudaMemcpyDeviceToHost));
+#undef ROW
+    cleanup();
+    return MMBA_OK;
+}
+
+int mmba_rotate(int device, int64_t n, const double* points, const double* rot_vecs, double* out) {
+    return rows_op(device, n, points, rot_vecs, 3, nullptr, out, 3);
+}
+
+int mmba_project(int device, int64_t n, const double* points, const double* frame_params, int64_t param_stride, const double K[9],
+                 double* out) {
+    if (!K || param_stride < 6) return fail(nullptr, MMBA_ERR_ARG, "project: null K or fewer than 6 parameters per row");
+    return rows_op(device, n, points, frame_params, (int)param_stride, K, out, 2);
 }
 
 // ---- host-only functions ------------------------------------------------------------------------

@@ -771,4 +771,28 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
     }
 }
 
+// Round trip of one self-validating line between two CTAs that sit far apart (first and last CTA of a grid that
+// fills the device): the latency unit of the PCG's grid-wide exchange (bench.py: latency model of rcm_pcg_kernel).
+__global__ void ll_pingpong_kernel(LLLine* a, LLLine* b, int iters, unsigned seq0) {
+    if (threadIdx.x != 0) return;
+    double v = 0.0;
+    if (blockIdx.x == 0) {
+        for (int i = 0; i < iters; ++i) {
+            const unsigned seq = seq0 + 1u + (unsigned)i;
+            ll_store(a, (double)i, seq);
+            const long long t0 = clock64();
+            while (!ll_try_load(b, seq, v))
+                if (clock64() - t0 > (1ll << 31)) return;
+        }
+    } else if (blockIdx.x == gridDim.x - 1) {
+        for (int i = 0; i < iters; ++i) {
+            const unsigned seq = seq0 + 1u + (unsigned)i;
+            const long long t0 = clock64();
+            while (!ll_try_load(a, seq, v))
+                if (clock64() - t0 > (1ll << 31)) return;
+            ll_store(b, v, seq);
+        }
+    }
+}
+
 }  // namespace mmba

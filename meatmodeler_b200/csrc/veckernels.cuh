@@ -813,4 +813,49 @@ __global__ void __launch_bounds__(256) stream_read_kernel(const double2* __restr
     if (acc == 1.2345e-300) out[0] = acc;   // never true: keeps the loads alive
 }
 
+// ---------------------------------------------------------------------------------------------
+// rotate / project as stand-alone row-wise kernels (bundleAdjuster.py:7-52): one thread per row, the
+// row's own rotation vector (no per-camera hoisting here: the reference passes one parameter row per point)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rodrigues_row(const double* __restrict__ X, const double* __restrict__ w, double (&Y)[3]) {
+    const double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    const double t = sqrt(t2);
+    if (!(t > 0.0)) {          // theta = 0: v = nan_to_num(0 / 0) = 0 -> the point itself (bundleAdjuster.py:19-28)
+        Y[0] = X[0];
+        Y[1] = X[1];
+        Y[2] = X[2];
+        return;
+    }
+    const double v0 = w[0] / t, v1 = w[1] / t, v2 = w[2] / t;
+    double s, c;
+    sincos(t, &s, &c);
+    const double dot = X[0] * v0 + X[1] * v1 + X[2] * v2;
+    const double c0 = v1 * X[2] - v2 * X[1], c1 = v2 * X[0] - v0 * X[2], c2 = v0 * X[1] - v1 * X[0];
+    Y[0] = c * X[0] + s * c0 + dot * (1.0 - c) * v0;
+    Y[1] = c * X[1] + s * c1 + dot * (1.0 - c) * v1;
+    Y[2] = c * X[2] + s * c2 + dot * (1.0 - c) * v2;
+}
+__global__ void rotate_rows_kernel(const double* __restrict__ pts, const double* __restrict__ rvec, double* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double Y[3];
+    rodrigues_row(pts + 3 * i, rvec + 3 * i, Y);
+    out[3 * i] = Y[0];
+    out[3 * i + 1] = Y[1];
+    out[3 * i + 2] = Y[2];
+}
+__global__ void project_rows_kernel(const double* __restrict__ pts, const double* __restrict__ params, int stride, double k0, double k1,
+                                    double k2, double k3, double k4, double k5, double k6, double k7, double k8,
+                                    double* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double Y[3];
+    const double* p = params + (int64_t)stride * i;
+    rodrigues_row(pts + 3 * i, p, Y);
+    const double C0 = Y[0] + p[3], C1 = Y[1] + p[4], C2 = Y[2] + p[5];
+    const double q0 = k0 * C0 + k1 * C1 + k2 * C2, q1 = k3 * C0 + k4 * C1 + k5 * C2, q2 = k6 * C0 + k7 * C1 + k8 * C2;
+    out[2 * i] = q0 / q2;
+    out[2 * i + 1] = q1 / q2;
+}
+
 }  // namespace mmba

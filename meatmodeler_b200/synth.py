@@ -62,18 +62,25 @@ def _project(ext, K, X, cam_idx, pt_idx):
 
 
 def make_problem(n_cams: int, n_points: int, n_obs: int, seed: int = 0, noise_px: float = 0.5,
-                 hard: bool = False, windowed: bool = True) -> Problem:
+                 hard: bool = False, windowed: bool = True, arc: int | None = None) -> Problem:
     """Build one synthetic problem.
 
     windowed=True: each track sees a contiguous window of ring neighbours (video-like);
     windowed=False: uniform-random camera subsets (the survey's stress variant).
     hard=True perturbs the initial guess more (points 0.15, tvec 0.1) so that >= 3 LM iterations run.
+    arc: use only the first ``arc`` cameras of the ``n_cams`` ring (same angular spacing, no wrap-around): a bounded
+    sample of a large config that keeps its geometry and its observations per camera.
     """
     if n_obs < 2 * n_points:
         raise ValueError("every point needs at least two observations")
     rng = np.random.default_rng(seed)
     K = np.array([[1000.0, 0, 640.0], [0, 1000.0, 360.0], [0, 0, 1.0]])
     ext = ring_cameras(n_cams)
+    if arc is not None:
+        if not windowed:
+            raise ValueError("arc needs windowed visibility")
+        ext = ext[:arc]
+        n_cams = arc
     X = rng.normal(0.0, 1.0, (n_points, 3))
 
     base = n_obs // n_points
@@ -83,7 +90,10 @@ def make_problem(n_cams: int, n_points: int, n_obs: int, seed: int = 0, noise_px
         raise ValueError("track length exceeds the number of cameras")
     pt_idx = np.repeat(np.arange(n_points, dtype=np.int64), lengths)
     offs = np.arange(n_obs, dtype=np.int64) - np.repeat(np.cumsum(lengths) - lengths, lengths)
-    if windowed:
+    if windowed and arc is not None:
+        start = rng.integers(n_cams - lengths.max() + 1, size=n_points)
+        cam_idx = np.repeat(start, lengths) + offs
+    elif windowed:
         start = rng.integers(n_cams, size=n_points)
         cam_idx = (np.repeat(start, lengths) + offs) % n_cams
         # frames inside a track in ascending keyframe order (track.py:12-18)
@@ -112,11 +122,16 @@ def make_problem(n_cams: int, n_points: int, n_obs: int, seed: int = 0, noise_px
     return Problem(ext0, K, X0.reshape(n_points, 1, 3), uv, cam_idx, pt_idx, ext, X)
 
 
-def make_config(name: str, hard: bool = True, windowed: bool = True, scale: float = 1.0) -> Problem:
-    """One of BASELINE.json's configs; ``scale`` < 1 shrinks points/observations proportionally
-    (cameras kept) for bounded CPU samples."""
+def make_config(name: str, hard: bool = True, windowed: bool = True, scale: float = 1.0, arc: bool = False) -> Problem:
+    """One of BASELINE.json's configs; ``scale`` < 1 shrinks points/observations proportionally for bounded CPU
+    samples: with ``arc=False`` all cameras are kept (fewer observations per camera), with ``arc=True`` the sample is
+    an arc of the camera ring with the config's own observations per camera (the choice for the many-camera configs,
+    where keeping every camera would leave most of them with a handful of observations)."""
     nc, npts, nobs = CONFIGS[name]
     if scale != 1.0:
         npts = max(2, int(round(npts * scale)))
         nobs = max(2 * npts, int(round(nobs * scale)))
+    if arc and scale != 1.0:
+        n_arc = min(nc, max(3 * (nobs // npts + 1), int(round(nc * scale))))
+        return make_problem(nc, npts, nobs, seed=CONFIG_SEEDS[name], hard=hard, windowed=True, arc=n_arc)
     return make_problem(nc, npts, nobs, seed=CONFIG_SEEDS[name], hard=hard, windowed=windowed)

@@ -9,13 +9,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--ref-scale", "0.002"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["higher_is_better"] is True and line["dtype"] == "f64"
     assert line["unit"] == "observations/s" and line["value"] > 0 and line["vs_baseline"] is None
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference module where /root/reference exists (build container), its restatement elsewhere
+    assert line["cpu_baseline"]["kind"] == ("reference" if os.path.exists("/root/reference/bundleAdjuster.py") else "port")
+    assert line["cpu_baseline"]["cores"] == 1 and line["scaling"] == "strong"
+    full = line["cpu_baseline"]["full_size"]       # full-size wall time of the unmodified reference (golden file)
+    assert full["config"] == "C4" and full["wall_s"] > 100 and full["value"] > 0
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
 

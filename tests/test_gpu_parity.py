@@ -58,6 +58,26 @@ def test_pointfun_dropin(small):
     assert np.abs(f - small["f64"]).max() <= 1e-9 * np.abs(small["uv"]).max()
 
 
+def test_rotate_project_dropin_vs_reference_golden(small):
+    """Module-level ``rotate`` / ``project`` of the drop-in (bundleAdjuster.py:7-52) on the GPU: the projections of the
+    golden problem minus the observed pixels are the reference's own pointFun output; rotate against the oracle,
+    including rows with a zero rotation vector (returned unchanged, exactly)."""
+    nc = len(small["ext"])
+    pts = small["pts"].reshape(-1, 3)[small["pi"]]
+    params = small["x0"][:6 * nc].reshape(nc, 6)[small["fi"]]
+    proj = mm.project(pts, params, small["K"])
+    assert proj.shape == (len(pts), 2)
+    scale = np.abs(small["uv"]).max()
+    assert np.abs((proj - small["uv"]).reshape(-1) - small["f64"]).max() <= 1e-9 * scale
+    rot = mm.rotate(pts, params[:, :3])
+    ref = ba.rotate(pts, params[:, :3])
+    assert np.abs(rot - ref).max() <= 1e-12 * np.abs(ref).max()
+    zero = np.linalg.norm(params[:, :3], axis=1) == 0
+    assert zero.any()
+    np.testing.assert_array_equal(rot[zero], pts[zero])
+    assert mm.project(np.zeros((0, 3)), np.zeros((0, 6)), small["K"]).shape == (0, 2)
+
+
 # ---- kernels against the oracle on seeded problems ---------------------------------------------
 
 PROBLEMS = {

@@ -6,7 +6,7 @@ import pytest
 
 from conftest import GOLDEN
 from meatmodeler_b200 import _capi
-from meatmodeler_b200 import processor as mp
+from meatmodeler_b200 import processor_ops as mp
 from oracle import processor_oracle as po       # checker only
 from oracle import triangulate_oracle as tri   # checker only
 
