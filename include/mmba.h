@@ -56,7 +56,8 @@ typedef struct mmba_options {
     double pcg_rtol;      /* relative residual stop of the reduced-system PCG */
     int32_t pcg_maxit;
     int32_t profile;      /* bit 0: bracket kernels with CUDA events (mmba_get_profile); bit 1: keep the residual history
-                             of every reduced-system PCG solve (mmba_get_pcg_history; read by mmba_set_problem) */
+                             of every reduced-system PCG solve (mmba_get_pcg_history; read by mmba_set_problem); bit 2:
+                             per-phase cycle counters inside the PCG and S-build kernels (mmba_get_phase_cycles) */
     uint8_t nccl_id[128]; /* ncclUniqueId bytes, same on all ranks (nranks > 1 only) */
     int32_t schur_mode;   /* MMBA_SCHUR_*: how the PCG applies the reduced camera system (read by mmba_set_problem) */
     int32_t reserved;
@@ -160,6 +161,9 @@ int mmba_get_x(mmba_handle* h, double* x);
 
 int mmba_get_log(const mmba_handle* h, mmba_iter_log* out, int capacity); /* returns row count */
 int mmba_get_profile(const mmba_handle* h, int64_t launches[MMBA_K_COUNT], double ms[MMBA_K_COUNT]);
+/* diagnostics (options.profile bit 2): cycles one CTA spent in each phase of the instrumented kernels since the last
+ * reset; [0..7] PCG iteration phases, [16..31] S-build tile phases */
+int mmba_get_phase_cycles(mmba_handle* h, int64_t out[64], int reset);
 /* residual history of the reduced-system PCG solves of the last mmba_solve* call (explicit Schur path, handles whose
  * options had profile bit 1 set at mmba_set_problem): outer_iteration < 0 returns the number of inner solves recorded;
  * otherwise the pairs (||r_k||^2, r_k . Pinv r_k), k = 0 .. iterations, are copied to out (capacity doubles) and

@@ -10,7 +10,8 @@ import os
 
 import numpy as np
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmmba.so")
+# MMBA_LIB: another build of the same library (e.g. the -DMMBA_PHASE_TIMING diagnostics build)
+_LIB_PATH = os.environ.get("MMBA_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmmba.so")
 
 K_NAMES = ("cam_prep", "build", "resid", "point_invert", "schur_rhs", "schur_matvec", "backsub", "jv",
            "vec", "allreduce", "schur_build", "schur_pcg")
@@ -73,6 +74,7 @@ SIGNATURES = {
     "mmba_get_log": (C.c_int, [_H, C.POINTER(IterLog), C.c_int]),
     "mmba_get_profile": (C.c_int, [_H, C.POINTER(C.c_int64 * K_COUNT), C.POINTER(C.c_double * K_COUNT)]),
     "mmba_get_pcg_history": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int]),
+    "mmba_get_phase_cycles": (C.c_int, [_H, C.POINTER(C.c_int64 * 64), C.c_int]),
     "mmba_get_shard": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mmba_eval_residual": (C.c_int, [_H, _f64, _f64]),
     "mmba_eval_jacobian": (C.c_int, [_H, _f64, _f64, _f64]),
@@ -281,6 +283,11 @@ class Engine:
             lib().mmba_get_pcg_history(self._h, i, buf.ctypes.data, n)
             out.append(buf[:n].reshape(-1, 2))
         return out
+
+    def phase_cycles(self, reset=True):
+        out = (C.c_int64 * 64)()
+        _check(lib().mmba_get_phase_cycles(self._h, C.byref(out), int(reset)), self._h)
+        return np.array(list(out), dtype=np.int64)
 
     def profile(self):
         launches, ms = (C.c_int64 * K_COUNT)(), (C.c_double * K_COUNT)()

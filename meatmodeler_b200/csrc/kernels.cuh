@@ -111,6 +111,7 @@ struct TileArgs {
     const double* uv;
     int n_tiles, cam_stride, max_cams, max_pts;
     int n_cams, ytab_cams;   // ytab_cams = n_cams when MATVEC keeps a per-CTA camera table in shared memory, else 0
+    long long* dbg;          // optional phase cycle counters (diagnostics, options.profile bit 2), else nullptr
     double K[9];
 };
 
@@ -187,7 +188,7 @@ __host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts, int
     L.off_pstart = o;
     if (MODE == M_SBUILD) o += 2 * align_up((max_pts + 2) * 4, 16);  // first slot / pair offset of every point
     L.off_run = o;
-    if (MODE == M_SBUILD) o += 48 * 4;                             // cameras of the current accumulation run + flag
+    if (MODE == M_SBUILD) o += 80 * 4;                             // accumulation run: cameras [0..31], flags [32..35], map [40..71]
     L.total = o;
     return L;
 }
@@ -723,33 +724,66 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
     double sacc[MODE == M_SBUILD ? 36 : 1];
 #pragma unroll
     for (int i = 0; i < (MODE == M_SBUILD ? 36 : 1); ++i) sacc[i] = 0.0;
-    int run_ncams = 0;
+    // An accumulation RUN: a list of cameras (ascending ids, s_run[0..run_n)) whose pair blocks are being accumulated
+    // in registers.  Thread (slice my_sl, pair my_pr) owns the block of cameras (run[my_a], run[my_b]), my_a <= my_b,
+    // pairs numbered column by column (pr = b (b + 1) / 2 + a) so that appending a camera to the list adds pairs
+    // without renumbering the existing ones.  A tile continues the run when its cameras are a subset of the list,
+    // extends it when the new cameras are larger than the last one and the pairs still fit, else the run is flushed
+    // (one RED per entry) and restarted.  Video-like visibility: one flush per ~10..40 tiles.
+    int run_n = 0, run_ns = 1, run_P = kConsumers;     // cameras, point slices, pair capacity (= 256 / slices)
+    int my_sl = 0, my_pr = 0, my_a = 0, my_b = 0;
     bool run_touched = false;
-    int* s_run = reinterpret_cast<int*>(smem + L.off_run);   // [0..31] cameras of the run, [32] "list differs" flag
+    int* s_run = reinterpret_cast<int*>(smem + L.off_run);   // [0..31] cameras, [32] flags, [33] missing count
+    int* s_map = s_run + 40;                                  // run index -> local camera slot of the current tile, -1 = absent
+    auto run_pairs = [](int n) { return n * (n + 1) / 2; };
     auto sbuild_flush = [&]() {
         if constexpr (MODE == M_SBUILD) {
-            if (run_ncams) {
-                const int npair = run_ncams * (run_ncams + 1) / 2, nslice = sbuild_slices(npair);
-                const int pr = tid / nslice;
-                if (pr < npair && run_touched) {
-                    int a, b;
-                    tri_decode(pr, run_ncams, a, b);
-                    double* dst = P.Tup + (int64_t)rcm_lookup(P.up_rowptr, P.up_cols, s_run[a], s_run[b]) * 36;
+            if (run_n) {
+                if (my_sl < run_ns && my_pr < run_pairs(run_n) && run_touched) {
+                    double* dst = P.Tup + (int64_t)rcm_lookup(P.up_rowptr, P.up_cols, s_run[my_a], s_run[my_b]) * 36;
 #pragma unroll
                     for (int e = 0; e < 36; ++e) red_add(dst + e, sacc[e]);
                 }
 #pragma unroll
                 for (int e = 0; e < 36; ++e) sacc[e] = 0.0;
                 run_touched = false;
-                run_ncams = 0;
+                run_n = 0;
             }
         }
     };
+    auto run_start = [&](int ncams) {      // thread mapping of a new run of `ncams` cameras
+        run_n = ncams;
+        run_ns = sbuild_slices(run_pairs(ncams));
+        run_P = kConsumers / run_ns;
+        my_sl = tid / run_P;
+        my_pr = tid - my_sl * run_P;
+        int b = (int)((sqrt(8.0 * my_pr + 1.0) - 1.0) * 0.5);
+        while (b * (b + 1) / 2 > my_pr) --b;
+        while ((b + 1) * (b + 2) / 2 <= my_pr) ++b;
+        my_b = b;
+        my_a = my_pr - b * (b + 1) / 2;
+    };
     int stage = 0;
     unsigned phase = 0;
+    // diagnostics (-DMMBA_PHASE_TIMING builds only): cycles per phase of the S-build tile loop as seen by thread 0 of CTA 0
+#ifdef MMBA_PHASE_TIMING
+    long long t_last = 0, phc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool timing = MODE == M_SBUILD && A.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    auto lap = [&](int k) {
+        if (MODE == M_SBUILD && timing) {
+            const long long tt = clock64();
+            phc[k] += tt - t_last;
+            t_last = tt;
+        }
+    };
+    if (timing) t_last = clock64();
+#else
+    auto lap = [](int) {};
+#endif
     for (int t = t_begin; t < t_end; ++t) {
         unsigned char* st = smem + L.off_stages + stage * L.stage_bytes;
         mbar_wait(&full[stage], phase);
+        lap(0);
         const TileMeta* mt = reinterpret_cast<const TileMeta*>(st + L.off_meta);
         const double* sJ = reinterpret_cast<const double*>(st + L.off_J);
         const double* s_cv = reinterpret_cast<const double*>(st + L.off_camvec);
@@ -928,18 +962,42 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                     s_pm[(r * 3 + 1) * kBufStride + tid] = a0 * m1 + a1 * m3 + a2 * m4;
                     s_pm[(r * 3 + 2) * kBufStride + tid] = a0 * m2 + a1 * m4 + a2 * m5;
                 }
-                if (tid == 0) s_run[32] = 0;
+                if (tid == 0) {
+                    s_run[32] = 0;
+                    s_run[33] = 0;
+                }
                 if (pair_mode) {
                     for (int i = tid; i < npts * ncams; i += kConsumers) s_tab[i] = 0xFFFF;
                 } else {
                     if (valid && (tid == 0 || mt->slot_pt[tid - 1] != lp)) s_pstart[lp] = tid;
                     if (tid == 0) s_pstart[npts] = mt->nobs;
                 }
+                lap(1);
                 camera_scatter_round<6>(cv, s_buf, mt, s_camid, P.y, 6, 0);   // one consumer barrier inside
+                lap(2);
             }
             if (pair_mode) {
                 if (valid) s_tab[lp * ncams + lc] = (uint16_t)tid;
-                if (pair_mode == 2 && tid < ncams && (ncams != run_ncams || s_camid[tid] != s_run[tid])) s_run[32] = 1;
+                if (pair_mode == 2) {
+                    // is every camera of the tile in the run's list?  (bit 0: some are missing, bit 1: a missing one
+                    // is not larger than the list's last camera, i.e. the list cannot simply be extended)
+                    if (tid < ncams) {
+                        const int cam = s_camid[tid];
+                        bool found = false;
+                        for (int r = 0; r < run_n; ++r) found |= s_run[r] == cam;
+                        if (!found) {
+                            atomicOr(&s_run[32], (run_n > 0 && cam < s_run[run_n - 1]) ? 3 : 1);
+                            atomicAdd(&s_run[33], 1);
+                        }
+                    } else if (tid >= 32 && tid < 32 + run_n) {
+                        // local camera slot of every run camera in this tile (valid if the run goes on)
+                        const int cam = s_run[tid - 32];
+                        int at = -1;
+                        for (int c = 0; c < ncams; ++c)
+                            if (s_camid[c] == cam) at = c;
+                        s_map[tid - 32] = at;
+                    }
+                }
             } else if (tid == 0) {
                 int o = 0;
                 for (int p = 0; p < npts; ++p) {
@@ -950,34 +1008,59 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                 s_poff[npts] = o;
             }
             consumer_sync();
-            if (!(pair_mode == 2 && run_ncams == ncams && s_run[32] == 0)) {
-                // this tile does not continue the current run: add the run's blocks to HBM, start a new one
-                const bool had_run = run_ncams != 0;
-                sbuild_flush();
-                if (pair_mode == 2) {
-                    if (had_run) consumer_sync();   // every thread has read the old camera list
-                    if (tid < ncams) s_run[tid] = s_camid[tid];
-                    run_ncams = ncams;
+            lap(3);
+            if (pair_mode == 2) {
+                const int flags = s_run[32], n_missing = s_run[33];
+                if (flags & 1) {
+                    const int new_n = run_n + n_missing;
+                    if (run_n > 0 && !(flags & 2) && new_n <= 31 && run_pairs(new_n) <= run_P) {
+                        // extend: the missing cameras are the last n_missing of the tile's (ascending) list
+                        if (tid >= ncams - n_missing && tid < ncams) {
+                            const int pos = run_n + (tid - (ncams - n_missing));
+                            s_run[pos] = s_camid[tid];
+                            s_map[pos] = tid;
+                        }
+                        run_n = new_n;
+                    } else {
+                        const bool had_run = run_n != 0;
+                        sbuild_flush();
+                        if (had_run) consumer_sync();   // every thread has read the old camera list
+                        if (tid < ncams) {
+                            s_run[tid] = s_camid[tid];
+                            s_map[tid] = tid;
+                        }
+                        run_start(ncams);
+                    }
                     consumer_sync();
                 }
-            }
-            if (pair_mode == 2) {
-                // unit = (camera pair a <= b, point slice): whole 6x6 block in registers
-                const int npair = ncams * (ncams + 1) / 2, nslice = sbuild_slices(npair);
-                const int sl = tid % nslice, pr = tid / nslice;
-                if (pr < npair) {
-                    int a, b;
-                    tri_decode(pr, ncams, a, b);
-                    for (int p = sl; p < npts; p += nslice) {
-                        const unsigned i = s_tab[p * ncams + a];
-                        if (i == 0xFFFFu) continue;
-                        const unsigned j = s_tab[p * ncams + b];
-                        if (j == 0xFFFFu) continue;
-                        run_touched = true;
-                        sbuild_block(sJ, s_pm, (int)i, (int)j, sacc);
+                lap(4);
+                // unit = (camera pair a <= b of the run, point slice): whole 6x6 block in registers.  Lanes of a warp
+                // are consecutive pairs of ONE slice: they walk the same points, so the J rows they read are a
+                // handful of neighbouring slots (broadcast / conflict-free); a lane whose pair is absent from a
+                // point skips ahead on its own instead of idling through the other lanes' block.
+                if (my_sl < run_ns && my_pr < run_pairs(run_n)) {
+                    const int la = s_map[my_a], lb = s_map[my_b];
+                    if (la >= 0 && lb >= 0) {
+                        int p = my_sl;
+                        while (true) {
+                            unsigned i = 0xFFFFu, j = 0xFFFFu;
+                            while (p < npts) {
+                                i = s_tab[p * ncams + la];
+                                j = s_tab[p * ncams + lb];
+                                if (i != 0xFFFFu && j != 0xFFFFu) break;
+                                p += run_ns;
+                            }
+                            if (p >= npts) break;
+                            run_touched = true;
+                            sbuild_block(sJ, s_pm, (int)i, (int)j, sacc);
+                            p += run_ns;
+                        }
                     }
                 }
-            } else if (pair_mode) {
+            } else {
+                sbuild_flush();     // a tile of another strategy ends the run
+            }
+            if (pair_mode == 1) {
                 // unit = (camera pair a <= b of the tile, block row, point slice): register accumulation over the
                 // tile's points, then one RED per entry
                 const int npair = ncams * (ncams + 1) / 2;
@@ -1006,7 +1089,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                         for (int bb = 0; bb < 6; ++bb) red_add(dst + bb, acc[bb]);
                     }
                 }
-            } else {
+            } else if (pair_mode == 0) {
                 // unit = (observation pair i <= j of one point, block row): cameras ascend inside a point
                 const int units = mt->npairs * 6;
                 for (int u = tid; u < units; u += kConsumers) {
@@ -1035,7 +1118,9 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                     }
                 }
             }
+            lap(5);
             consumer_sync();   // staging rows and tables are rewritten by the next tile
+            lap(6);
         } else {
             // ---- Schur passes: MATVEC / RHS / BACKSUB ----
             double jc[12], jp[6];
@@ -1165,6 +1250,13 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
         }
     }
     sbuild_flush();
+#ifdef MMBA_PHASE_TIMING
+    if (MODE == M_SBUILD && timing) {
+        lap(7);
+        for (int k = 0; k < 8; ++k) A.dbg[16 + k] += phc[k];
+        A.dbg[24] += t_end - t_begin;
+    }
+#endif
     if constexpr (MODE == M_MATVEC) {
         // few cameras (heavy RED contention on few addresses): the CTA's sums were kept in shared memory
         if (A.ytab_cams) {

@@ -128,6 +128,7 @@ struct Dev {
     RcmSlot* rcm_slots;
     LLLine* rcm_z;
     double* rcm_hist;   // (||r||^2, r.z) of every PCG iterate of the last inner solve (profile & 2)
+    long long* dbg;     // [64] phase cycle counters of the instrumented kernels (profile & 4)
 };
 
 // One-shot peer all-reduce of the per-iteration Schur product (see xchg_push_kernel)
@@ -171,7 +172,7 @@ struct mmba_handle {
     DevPlan dp;                    // the current problem's plan: sizes on the host, tables on the device
     std::vector<int32_t> h_point_perm, h_rc_rows, h_rc_cols;   // host copies for the evaluation hooks (downloaded on demand)
     bool rcm_ready = false;        // pattern built and device arrays carved for the current problem
-    int rcm_warps = 0, rcm_s_in_smem = 0, rcm_nsub = 1;
+    int rcm_warps = 0, rcm_s_in_smem = 0;
     unsigned rcm_seq = 0;          // sequence numbers handed to the PCG launches of this problem (never reused)
     int hist_cap = 0;              // iterations the history buffer holds (pcg_maxit at set_problem time)
     std::vector<std::vector<double>> pcg_hist;   // per outer iteration: (||r_k||^2, r_k.z_k), k = 0 .. its
@@ -378,6 +379,7 @@ void carve(mmba_handle* h, Arena& a) {
     d.flags = a.take<int>(4);
     d.scal = a.take<double>(S_COUNT);
     d.x_io = a.take<double>(6 * Nc + 3 * (size_t)dp.n_points);
+    d.dbg = a.take<long long>(64);
     if (h->rcm_ready) {
         d.Tup = a.take<double>(36 * (size_t)dp.nnz_up);
         d.S = a.take<double>(36 * (size_t)dp.nnz_full);
@@ -833,11 +835,11 @@ RcmPcgArgs rcm_pcg_args(mmba_handle* h, double f2) {
     A.nblk_max = h->dp.nblk_max;
     A.nh_max = h->dp.nh_max;
     A.s_in_smem = h->rcm_s_in_smem;
-    A.nsub = h->rcm_nsub;
     A.rtol2 = h->opt.pcg_rtol * h->opt.pcg_rtol;
     A.atol2f = h->opt.pcg_atol * h->opt.pcg_atol * f2;
     A.ktol2f = h->opt.pcg_ktol * h->opt.pcg_ktol * f2;
     A.hist = (d.rcm_hist && h->opt.pcg_maxit <= h->hist_cap) ? d.rcm_hist : nullptr;
+    A.phase = (h->opt.profile & 4) ? d.dbg : nullptr;
     A.seq0 = h->rcm_seq;
     h->rcm_seq += (unsigned)h->opt.pcg_maxit + 2u;
     return A;
@@ -871,10 +873,9 @@ int rcm_pcg(mmba_handle* h, double f2) {
     CU(cudaMemsetAsync(d.flags, 0, 3 * sizeof(int), h->stream));
     RcmPcgArgs A = rcm_pcg_args(h, f2);
     void* args[] = {&A};
-    static const bool classic = getenv("MMBA_PCG_CLASSIC") && getenv("MMBA_PCG_CLASSIC")[0] == '1';
     prof_begin(h, MMBA_K_PCG);
-    CU(cudaLaunchCooperativeKernel(classic ? (const void*)rcm_pcg_classic_kernel : (const void*)rcm_pcg_kernel,
-                                   dim3(h->dp.n_ctas), dim3(32 * h->rcm_warps), args, h->rcm_smem_bytes, h->stream));
+    CU(cudaLaunchCooperativeKernel((const void*)rcm_pcg_kernel, dim3(h->dp.n_ctas), dim3(32 * h->rcm_warps), args,
+                                   h->rcm_smem_bytes, h->stream));
     prof_end(h, MMBA_K_PCG);
     return MMBA_OK;
 }
@@ -1182,14 +1183,12 @@ int configure_kernels(mmba_handle* h) {
         // camera of the range.  The CTA's rows of S stay in shared memory when they fit, else they are re-read
         // from L2 every iteration.
         const DevPlan& pt = h->dp;
-        h->rcm_nsub = std::max(1, (kRcmPcgThreads / 32) / pt.cpc);
-        h->rcm_warps = std::min(kRcmPcgThreads / 32, pt.cpc * h->rcm_nsub);
+        h->rcm_warps = kRcmPcgThreads / 32;
         h->rcm_s_in_smem = rcm_smem(pt.cpc, pt.nblk_max, pt.nh_max, 1, pt.n_ctas).total <= 200 * 1024 ? 1 : 0;
         const RcmSmem rl = rcm_smem(pt.cpc, pt.nblk_max, pt.nh_max, h->rcm_s_in_smem, pt.n_ctas);
         if (rl.total > 200 * 1024) return fail(h, MMBA_ERR_NOMEM, "reduced-system PCG: too many cameras per CTA");
         h->rcm_smem_bytes = (size_t)rl.total;
         CU(cudaFuncSetAttribute(rcm_pcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rl.total));
-        CU(cudaFuncSetAttribute(rcm_pcg_classic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rl.total));
     }
     return MMBA_OK;
 }
@@ -1708,6 +1707,7 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     A.max_pts = std::max(D.max_tile_pts, 1);
     A.n_cams = (int)h->Nc;
     A.ytab_cams = h->Nc <= 340 ? (int)h->Nc : 0;   // <= 16 KB of shared memory
+    A.dbg = (h->opt.profile & 4) ? d.dbg : nullptr;
     std::memcpy(A.K, K, sizeof(A.K));
     TRY(configure_kernels(h));
     lap("configure kernels");
@@ -1800,6 +1800,16 @@ int mmba_get_pcg_history(const mmba_handle* h, int outer_iteration, double* out,
     if (out)
         for (int i = 0; i < (int)v.size() && i < capacity; ++i) out[i] = v[i];
     return (int)v.size();
+}
+
+int mmba_get_phase_cycles(mmba_handle* h, int64_t out[64], int reset) {
+    TRY(need_problem(h));
+    if (!out) return fail(h, MMBA_ERR_ARG, "get_phase_cycles: null argument");
+    static_assert(sizeof(long long) == sizeof(int64_t), "counter width");
+    CU(cudaMemcpyAsync(out, h->d.dbg, 64 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (reset) CU(cudaMemsetAsync(h->d.dbg, 0, 64 * sizeof(int64_t), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MMBA_OK;
 }
 
 int mmba_get_profile(const mmba_handle* h, int64_t launches[MMBA_K_COUNT], double ms[MMBA_K_COUNT]) {

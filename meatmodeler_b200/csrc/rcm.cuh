@@ -101,14 +101,14 @@ struct RcmPcgArgs {
     const double* Pinv;         // [Nc][21]
     const double* b;            // [Nc][6]
     double* x;                  // [Nc][6]  result (scaled step)
-    LLLine* z;                  // [2 parities][Nc][6]  the one vector exchanged through L2 (Pinv q; classic kernel: z)
+    LLLine* z;                  // [2 parities][Nc][6]  the one vector exchanged through L2 (z = Pinv r at the start, then Pinv q)
     RcmSlot* slots;             // [2 parities][kRcmMaxCtas] partial sums of the grid-wide reductions
     int* flags;                 // [0] stop code (0 = maxit reached, 1 = converged, 2 = breakdown), [1] iterations,
                                 // [2] set when an exchange timed out
     double* state;              // [1] ||b||^2, [2] ||r||^2
     double* hist;               // optional [2 (maxit + 1)]: (||r_k||^2, r_k.z_k) of every iterate, k = 0 first
+    long long* phase;           // optional [8]: cycles CTA 0 spent per phase of the iteration loop (diagnostics)
     int n_cams, maxit, cpc, nblk_max, nh_max, s_in_smem;
-    int nsub;                   // warps that share one camera row in the product q = S p
     unsigned seq0;              // sequence numbers of this launch are seq0 + 1 ...: lines of earlier launches never match,
                                 // so neither z nor slots are cleared between launches
     double rtol2;
@@ -122,7 +122,7 @@ __device__ __forceinline__ double warp_sum_all(double v) {
     return v;
 }
 
-constexpr int kRcmPcgThreads = 256;
+constexpr int kRcmPcgThreads = 512;      // 16 warps, one CTA per SM: every phase of an iteration is latency bound, more warps hide it
 
 // shared-memory carve-up of rcm_pcg_kernel (same arithmetic on the host)
 struct RcmSmem {
@@ -146,7 +146,7 @@ __host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, i
     L.off_sums = o;
     o += n_ctas * kRcmSums * 8;              // every CTA's partial sums, as polled
     L.off_qp = o;
-    o += (cpc + 8) * 6 * 8;                  // partial products [camera x sub-warp][6]: at most max(cpc, 8) items
+    o += (nblk_max > cpc + 8 ? nblk_max : cpc + 8) * 6 * 8;   // row products of q = S p: [block][6]
     L.off_hcols = o;
     o += nh_max * 4;
     L.off_rowptr = o;
@@ -158,311 +158,6 @@ __host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, i
     L.total = o;
     return L;
 }
-
-// CLASSIC two-exchange variant, kept for A/B measurements (MMBA_PCG_CLASSIC=1); the solve uses rcm_pcg_kernel below.
-// Preconditioned conjugate gradients on S x = b, zero initial guess, block-Jacobi preconditioner, relative
-// residual stop (the recurrences and stopping rules of pcg_update_kernel).  CTA `b` owns `cpc` consecutive
-// cameras: its rows of S, their preconditioner blocks and x, r, q live in shared memory for the whole solve;
-// one warp per camera (strided), lane = (block slot 0..4, row 0..5).
-// Only z = Pinv r travels through L2.  Every CTA keeps its own copy of the search direction on its halo (the
-// columns its rows touch) and advances it with the owner's recurrence p_j = z_j + beta p_j, so the new
-// direction is never waited for: an iteration has two grid-wide reductions (p.q, then r.z and ||r||^2) and
-// nothing else crosses CTAs.  Both the z entries and the partial sums travel as self-validating LL lines
-// (see ll_store): a reduction is one 16-byte store per CTA and value, polled by warp 0 of every CTA; no fences.
-// Partials are added in CTA order by every CTA, so all CTAs (and all ranks of a sharded solve: S and b are
-// all-reduced, the PCG is replicated) take identical decisions.
-// Buffer reuse is safe without extra synchronisation: a CTA rewrites its z lines / slot only after it has passed
-// the next reduction, which every other CTA joins only after it has consumed the previous values.
-__global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_classic_kernel(const RcmPcgArgs A) {
-    extern __shared__ __align__(16) unsigned char rsm[];
-    __shared__ double s_part[kRcmPcgThreads / 32][2];
-    __shared__ double s_tot[2];
-    __shared__ int s_dead;
-    const RcmSmem L = rcm_smem(A.cpc, A.nblk_max, A.nh_max, A.s_in_smem, (int)gridDim.x);
-    double* S_s = reinterpret_cast<double*>(rsm + L.off_S);
-    double* pinv_s = reinterpret_cast<double*>(rsm + L.off_pinv);
-    double* vec = reinterpret_cast<double*>(rsm + L.off_vec);
-    double* ph = reinterpret_cast<double*>(rsm + L.off_ph);
-    double* zh = reinterpret_cast<double*>(rsm + L.off_zh);
-    double* qp = reinterpret_cast<double*>(rsm + L.off_qp);
-    int* hcols_s = reinterpret_cast<int*>(rsm + L.off_hcols);
-    int* rowptr_s = reinterpret_cast<int*>(rsm + L.off_rowptr);
-    int* own_s = reinterpret_cast<int*>(rsm + L.off_own);
-    uint16_t* lcol_s = reinterpret_cast<uint16_t*>(rsm + L.off_lcol);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int G = gridDim.x;
-    const int a = lane % 6, slot = lane / 6;
-    const bool rowlane = lane < 6;
-    const int c0 = blockIdx.x * A.cpc, ncam = min(A.cpc, A.n_cams - c0);
-    const int e0 = A.rowptr[c0], nblk = A.rowptr[c0 + ncam] - e0;
-    const int h0 = A.halo_ptr[blockIdx.x], nh = A.halo_ptr[blockIdx.x + 1] - h0;
-    if (tid == 0) s_dead = 0;
-    if (A.s_in_smem) {
-        // blocks are 288 bytes: 16-byte loads, four in flight per thread
-        const double2* src = reinterpret_cast<const double2*>(A.S + (int64_t)e0 * 36);
-        double2* dst = reinterpret_cast<double2*>(S_s);
-        const int n2 = nblk * 18;
-        for (int i = tid; i < n2; i += 4 * blockDim.x) {
-            double2 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i + u * blockDim.x < n2) v[u] = __ldg(src + i + u * blockDim.x);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i + u * blockDim.x < n2) dst[i + u * blockDim.x] = v[u];
-        }
-    }
-    for (int i = tid; i < nblk; i += blockDim.x) lcol_s[i] = A.lcol[e0 + i];
-    for (int i = tid; i < nh; i += blockDim.x) hcols_s[i] = A.halo_cols[h0 + i];
-    for (int i = tid; i < nh * 6; i += blockDim.x) ph[i] = 0.0;
-    for (int i = tid; i < ncam * 21; i += blockDim.x) pinv_s[i] = A.Pinv[(int64_t)c0 * 21 + i];
-    for (int i = tid; i <= ncam; i += blockDim.x) rowptr_s[i] = A.rowptr[c0 + i] - e0;
-    for (int i = tid; i < ncam; i += blockDim.x) own_s[i] = A.own_l[c0 + i];
-    const double* S_rows = A.s_in_smem ? S_s : A.S + (int64_t)e0 * 36;
-    __syncthreads();
-    constexpr long long kSpinLimit = 1ll << 31;   // ~1 s: give up instead of hanging the device
-
-    // grid-wide sums: `which` = 0 -> slot.pq (v0 only), 1 -> slot.rz / slot.rr.  false when the other CTAs did
-    // not arrive within ~1 s (never expected)
-    // gather_z: while warp 0 polls the partial sums, the other warps fetch the z lines of the same sequence number
-    // on the CTA's halo into zh (both were published together, so the two waits overlap)
-    auto reduce2 = [&](double v0, double v1, int which, unsigned seq, bool gather_z, double& o0, double& o1) -> bool {
-        v0 = warp_sum_all(v0);
-        if (which) v1 = warp_sum_all(v1);
-        if (lane == 0) {
-            s_part[warp][0] = v0;
-            s_part[warp][1] = v1;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            if (lane == 0) {
-                double t0 = 0, t1 = 0;
-                for (int w = 0; w < nwarps; ++w) {
-                    t0 += s_part[w][0];
-                    t1 += s_part[w][1];
-                }
-                RcmSlot* mine = A.slots + blockIdx.x;
-                if (which) {
-                    ll_store(&mine->v[1], t0, seq);
-                    ll_store(&mine->v[2], t1, seq);
-                } else {
-                    ll_store(&mine->v[0], t0, seq);
-                }
-            }
-            // lane l polls the slots of CTAs l, l + 32, ...: all of them in flight at once
-            constexpr int kPer = kRcmMaxCtas / 32;
-            double a0[kPer], a1[kPer];
-            unsigned pend = 0;
-#pragma unroll
-            for (int u = 0; u < kPer; ++u) {
-                a0[u] = a1[u] = 0.0;
-                if (lane + 32 * u < G) pend |= 1u << u;
-            }
-            const long long t_start = clock64();
-            while (pend) {
-                bool ok[kPer];
-#pragma unroll
-                for (int u = 0; u < kPer; ++u) {
-                    ok[u] = false;
-                    if (pend >> u & 1) {
-                        const RcmSlot* sl = A.slots + lane + 32 * u;
-                        ok[u] = which ? (ll_try_load(&sl->v[1], seq, a0[u]) & ll_try_load(&sl->v[2], seq, a1[u]))
-                                      : ll_try_load(&sl->v[0], seq, a0[u]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kPer; ++u)
-                    if (ok[u]) pend &= ~(1u << u);
-                if (pend && clock64() - t_start > kSpinLimit) {
-                    s_dead = 1;
-                    break;
-                }
-            }
-            double s0 = 0, s1 = 0;
-#pragma unroll
-            for (int u = 0; u < kPer; ++u) {
-                s0 += a0[u];
-                s1 += a1[u];
-            }
-            s0 = warp_sum_all(s0);
-            s1 = warp_sum_all(s1);
-            if (lane == 0) {
-                s_tot[0] = s0;
-                s_tot[1] = s1;
-            }
-        }
-        if (gather_z && (warp > 0 || nwarps == 1)) {
-            const int first = nwarps == 1 ? tid : tid - 32, step = nwarps == 1 ? 32 : (int)blockDim.x - 32;
-            const long long t_start = clock64();
-            const int n6 = nh * 6;
-            for (int base = first; base < n6; base += 4 * step) {
-                double zv[4];
-                bool ok[4];
-                const LLLine* line[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = base + u * step;
-                    ok[u] = true;
-                    zv[u] = 0.0;
-                    if (i < n6) {
-                        const int j = i / 6;
-                        line[u] = A.z + (int64_t)hcols_s[j] * 6 + (i - j * 6);
-                        ok[u] = ll_try_load(line[u], seq, zv[u]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    while (!ok[u]) {
-                        ok[u] = ll_try_load(line[u], seq, zv[u]);
-                        if (!ok[u] && clock64() - t_start > kSpinLimit) {
-                            s_dead = 1;
-                            break;
-                        }
-                    }
-                    const int i = base + u * step;
-                    if (i < n6) zh[i] = zv[u];
-                }
-            }
-        }
-        __syncthreads();
-        if (s_dead) {
-            if (tid == 0) A.flags[2] = 1;
-            return false;
-        }
-        o0 = s_tot[0];
-        o1 = s_tot[1];
-        return true;
-    };
-    // z = Pinv_k r for camera k of this CTA (r in lanes 0..5); valid in lanes 0..5
-    auto precond = [&](int k, double r_a) {
-        double z = 0;
-        const double* pin = pinv_s + k * 21;
-#pragma unroll
-        for (int bb = 0; bb < 6; ++bb) {
-            const double rb = __shfl_sync(0xffffffffu, r_a, bb);
-            z += pin[a <= bb ? tri6(a, bb) : tri6(bb, a)] * rb;
-        }
-        return z;
-    };
-
-    // x = 0, r = b, z = Pinv r
-    double rz = 0, rr = 0;
-    for (int k = warp; k < ncam; k += nwarps) {
-        const int c = c0 + k;
-        const double r_a = rowlane ? A.b[c * 6 + a] : 0.0;
-        const double z = precond(k, r_a);
-        if (rowlane) {
-            vec[k * 18 + a] = 0.0;
-            vec[k * 18 + 6 + a] = r_a;
-            ll_store(A.z + c * 6 + a, z, A.seq0 + 1u);
-            rz += r_a * z;
-            rr += r_a * r_a;
-        }
-    }
-    double rho, b2;
-    if (!reduce2(rz, rr, 1, A.seq0 + 1u, true, rho, b2)) return;
-    int its = 0, done = 0;
-    double beta = 0.0, rr_last = b2;
-    if (!(b2 > 0.0)) {
-        done = 1;
-    } else {
-        for (int it = 0; it < A.maxit; ++it) {
-            // p = z + beta p on the halo (z of this iteration was gathered together with the last reduction)
-            for (int i = tid; i < nh * 6; i += blockDim.x) ph[i] = it == 0 ? zh[i] : fma(beta, ph[i], zh[i]);
-            __syncthreads();
-            // q = S p: nsub warps share a camera row (blocks dealt round-robin to nsub x 5 lane groups); two
-            // accumulators per lane keep the dependent DFMA chains short
-            const int nsub = A.nsub;
-            for (int item = warp; item < ncam * nsub; item += nwarps) {
-                const int k = item / nsub, sub = item - k * nsub;
-                double acc0 = 0, acc1 = 0;
-                if (slot < kRcmSlots) {
-                    const int e1 = rowptr_s[k + 1];
-                    for (int e = rowptr_s[k] + slot + kRcmSlots * sub; e < e1; e += kRcmSlots * nsub) {
-                        const double* srow = S_rows + e * 36 + a * 6;
-                        const double* pj = ph + lcol_s[e] * 6;
-                        if (A.s_in_smem) {
-                            acc0 += srow[0] * pj[0];
-                            acc1 += srow[1] * pj[1];
-                            acc0 += srow[2] * pj[2];
-                            acc1 += srow[3] * pj[3];
-                            acc0 += srow[4] * pj[4];
-                            acc1 += srow[5] * pj[5];
-                        } else {
-                            acc0 += __ldg(srow + 0) * pj[0];
-                            acc1 += __ldg(srow + 1) * pj[1];
-                            acc0 += __ldg(srow + 2) * pj[2];
-                            acc1 += __ldg(srow + 3) * pj[3];
-                            acc0 += __ldg(srow + 4) * pj[4];
-                            acc1 += __ldg(srow + 5) * pj[5];
-                        }
-                    }
-                }
-                const double acc = acc0 + acc1;
-                double q = acc;
-                q += __shfl_down_sync(0xffffffffu, acc, 6);
-                q += __shfl_down_sync(0xffffffffu, acc, 12);
-                q += __shfl_down_sync(0xffffffffu, acc, 18);
-                q += __shfl_down_sync(0xffffffffu, acc, 24);
-                if (rowlane) qp[item * 6 + a] = q;
-            }
-            __syncthreads();
-            double pq = 0;
-            for (int k = warp; k < ncam; k += nwarps) {
-                if (rowlane) {
-                    double q = 0;
-                    for (int sub = 0; sub < nsub; ++sub) q += qp[(k * nsub + sub) * 6 + a];
-                    vec[k * 18 + 12 + a] = q;
-                    pq += ph[own_s[k] * 6 + a] * q;
-                }
-            }
-            double pq_tot, unused;
-            if (!reduce2(pq, 0.0, 0, A.seq0 + (unsigned)it + 1u, false, pq_tot, unused)) return;
-            const double alpha = rho / pq_tot;
-            rz = 0;
-            rr = 0;
-            for (int k = warp; k < ncam; k += nwarps) {
-                double* v = vec + k * 18;
-                double r_a = 0;
-                if (rowlane) {
-                    v[a] += alpha * ph[own_s[k] * 6 + a];
-                    r_a = v[6 + a] - alpha * v[12 + a];
-                    v[6 + a] = r_a;
-                }
-                const double z = precond(k, r_a);
-                if (rowlane) {
-                    ll_store(A.z + (c0 + k) * 6 + a, z, A.seq0 + (unsigned)it + 2u);
-                    rz += r_a * z;
-                    rr += r_a * r_a;
-                }
-            }
-            double rz_tot, rr_tot;
-            if (!reduce2(rz, rr, 1, A.seq0 + (unsigned)it + 2u, true, rz_tot, rr_tot)) return;
-            its = it + 1;
-            rr_last = rr_tot;
-            if (rr_tot <= A.rtol2 * b2 || rr_tot <= A.atol2f) {
-                done = 1;
-                break;
-            }
-            if (!(pq_tot > 0.0) || !isfinite(rr_tot) || !(rz_tot > 0.0)) {
-                done = 2;
-                break;
-            }
-            beta = rz_tot / rho;
-            rho = rz_tot;
-        }
-    }
-    for (int k = warp; k < ncam; k += nwarps)
-        if (rowlane) A.x[(c0 + k) * 6 + a] = vec[k * 18 + a];
-    if (blockIdx.x == 0 && tid == 0) {
-        A.flags[0] = done;
-        A.flags[1] = its;
-        A.state[1] = b2;
-        A.state[2] = rr_last;
-    }
-}
-
 
 // ---- the PCG kernel of the solve: ONE grid-wide exchange per iteration -------------------------------------------
 // Same method (preconditioned CG, zero initial guess, block-Jacobi), reorganised so that everything that crosses
@@ -499,15 +194,13 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
     double* zh = reinterpret_cast<double*>(rsm + L.off_zh);
     double* wh = reinterpret_cast<double*>(rsm + L.off_zqh);
     double* sums_s = reinterpret_cast<double*>(rsm + L.off_sums);
-    double* qp = reinterpret_cast<double*>(rsm + L.off_qp);
+    double* prod = reinterpret_cast<double*>(rsm + L.off_qp);      // [block][6] row products of q = S p
     int* hcols_s = reinterpret_cast<int*>(rsm + L.off_hcols);
     int* rowptr_s = reinterpret_cast<int*>(rsm + L.off_rowptr);
-    int* own_s = reinterpret_cast<int*>(rsm + L.off_own);
     uint16_t* lcol_s = reinterpret_cast<uint16_t*>(rsm + L.off_lcol);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int a = lane % 6, slot = lane / 6;
-    const bool rowlane = lane < 6;
+    const int a = lane % 6, slot = lane / 6;       // 6-lane groups: five cameras per warp, lanes 30 and 31 idle
     const int c0 = blockIdx.x * A.cpc, ncam = min(A.cpc, A.n_cams - c0);
     const int e0 = A.rowptr[c0], nblk = A.rowptr[c0 + ncam] - e0;
     const int h0 = A.halo_ptr[blockIdx.x], nh = A.halo_ptr[blockIdx.x + 1] - h0;
@@ -530,35 +223,55 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
     for (int i = tid; i < nh; i += blockDim.x) hcols_s[i] = A.halo_cols[h0 + i];
     for (int i = tid; i < ncam * 21; i += blockDim.x) pinv_s[i] = A.Pinv[(int64_t)c0 * 21 + i];
     for (int i = tid; i <= ncam; i += blockDim.x) rowptr_s[i] = A.rowptr[c0 + i] - e0;
-    for (int i = tid; i < ncam; i += blockDim.x) own_s[i] = A.own_l[c0 + i];
     const double* S_rows = A.s_in_smem ? S_s : A.S + (int64_t)e0 * 36;
+    const int own0 = A.own_l[c0];      // the CTA's own cameras are consecutive entries of its (ascending) halo list
     __syncthreads();
-    const int own0 = own_s[0];      // the CTA's own cameras are consecutive entries of its (ascending) halo list
     constexpr long long kSpinLimit = 1ll << 31;   // ~1 s: give up instead of hanging the device
+    // diagnostics (-DMMBA_PHASE_TIMING builds only): cycles per phase as seen by thread 0 of CTA 0
+#ifdef MMBA_PHASE_TIMING
+    long long t_last = 0, phc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto lap = [&](int k) {
+        if (A.phase) {
+            const long long t = clock64();
+            phc[k] += t - t_last;
+            t_last = t;
+        }
+    };
+#else
+    auto lap = [](int) {};
+#endif
+    // the warps that own camera rows in the "row" phase (five cameras each); the others go straight to polling
+    // (measured on C4 / C2: 4.15 / 4.20 us per iteration; one camera per warp with the row's blocks spread over the
+    // lanes: 4.72 / 4.04)
+    const int row_warps = min(nwarps, (ncam + 4) / 5);
+    auto row_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(32 * row_warps) : "memory"); };
 
-    // One exchange: the per-thread partial sums v[0..nv) are reduced over the grid (every CTA adds the published
-    // CTA totals in CTA order: identical bits everywhere) and the lines of sequence number `seq` on the CTA's halo
-    // are gathered into `gather`.  All threads share the polling: item i < G nv is a partial sum, the rest are
-    // halo lines; eight polls in flight per thread.
-    auto exchange = [&](const double (&v)[kRcmSums], int nv, unsigned seq, double* gather, double (&tot)[kRcmSums]) -> bool {
-        const int par = (int)(seq & 1u);
+    // Publish: the per-thread partial sums v[0..nv) of the row warps are reduced over the CTA and stored to this
+    // CTA's slot (every CTA later adds the published CTA totals in CTA order: identical bits everywhere).
+    auto publish = [&](const double (&v)[kRcmSums], int nv, unsigned seq) {
 #pragma unroll
         for (int i = 0; i < kRcmSums; ++i)
             if (i < nv) {
                 const double w = warp_sum_all(v[i]);
                 if (lane == 0) s_part[warp][i] = w;
             }
-        __syncthreads();
-        RcmSlot* slots = A.slots + par * kRcmMaxCtas;
+        row_sync();
         if (tid < nv) {
             double t = 0;
-            for (int w = 0; w < nwarps; ++w) t += s_part[w][tid];
-            ll_store(&slots[blockIdx.x].v[tid], t, seq);
+            for (int w = 0; w < row_warps; ++w) t += s_part[w][tid];
+            ll_store(&(A.slots + (int)(seq & 1u) * kRcmMaxCtas)[blockIdx.x].v[tid], t, seq);
         }
+    };
+    // Collect: poll every CTA's partial sums and the lines of sequence number `seq` on the CTA's halo (gathered into
+    // `gather`).  All threads share the polling: item i < G nv is a partial sum, the rest are halo lines; eight
+    // polls in flight per thread.  Returns the grid totals.
+    auto collect = [&](int nv, unsigned seq, double* gather, double (&tot)[kRcmSums]) -> bool {
+        const int par = (int)(seq & 1u);
+        const RcmSlot* slots = A.slots + par * kRcmMaxCtas;
         const LLLine* zl = A.z + (int64_t)par * 6 * A.n_cams;
         const int n_sum = G * nv, n_items = n_sum + nh * 6;
         const long long t_start = clock64();
-        constexpr int kFly = 8;      // polls in flight per thread: G nv + 6 nh <= 8 x 256 items go out in one batch
+        constexpr int kFly = 8;
         for (int base = tid; base < n_items; base += kFly * (int)blockDim.x) {
             const LLLine* line[kFly];
             double val[kFly];
@@ -597,6 +310,7 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
             }
         }
         __syncthreads();
+        lap(3);
         if (s_dead) {
             if (tid == 0) A.flags[2] = 1;
             return false;
@@ -612,13 +326,14 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
         for (int i = 0; i < kRcmSums; ++i) tot[i] = i < nv ? s_tot[i] : 0.0;
         return true;
     };
-    // Pinv_k v for camera k of this CTA (v in lanes 0..5); valid in lanes 0..5
+    // Pinv_k v for camera k of this CTA, v spread over the six lanes of the group `slot`; valid where slot < 5
     auto precond = [&](int k, double v_a) {
         double z = 0;
         const double* pin = pinv_s + k * 21;
+        const int base = slot < 5 ? slot * 6 : 24;
 #pragma unroll
         for (int bb = 0; bb < 6; ++bb) {
-            const double vb = __shfl_sync(0xffffffffu, v_a, bb);
+            const double vb = __shfl_sync(0xffffffffu, v_a, base + bb);
             z += pin[a <= bb ? tri6(a, bb) : tri6(bb, a)] * vb;
         }
         return z;
@@ -631,19 +346,24 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
     {
         const unsigned seq = A.seq0 + 1u;
         LLLine* zl = A.z + (int64_t)(seq & 1u) * 6 * A.n_cams;
-        for (int k = warp; k < ncam; k += nwarps) {
-            const int c = c0 + k;
-            const double r_a = rowlane ? A.b[c * 6 + a] : 0.0;
-            const double z = precond(k, r_a);
-            if (rowlane) {
-                vec[k * 18 + a] = 0.0;
-                vec[k * 18 + 6 + a] = r_a;
-                ll_store(zl + c * 6 + a, z, seq);
-                v[0] += r_a * z;
-                v[1] += r_a * r_a;
+        if (warp < row_warps) {
+            for (int k0 = 0; k0 < ncam; k0 += 5 * row_warps) {
+                const int k = k0 + warp * 5 + slot;
+                const bool act = slot < 5 && k < ncam;
+                const int kk = act ? k : 0;
+                const double r_a = act ? A.b[(c0 + kk) * 6 + a] : 0.0;
+                const double z = precond(kk, r_a);
+                if (act) {
+                    vec[k * 18 + a] = 0.0;
+                    vec[k * 18 + 6 + a] = r_a;
+                    ll_store(zl + (c0 + k) * 6 + a, z, seq);
+                    v[0] += r_a * z;
+                    v[1] += r_a * r_a;
+                }
             }
+            publish(v, 2, seq);
         }
-        if (!exchange(v, 2, seq, zh, tot)) return;
+        if (!collect(2, seq, zh, tot)) return;
     }
     const double rho0 = tot[0], b2 = tot[1];
     int its = 0, done = 0;
@@ -658,72 +378,102 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
     } else {
         for (int i = tid; i < nh * 6; i += blockDim.x) ph[i] = zh[i];
         __syncthreads();
-        const int nsub = A.nsub;
+#ifdef MMBA_PHASE_TIMING
+        t_last = clock64();
+#endif
         for (int it = 0; it < A.maxit; ++it) {
             const unsigned seq = A.seq0 + (unsigned)it + 2u;
-            // q = S p: nsub warps share a camera row (blocks dealt round-robin to nsub x 5 lane groups)
-            for (int item = warp; item < ncam * nsub; item += nwarps) {
-                const int k = item / nsub, sub = item - k * nsub;
-                double acc0 = 0, acc1 = 0;
-                if (slot < kRcmSlots) {
-                    const int e1 = rowptr_s[k + 1];
-                    for (int e = rowptr_s[k] + slot + kRcmSlots * sub; e < e1; e += kRcmSlots * nsub) {
-                        const double* srow = S_rows + e * 36 + a * 6;
-                        const double* pj = ph + lcol_s[e] * 6;
-                        if (A.s_in_smem) {
-                            acc0 += srow[0] * pj[0];
-                            acc1 += srow[1] * pj[1];
-                            acc0 += srow[2] * pj[2];
-                            acc1 += srow[3] * pj[3];
-                            acc0 += srow[4] * pj[4];
-                            acc1 += srow[5] * pj[5];
-                        } else {
-                            acc0 += __ldg(srow + 0) * pj[0];
-                            acc1 += __ldg(srow + 1) * pj[1];
-                            acc0 += __ldg(srow + 2) * pj[2];
-                            acc1 += __ldg(srow + 3) * pj[3];
-                            acc0 += __ldg(srow + 4) * pj[4];
-                            acc1 += __ldg(srow + 5) * pj[5];
+            lap(5);
+            // q = S p, step 1: every (block, row) pair is one unit of six multiply-adds, dealt to all threads
+            const int n_units = nblk * 6;
+            for (int u0 = tid; u0 < n_units; u0 += 2 * blockDim.x) {
+                // two units per trip: their loads are independent and overlap
+                const int u1 = u0 + blockDim.x;
+                const bool two = u1 < n_units;
+                const int ea = u0 / 6, eb = two ? u1 / 6 : ea;
+                const double* sa = S_rows + (int64_t)ea * 36 + (u0 - ea * 6) * 6;
+                const double* sb = S_rows + (int64_t)eb * 36 + ((two ? u1 : u0) - eb * 6) * 6;
+                const double* pa = ph + lcol_s[ea] * 6;
+                const double* pb = ph + lcol_s[eb] * 6;
+                double a0, a1, b0, b1;
+                if (A.s_in_smem) {
+                    a0 = sa[0] * pa[0];
+                    b0 = sb[0] * pb[0];
+                    a1 = sa[1] * pa[1];
+                    b1 = sb[1] * pb[1];
+                    a0 = fma(sa[2], pa[2], a0);
+                    b0 = fma(sb[2], pb[2], b0);
+                    a1 = fma(sa[3], pa[3], a1);
+                    b1 = fma(sb[3], pb[3], b1);
+                    a0 = fma(sa[4], pa[4], a0);
+                    b0 = fma(sb[4], pb[4], b0);
+                    a1 = fma(sa[5], pa[5], a1);
+                    b1 = fma(sb[5], pb[5], b1);
+                } else {
+                    a0 = __ldg(sa + 0) * pa[0];
+                    b0 = __ldg(sb + 0) * pb[0];
+                    a1 = __ldg(sa + 1) * pa[1];
+                    b1 = __ldg(sb + 1) * pb[1];
+                    a0 = fma(__ldg(sa + 2), pa[2], a0);
+                    b0 = fma(__ldg(sb + 2), pb[2], b0);
+                    a1 = fma(__ldg(sa + 3), pa[3], a1);
+                    b1 = fma(__ldg(sb + 3), pb[3], b1);
+                    a0 = fma(__ldg(sa + 4), pa[4], a0);
+                    b0 = fma(__ldg(sb + 4), pb[4], b0);
+                    a1 = fma(__ldg(sa + 5), pa[5], a1);
+                    b1 = fma(__ldg(sb + 5), pb[5], b1);
+                }
+                prod[u0] = a0 + a1;
+                if (two) prod[u1] = b0 + b1;
+            }
+            lap(0);
+            __syncthreads();
+            lap(1);
+            // step 2 (row warps): q = sums of the row's products, w = Pinv q (published), the seven partial sums
+            if (warp < row_warps) {
+#pragma unroll
+                for (int i = 0; i < kRcmSums; ++i) v[i] = 0.0;
+                LLLine* wl = A.z + (int64_t)(seq & 1u) * 6 * A.n_cams;
+                for (int k0 = 0; k0 < ncam; k0 += 5 * row_warps) {
+                    const int k = k0 + warp * 5 + slot;
+                    const bool act = slot < 5 && k < ncam;
+                    const int kk = act ? k : 0;
+                    double q = 0, pk = 0, zk = 0, rk = 0;
+                    if (act) {
+                        double q0 = 0, q1 = 0, q2 = 0, q3 = 0;      // independent partial sums: the loads overlap
+                        const int e1 = rowptr_s[k + 1];
+                        int e = rowptr_s[k];
+                        for (; e + 3 < e1; e += 4) {
+                            q0 += prod[e * 6 + a];
+                            q1 += prod[e * 6 + 6 + a];
+                            q2 += prod[e * 6 + 12 + a];
+                            q3 += prod[e * 6 + 18 + a];
                         }
+                        for (; e < e1; ++e) q0 += prod[e * 6 + a];
+                        q = (q0 + q1) + (q2 + q3);
+                        vec[k * 18 + 12 + a] = q;
+                        pk = ph[(own0 + k) * 6 + a];
+                        zk = zh[(own0 + k) * 6 + a];
+                        rk = vec[k * 18 + 6 + a];
+                    }
+                    const double w = precond(kk, q);
+                    if (act) {
+                        ll_store(wl + (c0 + k) * 6 + a, w, seq);
+                        v[0] += pk * q;
+                        v[1] += q * zk;
+                        v[2] += q * w;
+                        v[3] += rk * q;
+                        v[4] += q * q;
+                        v[5] += rk * zk;
+                        v[6] += rk * rk;
                     }
                 }
-                const double acc = acc0 + acc1;
-                double q = acc;
-                q += __shfl_down_sync(0xffffffffu, acc, 6);
-                q += __shfl_down_sync(0xffffffffu, acc, 12);
-                q += __shfl_down_sync(0xffffffffu, acc, 18);
-                q += __shfl_down_sync(0xffffffffu, acc, 24);
-                if (rowlane) qp[item * 6 + a] = q;
+                publish(v, kRcmSums, seq);
             }
-            __syncthreads();
-            // w = Pinv q on the own rows (published), and the seven partial sums
-#pragma unroll
-            for (int i = 0; i < kRcmSums; ++i) v[i] = 0.0;
-            LLLine* wl = A.z + (int64_t)(seq & 1u) * 6 * A.n_cams;
-            for (int k = warp; k < ncam; k += nwarps) {
-                double q = 0, pk = 0, zk = 0, rk = 0;
-                if (rowlane) {
-                    for (int sub = 0; sub < nsub; ++sub) q += qp[(k * nsub + sub) * 6 + a];
-                    vec[k * 18 + 12 + a] = q;
-                    pk = ph[(own0 + k) * 6 + a];
-                    zk = zh[(own0 + k) * 6 + a];
-                    rk = vec[k * 18 + 6 + a];
-                }
-                const double w = precond(k, q);
-                if (rowlane) {
-                    ll_store(wl + (c0 + k) * 6 + a, w, seq);
-                    v[0] += pk * q;
-                    v[1] += q * zk;
-                    v[2] += q * w;
-                    v[3] += rk * q;
-                    v[4] += q * q;
-                    v[5] += rk * zk;
-                    v[6] += rk * rk;
-                }
-            }
-            if (!exchange(v, kRcmSums, seq, wh, tot)) return;
+            lap(2);
+            if (!collect(kRcmSums, seq, wh, tot)) return;
             const double pq = tot[0], rho = tot[5];
-            const double alpha = rho / pq;
+            const double alpha = rho / pq, inv_rho = 1.0 / rho;      // independent divisions
             const double rho_n = fma(alpha, fma(alpha, tot[2], -2.0 * tot[1]), rho);
             double rr_n = fma(alpha, fma(alpha, tot[4], -2.0 * tot[3]), tot[6]);
             if (!(pq > 0.0) || !(rho > 0.0) || !isfinite(alpha) || !isfinite(rho_n) || !isfinite(rr_n)) {
@@ -731,7 +481,7 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                 break;
             }
             if (rr_n < 0.0) rr_n = 0.0;
-            const double beta = rho_n > 0.0 ? rho_n / rho : 0.0;
+            const double beta = rho_n > 0.0 ? rho_n * inv_rho : 0.0;
             // x += alpha p, r -= alpha q (own rows); z -= alpha w, p = z + beta p (whole halo)
             for (int i = tid; i < nh * 6; i += blockDim.x) {
                 const int j = i / 6;
@@ -757,12 +507,16 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                 done = 1;
                 break;
             }
+            lap(4);
             __syncthreads();
         }
+#ifdef MMBA_PHASE_TIMING
+        if (A.phase && blockIdx.x == 0 && tid == 0)
+            for (int k = 0; k < 8; ++k) A.phase[k] += phc[k];
+#endif
     }
     __syncthreads();
-    for (int k = warp; k < ncam; k += nwarps)
-        if (rowlane) A.x[(c0 + k) * 6 + a] = vec[k * 18 + a];
+    for (int i = tid; i < ncam * 6; i += blockDim.x) A.x[c0 * 6 + i] = vec[(i / 6) * 18 + (i % 6)];
     if (blockIdx.x == 0 && tid == 0) {
         A.flags[0] = done;
         A.flags[1] = its;

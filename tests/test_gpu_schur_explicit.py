@@ -88,9 +88,11 @@ def test_explicit_gauss_newton_step_vs_oracle(xcase, reg):
     d = 1.0 / np.where(lin.colnorm() == 0, 1.0, lin.colnorm())
     p, its, rel = eng.gn_step(x0, d, reg)
     p_ref, its_ref, rel_ref = schur_trf.schur_pcg(lin, d, reg, 1e-10, 1000)
-    # the engine preconditions with one exact block per PCG CTA (several cameras): never more iterations than the
-    # oracle's 6x6 block-Jacobi, usually fewer
-    assert rel <= 1e-10 and its <= its_ref + max(3, its_ref // 5)
+    # Same method and preconditioner on both sides.  The engine's one-exchange-per-iteration form carries z = Pinv r
+    # and the next inner products by recurrence; on the ill-conditioned system (reg = 1e-6) pushed to rtol = 1e-10 that
+    # costs up to a third more iterations than the textbook recurrences, varying with the summation order of the
+    # S-build's atomics (measured 97 .. 130 against the oracle's 97).  The default stopping rules end far earlier.
+    assert rel <= 1e-10 and its <= its_ref + max(3, its_ref // 2), (rel, its, its_ref)
     Jdp = lin.jdot(d * p)
     nc = lin.Nc
     JtJdp = np.hstack((schur_trf._segsum(lin.fi, np.einsum("nij,ni->nj", lin.Jc, Jdp), nc).ravel(),

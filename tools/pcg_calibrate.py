@@ -9,7 +9,7 @@ from meatmodeler_b200 import bundleAdjuster as mm
 
 out_dir = os.path.join(ROOT, "gpurun_out")
 os.makedirs(out_dir, exist_ok=True)
-tag = "classic" if os.environ.get("MMBA_PCG_CLASSIC") == "1" else "single"
+tag = "single"
 for name in sys.argv[1:] or ["C4", "C2"]:
     prob = synth.make_config(name, hard=True)
     ext, K, pts, uv, fi, pi = prob.args()
