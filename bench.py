@@ -273,6 +273,14 @@ def measure(args, ctx, prob, label, scaling, cfg, clocks=None):
     wall_ms = max_over_ranks(wall_ms)
     value = nobs * its / (dev_ms * 1e-3)
     final_cost, nit_per_step, nfev = r.cost, r.nit, r.nfev
+    costs = [row["cost"] for row in eng.log()]
+    # size-independent properties of the solve: the cost never increases over the accepted iterations, and the final
+    # reprojection RMS sits at the noise floor of the synthetic data (0.5 px per coordinate -> 0.707 px per observation,
+    # times sqrt((m - n) / m) for the fitted parameters)
+    checks = {"cost_monotone": bool(all(b <= a for a, b in zip(costs, costs[1:]))), "costs": costs,
+              "rms_px": float(np.sqrt(2.0 * final_cost / nobs)),
+              "expected_rms_px": float(0.5 * np.sqrt(2.0) * np.sqrt(max(2 * nobs - (6 * nc + 3 * npts), 1) / (2 * nobs))),
+              "status": int(r.status), "nfev": int(nfev)}
     pcg_rtol, pcg_atol, pcg_ktol = eng.options.pcg_rtol, eng.options.pcg_atol, eng.options.pcg_ktol
 
     # ---- sharded solve == single-GPU solve (rank 0 solves the whole problem on its own GPU) ------------------
@@ -410,7 +418,7 @@ def measure(args, ctx, prob, label, scaling, cfg, clocks=None):
         "lm_iterations_per_step": nit_per_step, "lm_iterations_per_s": its / (dev_ms * 1e-3),
         "pcg_iterations_per_step": pcg / args.steps, "final_cost": final_cost,
         "wall_ms_per_step": wall_ms / args.steps, "setup_ms": setup_ms,
-        "gpu_launches": launches, "e2e": e2e, "roofline": roofline,
+        "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "checks": checks,
         **({"sharded_vs_single": sharded_vs_single} if sharded_vs_single else {}),
     }
 
@@ -469,6 +477,7 @@ def run_mmba(args):
         line["clocks"] = clocks.summary()
         line["e2e"] = m["e2e"]
         line["roofline"] = m["roofline"]
+        line["checks"] = m["checks"]
         if "sharded_vs_single" in m:
             line["sharded_vs_single"] = m["sharded_vs_single"]
         if also:

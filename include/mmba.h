@@ -69,7 +69,9 @@ typedef struct mmba_options {
                              ||res||, ||A||_est ~ sqrt(k) for unit-norm columns) on the reduced system.  LSMR is a
                              minimal-residual method on the normal equations; the minimal-residual norm of the PCG
                              process is nu_k, 1 / nu_k^2 = sum_{j<=k} 1 / ||r_j||^2: stop when
-                             nu_k <= pcg_ktol sqrt(k) ||f||.  0 = off. */
+                             nu_k <= pcg_ktol sqrt(k) ||f||.  0 = off.  Default 1.23e-6 = LSMR's atol (1e-6, scipy's default,
+                             the one the reference gets) x the measured growth of its estimate, ||A||_est = 1.23 sqrt(k)
+                             (tools/lsmr_spy.py): the literal translation, not a calibration. */
 } mmba_options;
 
 /* The reduced camera system S = U - W V'^-1 W^T of the damped Gauss-Newton step:
@@ -145,6 +147,12 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
  * (bundleAdjuster.py:180-192).  x is in/out (n = 6*n_cams + 3*n_points); fun_out (2*n_obs, may be
  * NULL) receives the residuals at the returned x in the caller's observation order. */
 int mmba_solve(mmba_handle* h, double* x, mmba_result* result, double* fun_out);
+
+/* The same solve with the two halves of the parameter vector in separate, caller-owned arrays — what adjustPoints holds
+ * before it packs them (bundleAdjuster.py:172-176: frameParameters(...) (6 n_cams) and points_3D (3 n_points)) and what it
+ * unpacks them into afterwards (:137-157): saves the packed host copies in both directions.  Inputs are not modified. */
+int mmba_solve_split(mmba_handle* h, const double* cams_in, const double* points_in, double* cams_out, double* points_out,
+                     mmba_result* result, double* fun_out);
 
 /* replaces: least_squares(poseFun, parameters, ftol=1e-4) inside adjustPose (bundleAdjuster.py:232-241):
  * dense-Jacobian defaults, i.e. method='trf', tr_solver='exact', x_scale=1.  Only the 6*n_cams camera

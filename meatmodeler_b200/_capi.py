@@ -67,6 +67,7 @@ SIGNATURES = {
     "mmba_set_options": (C.c_int, [_H, C.POINTER(Options)]),
     "mmba_set_problem": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, _f64, _i64, _i64, _f64]),
     "mmba_solve": (C.c_int, [_H, _f64, C.POINTER(Result), C.c_void_p]),
+    "mmba_solve_split": (C.c_int, [_H, _f64, _f64, _f64, _f64, C.POINTER(Result), C.c_void_p]),
     "mmba_solve_pose": (C.c_int, [_H, _f64, C.POINTER(Result), C.c_void_p]),
     "mmba_set_x": (C.c_int, [_H, _f64]),
     "mmba_solve_resident": (C.c_int, [_H, C.POINTER(Result)]),
@@ -243,6 +244,21 @@ class Engine:
         fun = np.empty(2 * self.sizes[2]) if want_fun else None
         _check(lib().mmba_solve(self._h, x, C.byref(res), fun.ctypes.data if want_fun else None), self._h)
         return x, res, fun
+
+    def solve_split(self, cams, points, want_fun=False):
+        """The solve with cameras (6 per camera) and points (3 per point) in separate arrays, as adjustPoints holds them:
+        returns (cams_out (Nc,6), points_out (Np,3), Result, fun or None); inputs are read in place, never copied or modified."""
+        cams = _c(cams, np.float64).reshape(-1)
+        points = _c(points, np.float64).reshape(-1)
+        if cams.size != 6 * self.sizes[0] or points.size != 3 * self.sizes[1]:
+            raise ValueError("cams / points do not match the problem's sizes")
+        cams_out = np.empty((self.sizes[0], 6))
+        points_out = np.empty((self.sizes[1], 3))
+        res = Result()
+        fun = np.empty(2 * self.sizes[2]) if want_fun else None
+        _check(lib().mmba_solve_split(self._h, cams, points, cams_out.reshape(-1), points_out.reshape(-1), C.byref(res),
+                                      fun.ctypes.data if want_fun else None), self._h)
+        return cams_out, points_out, res, fun
 
     def solve_pose(self, x0, want_fun=False):
         """Pose-only solve: cameras are variables, the points in x0 are constants."""

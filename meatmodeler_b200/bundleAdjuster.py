@@ -61,6 +61,20 @@ class SolveResult(dict):
         return list(self.keys())
 
 
+class _SplitX:
+    """Result parameters held as (cameras (Nc,6), points (Np,3)); ``np.asarray`` gives the packed vector."""
+
+    def __init__(self, cams, points):
+        self.cams, self.points = cams, points
+
+    def __array__(self, dtype=None, copy=None):
+        x = np.hstack((self.cams.reshape(-1), self.points.reshape(-1)))
+        return x if dtype is None else x.astype(dtype)
+
+    def __len__(self):
+        return self.cams.size + self.points.size
+
+
 def rotate(points, rot_vecs):
     """Rodrigues rotation of ``points[i]`` by ``rot_vecs[i]`` (bundleAdjuster.py:7-28), on the GPU."""
     return _capi.rotate(points, rot_vecs, device=_current_device())
@@ -120,9 +134,12 @@ def _rodrigues(rvecs):
 
 def reformatPointResult(result, n_frames, n_points):
     """``result.x`` -> ((Np,3) points, list of Nc 4x4 extrinsics)   (bundleAdjuster.py:137-157)."""
-    x = np.asarray(result.x)
-    points = x[n_frames * 6:].reshape((n_points, 3))
-    frames = x[:n_frames * 6].reshape((n_frames, 6))
+    if isinstance(result.x, _SplitX):
+        points, frames = result.x.points, result.x.cams
+    else:
+        x = np.asarray(result.x)
+        points = x[n_frames * 6:].reshape((n_points, 3))
+        frames = x[:n_frames * 6].reshape((n_frames, 6))
     ext = np.zeros((n_frames, 4, 4))
     ext[:, :3, :3] = _rodrigues(frames[:, :3])
     ext[:, :3, 3] = frames[:, 3:]
@@ -263,7 +280,13 @@ def solve(parameters, camera_matrix, n_frames, n_points, frame_indices, point_in
         camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D,
         ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=0 if max_nfev is None else int(max_nfev), **options)
     try:
-        x, r, fun = eng.solve(parameters, want_fun=want_fun)
+        if isinstance(parameters, tuple):
+            # (camera parameters, points) as adjustPoints holds them: no packed host copy in either direction; the
+            # packed vector scipy's OptimizeResult carries is available as ``res.x`` on demand (SolveResult.x)
+            cams_out, points_out, r, fun = eng.solve_split(parameters[0], parameters[1], want_fun=want_fun)
+            x = _SplitX(cams_out, points_out)
+        else:
+            x, r, fun = eng.solve(parameters, want_fun=want_fun)
     except _capi.MmbaError as e:
         if e.code == -4:   # scipy raises ValueError here (least_squares.py:945-946)
             raise ValueError("Residuals are not finite in the initial point.") from e
@@ -379,8 +402,9 @@ def adjustPoints(frame_extrinsic_matrices, camera_intrinsic_matrix, points_3D, p
     ext = np.asarray(frame_extrinsic_matrices, dtype=np.float64)
     pts = np.asarray(points_3D, dtype=np.float64)
     n_frames, n_points = len(ext), len(pts)
-    parameters = np.hstack((frameParameters(ext), pts.reshape((n_points * 3,))))
-    res = solve(parameters, camera_intrinsic_matrix, n_frames, n_points, frame_indices, point_indices,
-                points_2D, ftol=FTOL, verbose=VERBOSE)
+    # the reference packs np.hstack((frameParameters(...), points)) (bundleAdjuster.py:172-176); the two halves go to
+    # the engine as they are (mmba_solve_split), the packed vector is never materialised on the host
+    res = solve((frameParameters(ext), pts.reshape((n_points * 3,))), camera_intrinsic_matrix, n_frames, n_points,
+                frame_indices, point_indices, points_2D, ftol=FTOL, verbose=VERBOSE)
     last_result = res
     return reformatPointResult(res, n_frames, n_points)

@@ -582,14 +582,26 @@ int put_x(mmba_handle* h, const double* x, double* dst) {
     return MMBA_OK;
 }
 
-// device n-vector -> caller's layout.  With nranks > 1 the point part is completed over ranks.
-int get_x(mmba_handle* h, const double* src, double* x) {
+// the same with the camera and the point parameters in separate host arrays (no packed copy on the host)
+int put_x_split(mmba_handle* h, const double* cams, const double* points, double* dst) {
+    const DevPlan& dp = h->dp;
+    TRY(h2d(h, h->d.x_io, cams, (size_t)(6 * h->Nc) * sizeof(double)));
+    TRY(h2d(h, h->d.x_io + 6 * h->Nc, points, (size_t)(3 * dp.n_points) * sizeof(double)));
+    devplan_gather_x(h->d.x_io, dst, dp.point_perm, h->Nc, dp.pt_begin, h->npl, h->stream);
+    return MMBA_OK;
+}
+
+// device n-vector -> caller's layout (x, or cameras and points separately when x == nullptr).  With nranks > 1 the
+// point part is completed over ranks.
+int get_x(mmba_handle* h, const double* src, double* x, double* cams = nullptr, double* points = nullptr) {
     const DevPlan& dp = h->dp;
     const size_t n_total = (size_t)(6 * h->Nc + 3 * dp.n_points);
     if (h->opt.nranks > 1) CU(cudaMemsetAsync(h->d.x_io + 6 * h->Nc, 0, 3 * (size_t)dp.n_points * sizeof(double), h->stream));
     devplan_scatter_x(src, h->d.x_io, dp.point_perm, h->Nc, dp.pt_begin, h->npl, true, h->stream);
     if (h->opt.nranks > 1) TRY(allreduce(h, {{h->d.x_io + 6 * h->Nc, (size_t)(3 * dp.n_points), false}}));
-    return d2h(h, x, h->d.x_io, n_total * sizeof(double));
+    if (x) return d2h(h, x, h->d.x_io, n_total * sizeof(double));
+    TRY(d2h(h, cams, h->d.x_io, (size_t)(6 * h->Nc) * sizeof(double)));
+    return d2h(h, points, h->d.x_io + 6 * h->Nc, (size_t)(3 * dp.n_points) * sizeof(double));
 }
 
 // tile-major rows [row0, row0 + rows) of src ([tile][src_rows][256]) -> caller-ordered (n_obs, rows) row-major;
@@ -1335,7 +1347,7 @@ void mmba_default_options(mmba_options* opt) {
     opt->schur_mode = MMBA_SCHUR_AUTO;
     opt->reserved = 0;
     opt->pcg_atol = 1e-7;
-    opt->pcg_ktol = 3e-7;
+    opt->pcg_ktol = 1.23e-6;   // LSMR's atol (1e-6) x the growth of its ||A|| estimate (1.23 sqrt(k)): no calibration
 }
 
 int mmba_nccl_unique_id(uint8_t out[128]) {
@@ -1739,6 +1751,17 @@ int mmba_solve(mmba_handle* h, double* x, mmba_result* result, double* fun_out) 
     TRY(put_x(h, x, h->d.x));
     TRY(solve_on_device(h, result));
     TRY(get_x(h, h->d.x, x));
+    if (fun_out) TRY(get_slots(h, h->d.res, 2, 0, 2, fun_out));
+    return MMBA_OK;
+}
+
+int mmba_solve_split(mmba_handle* h, const double* cams_in, const double* points_in, double* cams_out, double* points_out,
+                     mmba_result* result, double* fun_out) {
+    TRY(need_problem(h));
+    if (!cams_in || !points_in || !cams_out || !points_out || !result) return fail(h, MMBA_ERR_ARG, "solve_split: null argument");
+    TRY(put_x_split(h, cams_in, points_in, h->d.x));
+    TRY(solve_on_device(h, result));
+    TRY(get_x(h, h->d.x, nullptr, cams_out, points_out));
     if (fun_out) TRY(get_slots(h, h->d.res, 2, 0, 2, fun_out));
     return MMBA_OK;
 }

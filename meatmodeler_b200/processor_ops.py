@@ -120,3 +120,24 @@ def managePoints(tracks):
         frame_indices.extend(coords.keys())
         point_indices.extend([point_index] * len(coords))
     return points, coordinates, frame_indices, point_indices
+
+
+def savePointCloud(points, filename):
+    """The output side of ``processor.process`` (processor.py:480-485):
+    ``PyntCloud(pd.DataFrame(adjusted_points, columns=['x', 'y', 'z'])).to_file(filename)`` without pandas / pyntcloud.
+
+    Writes the file pyntcloud's PLY writer produces for that frame (pyntcloud/io/ply.py ``write_ply``, ``as_text=False``):
+    a text header — ``ply``, ``format binary_<byteorder>_endian 1.0``, ``element vertex N``, one ``property double``
+    line per column, ``end_header`` — followed by the N x 3 float64 records, i.e. the result buffer of ``adjustPoints``
+    as it is.  pyntcloud is not installed in this image, so the format is restated from its source, not pinned.
+    """
+    import sys
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    header = ["ply", f"format binary_{sys.byteorder}_endian 1.0", f"element vertex {len(pts)}",
+              "property double x", "property double y", "property double z", "end_header"]
+    with open(filename, "w") as f:
+        for line in header:
+            f.write(f"{line}\n")
+    with open(filename, "ab") as f:
+        pts.tofile(f)
+    return filename

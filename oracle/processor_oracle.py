@@ -1,9 +1,11 @@
 """CPU restatement of the ``processor.py`` steps next to the bundle-adjustment path.  TEST INFRASTRUCTURE
 ONLY: nothing under meatmodeler_b200/ imports this module.
 
-``processor.py`` itself cannot be imported in the build container (pyntcloud is not installed), so the two functions
-are restated from the source; they are plain Python over duck-typed track objects (track.py:1-41) and need no pinning
-beyond the reference's own lines cited below.
+Parity status: PINNED.  tests/golden/make_golden_processor.py imports the unmodified ``processor.py`` (its pyntcloud /
+lxml imports, needed only by the PLY export, are satisfied by empty stand-in modules) and records what ``pointTracking``,
+``triangulatePoints`` and ``managePoints`` do on seeded scenarios with the reference's own ``Track`` class;
+tests/test_processor_ops.py checks this restatement and the product (meatmodeler_b200/processor_ops.py) against those
+vectors (tests/golden/processor.npz).
 """
 
 

@@ -145,7 +145,7 @@ def schur_pcg(lin: Linearisation, d, reg, rtol, maxit, atol=0.0, f2=0.0, ktol=0.
 
 
 def solve(x0, K, Nc, Np, fi, pi, uv, ftol=1e-4, xtol=1e-8, gtol=1e-8, max_nfev=None,
-          pcg_rtol=1e-10, pcg_maxit=1000, record=None, pcg_atol=1e-7, pcg_ktol=3e-7):
+          pcg_rtol=1e-10, pcg_maxit=1000, record=None, pcg_atol=1e-7, pcg_ktol=1.23e-6):
     """TRF outer loop (trf.py:415-587) around ``schur_pcg``.  Returns a dict with x, cost, fun,
     nfev, njev, nit, status, optimality and the per-iteration log (cost, reg, Delta, pcg its)."""
     x = np.array(x0, dtype=np.float64)

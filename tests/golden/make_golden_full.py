@@ -1,4 +1,5 @@
-"""Golden trajectories of the UNMODIFIED reference at BASELINE sizes (configs[1] = C2, configs[3] = C4).
+"""Golden trajectories of the UNMODIFIED reference at BASELINE sizes (configs[1] = C2, configs[2] = C3 / C3r,
+configs[3] = C4).
 
 Run in the build container only (needs /root/reference; C2 takes about a minute and 4 GB, C4 about 10 minutes and
 18 GB):  python tests/golden/make_golden_full.py [C2] [C4]
@@ -22,7 +23,10 @@ from meatmodeler_b200 import synth  # noqa: E402
 
 def main(names):
     for name in names:
-        prob = synth.make_config(name, hard=True)
+        # "C3r": BASELINE configs[2] with uniform-random camera subsets per point (the survey's stress variant, dense
+        # co-visibility: the engine's implicit Schur path) instead of video-like windows
+        random_vis = name.endswith("r")
+        prob = synth.make_config(name.rstrip("r"), hard=True, windowed=not random_vis)
         ext, K, pts, uv, fi, pi = prob.args()
         t0 = time.perf_counter()
         x0, res, costs, lsmr_its = mg.reference_trajectory(prob)

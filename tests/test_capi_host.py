@@ -37,7 +37,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_capi.IterLog) == 9 * 8
     opt = _capi.default_options()
     assert (opt.ftol, opt.xtol, opt.gtol, opt.nranks, opt.max_nfev) == (1e-4, 1e-8, 1e-8, 1, 0)
-    assert opt.schur_mode == _capi.SCHUR_AUTO and opt.pcg_atol == 1e-7 and opt.pcg_ktol == 3e-7
+    assert opt.schur_mode == _capi.SCHUR_AUTO and opt.pcg_atol == 1e-7 and opt.pcg_ktol == 1.23e-6
 
 
 def test_no_gpu_means_loud_failure():

@@ -160,3 +160,101 @@ def test_triangulate_edge_cases_and_large_batch(golden_tri):
     out, ms = _capi.triangulate(P, f1, f2, uv1, uv2, return_ms=True)
     assert np.abs(out - X).max() <= 1e-7
     assert ms > 0
+
+
+# ---- pinned against the UNMODIFIED reference (tests/golden/make_golden_processor.py -> processor.npz) -----------------
+
+@pytest.fixture(scope="module")
+def golden_proc():
+    return dict(np.load(os.path.join(GOLDEN, "processor.npz")))
+
+
+def _unpack_tracks(ptr, frames, xy, as_f32=True):
+    out = []
+    for i in range(len(ptr) - 1):
+        coords = {}
+        for j in range(ptr[i], ptr[i + 1]):
+            c = (np.float32(xy[j, 0]), np.float32(xy[j, 1])) if as_f32 else (float(xy[j, 0]), float(xy[j, 1]))
+            coords[int(frames[j])] = c
+        out.append(_Track(coords))
+    return out
+
+
+def _pack(tracks):
+    ptr, frames, xy = [0], [], []
+    for t in tracks:
+        for f, c in t.getCoordinates().items():
+            frames.append(f)
+            xy.append((float(c[0]), float(c[1])))
+        ptr.append(len(frames))
+    return np.array(ptr), np.array(frames), np.array(xy, dtype=np.float64).reshape(-1, 2)
+
+
+@pytest.mark.parametrize("impl", ["oracle", "product"])
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_point_tracking_vs_reference_golden(golden_proc, tag, impl):
+    """pointTracking of the unmodified reference (processor.py:190-243) on seeded scenarios: which tracks are popped, which
+    survive (in order), what the survivors and the new tracks contain — for the oracle restatement AND the hash join."""
+    g = golden_proc
+    tracks = _unpack_tracks(g[f"pt_{tag}_in_ptr"], g[f"pt_{tag}_in_frames"], g[f"pt_{tag}_in_xy"])
+    feats, corr = g[f"pt_{tag}_feats"], g[f"pt_{tag}_corr"]
+    if impl == "oracle":
+        popped, updated = po.point_tracking(tracks, 4, feats, 5, corr, _Track)
+    else:
+        popped, updated = mp.pointTracking(tracks, 4, feats, 5, corr, track_class=_Track)
+    ids = {id(t): i for i, t in enumerate(tracks)}
+    np.testing.assert_array_equal([ids[id(t)] for t in popped], g[f"pt_{tag}_popped"])
+    np.testing.assert_array_equal([ids.get(id(t), -1) for t in updated], g[f"pt_{tag}_updated_src"])
+    ptr, frames, xy = _pack(updated)
+    np.testing.assert_array_equal(ptr, g[f"pt_{tag}_up_ptr"])
+    np.testing.assert_array_equal(frames, g[f"pt_{tag}_up_frames"])
+    np.testing.assert_array_equal(xy, g[f"pt_{tag}_up_xy"])
+    np.testing.assert_array_equal([t.wasUpdated() for t in updated], g[f"pt_{tag}_updated_flags"])
+
+
+@pytest.mark.parametrize("impl", ["oracle", "product"])
+def test_manage_points_vs_reference_golden(golden_proc, impl):
+    g = golden_proc
+    tracks = _unpack_tracks(g["mp_ptr"], g["mp_frames"], g["mp_xy"], as_f32=False)
+    for t, p in zip(tracks, g["mp_points"]):
+        t.setPoint(p.reshape(tuple(g["mp_point_shape"])))
+    fn = po.manage_points if impl == "oracle" else mp.managePoints
+    points, coordinates, frame_indices, point_indices = fn(tracks)
+    np.testing.assert_array_equal(np.array(points).reshape(-1, 3), g["mp_points"])
+    assert np.array(points[0]).shape == tuple(g["mp_point_shape"])
+    np.testing.assert_array_equal(np.array(coordinates, dtype=np.float64), g["mp_coordinates"])
+    np.testing.assert_array_equal(frame_indices, g["mp_frame_indices"])
+    np.testing.assert_array_equal(point_indices, g["mp_point_indices"])
+
+
+def test_triangulate_oracle_vs_reference_processor_golden(golden_proc):
+    """The oracle's DLT against the points the unmodified processor.triangulatePoints stored on its tracks."""
+    g = golden_proc
+    ptr, frames, xy = g["mp_ptr"], g["mp_frames"], g["mp_xy"]
+    f1, f2 = frames[ptr[:-1]], frames[ptr[1:] - 1]
+    out = tri.triangulate(g["mp_projections"], f1, f2, xy[ptr[:-1]], xy[ptr[1:] - 1])
+    assert np.abs(out - g["mp_points"]).max() <= 1e-9 * np.abs(g["mp_points"]).max()
+
+
+@pytest.mark.gpu
+def test_triangulate_points_dropin_vs_reference_processor_golden(golden_proc):
+    """processor_ops.triangulatePoints (one kernel launch over all tracks) against the unmodified reference's per-track
+    cv2 loop: same points on the tracks, same (1, 3) shape."""
+    g = golden_proc
+    tracks = _unpack_tracks(g["mp_ptr"], g["mp_frames"], g["mp_xy"], as_f32=False)
+    mp.triangulatePoints(tracks, list(g["mp_projections"]))
+    got = np.array([t.getPoint() for t in tracks])
+    assert got.shape[1:] == tuple(g["mp_point_shape"])
+    assert np.abs(got.reshape(-1, 3) - g["mp_points"]).max() <= 1e-9 * np.abs(g["mp_points"]).max()
+
+
+def test_save_point_cloud_writes_a_binary_ply(tmp_path):
+    """processor.py:480-485 (PyntCloud(...).to_file): header + raw float64 records; read back with a minimal parser."""
+    pts = np.random.default_rng(3).normal(size=(257, 3))
+    path = mp.savePointCloud(pts, str(tmp_path / "Cloud.ply"))
+    raw = open(path, "rb").read()
+    head, _, body = raw.partition(b"end_header\n")
+    lines = head.decode().splitlines()
+    assert lines[0] == "ply" and lines[1].startswith("format binary_") and lines[1].endswith("_endian 1.0")
+    assert lines[2] == "element vertex 257" and lines[3:6] == ["property double x", "property double y", "property double z"]
+    np.testing.assert_array_equal(np.frombuffer(body, dtype=np.float64).reshape(-1, 3), pts)
