@@ -113,7 +113,7 @@ struct Dev {
     double *x, *xn, *x0, *camtab, *camtab_n;
     double *U, *Ud, *g, *V, *M, *zg, *dp;
     // n-vectors (camera part first, then the local points)
-    double *sinv, *gh, *gn, *s1, *s2, *v1, *v2, *tmp;
+    double *sinv, *gh, *gn, *tmp;
     // PCG (camera-sized)
     double *y, *Sd, *Pinv, *px, *pr, *pz, *pp, *pq, *pxt, *part, *state;
     double *pose_lam, *pose_suf, *pose_V, *pose_w;   // pose-only adjustment (per-camera eigen data)
@@ -356,10 +356,6 @@ void carve(mmba_handle* h, Arena& a) {
     d.sinv = a.take<double>(nloc);
     d.gh = a.take<double>(nloc);
     d.gn = a.take<double>(nloc);
-    d.s1 = a.take<double>(nloc);
-    d.s2 = a.take<double>(nloc);
-    d.v1 = a.take<double>(nloc);
-    d.v2 = a.take<double>(nloc);
     d.tmp = a.take<double>(nloc);
     d.y = a.take<double>(6 * Nc);
     d.Sd = a.take<double>(21 * Nc);
@@ -1069,40 +1065,34 @@ int run_trf(mmba_handle* h, mmba_result* out) {
         h->log.back().reg = reg;
         h->log.back().pcg_iterations = its;
 
-        // S = orth[g_h, gn_h], B_S = (J_h S)^T (J_h S), g_S = S^T g_h   (trf.py:496-500)
+        // S = orth[g_h, gn_h], B_S = (J_h S)^T (J_h S), g_S = S^T g_h   (trf.py:496-500).  The orthonormal basis is
+        // s1 = g_h / ||g_h||, s2 = (gn_h - c1 s1) / n2 with c1 = s1.gn_h, n2^2 = ||gn_h||^2 - c1^2; it is never formed:
+        // with u1 = d o g_h (d.tmp) and u2 = d o gn_h (d.gn) the products J_h s1 = J u1 / ||g_h|| and
+        // J_h s2 = (J u2 - kappa J u1) / n2, kappa = c1 / ||g_h||, follow from the Gram matrix of J [u1 u2]
+        // (one J pass) and five dot products (one vector pass): one host round trip instead of three.
         TRY(zero(h, d.scal + S_DOT0, 10));
-        LAUNCH(MMBA_K_VEC, gn_assemble_kernel<false>, gc_, 256, 0, d.px, d.sinv, d.gh, d.gn, ncam, d.scal, lead);
-        if (npt)
-            LAUNCH(MMBA_K_VEC, gn_assemble_kernel<true>, gp_, 256, 0, d.dp, d.sinv + ncam, d.gh + ncam, d.gn + ncam, npt,
-                   d.scal, 1);
-        TRY(allreduce(h, {{d.scal + S_DOT0, 2, false}}));
+        LAUNCH(MMBA_K_VEC, subspace_dots_kernel, gv, 256, 0, d.gh, d.tmp, d.sinv, d.px, d.pxt, d.dp, d.gn, ncam, nloc, d.scal, lead);
+        TRY(allreduce(h, {{d.scal + S_DOT0, 5, false}}));
+        TRY(jv2(h, d.tmp, d.gn));
         TRY(read_scalars(h));
+        const double D0 = h->h_scal[S_DOT0], D1 = h->h_scal[S_DOT1];
+        const double U11 = h->h_scal[S_DOT2], U12 = h->h_scal[S_DOT3], U22 = h->h_scal[S_DOT4];
+        const double G11 = h->h_scal[S_JV00], G12 = h->h_scal[S_JV01], G22 = h->h_scal[S_JV11];
         const double inv_gh = gh_norm > 0 ? 1.0 / gh_norm : 0.0;
-        const double c1 = h->h_scal[S_DOT0] * inv_gh;
-        LAUNCH(MMBA_K_VEC, orth_a_kernel, gc_, 256, 0, d.gh, d.gn, inv_gh, c1, d.s1, d.s2, ncam, d.scal, lead);
-        if (npt)
-            LAUNCH(MMBA_K_VEC, orth_a_kernel, gp_, 256, 0, d.gh + ncam, d.gn + ncam, inv_gh, c1, d.s1 + ncam, d.s2 + ncam,
-                   npt, d.scal, 1);
-        TRY(allreduce(h, {{d.scal + S_DOT2, 2, false}}));
-        TRY(read_scalars(h));
-        const double c2 = h->h_scal[S_DOT2];
-        LAUNCH(MMBA_K_VEC, orth_b_kernel, gc_, 256, 0, d.gh, d.sinv, c2, d.s1, d.s2, d.v1, d.v2, ncam, d.scal, lead);
-        if (npt)
-            LAUNCH(MMBA_K_VEC, orth_b_kernel, gp_, 256, 0, d.gh + ncam, d.sinv + ncam, c2, d.s1 + ncam, d.s2 + ncam,
-                   d.v1 + ncam, d.v2 + ncam, npt, d.scal, 1);
-        TRY(allreduce(h, {{d.scal + S_DOT4, 6, false}}));
-        TRY(jv2(h, d.v1, d.v2));
-        TRY(read_scalars(h));
-        const double n2 = std::sqrt(h->h_scal[S_DOT4]);
-        // second basis vector is s2/n2; degenerate (gn parallel to g_h) -> 1-D problem along s1
-        const double i2 = (n2 > 1e-300 && std::isfinite(n2)) ? 1.0 / n2 : 0.0;
-        double B[3] = {h->h_scal[S_JV00], h->h_scal[S_JV01] * i2, h->h_scal[S_JV11] * i2 * i2};
-        double gS[2] = {h->h_scal[S_DOT9], h->h_scal[S_DOT5] * i2};
-        const double vv00 = h->h_scal[S_DOT6], vv01 = h->h_scal[S_DOT7] * i2, vv11 = h->h_scal[S_DOT8] * i2 * i2;
+        const double kappa = D0 * inv_gh * inv_gh;                  // c1 / ||g_h||
+        const double n2sq = D1 - D0 * D0 * inv_gh * inv_gh;         // ||s2||^2 before normalisation
+        // second basis vector is s2 / n2; degenerate (gn_h parallel to g_h up to rounding, or not finite) -> 1-D
+        // problem along s1
+        const bool two_d = std::isfinite(n2sq) && std::isfinite(D1) && n2sq > 1e-24 * D1 && D1 > 0.0;
+        const double i2 = two_d ? 1.0 / std::sqrt(n2sq) : 0.0;
+        double B[3] = {G11 * inv_gh * inv_gh, (G12 - kappa * G11) * inv_gh * i2,
+                       (G22 - 2.0 * kappa * G12 + kappa * kappa * G11) * i2 * i2};
+        double gS[2] = {gh_norm, 0.0};                              // S^T g_h = (||g_h||, 0)
+        const double vv00 = U11 * inv_gh * inv_gh, vv01 = (U12 - kappa * U11) * inv_gh * i2,
+                     vv11 = (U22 - 2.0 * kappa * U12 + kappa * kappa * U11) * i2 * i2;
         if (i2 == 0.0) {
             B[1] = 0.0;
             B[2] = 1.0;
-            gS[1] = 0.0;
         }
 
         actual = -1;
@@ -1114,7 +1104,8 @@ int run_trf(mmba_handle* h, mmba_result* out) {
             if (i2 == 0.0) p[1] = 0.0;
             const double predicted = -(0.5 * (B[0] * p[0] * p[0] + 2 * B[1] * p[0] * p[1] + B[2] * p[1] * p[1]) +
                                        gS[0] * p[0] + gS[1] * p[1]);
-            LAUNCH(MMBA_K_VEC, trial_kernel, gv, 256, 0, d.x, d.v1, d.v2, p[0], p[1] * i2, d.xn, nloc);
+            // x + d o (p0 s1 + p1 s2) = x + (p0 / ||g_h|| - p1 kappa / n2) u1 + (p1 / n2) u2
+            LAUNCH(MMBA_K_VEC, trial_kernel, gv, 256, 0, d.x, d.tmp, d.gn, p[0] * inv_gh - p[1] * kappa * i2, p[1] * i2, d.xn, nloc);
             TRY(trial_cost(h, d.xn, d.camtab_n));
             TRY(read_scalars(h));
             nfev++;

@@ -82,8 +82,9 @@ __global__ void unscale_kernel(const double* __restrict__ a, const double* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// 2-D subspace construction  S = orth[g_h, gn_h]  (trf.py:496-500; scipy uses LAPACK QR, here
-// Gram-Schmidt with one re-orthogonalisation; the subspace and therefore the step are the same)
+// 2-D subspace construction  S = orth[g_h, gn_h]  (trf.py:496-500; scipy uses LAPACK QR; here the orthonormal
+// basis is expressed through dot products and one Gram matrix, see subspace_dots_kernel; the subspace and therefore
+// the step are the same)
 // ---------------------------------------------------------------------------------------------
 // gn = src * (sinv if MUL_SINV) ; D0 += gh.gn ; D1 += gn.gn
 template <bool MUL_SINV>
@@ -104,59 +105,49 @@ __global__ void gn_assemble_kernel(const double* __restrict__ src, const double*
     block_accumulate<2>(acc, s_red, outp);
 }
 
-// s1 = gh * inv_gh ; s2 = gn - c * s1 ; D2 += s1.s2 ; D3 += s2.s2
-__global__ void orth_a_kernel(const double* __restrict__ gh, const double* __restrict__ gn, double inv_gh, double c,
-                              double* __restrict__ s1, double* __restrict__ s2, int64_t n,
-                              double* __restrict__ scal, int accumulate) {
+// One pass for everything the 2-D subspace needs from the vectors (trf.py:496-500 builds S = orth[g_h, gn_h] with a QR
+// and multiplies J_h S; here the basis is never materialised: with u1 = d o g_h and u2 = d o gn_h (the unscaled images,
+// u2 = [pxt | dp] as the back-substitution left it) every quantity of the subspace problem is a combination of
+//   D0 = g_h.gn_h, D1 = gn_h.gn_h  (scaled),  U11 = u1.u1, U12 = u1.u2, U22 = u2.u2  (unscaled: step norm)
+// and of the Gram matrix of J [u1 u2] (one J pass, M_JV2).  Also writes u2 contiguously (camera part | local points).
+//   cam part (e < ncam): gn_h = px, u2 = pxt;  point part: u2 = dp, gn_h = u2 * sinv
+__global__ void subspace_dots_kernel(const double* __restrict__ gh, const double* __restrict__ u1, const double* __restrict__ sinv,
+                                     const double* __restrict__ px, const double* __restrict__ pxt, const double* __restrict__ dp,
+                                     double* __restrict__ u2, int64_t ncam, int64_t n, double* __restrict__ scal, int lead) {
     __shared__ double s_red[64];
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double acc[2] = {0, 0};
+    double acc[5] = {0, 0, 0, 0, 0};
     if (e < n) {
-        const double a = gh[e] * inv_gh;
-        const double b = gn[e] - c * a;
-        s1[e] = a;
-        s2[e] = b;
-        acc[0] = a * b;
-        acc[1] = b * b;
+        double gnh, w2;
+        const bool cam = e < ncam;
+        if (cam) {
+            gnh = px[e];
+            w2 = pxt[e];
+        } else {
+            w2 = dp[e - ncam];
+            gnh = w2 * sinv[e];
+        }
+        u2[e] = w2;
+        if (!cam || lead) {       // the replicated camera part is counted by one rank only
+            const double g = gh[e], w1 = u1[e];
+            acc[0] = g * gnh;
+            acc[1] = gnh * gnh;
+            acc[2] = w1 * w1;
+            acc[3] = w1 * w2;
+            acc[4] = w2 * w2;
+        }
     }
-    if (!accumulate) return;
-    double* outp[2] = {scal + S_DOT2, scal + S_DOT3};
-    block_accumulate<2>(acc, s_red, outp);
-}
-
-// s2 -= c2 * s1 (re-orthogonalisation, left unnormalised); v1 = s1/sinv, v2 = s2/sinv (unscaled);
-// D4 += s2.s2 ; D5 += s2.gh ; D6 += v1.v1 ; D7 += v1.v2 ; D8 += v2.v2 ; D9 += s1.gh
-__global__ void orth_b_kernel(const double* __restrict__ gh, const double* __restrict__ sinv, double c2,
-                              const double* __restrict__ s1, double* __restrict__ s2, double* __restrict__ v1,
-                              double* __restrict__ v2, int64_t n, double* __restrict__ scal, int accumulate) {
-    __shared__ double s_red[64];
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    if (e < n) {
-        const double a = s1[e];
-        const double b = s2[e] - c2 * a;
-        const double si = sinv[e];
-        const double va = a / si, vb = b / si;
-        s2[e] = b;
-        v1[e] = va;
-        v2[e] = vb;
-        acc[0] = b * b;
-        acc[1] = b * gh[e];
-        acc[2] = va * va;
-        acc[3] = va * vb;
-        acc[4] = vb * vb;
-        acc[5] = a * gh[e];
-    }
-    if (!accumulate) return;
-    double* outp[6] = {scal + S_DOT4, scal + S_DOT5, scal + S_DOT6, scal + S_DOT7, scal + S_DOT8, scal + S_DOT9};
-    block_accumulate<6>(acc, s_red, outp);
+    double* outp[5] = {scal + S_DOT0, scal + S_DOT1, scal + S_DOT2, scal + S_DOT3, scal + S_DOT4};
+    block_accumulate<5>(acc, s_red, outp);
 }
 
 // trial point x_new = x + p0 * v1 + p1 * v2   (x + d o step_h, trf.py:512-513)
 __global__ void trial_kernel(const double* __restrict__ x, const double* __restrict__ v1, const double* __restrict__ v2,
                              double p0, double p1, double* __restrict__ xn, int64_t n) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) xn[e] = x[e] + p0 * v1[e] + p1 * v2[e];
+    // a zero coefficient switches its vector off entirely (the Gauss-Newton direction may be non-finite after a PCG
+    // breakdown: the step then is the 1-D Cauchy step along v1)
+    if (e < n) xn[e] = x[e] + p0 * v1[e] + (p1 != 0.0 ? p1 * v2[e] : 0.0);
 }
 
 // ---------------------------------------------------------------------------------------------
