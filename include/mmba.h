@@ -186,6 +186,9 @@ int mmba_get_shard(const mmba_handle* h, int64_t* n_obs_local, int64_t* n_points
  * obs_perm (n_slots) / point_perm (n_points) as mmba_plan_export.  Any pointer may be NULL. */
 int mmba_get_plan_sizes(mmba_handle* h, int64_t sizes[8]);
 int mmba_get_plan_raw(mmba_handle* h, void* meta, int32_t* tile_cams, int64_t* obs_perm, int64_t* point_perm);
+/* per-point statistics the device plan is built from (n_points entries each, any pointer may be NULL; summed over ranks for
+ * a sharded handle): observation count, smallest / largest camera, smallest camera of the upper half of the ids */
+int mmba_get_plan_stats(mmba_handle* h, int32_t* count, int32_t* first_cam, int32_t* last_cam, int32_t* first_hi);
 /* the device-built block pattern of the reduced camera matrix: sizes[0..6] = upper blocks, full blocks, sum L (L + 1) / 2,
  * PCG CTAs, cameras per CTA, max blocks per CTA, max halo columns per CTA; up_rowptr / up_cols as mmba_host_rcm_pattern */
 int mmba_get_rcm_pattern(mmba_handle* h, int64_t sizes[8], int32_t* up_rowptr, int32_t* up_cols, int64_t capacity);

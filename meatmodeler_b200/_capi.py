@@ -104,6 +104,7 @@ SIGNATURES = {
     "mmba_plan_raw": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "mmba_get_plan_sizes": (C.c_int, [_H, C.POINTER(C.c_int64 * 8)]),
     "mmba_get_plan_raw": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmba_get_plan_stats": (C.c_int, [_H, _i32, _i32, _i32, _i32]),
     "mmba_get_rcm_pattern": (C.c_int, [_H, C.POINTER(C.c_int64 * 8), C.c_void_p, C.c_void_p, C.c_int64]),
 }
 
@@ -222,6 +223,12 @@ class Engine:
         _check(lib().mmba_get_plan_raw(self._h, meta.ctypes.data, tile_cams.ctypes.data, obs_perm.ctypes.data,
                                        point_perm.ctypes.data), self._h)
         out.update(meta=meta[:nt], tile_cams=tile_cams[:nt], obs_perm=obs_perm[:ns], point_perm=point_perm)
+        return out
+
+    def plan_stats(self):
+        """Per-point statistics of the device plan: (count, first camera, last camera, first camera of the upper half)."""
+        out = [np.zeros(self.sizes[1], dtype=np.int32) for _ in range(4)]
+        _check(lib().mmba_get_plan_stats(self._h, *out), self._h)
         return out
 
     def rcm_pattern(self):

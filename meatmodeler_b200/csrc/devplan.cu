@@ -235,7 +235,7 @@ __global__ void stats_init_kernel(int* count, int* first, int* last, int* first_
     if (p < n_points) {
         count[p] = 0;
         first[p] = n_cams;
-        last[p] = -1;
+        last[p] = 0;       // the smallest camera id is a neutral start; unobserved points are recognised by their count
         first_hi[p] = n_cams;
     }
 }
@@ -329,7 +329,7 @@ __global__ void cuts_kernel(const int* __restrict__ start_all, const u64* __rest
         }
         info->npo_local = max(0, min(lo, e) - b);
         info->n_obs_local = start_all[e] - start_all[b];
-        info->err_track = -1;
+        info->err_track = 0;
         info->n_tiles = 0;
         info->max_tile_cams = 0;
         info->max_tile_pts = 0;
@@ -418,7 +418,7 @@ __global__ void jump_init_kernel(const int* __restrict__ start, const int* __res
     }
     const int s0 = start[p];
     if (start[p + 1] - s0 > kTileObs) {
-        atomicMax(&info->err_track, perm[info->pt_begin + p]);
+        atomicMax(&info->err_track, perm[info->pt_begin + p] + 1);     // point index + 1: 0 = no error, max-reduced over ranks
         jump[p] = p + 1;
         return;
     }
@@ -816,10 +816,12 @@ int devplan_stats(DevPlanner& P, DevPlan& D, cudaStream_t s, std::string& err) {
     for (int pass = 0; pass < 2; ++pass) {
         Carver c;
         c.base = pass ? P.work.p : nullptr;
-        P.a.count = c.take<int>(np);
-        P.a.first = c.take<int>(np);
-        P.a.last = c.take<int>(np);
-        P.a.first_hi = c.take<int>(np);
+        // one block [count | first | last | first_hi], each np_pad ints: a sharded set-up all-gathers it as a whole
+        const size_t np_pad = (np + 63) / 64 * 64;
+        P.a.count = c.take<int>(4 * np_pad);
+        P.a.first = P.a.count + np_pad;
+        P.a.last = P.a.first + np_pad;
+        P.a.first_hi = P.a.last + np_pad;
         P.a.key = c.take<int>(np + 1);
         P.a.start_all = c.take<int>(np + 2);
         P.a.hist = c.take<int>(kHistInts);
@@ -839,6 +841,36 @@ int devplan_stats(DevPlanner& P, DevPlan& D, cudaStream_t s, std::string& err) {
                                                         P.a.first_hi);
     DP_CU(cudaGetLastError());
     return MMBA_OK;
+}
+
+// combine the all-gathered per-rank statistics blocks: counts add, first / first_hi take the minimum, last the maximum
+__global__ void combine_stats_kernel(const int* __restrict__ gathered, int nranks, size_t np_pad, int n_points, int* __restrict__ count,
+                                     int* __restrict__ first, int* __restrict__ last, int* __restrict__ first_hi) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_points) return;
+    int c = 0, f = 0x7fffffff, l = 0, fh = 0x7fffffff;
+    for (int r = 0; r < nranks; ++r) {
+        const int* blk = gathered + (size_t)r * 4 * np_pad;
+        c += blk[p];
+        f = min(f, blk[np_pad + p]);
+        l = max(l, blk[2 * np_pad + p]);
+        fh = min(fh, blk[3 * np_pad + p]);
+    }
+    count[p] = c;
+    first[p] = f;
+    last[p] = l;
+    first_hi[p] = fh;
+}
+
+void devplan_stat_block(DevPlanner& P, const DevPlan& D, int** block, size_t* n_ints) {
+    *block = P.a.count;
+    *n_ints = 4 * (((size_t)D.n_points + 63) / 64 * 64);
+}
+
+void devplan_combine_stats(DevPlanner& P, const DevPlan& D, const int* gathered, int nranks, cudaStream_t s) {
+    const size_t np_pad = ((size_t)D.n_points + 63) / 64 * 64;
+    combine_stats_kernel<<<cdiv64(D.n_points, 256), 256, 0, s>>>(gathered, nranks, np_pad, (int)D.n_points, P.a.count, P.a.first,
+                                                                 P.a.last, P.a.first_hi);
 }
 
 void devplan_stat_arrays(DevPlanner& P, const DevPlan&, int** count, int** first, int** last, int** first_hi) {
@@ -1009,8 +1041,8 @@ int devplan_sync_sizes(DevPlanner& P, DevPlan& D, cudaStream_t s, std::string& e
     DP_CU(cudaMemcpyAsync(P.h_info, P.d_info, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
     DP_CU(cudaStreamSynchronize(s));
     const PlanInfo& I = *P.h_info;
-    if (I.err_track >= 0) {
-        err = "set_problem: point " + std::to_string(I.err_track) + " has more observations than one tile holds (" +
+    if (I.err_track > 0) {
+        err = "set_problem: point " + std::to_string(I.err_track - 1) + " has more observations than one tile holds (" +
               std::to_string(kTileObs) + ")";
         return MMBA_ERR_TRACK;
     }

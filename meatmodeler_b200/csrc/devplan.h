@@ -47,7 +47,7 @@ struct Carver {
 
 // scalars the kernels leave for the host (one D2H copy per synchronisation point)
 struct PlanInfo {
-    int n_tiles, n_obs_local, npo_local, err_track;     // err_track: caller's point index with > 256 observations, or -1
+    int n_tiles, n_obs_local, npo_local, err_track;     // err_track: 1 + caller's point index with > 256 observations, 0 = none
     int max_tile_cams, max_tile_pts, pt_begin, pt_end;
     int nnz_up, nnz_full, nblk_max, nh_max;
     long long total_pairs;
@@ -113,10 +113,14 @@ struct DevPlanner {
     void release();
 };
 
-// Stage A (enqueue only): per-point statistics of the staged observations.  After it, a sharded solve sums
-// count / first / last / first_hi over ranks (arrays of n_points int32, see devplan_stat_arrays).
+// Stage A (enqueue only): per-point statistics of the staged observations.  After it, a sharded solve combines
+// count / first / last / first_hi over ranks (devplan_stat_block + devplan_combine_stats).
 int devplan_stats(DevPlanner& P, DevPlan& D, cudaStream_t s, std::string& err);
 void devplan_stat_arrays(DevPlanner& P, const DevPlan& D, int** count, int** first, int** last, int** first_hi);
+// the four arrays as one contiguous block (what a sharded set-up all-gathers) and the kernel that combines the gathered
+// per-rank blocks (counts add, first / first_hi: minimum, last: maximum)
+void devplan_stat_block(DevPlanner& P, const DevPlan& D, int** block, size_t* n_ints);
+void devplan_combine_stats(DevPlanner& P, const DevPlan& D, const int* gathered, int nranks, cudaStream_t s);
 // Stage B (enqueue only): point order, prefix sums, shard cuts (info.shard_begin, pt_begin, pt_end).
 int devplan_order(DevPlanner& P, DevPlan& D, cudaStream_t s, std::string& err);
 // Sharded set-up between stages B and C.  Every observation belongs to the rank that owns its point:

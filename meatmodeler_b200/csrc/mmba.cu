@@ -1568,10 +1568,13 @@ static int upload_observations(mmba_handle* h, int64_t n_cams, int64_t n_points,
         if (!P.d_counts) CU(cudaMalloc(&P.d_counts, (16 + 16 * 16) * sizeof(int)));
         long long v = first_bad < 0 ? INT64_MAX : first_bad;
         long long* d_v = reinterpret_cast<long long*>(P.d_counts);
+        long long* d_all = reinterpret_cast<long long*>(P.d_counts + 16);
+        std::vector<long long> all(h->opt.nranks);
         CU(cudaMemcpyAsync(d_v, &v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
-        NC(g_nccl.AllReduce(d_v, d_v, 1, ncclInt64, ncclMin, h->comm, h->stream));
-        CU(cudaMemcpyAsync(&v, d_v, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+        NC(g_nccl.AllGather(d_v, d_all, 1, ncclInt64, h->comm, h->stream));
+        CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
+        for (long long w : all) v = std::min(v, w);
         first_bad = v == INT64_MAX ? -1 : (int64_t)v;
     }
     if (first_bad >= 0) {
@@ -1620,16 +1623,19 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     int rc = devplan_stats(P, D, h->stream, err);
     if (rc != MMBA_OK) return fail(h, rc, err);
     if (nr > 1) {
-        int *cnt, *first, *last, *first_hi;
-        devplan_stat_arrays(P, D, &cnt, &first, &last, &first_hi);
+        // Per-point statistics over all ranks: ONE all-gather of the per-rank blocks, combined by a kernel of ours.
+        // (Four grouped ncclAllReduce calls — sum / min / max / min over int32 — left a block of ~70 k entries of one of
+        // the 4 MB arrays unreduced on 8 GPUs, NCCL 2.28.9: measured twice, a different array each time; an all-gather
+        // has no reduction to get wrong, and the combine is deterministic.)
+        int* block;
+        size_t n_ints;
+        devplan_stat_block(P, D, &block, &n_ints);
+        cudaError_t e = P.tmp.ensure((size_t)nr * n_ints * sizeof(int));
+        if (e != cudaSuccess) return fail(h, MMBA_ERR_NOMEM, std::string("set_problem: statistics exchange buffer: ") + cudaGetErrorString(e));
         prof_begin(h, MMBA_K_ALLREDUCE);
-        NC(g_nccl.GroupStart());
-        NC(g_nccl.AllReduce(cnt, cnt, (size_t)n_points, ncclInt32, ncclSum, h->comm, h->stream));
-        NC(g_nccl.AllReduce(first, first, (size_t)n_points, ncclInt32, ncclMin, h->comm, h->stream));
-        NC(g_nccl.AllReduce(last, last, (size_t)n_points, ncclInt32, ncclMax, h->comm, h->stream));
-        NC(g_nccl.AllReduce(first_hi, first_hi, (size_t)n_points, ncclInt32, ncclMin, h->comm, h->stream));
-        NC(g_nccl.GroupEnd());
+        NC(g_nccl.AllGather(block, P.tmp.p, n_ints, ncclInt32, h->comm, h->stream));
         prof_end(h, MMBA_K_ALLREDUCE);
+        devplan_combine_stats(P, D, reinterpret_cast<const int*>(P.tmp.p), nr, h->stream);
     }
     rc = devplan_order(P, D, h->stream, err);
     if (rc != MMBA_OK) return fail(h, rc, err);
@@ -1646,8 +1652,18 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
         if (rc != MMBA_OK) return fail(h, rc, err);
     }
     // (sharded: a too-long track is seen by the rank that owns the point only; all ranks must fail together)
-    if (nr > 1) NC(g_nccl.AllReduce(&P.d_info->err_track, &P.d_info->err_track, 1, ncclInt32, ncclMax, h->comm, h->stream));
+    std::vector<int> err_all;
+    if (nr > 1) {
+        NC(g_nccl.AllGather(&P.d_info->err_track, P.d_counts + 16, 1, ncclInt32, h->comm, h->stream));
+        err_all.resize(nr);
+        CU(cudaMemcpyAsync(err_all.data(), P.d_counts + 16, nr * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
     rc = devplan_sync_sizes(P, D, h->stream, err);
+    for (int v : err_all)
+        if (rc == MMBA_OK && v > 0) {
+            err = "set_problem: point " + std::to_string(v - 1) + " has more observations than one tile holds (" + std::to_string(kTileObs) + ")";
+            rc = MMBA_ERR_TRACK;
+        }
     if (rc != MMBA_OK) return fail(h, rc, err);
     lap("tiles + pattern bitmap");
     h->Nc = n_cams;
@@ -2338,6 +2354,19 @@ int mmba_get_plan_raw(mmba_handle* h, void* meta, int32_t* tile_cams, int64_t* o
         for (int64_t i = 0; i < D.n_slots; ++i) obs_perm[i] = so[i];
     if (point_perm)
         for (int64_t i = 0; i < D.n_points; ++i) point_perm[i] = pp[i];
+    return MMBA_OK;
+}
+
+int mmba_get_plan_stats(mmba_handle* h, int32_t* count, int32_t* first_cam, int32_t* last_cam, int32_t* first_hi) {
+    TRY(need_problem(h));
+    int *c, *f, *l, *fh;
+    devplan_stat_arrays(h->planner, h->dp, &c, &f, &l, &fh);
+    const size_t bytes = (size_t)h->dp.n_points * sizeof(int32_t);
+    if (count) CU(cudaMemcpyAsync(count, c, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (first_cam) CU(cudaMemcpyAsync(first_cam, f, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (last_cam) CU(cudaMemcpyAsync(last_cam, l, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (first_hi) CU(cudaMemcpyAsync(first_hi, fh, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return MMBA_OK;
 }
 
