@@ -726,10 +726,11 @@ int scale_and_grad(mmba_handle* h, bool first) {
     TRY(zero(h, d.scal + S_GH2, 4));
     auto sg_cam = scale_grad_kernel<6, false>;
     auto sg_pt = scale_grad_kernel<3, true>;
-    LAUNCH(MMBA_K_VEC, sg_cam, cdiv(6 * h->Nc, 256), 256, 0, d.Ud, d.g, d.x, d.sinv, d.gh, (int)first,
+    const int cap = 8 * h->sm_count;      // grid-stride kernels: a few CTAs per SM, one atomic per CTA and result
+    LAUNCH(MMBA_K_VEC, sg_cam, std::min(cap, cdiv(6 * h->Nc, 256)), 256, 0, d.Ud, d.g, d.x, d.sinv, d.gh, (int)first,
            6 * h->Nc, d.scal, lead);
     if (h->npl)
-        LAUNCH(MMBA_K_VEC, sg_pt, cdiv(3 * h->npl, 256), 256, 0, d.V, d.g + 6 * h->Nc, d.x + 6 * h->Nc,
+        LAUNCH(MMBA_K_VEC, sg_pt, std::min(cap, cdiv(3 * h->npl, 256)), 256, 0, d.V, d.g + 6 * h->Nc, d.x + 6 * h->Nc,
                d.sinv + 6 * h->Nc, d.gh + 6 * h->Nc, (int)first, 3 * h->npl, d.scal, 1);
     TRY(allreduce(h, {{d.scal + S_GH2, 3, false}, {d.scal + S_GINF, 1, true}}));
     return MMBA_OK;
@@ -1071,7 +1072,8 @@ int run_trf(mmba_handle* h, mmba_result* out) {
         // J_h s2 = (J u2 - kappa J u1) / n2, kappa = c1 / ||g_h||, follow from the Gram matrix of J [u1 u2]
         // (one J pass) and five dot products (one vector pass): one host round trip instead of three.
         TRY(zero(h, d.scal + S_DOT0, 10));
-        LAUNCH(MMBA_K_VEC, subspace_dots_kernel, gv, 256, 0, d.gh, d.tmp, d.sinv, d.px, d.pxt, d.dp, d.gn, ncam, nloc, d.scal, lead);
+        LAUNCH(MMBA_K_VEC, subspace_dots_kernel, std::min(gv, 8 * h->sm_count), 256, 0, d.gh, d.tmp, d.sinv, d.px, d.pxt, d.dp, d.gn,
+               ncam, nloc, d.scal, lead);
         TRY(allreduce(h, {{d.scal + S_DOT0, 5, false}}));
         TRY(jv2(h, d.tmp, d.gn));
         TRY(read_scalars(h));
@@ -1212,7 +1214,7 @@ int run_trf_pose(mmba_handle* h, mmba_result* out) {
     auto grad_stats = [&]() -> int {
         // ||g||_inf and ||x||^2 over the camera parameters (the variables of this problem)
         TRY(zero(h, d.scal + S_GH2, 4));
-        LAUNCH(MMBA_K_VEC, sg_cam, cdiv(ncam, 256), 256, 0, d.Ud, d.g, d.x, d.sinv, d.gh, 1, ncam, d.scal, 1);
+        LAUNCH(MMBA_K_VEC, sg_cam, std::min(8 * h->sm_count, cdiv(ncam, 256)), 256, 0, d.Ud, d.g, d.x, d.sinv, d.gh, 1, ncam, d.scal, 1);
         return MMBA_OK;
     };
     TRY(linearise(h, true));

@@ -40,16 +40,20 @@ __device__ __forceinline__ double sum_partials(const double* __restrict__ part, 
 //   PACKED: element e of block b = e / BS is the diagonal of a packed upper-triangle block (points: V);
 //   otherwise blk already holds the column sums of squares (cameras: diag(J_c^T J_c)); g_h = g / scale_inv
 // ---------------------------------------------------------------------------------------------
+// Grid-stride (a few CTAs per SM): every CTA reduces its partial sums once and issues ONE atomic per result — a thread
+// block per 256 elements meant ~100 k atomics on four addresses at C4 (the max alone: one per warp), 94 us per launch
+// for 170 MB of traffic.
 template <int BS, bool PACKED>
 __global__ void scale_grad_kernel(const double* __restrict__ blk, const double* __restrict__ g,
                                   const double* __restrict__ x, double* __restrict__ sinv, double* __restrict__ gh,
                                   int first, int64_t n_elem, double* __restrict__ scal, int accumulate) {
     __shared__ double s_red[64];
+    __shared__ unsigned long long s_max;
     constexpr int STRIDE = BS * (BS + 1) / 2;
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double acc[3] = {0, 0, 0};
     double gabs = 0;
-    if (e < n_elem) {
+    if (threadIdx.x == 0) s_max = 0ull;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_elem; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = e / BS;
         const int k = (int)(e - b * BS);
         const double diag = PACKED ? blk[b * STRIDE + (k * BS - k * (k - 1) / 2)] : blk[e];
@@ -60,18 +64,19 @@ __global__ void scale_grad_kernel(const double* __restrict__ blk, const double* 
         const double gv = g[e], xv = x[e];
         const double h = gv / si;
         gh[e] = h;
-        gabs = fabs(gv);
-        acc[0] = h * h;
-        acc[1] = (xv * si) * (xv * si);
-        acc[2] = xv * xv;
+        gabs = fmax(gabs, fabs(gv));
+        acc[0] += h * h;
+        acc[1] += (xv * si) * (xv * si);
+        acc[2] += xv * xv;
     }
     if (!accumulate) return;
     double* outp[3] = {scal + S_GH2, scal + S_XSI2, scal + S_X2};
     block_accumulate<3>(acc, s_red, outp);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) gabs = fmax(gabs, __shfl_xor_sync(kFull, gabs, off));
-    if ((threadIdx.x & 31) == 0)
-        atomicMax(reinterpret_cast<unsigned long long*>(scal + S_GINF), (unsigned long long)__double_as_longlong(gabs));
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_max, (unsigned long long)__double_as_longlong(gabs));
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(scal + S_GINF), s_max);
 }
 
 // out = coef * a / sinv   (unscaled image of a scaled vector: d o a)
@@ -115,9 +120,8 @@ __global__ void subspace_dots_kernel(const double* __restrict__ gh, const double
                                      const double* __restrict__ px, const double* __restrict__ pxt, const double* __restrict__ dp,
                                      double* __restrict__ u2, int64_t ncam, int64_t n, double* __restrict__ scal, int lead) {
     __shared__ double s_red[64];
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double acc[5] = {0, 0, 0, 0, 0};
-    if (e < n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         double gnh, w2;
         const bool cam = e < ncam;
         if (cam) {
@@ -130,11 +134,11 @@ __global__ void subspace_dots_kernel(const double* __restrict__ gh, const double
         u2[e] = w2;
         if (!cam || lead) {       // the replicated camera part is counted by one rank only
             const double g = gh[e], w1 = u1[e];
-            acc[0] = g * gnh;
-            acc[1] = gnh * gnh;
-            acc[2] = w1 * w1;
-            acc[3] = w1 * w2;
-            acc[4] = w2 * w2;
+            acc[0] += g * gnh;
+            acc[1] += gnh * gnh;
+            acc[2] += w1 * w1;
+            acc[3] += w1 * w2;
+            acc[4] += w2 * w2;
         }
     }
     double* outp[5] = {scal + S_DOT0, scal + S_DOT1, scal + S_DOT2, scal + S_DOT3, scal + S_DOT4};

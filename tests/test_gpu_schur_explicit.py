@@ -100,7 +100,11 @@ def test_explicit_gauss_newton_step_vs_oracle(xcase, reg):
     rhs = d * lin.grad()
     resid = d * JtJdp + reg * p - rhs
     assert np.linalg.norm(resid) <= 1e-8 * np.linalg.norm(rhs)
-    assert np.linalg.norm(p - p_ref) <= 1e-5 * np.linalg.norm(p_ref)
+    # The step itself is only determined to cond(S) x the residual: at reg = 1e-6 the 'windowed' chain has near-gauge
+    # directions, and two solves that both reach 1e-10 relative residual differ by up to 1.3e-5 in p depending on the
+    # summation order of the S-build's atomics (tools/pcg_flaky.py: 6 of 8 runs 1e-9, 2 of 8 runs 1.29e-5).  The
+    # residual bar above is the parity statement; this one only guards against a wrong solution.
+    assert np.linalg.norm(p - p_ref) <= (1e-5 if reg >= 1e-3 else 1e-4) * np.linalg.norm(p_ref)
 
 
 def test_explicit_solve_vs_oracle_and_implicit(xcase):
