@@ -55,6 +55,14 @@ constexpr int kUVTileBytes = 2 * kT * 8;
 static_assert(sizeof(TileMeta) == 2592 && sizeof(TileMeta) % 16 == 0, "TileMeta is bulk-copied: 16-byte multiple");
 static_assert(9 * (kTileObs + 1) * 8 <= 18 * kTileObs * 8, "scatter staging rows must fit inside a J block");
 constexpr int kBufStride = kT + 1;         // row stride of the scatter staging buffer (bank spread)
+// S-build, register-accumulation strategy (pair mode 2): the (point, camera) -> slot table has two parities of
+// kRcmTab2Cap entries {generation << 8 | slot}; a tile whose table would not fit is handled by strategy 1.
+constexpr int kRcmTab2Cap = kRcmTabCap / 2;
+// ints of the accumulation-run scratch: cameras [0..31], per parity {flags, missing} [32..35], per parity the
+// run index -> local camera slot map [40..103], block index of every pair of the run (flush) [112..239], per parity
+// the camera list of the tile [240..303]
+constexpr int kRunInts = 304;
+constexpr int kRunMap = 40, kRunBlk = 112, kRunPrev = 240;
 
 // scalar slots in device memory (doubles).  Groups that are reduced across ranks together are
 // contiguous: [S_COST] sum, [S_GH2..S_X2] sum, S_GINF max, S_COST_NEW sum, [S_JV00..S_JV11] sum,
@@ -98,9 +106,10 @@ struct Traits {
     // own buffer.  The Schur passes stage 6 / 9 rows INSIDE the current pipeline stage's J block:
     // every consumer holds its 18 J values in registers by then, the block is dead until the stage
     // is released, and consecutive tiles use different stages (free double buffering).
-    // SBUILD keeps the J block intact for its pair phase: 6 rows stage the right-hand-side scatter, 6 rows hold
-    // Jp M per observation.
-    static constexpr int kStageRows = is_build(MODE) ? 22 : MODE == M_SBUILD ? 12 : 0;
+    // SBUILD keeps the J block intact for its pair phase and stages two parities of 8 rows per observation
+    // (6 rows Jp M, 2 rows v = Jp M g_p), so that consecutive tiles need ONE consumer barrier each; the per-tile
+    // strategies (pair modes 0 / 1) use rows 0..5 for the right-hand-side scatter and rows 8..13 for Jp M.
+    static constexpr int kStageRows = is_build(MODE) ? 22 : MODE == M_SBUILD ? 16 : 0;
     static constexpr int kStageBufs = 1;
     static constexpr int kMinBlocks = MODE == M_SBUILD ? 1 : 2;   // SBUILD: one CTA per SM, up to 204 registers per thread
 };
@@ -111,6 +120,7 @@ struct TileArgs {
     const double* uv;
     int n_tiles, cam_stride, max_cams, max_pts;
     int n_cams, ytab_cams;   // ytab_cams = n_cams when MATVEC keeps a per-CTA camera table in shared memory, else 0
+    int sb_stages;           // SBUILD: pipeline stages in use (3, or 2 when the tiles' point payloads are large)
     long long* dbg;          // optional phase cycle counters (diagnostics, options.profile bit 2), else nullptr
     double K[9];
 };
@@ -145,14 +155,15 @@ struct ModeArgs {
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
     int off_J, off_meta, off_uv, off_camid, off_camvec, off_pa, off_pb, stage_bytes;
-    int off_stages, off_pt, off_z, off_buf, off_red, off_ids, off_ytab, off_tab, off_pstart, off_run, total;
+    int off_stages, off_pt, off_z, off_buf, off_red, off_ids, off_ytab, off_tab, off_pstart, off_run, off_yacc, total;
 };
 
 __host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 template <int MODE>
-__host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts, int ytab_cams = 0) {
+__host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts, int ytab_cams = 0, int n_stages = 0) {
     using T = Traits<MODE>;
+    if (n_stages <= 0) n_stages = T::kStages;
     SmemLayout L{};
     int o = 0;
     L.off_J = o;
@@ -171,7 +182,7 @@ __host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts, int
     o += align_up(max_pts * T::kPB * 8, 16);
     L.stage_bytes = align_up(o, 128);
     L.off_stages = 128;                                   // mbarriers live in the first 128 bytes
-    o = L.off_stages + T::kStages * L.stage_bytes;
+    o = L.off_stages + n_stages * L.stage_bytes;
     L.off_pt = o;
     o += 2 * align_up(max_pts * T::kPtAcc * 8, 16);       // two parities (see the MATVEC / BACKSUB flow)
     L.off_z = o;
@@ -188,7 +199,9 @@ __host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts, int
     L.off_pstart = o;
     if (MODE == M_SBUILD) o += 2 * align_up((max_pts + 2) * 4, 16);  // first slot / pair offset of every point
     L.off_run = o;
-    if (MODE == M_SBUILD) o += 80 * 4;                             // accumulation run: cameras [0..31], flags [32..35], map [40..71]
+    if (MODE == M_SBUILD) o += kRunInts * 4;                       // accumulation run (see kRunInts)
+    L.off_yacc = o;
+    if (MODE == M_SBUILD) o += 6 * kT * 8;                         // right-hand-side sums of the run, one column per thread
     L.total = o;
     return L;
 }
@@ -487,7 +500,7 @@ __device__ __forceinline__ void sbuild_row(const double* __restrict__ sJ, const 
     const double c0 = sJ[row * kT + i], c1 = sJ[(6 + row) * kT + i];
     const double t0 = c0 * g00 + c1 * g10, t1 = c0 * g01 + c1 * g11;
 #pragma unroll
-    for (int b = 0; b < 6; ++b) acc[b] += t0 * sJ[b * kT + j] + t1 * sJ[(6 + b) * kT + j];
+    for (int b = 0; b < 6; ++b) acc[b] = fma(t0, sJ[b * kT + j], fma(t1, sJ[(6 + b) * kT + j], acc[b]));
 }
 
 // acc (6x6, row-major) += Jc_i^T (delta_ij I - Jp_i M Jp_j^T) Jc_j : the whole block of one observation pair
@@ -514,16 +527,14 @@ __device__ __forceinline__ void sbuild_block(const double* __restrict__ sJ, cons
     for (int a = 0; a < 6; ++a) {
         const double c0 = sJ[a * kT + i], c1 = sJ[(6 + a) * kT + i];
 #pragma unroll
-        for (int b = 0; b < 6; ++b) acc[a * 6 + b] += c0 * h0[b] + c1 * h1[b];
+        for (int b = 0; b < 6; ++b) acc[a * 6 + b] = fma(c0, h0[b], fma(c1, h1[b], acc[a * 6 + b]));   // 2 DFMA per entry
     }
 }
 
-// point slices per camera pair of the persistent S-build path: a power of two, 256 threads in all
-__device__ __forceinline__ int sbuild_slices(int npair) {
-    int s = 1;
-    while (s < 8 && 2 * s * npair <= kConsumers) s *= 2;
-    return s;
-}
+// point slices per camera pair of the register-accumulation S-build path: slices x pair capacity <= 256 threads with
+// the capacity as tight as possible (whole warps of live lanes: a DFMA costs the same issue time with 15 live lanes
+// as with 32); at most 32 slices (the flush sums the slices in shared memory)
+__device__ __forceinline__ int sbuild_slices(int npair) { return max(1, min(32, kConsumers / max(1, npair))); }
 
 // ---------------------------------------------------------------------------------------------
 // The streaming kernel.  Algorithmic bytes per observation:
@@ -546,7 +557,8 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (MODE == M_MATVEC && P.done && *P.done) return;
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout L = smem_layout<MODE>(A.max_cams, A.max_pts, A.ytab_cams);
+    const int nst = MODE == M_SBUILD ? A.sb_stages : kStages;      // stages in use (<= kStages producer warps)
+    const SmemLayout L = smem_layout<MODE>(A.max_cams, A.max_pts, A.ytab_cams, nst);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + kStages;
     const int tid = threadIdx.x;
@@ -569,6 +581,10 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
         double* s_ytab = reinterpret_cast<double*>(smem + L.off_ytab);
         for (int i = tid; i < A.ytab_cams * 6; i += kThreads) s_ytab[i] = 0.0;
     }
+    if (MODE == M_SBUILD) {
+        double* s_yacc = reinterpret_cast<double*>(smem + L.off_yacc);
+        for (int i = tid; i < 6 * kT; i += kThreads) s_yacc[i] = 0.0;
+    }
     if (T::kPtAcc) {
         double* s_pt = reinterpret_cast<double*>(smem + L.off_pt);
         for (int i = tid; i < 2 * align_up(A.max_pts * T::kPtAcc * 8, 16) / 8; i += kThreads) s_pt[i] = 0.0;
@@ -584,6 +600,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
         // consumers release the stage the producer only issues the bulk copies, stores registers to
         // shared memory and arrives, so a stage is almost never without a copy in flight.
         const int pw = (tid - kConsumers) >> 5, lane = tid & 31;
+        if (pw >= nst) return;
         constexpr int kCPL = kT / 32;   // camera ids per lane (registers)
         // gathered values prefetched one tile ahead per lane (SBUILD stages 9 values per point: up to 1 152 per tile)
         constexpr int kBatch = MODE == M_SBUILD ? 16 : 8;
@@ -658,7 +675,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
         int t = t_begin + pw;
         unsigned phase = 0;
         bool first = true;
-        for (; t < t_end; t += kStages) {
+        for (; t < t_end; t += nst) {
             mbar_wait(&empty[stage], phase ^ 1);
             if (lane == 0) {
                 if (T::kLoadJ) bulk_g2s(st + L.off_J, P.J + (int64_t)t * kJRows * kT, kJTileBytes, &full[stage]);
@@ -670,7 +687,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                 first = false;
                 fetch_far(t);
                 advance();
-                fetch_far(t + kStages);
+                fetch_far(t + nst);
             }
 #pragma unroll
             for (int j = 0; j < kCPL; ++j) {
@@ -704,9 +721,9 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                 mbar_arrive_expect_tx(&full[stage], tx);
             }
             phase ^= 1;
-            if (t + kStages < t_end) {
+            if (t + nst < t_end) {
                 advance();                       // next tile of this warp: ids + first batch in flight
-                fetch_far(t + 2 * kStages);
+                fetch_far(t + 2 * nst);
             }
         }
         return;
@@ -725,30 +742,85 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
 #pragma unroll
     for (int i = 0; i < (MODE == M_SBUILD ? 36 : 1); ++i) sacc[i] = 0.0;
     // An accumulation RUN: a list of cameras (ascending ids, s_run[0..run_n)) whose pair blocks are being accumulated
-    // in registers.  Thread (slice my_sl, pair my_pr) owns the block of cameras (run[my_a], run[my_b]), my_a <= my_b,
-    // pairs numbered column by column (pr = b (b + 1) / 2 + a) so that appending a camera to the list adds pairs
-    // without renumbering the existing ones.  A tile continues the run when its cameras are a subset of the list,
-    // extends it when the new cameras are larger than the last one and the pairs still fit, else the run is flushed
-    // (one RED per entry) and restarted.  Video-like visibility: one flush per ~10..40 tiles.
+    // in registers.  Thread (slice my_sl, pair my_pr) = thread my_sl * run_P + my_pr owns the block of cameras
+    // (run[my_a], run[my_b]), my_a <= my_b, for the points p = my_sl (mod run_ns) of every tile; pairs are numbered
+    // column by column (pr = b (b + 1) / 2 + a) so that appending a camera to the list adds pairs without renumbering
+    // the existing ones.  A tile continues the run when its cameras are a subset of the list, extends it when the new
+    // cameras are larger than the last one and the pairs still fit the capacity run_P, else the run is flushed and
+    // restarted.  Video-like visibility: one flush per 10..40 tiles.
     int run_n = 0, run_ns = 1, run_P = kConsumers;     // cameras, point slices, pair capacity (= 256 / slices)
     int my_sl = 0, my_pr = 0, my_a = 0, my_b = 0;
+    int my_blk = 0;                                           // block of (run[my_a], run[my_b]) in the upper pattern (slice 0)
+    // right-hand side y_c += Jc^T Jp M g_p: thread (camera y_a of the run, point slice y_sl) = thread y_sl * y_cap + y_a
+    // walks the points of its slice that camera y_a observes and keeps six sums in its column of s_yacc
+    int y_cap = 1, y_ns = 1, y_sl = 0, y_a = 0;
+    int prev_n = -1;                                          // cameras of the previous tile (register-accumulation tiles), else -1
     bool run_touched = false;
-    int* s_run = reinterpret_cast<int*>(smem + L.off_run);   // [0..31] cameras, [32] flags, [33] missing count
-    int* s_map = s_run + 40;                                  // run index -> local camera slot of the current tile, -1 = absent
+    bool prev_mode2 = false;                                  // the previous tile left no closing barrier behind
+    int* s_run = reinterpret_cast<int*>(smem + L.off_run);   // layout: kRunInts
+    double* s_yacc = reinterpret_cast<double*>(smem + L.off_yacc);
     auto run_pairs = [](int n) { return n * (n + 1) / 2; };
-    auto sbuild_flush = [&]() {
+    // Adds the run's blocks and right-hand-side sums to HBM and ends the run.  One slice: every thread adds its own
+    // block.  Several slices: the slices are summed through `scratch` (6 staging rows nobody reads at this point),
+    // one block row per round, so that a block costs 36 REDs whatever the number of slices.  Every consumer thread
+    // must call it after a consumer barrier (all accumulation of the run is complete); barriers inside.
+    auto sbuild_flush = [&](double* scratch) {
         if constexpr (MODE == M_SBUILD) {
-            if (run_n) {
-                if (my_sl < run_ns && my_pr < run_pairs(run_n) && run_touched) {
-                    double* dst = P.Tup + (int64_t)rcm_lookup(P.up_rowptr, P.up_cols, s_run[my_a], s_run[my_b]) * 36;
+            if (run_n == 0) return;
+            const int np = run_pairs(run_n);
+            // right-hand side: (camera, component) sums over the point slices
+            for (int q = tid; q < run_n * 6; q += kConsumers) {
+                const int a = q / 6, k = q - a * 6;
+                double* col = s_yacc + k * kT + a;
+                double s0 = 0.0, s1 = 0.0;
+                int sl = 0;
+                for (; sl + 1 < y_ns; sl += 2) {
+                    s0 += col[sl * y_cap];
+                    s1 += col[(sl + 1) * y_cap];
+                    col[sl * y_cap] = 0.0;
+                    col[(sl + 1) * y_cap] = 0.0;
+                }
+                if (sl < y_ns) {
+                    s0 += col[sl * y_cap];
+                    col[sl * y_cap] = 0.0;
+                }
+                red_add(P.y + (int64_t)s_run[a] * 6 + k, s0 + s1);
+            }
+            if (run_ns == 1) {
+                if (my_pr < np && run_touched) {
+                    double* dst = P.Tup + (int64_t)my_blk * 36;
 #pragma unroll
                     for (int e = 0; e < 36; ++e) red_add(dst + e, sacc[e]);
                 }
+            } else {
+                int* s_blk = s_run + kRunBlk;
+                // (a pair of the list that no point sees has no block: its sums are zero and never added)
+                if (my_sl == 0 && my_pr < np) s_blk[my_pr] = my_blk;
 #pragma unroll
-                for (int e = 0; e < 36; ++e) sacc[e] = 0.0;
-                run_touched = false;
-                run_n = 0;
+                for (int rd = 0; rd < 6; ++rd) {      // one block row per round
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) scratch[e * kBufStride + tid] = sacc[rd * 6 + e];
+                    consumer_sync();
+                    for (int q = tid; q < np * 6; q += kConsumers) {
+                        const int pr = q / 6, e = q - pr * 6;
+                        const double* col = scratch + e * kBufStride + pr;
+                        double s0 = 0.0, s1 = 0.0;
+                        int sl = 0;
+                        for (; sl + 1 < run_ns; sl += 2) {
+                            s0 += col[sl * run_P];
+                            s1 += col[(sl + 1) * run_P];
+                        }
+                        if (sl < run_ns) s0 += col[sl * run_P];
+                        s0 += s1;
+                        if (s0 != 0.0) red_add(P.Tup + (int64_t)s_blk[pr] * 36 + rd * 6 + e, s0);
+                    }
+                    consumer_sync();
+                }
             }
+#pragma unroll
+            for (int e = 0; e < 36; ++e) sacc[e] = 0.0;
+            run_touched = false;
+            run_n = 0;
         }
     };
     auto run_start = [&](int ncams) {      // thread mapping of a new run of `ncams` cameras
@@ -757,11 +829,23 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
         run_P = kConsumers / run_ns;
         my_sl = tid / run_P;
         my_pr = tid - my_sl * run_P;
-        int b = (int)((sqrt(8.0 * my_pr + 1.0) - 1.0) * 0.5);
+        int b = (int)((sqrtf(8.0f * (float)my_pr + 1.0f) - 1.0f) * 0.5f);
         while (b * (b + 1) / 2 > my_pr) --b;
         while ((b + 1) * (b + 2) / 2 <= my_pr) ++b;
         my_b = b;
         my_a = my_pr - b * (b + 1) / 2;
+        // cameras the list can grow to within the pair capacity
+        y_cap = ncams;
+        while (y_cap < 31 && run_pairs(y_cap + 1) <= run_P) ++y_cap;
+        y_ns = max(1, kConsumers / y_cap);
+        y_sl = tid / y_cap;
+        y_a = tid - y_sl * y_cap;
+    };
+    // block index of this thread's pair (slice 0): the loads are in flight while the run accumulates
+    auto run_lookup = [&]() {
+        if constexpr (MODE == M_SBUILD) {
+            if (my_sl == 0 && my_pr < run_pairs(run_n)) my_blk = rcm_lookup(P.up_rowptr, P.up_cols, s_run[my_a], s_run[my_b]);
+        }
     };
     int stage = 0;
     unsigned phase = 0;
@@ -934,27 +1018,37 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
             }
         } else if constexpr (MODE == M_SBUILD) {
             // ---- explicit reduced camera matrix (upper blocks) + Schur right-hand side ----
-            double jc[12], jp[6];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) jc[i] = valid ? sJ[i * kT + tid] : 0.0;
+            const int ncams = mt->ncams;
+            int pair_mode = mt->pair_mode;
+            // the register-accumulation strategy needs the tile's table in one parity half and its camera list in one warp
+            if (pair_mode == 2 && (npts * ncams > kRcmTab2Cap || ncams > 32)) pair_mode = 1;
+            uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + L.off_tab);
+            double jp[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) jp[i] = valid ? sJ[(12 + i) * kT + tid] : 0.0;
-            const int ncams = mt->ncams, pair_mode = mt->pair_mode;
-            uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + L.off_tab);
-            int* s_pstart = reinterpret_cast<int*>(smem + L.off_pstart);
-            int* s_poff = s_pstart + align_up((A.max_pts + 2) * 4, 16) / 4;
-            double* s_pm = s_buf + 6 * kBufStride;
-            {
-                const double* m = s_pa + lps * 6;
-                const double* zg = s_pb + lps * 3;
-                // y_c += Jc^T Jp (M_p g_p)
-                const double v0 = jp[0] * zg[0] + jp[1] * zg[1] + jp[2] * zg[2];
-                const double v1 = jp[3] * zg[0] + jp[4] * zg[1] + jp[5] * zg[2];
-                double cv[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) cv[k] = jc[k] * v0 + jc[6 + k] * v1;
-                // Jp M (2x3) of this observation
-                const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5];
+            const double* m = s_pa + lps * 6;
+            const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5];
+            if (pair_mode == 2) {
+                // One consumer barrier per tile: the staged rows, the table and the run bookkeeping alternate between
+                // two parities, so a warp that is done with this tile's pairs stages the next tile while the others
+                // still accumulate.  The right-hand side's camera-run sums are taken AFTER the barrier, a few per
+                // warp, so that their latency chains hide behind the other warps' pair arithmetic.
+                const int k_loc = t - t_begin, q = k_loc & 1;
+                const unsigned gen = 1u + (unsigned)((k_loc >> 1) % 255);     // (q, gen) identifies the tile among 510
+                if (!prev_mode2) {
+                    // first tile of its kind: forget whatever the table region held (the previous tile closed with a barrier)
+                    for (int i = tid; i < kRcmTabCap / 4; i += kConsumers) reinterpret_cast<uint2*>(s_tab)[i] = make_uint2(0u, 0u);
+                    consumer_sync();
+                } else if (k_loc >= 510 && k_loc % 510 < 2) {
+                    // (q, gen) repeats: forget this parity's stale entries (its last readers passed the previous barrier)
+                    for (int i = tid; i < kRcmTab2Cap / 4; i += kConsumers)
+                        reinterpret_cast<uint2*>(s_tab + q * kRcmTab2Cap)[i] = make_uint2(0u, 0u);
+                    consumer_sync();
+                }
+                double* s_pm = s_buf + q * 8 * kBufStride;      // rows 0..5: Jp M (2x3), rows 6..7: v = Jp (M_p g_p)
+                uint16_t* tab = s_tab + q * kRcmTab2Cap;
+                int* s_flag = s_run + 32 + 2 * q;
+                int* s_map = s_run + kRunMap + 32 * q;          // run index -> local camera slot of this tile, -1 = absent
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     const double a0 = jp[r * 3], a1 = jp[r * 3 + 1], a2 = jp[r * 3 + 2];
@@ -962,55 +1056,55 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                     s_pm[(r * 3 + 1) * kBufStride + tid] = a0 * m1 + a1 * m3 + a2 * m4;
                     s_pm[(r * 3 + 2) * kBufStride + tid] = a0 * m2 + a1 * m4 + a2 * m5;
                 }
-                if (tid == 0) {
-                    s_run[32] = 0;
-                    s_run[33] = 0;
+                {
+                    const double* zg = s_pb + lps * 3;
+                    s_pm[6 * kBufStride + tid] = jp[0] * zg[0] + jp[1] * zg[1] + jp[2] * zg[2];
+                    s_pm[7 * kBufStride + tid] = jp[3] * zg[0] + jp[4] * zg[1] + jp[5] * zg[2];
                 }
-                if (pair_mode) {
-                    for (int i = tid; i < npts * ncams; i += kConsumers) s_tab[i] = 0xFFFF;
-                } else {
-                    if (valid && (tid == 0 || mt->slot_pt[tid - 1] != lp)) s_pstart[lp] = tid;
-                    if (tid == 0) s_pstart[npts] = mt->nobs;
-                }
-                lap(1);
-                camera_scatter_round<6>(cv, s_buf, mt, s_camid, P.y, 6, 0);   // one consumer barrier inside
-                lap(2);
-            }
-            if (pair_mode) {
-                if (valid) s_tab[lp * ncams + lc] = (uint16_t)tid;
-                if (pair_mode == 2) {
-                    // is every camera of the tile in the run's list?  (bit 0: some are missing, bit 1: a missing one
-                    // is not larger than the list's last camera, i.e. the list cannot simply be extended)
-                    if (tid < ncams) {
-                        const int cam = s_camid[tid];
-                        bool found = false;
-                        for (int r = 0; r < run_n; ++r) found |= s_run[r] == cam;
-                        if (!found) {
-                            atomicOr(&s_run[32], (run_n > 0 && cam < s_run[run_n - 1]) ? 3 : 1);
-                            atomicAdd(&s_run[33], 1);
+                if (valid) tab[lp * ncams + lc] = (uint16_t)((unsigned)tid | (gen << 8));
+                if (tid < 32) {
+                    // Warp 0: is every camera of the tile in the run's list?  (bit 0: some are missing, bit 1: a missing
+                    // one is not larger than the list's last camera, i.e. the list cannot simply be extended), and the
+                    // local camera slot of every run camera in this tile.  Usual case: the same cameras as the previous
+                    // tile — nothing is missing and the map carries over.
+                    int* s_prev = s_run + kRunPrev + 32 * q;
+                    const int* s_prev_o = s_run + kRunPrev + 32 * (q ^ 1);
+                    const int mycam = tid < ncams ? s_camid[tid] : -1;
+                    s_prev[tid] = mycam;
+                    const bool same = __all_sync(kFull, prev_n == ncams && s_prev_o[tid] == mycam);
+                    if (same) {
+                        if (tid < run_n) s_map[tid] = s_run[kRunMap + 32 * (q ^ 1) + tid];
+                        if (tid == 0) {
+                            s_flag[0] = 0;
+                            s_flag[1] = 0;
                         }
-                    } else if (tid >= 32 && tid < 32 + run_n) {
-                        // local camera slot of every run camera in this tile (valid if the run goes on)
-                        const int cam = s_run[tid - 32];
-                        int at = -1;
-                        for (int c = 0; c < ncams; ++c)
-                            if (s_camid[c] == cam) at = c;
-                        s_map[tid - 32] = at;
+                    } else {
+                        bool miss = false, low = false;
+                        if (tid < ncams) {
+                            bool found = false;
+                            for (int r = 0; r < run_n; ++r) found |= s_run[r] == mycam;
+                            miss = !found;
+                            low = miss && run_n > 0 && mycam < s_run[run_n - 1];
+                        }
+                        const unsigned mm = __ballot_sync(kFull, miss), ml = __ballot_sync(kFull, low);
+                        if (tid == 0) {
+                            s_flag[0] = (mm ? 1 : 0) | (ml ? 2 : 0);
+                            s_flag[1] = __popc(mm);
+                        }
+                        if (tid < run_n) {
+                            const int cam = s_run[tid];
+                            int at = -1;
+                            for (int c = 0; c < ncams; ++c)
+                                if (s_camid[c] == cam) at = c;
+                            s_map[tid] = at;
+                        }
                     }
                 }
-            } else if (tid == 0) {
-                int o = 0;
-                for (int p = 0; p < npts; ++p) {
-                    s_poff[p] = o;
-                    const int len = s_pstart[p + 1] - s_pstart[p];
-                    o += len * (len + 1) / 2;
-                }
-                s_poff[npts] = o;
-            }
-            consumer_sync();
-            lap(3);
-            if (pair_mode == 2) {
-                const int flags = s_run[32], n_missing = s_run[33];
+                prev_n = ncams;
+                lap(1);
+                consumer_sync();
+                lap(3);
+                const int flags = s_flag[0], n_missing = s_flag[1];
                 if (flags & 1) {
                     const int new_n = run_n + n_missing;
                     if (run_n > 0 && !(flags & 2) && new_n <= 31 && run_pairs(new_n) <= run_P) {
@@ -1023,7 +1117,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                         run_n = new_n;
                     } else {
                         const bool had_run = run_n != 0;
-                        sbuild_flush();
+                        sbuild_flush(s_buf + (q ^ 1) * 8 * kBufStride);   // the other parity's rows: their readers are done
                         if (had_run) consumer_sync();   // every thread has read the old camera list
                         if (tid < ncams) {
                             s_run[tid] = s_camid[tid];
@@ -1032,95 +1126,171 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                         run_start(ncams);
                     }
                     consumer_sync();
+                    run_lookup();
                 }
                 lap(4);
+                if (y_sl < y_ns && y_a < run_n) {
+                    // right-hand side: the observations of camera y_a among the points of slice y_sl
+                    const int la = s_map[y_a];
+                    if (la >= 0) {
+                        double ty[6] = {0, 0, 0, 0, 0, 0};
+                        bool any = false;
+                        for (int p = y_sl; p < npts; p += y_ns) {
+                            const unsigned e = tab[p * ncams + la];
+                            if ((e >> 8) != gen) continue;
+                            const int sl = (int)(e & 255u);
+                            const double w0 = s_pm[6 * kBufStride + sl], w1 = s_pm[7 * kBufStride + sl];
+                            any = true;
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) ty[k] = fma(sJ[k * kT + sl], w0, fma(sJ[(6 + k) * kT + sl], w1, ty[k]));
+                        }
+                        if (any) {
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) s_yacc[k * kT + tid] += ty[k];
+                        }
+                    }
+                }
+                lap(2);
                 // unit = (camera pair a <= b of the run, point slice): whole 6x6 block in registers.  Lanes of a warp
-                // are consecutive pairs of ONE slice: they walk the same points, so the J rows they read are a
-                // handful of neighbouring slots (broadcast / conflict-free); a lane whose pair is absent from a
+                // are consecutive pairs of one or two slices: they walk the same few points, so the J rows they read
+                // are a handful of neighbouring slots (broadcast / conflict-free); a lane whose pair is absent from a
                 // point skips ahead on its own instead of idling through the other lanes' block.
                 if (my_sl < run_ns && my_pr < run_pairs(run_n)) {
                     const int la = s_map[my_a], lb = s_map[my_b];
                     if (la >= 0 && lb >= 0) {
                         int p = my_sl;
                         while (true) {
-                            unsigned i = 0xFFFFu, j = 0xFFFFu;
+                            unsigned i = 0u, j = 0u;
                             while (p < npts) {
-                                i = s_tab[p * ncams + la];
-                                j = s_tab[p * ncams + lb];
-                                if (i != 0xFFFFu && j != 0xFFFFu) break;
+                                i = tab[p * ncams + la];
+                                j = tab[p * ncams + lb];
+                                if ((i >> 8) == gen && (j >> 8) == gen) break;
                                 p += run_ns;
                             }
                             if (p >= npts) break;
                             run_touched = true;
-                            sbuild_block(sJ, s_pm, (int)i, (int)j, sacc);
+                            const int si = (int)(i & 255u), sj = (int)(j & 255u);
+                            sbuild_block(sJ, s_pm, si, sj, sacc);
                             p += run_ns;
                         }
                     }
                 }
+                lap(5);
+                prev_mode2 = true;
+                lap(6);
             } else {
-                sbuild_flush();     // a tile of another strategy ends the run
-            }
-            if (pair_mode == 1) {
-                // unit = (camera pair a <= b of the tile, block row, point slice): register accumulation over the
-                // tile's points, then one RED per entry
-                const int npair = ncams * (ncams + 1) / 2;
-                int nslice = 1;
-                if (npair * 6 < kConsumers) nslice = max(1, min(npts, kConsumers / (npair * 6)));
-                const int units = npair * 6 * nslice;
-                for (int u = tid; u < units; u += kConsumers) {
-                    const int sl = u % nslice, rest = u / nslice;
-                    const int row = rest % 6, pr = rest / 6;
-                    int a, b;
-                    tri_decode(pr, ncams, a, b);
-                    double acc[6] = {0, 0, 0, 0, 0, 0};
-                    bool hit = false;
-                    for (int p = sl; p < npts; p += nslice) {
-                        const unsigned i = s_tab[p * ncams + a];
-                        if (i == 0xFFFFu) continue;
-                        const unsigned j = s_tab[p * ncams + b];
-                        if (j == 0xFFFFu) continue;
-                        hit = true;
-                        sbuild_row(sJ, s_pm, (int)i, (int)j, row, acc);
-                    }
-                    if (hit) {
-                        const int k = rcm_lookup(P.up_rowptr, P.up_cols, s_camid[a], s_camid[b]);
-                        double* dst = P.Tup + (int64_t)k * 36 + row * 6;
+                // ---- per-tile strategies (many cameras per tile / duplicate observations): flushed tile by tile ----
+                if (prev_mode2) consumer_sync();     // the previous tile's pair phase still reads its staged rows and table
+                sbuild_flush(s_buf);                 // a tile of another strategy ends the run
+                prev_mode2 = false;
+                prev_n = -1;
+                double jc[12];
 #pragma unroll
-                        for (int bb = 0; bb < 6; ++bb) red_add(dst + bb, acc[bb]);
+                for (int i = 0; i < 12; ++i) jc[i] = valid ? sJ[i * kT + tid] : 0.0;
+                int* s_pstart = reinterpret_cast<int*>(smem + L.off_pstart);
+                int* s_poff = s_pstart + align_up((A.max_pts + 2) * 4, 16) / 4;
+                double* s_pm = s_buf + 8 * kBufStride;
+                {
+                    // y_c += Jc^T Jp (M_p g_p)
+                    const double* zg = s_pb + lps * 3;
+                    const double v0 = jp[0] * zg[0] + jp[1] * zg[1] + jp[2] * zg[2];
+                    const double v1 = jp[3] * zg[0] + jp[4] * zg[1] + jp[5] * zg[2];
+                    double cv[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) cv[k] = jc[k] * v0 + jc[6 + k] * v1;
+                    // Jp M (2x3) of this observation
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const double a0 = jp[r * 3], a1 = jp[r * 3 + 1], a2 = jp[r * 3 + 2];
+                        s_pm[(r * 3 + 0) * kBufStride + tid] = a0 * m0 + a1 * m1 + a2 * m2;
+                        s_pm[(r * 3 + 1) * kBufStride + tid] = a0 * m1 + a1 * m3 + a2 * m4;
+                        s_pm[(r * 3 + 2) * kBufStride + tid] = a0 * m2 + a1 * m4 + a2 * m5;
+                    }
+                    if (pair_mode) {
+                        for (int i = tid; i < npts * ncams; i += kConsumers) s_tab[i] = 0xFFFF;
+                    } else {
+                        if (valid && (tid == 0 || mt->slot_pt[tid - 1] != lp)) s_pstart[lp] = tid;
+                        if (tid == 0) s_pstart[npts] = mt->nobs;
+                    }
+                    lap(1);
+                    camera_scatter_round<6>(cv, s_buf, mt, s_camid, P.y, 6, 0);   // one consumer barrier inside
+                    lap(2);
+                }
+                if (pair_mode) {
+                    if (valid) s_tab[lp * ncams + lc] = (uint16_t)tid;
+                } else if (tid == 0) {
+                    int o = 0;
+                    for (int p = 0; p < npts; ++p) {
+                        s_poff[p] = o;
+                        const int len = s_pstart[p + 1] - s_pstart[p];
+                        o += len * (len + 1) / 2;
+                    }
+                    s_poff[npts] = o;
+                }
+                consumer_sync();
+                lap(3);
+                if (pair_mode == 1) {
+                    // unit = (camera pair a <= b of the tile, block row, point slice): register accumulation over the
+                    // tile's points, then one RED per entry
+                    const int npair = ncams * (ncams + 1) / 2;
+                    int nslice = 1;
+                    if (npair * 6 < kConsumers) nslice = max(1, min(npts, kConsumers / (npair * 6)));
+                    const int units = npair * 6 * nslice;
+                    for (int u = tid; u < units; u += kConsumers) {
+                        const int sl = u % nslice, rest = u / nslice;
+                        const int row = rest % 6, pr = rest / 6;
+                        int a, b;
+                        tri_decode(pr, ncams, a, b);
+                        double acc[6] = {0, 0, 0, 0, 0, 0};
+                        bool hit = false;
+                        for (int p = sl; p < npts; p += nslice) {
+                            const unsigned i = s_tab[p * ncams + a];
+                            if (i == 0xFFFFu) continue;
+                            const unsigned j = s_tab[p * ncams + b];
+                            if (j == 0xFFFFu) continue;
+                            hit = true;
+                            sbuild_row(sJ, s_pm, (int)i, (int)j, row, acc);
+                        }
+                        if (hit) {
+                            const int k = rcm_lookup(P.up_rowptr, P.up_cols, s_camid[a], s_camid[b]);
+                            double* dst = P.Tup + (int64_t)k * 36 + row * 6;
+#pragma unroll
+                            for (int bb = 0; bb < 6; ++bb) red_add(dst + bb, acc[bb]);
+                        }
+                    }
+                } else {
+                    // unit = (observation pair i <= j of one point, block row): cameras ascend inside a point
+                    const int units = mt->npairs * 6;
+                    for (int u = tid; u < units; u += kConsumers) {
+                        const int row = u % 6, q = u / 6;
+                        int lo = 0, hi = npts;
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (s_poff[mid] <= q) lo = mid;
+                            else hi = mid;
+                        }
+                        const int start = s_pstart[lo], len = s_pstart[lo + 1] - start;
+                        int ii, jj;
+                        tri_decode(q - s_poff[lo], len, ii, jj);
+                        const int i = start + ii, j = start + jj;
+                        double acc[6] = {0, 0, 0, 0, 0, 0};
+                        sbuild_row(sJ, s_pm, i, j, row, acc);
+                        const int ci = s_camid[mt->slot_cam[i]], cj = s_camid[mt->slot_cam[j]];
+                        const int k = rcm_lookup(P.up_rowptr, P.up_cols, ci, cj);
+                        double* dst = P.Tup + (int64_t)k * 36;
+#pragma unroll
+                        for (int bb = 0; bb < 6; ++bb) red_add(dst + row * 6 + bb, acc[bb]);
+                        if (ci == cj && i != j) {
+                            // one camera observing the point twice: the mirrored pair lands in the same diagonal block
+#pragma unroll
+                            for (int bb = 0; bb < 6; ++bb) red_add(dst + bb * 6 + row, acc[bb]);
+                        }
                     }
                 }
-            } else if (pair_mode == 0) {
-                // unit = (observation pair i <= j of one point, block row): cameras ascend inside a point
-                const int units = mt->npairs * 6;
-                for (int u = tid; u < units; u += kConsumers) {
-                    const int row = u % 6, q = u / 6;
-                    int lo = 0, hi = npts;
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (s_poff[mid] <= q) lo = mid;
-                        else hi = mid;
-                    }
-                    const int start = s_pstart[lo], len = s_pstart[lo + 1] - start;
-                    int ii, jj;
-                    tri_decode(q - s_poff[lo], len, ii, jj);
-                    const int i = start + ii, j = start + jj;
-                    double acc[6] = {0, 0, 0, 0, 0, 0};
-                    sbuild_row(sJ, s_pm, i, j, row, acc);
-                    const int ci = s_camid[mt->slot_cam[i]], cj = s_camid[mt->slot_cam[j]];
-                    const int k = rcm_lookup(P.up_rowptr, P.up_cols, ci, cj);
-                    double* dst = P.Tup + (int64_t)k * 36;
-#pragma unroll
-                    for (int bb = 0; bb < 6; ++bb) red_add(dst + row * 6 + bb, acc[bb]);
-                    if (ci == cj && i != j) {
-                        // one camera observing the point twice: the mirrored pair lands in the same diagonal block
-#pragma unroll
-                        for (int bb = 0; bb < 6; ++bb) red_add(dst + bb * 6 + row, acc[bb]);
-                    }
-                }
+                lap(5);
+                consumer_sync();   // staging rows and tables are rewritten by the next tile
+                lap(6);
             }
-            lap(5);
-            consumer_sync();   // staging rows and tables are rewritten by the next tile
-            lap(6);
         } else {
             // ---- Schur passes: MATVEC / RHS / BACKSUB ----
             double jc[12], jp[6];
@@ -1244,12 +1414,15 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
         par ^= 1;
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
-        if (++stage == kStages) {
+        if (++stage == nst) {
             stage = 0;
             phase ^= 1;
         }
     }
-    sbuild_flush();
+    if constexpr (MODE == M_SBUILD) {
+        if (prev_mode2) consumer_sync();     // the last tile's pair phase still reads its staged rows
+        sbuild_flush(reinterpret_cast<double*>(smem + L.off_buf));
+    }
 #ifdef MMBA_PHASE_TIMING
     if (MODE == M_SBUILD && timing) {
         lap(7);

@@ -1161,7 +1161,12 @@ int run_trf(mmba_handle* h, mmba_result* out) {
 
 template <int MODE>
 int configure_mode(mmba_handle* h) {
-    const SmemLayout L = smem_layout<MODE>(h->targs.max_cams, h->targs.max_pts, h->targs.ytab_cams);
+    SmemLayout L = smem_layout<MODE>(h->targs.max_cams, h->targs.max_pts, h->targs.ytab_cams);
+    if (MODE == M_SBUILD) {
+        // three stages unless the tiles' point payloads are large (tiles of single-observation points)
+        h->targs.sb_stages = L.total <= 227 * 1024 ? Traits<MODE>::kStages : 2;
+        L = smem_layout<MODE>(h->targs.max_cams, h->targs.max_pts, h->targs.ytab_cams, h->targs.sb_stages);
+    }
     h->smem[MODE] = (size_t)L.total;
     if (L.total > 227 * 1024) return fail(h, MMBA_ERR_NOMEM, "tile_kernel needs " + std::to_string(L.total) + " bytes of shared memory");
     CU(cudaFuncSetAttribute(tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
@@ -1728,6 +1733,7 @@ int mmba_set_problem(mmba_handle* h, int64_t n_cams, int64_t n_points, int64_t n
     A.max_pts = std::max(D.max_tile_pts, 1);
     A.n_cams = (int)h->Nc;
     A.ytab_cams = h->Nc <= 340 ? (int)h->Nc : 0;   // <= 16 KB of shared memory
+    A.sb_stages = Traits<M_SBUILD>::kStages;
     A.dbg = (h->opt.profile & 4) ? d.dbg : nullptr;
     std::memcpy(A.K, K, sizeof(A.K));
     TRY(configure_kernels(h));
