@@ -760,6 +760,29 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
     int* s_run = reinterpret_cast<int*>(smem + L.off_run);   // layout: kRunInts
     double* s_yacc = reinterpret_cast<double*>(smem + L.off_yacc);
     auto run_pairs = [](int n) { return n * (n + 1) / 2; };
+    // diagnostics (-DMMBA_PHASE_TIMING builds only): cycles per phase of the S-build tile loop as seen by thread 0 of CTA 0
+#ifdef MMBA_PHASE_TIMING
+    long long t_last = 0, phc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_fl = 0, flc[6] = {0, 0, 0, 0, 0, 0};
+    const bool timing = MODE == M_SBUILD && A.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    auto lap = [&](int k) {
+        if (MODE == M_SBUILD && timing) {
+            const long long tt = clock64();
+            phc[k] += tt - t_last;
+            t_last = tt;
+        }
+    };
+    auto flap = [&](int k) {      // sub-phases of a flush: k < 0 starts the clock
+        if (MODE == M_SBUILD && timing) {
+            const long long tt = clock64();
+            if (k >= 0) flc[k] += tt - t_fl;
+            t_fl = tt;
+        }
+    };
+    if (timing) t_last = clock64();
+#else
+    auto lap = [](int) {};
+    auto flap = [](int) {};
+#endif
     // Adds the run's blocks and right-hand-side sums to HBM and ends the run.  One slice: every thread adds its own
     // block.  Several slices: the slices are summed through `scratch` (6 staging rows nobody reads at this point),
     // one block row per round, so that a block costs 36 REDs whatever the number of slices.  Every consumer thread
@@ -768,24 +791,23 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
         if constexpr (MODE == M_SBUILD) {
             if (run_n == 0) return;
             const int np = run_pairs(run_n);
-            // right-hand side: (camera, component) sums over the point slices
-            for (int q = tid; q < run_n * 6; q += kConsumers) {
-                const int a = q / 6, k = q - a * 6;
-                double* col = s_yacc + k * kT + a;
-                double s0 = 0.0, s1 = 0.0;
-                int sl = 0;
-                for (; sl + 1 < y_ns; sl += 2) {
-                    s0 += col[sl * y_cap];
-                    s1 += col[(sl + 1) * y_cap];
-                    col[sl * y_cap] = 0.0;
-                    col[(sl + 1) * y_cap] = 0.0;
+            flap(-1);
+            {
+                // right-hand side: (camera, component, group of point slices) sums, one RED each
+                const int G = max(1, min(8, kConsumers / (run_n * 6)));
+                for (int q = tid; q < run_n * 6 * G; q += kConsumers) {
+                    const int g = q % G, ak = q / G;
+                    const int a = ak / 6, k = ak - a * 6;
+                    double* col = s_yacc + k * kT + a;
+                    double sum = 0.0;
+                    for (int sl = g; sl < y_ns; sl += G) {
+                        sum += col[sl * y_cap];
+                        col[sl * y_cap] = 0.0;
+                    }
+                    if (sum != 0.0) red_add(P.y + (int64_t)s_run[a] * 6 + k, sum);
                 }
-                if (sl < y_ns) {
-                    s0 += col[sl * y_cap];
-                    col[sl * y_cap] = 0.0;
-                }
-                red_add(P.y + (int64_t)s_run[a] * 6 + k, s0 + s1);
             }
+            flap(0);
             if (run_ns == 1) {
                 if (my_pr < np && run_touched) {
                     double* dst = P.Tup + (int64_t)my_blk * 36;
@@ -796,31 +818,39 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                 int* s_blk = s_run + kRunBlk;
                 // (a pair of the list that no point sees has no block: its sums are zero and never added)
                 if (my_sl == 0 && my_pr < np) s_blk[my_pr] = my_blk;
+                flap(1);
 #pragma unroll
                 for (int rd = 0; rd < 6; ++rd) {      // one block row per round
 #pragma unroll
                     for (int e = 0; e < 6; ++e) scratch[e * kBufStride + tid] = sacc[rd * 6 + e];
                     consumer_sync();
+                    flap(2);
                     for (int q = tid; q < np * 6; q += kConsumers) {
-                        const int pr = q / 6, e = q - pr * 6;
+                        const int e = q / np, pr = q - e * np;      // lanes: consecutive pairs (conflict-free columns)
                         const double* col = scratch + e * kBufStride + pr;
-                        double s0 = 0.0, s1 = 0.0;
-                        int sl = 0;
-                        for (; sl + 1 < run_ns; sl += 2) {
-                            s0 += col[sl * run_P];
-                            s1 += col[(sl + 1) * run_P];
+                        const int blk = s_blk[pr];
+                        double s0 = 0.0;
+                        for (int sl = 0; sl < run_ns; sl += 8) {      // eight independent loads, then a tree
+                            double v[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) v[u] = sl + u < run_ns ? col[(sl + u) * run_P] : 0.0;
+                            s0 += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
                         }
-                        if (sl < run_ns) s0 += col[sl * run_P];
-                        s0 += s1;
-                        if (s0 != 0.0) red_add(P.Tup + (int64_t)s_blk[pr] * 36 + rd * 6 + e, s0);
+                        if (s0 != 0.0) red_add(P.Tup + (int64_t)blk * 36 + rd * 6 + e, s0);
                     }
+                    flap(3);
                     consumer_sync();
+                    flap(4);
                 }
             }
 #pragma unroll
             for (int e = 0; e < 36; ++e) sacc[e] = 0.0;
             run_touched = false;
             run_n = 0;
+            flap(5);
+#ifdef MMBA_PHASE_TIMING
+            if (timing) A.dbg[40] += 1;
+#endif
         }
     };
     auto run_start = [&](int ncams) {      // thread mapping of a new run of `ncams` cameras
@@ -849,21 +879,6 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
     };
     int stage = 0;
     unsigned phase = 0;
-    // diagnostics (-DMMBA_PHASE_TIMING builds only): cycles per phase of the S-build tile loop as seen by thread 0 of CTA 0
-#ifdef MMBA_PHASE_TIMING
-    long long t_last = 0, phc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const bool timing = MODE == M_SBUILD && A.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-    auto lap = [&](int k) {
-        if (MODE == M_SBUILD && timing) {
-            const long long tt = clock64();
-            phc[k] += tt - t_last;
-            t_last = tt;
-        }
-    };
-    if (timing) t_last = clock64();
-#else
-    auto lap = [](int) {};
-#endif
     for (int t = t_begin; t < t_end; ++t) {
         unsigned char* st = smem + L.off_stages + stage * L.stage_bytes;
         mbar_wait(&full[stage], phase);
@@ -1075,7 +1090,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                     if (same) {
                         if (tid < run_n) s_map[tid] = s_run[kRunMap + 32 * (q ^ 1) + tid];
                         if (tid == 0) {
-                            s_flag[0] = 0;
+                            s_flag[0] = 4;      // bit 2: the same cameras as the previous tile
                             s_flag[1] = 0;
                         }
                     } else {
@@ -1105,9 +1120,12 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                 consumer_sync();
                 lap(3);
                 const int flags = s_flag[0], n_missing = s_flag[1];
-                if (flags & 1) {
+                // Re-pack: the second tile in a row that uses at most 3/4 of the run's pairs restarts the run on its own
+                // cameras (tighter capacity -> more point slices, no idle pair lanes); a single such tile does not.
+                const bool repack = false;      // measured: the extra flushes cost more than the tighter lanes gain (pairs are latency-bound)
+                if ((flags & 1) || repack) {
                     const int new_n = run_n + n_missing;
-                    if (run_n > 0 && !(flags & 2) && new_n <= 31 && run_pairs(new_n) <= run_P) {
+                    if (!repack && run_n > 0 && !(flags & 2) && new_n <= 31 && run_pairs(new_n) <= run_P) {
                         // extend: the missing cameras are the last n_missing of the tile's (ascending) list
                         if (tid >= ncams - n_missing && tid < ncams) {
                             const int pos = run_n + (tid - (ncams - n_missing));
@@ -1126,7 +1144,13 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                         run_start(ncams);
                     }
                     consumer_sync();
+#ifdef MMBA_PHASE_TIMING
+                    const long long tl0 = timing ? clock64() : 0;
+#endif
                     run_lookup();
+#ifdef MMBA_PHASE_TIMING
+                    if (timing) A.dbg[41] += (my_blk >= 0 ? clock64() : 0) - tl0;     // (reads my_blk: waits for the loads)
+#endif
                 }
                 lap(4);
                 if (y_sl < y_ns && y_a < run_n) {
@@ -1158,20 +1182,28 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                 if (my_sl < run_ns && my_pr < run_pairs(run_n)) {
                     const int la = s_map[my_a], lb = s_map[my_b];
                     if (la >= 0 && lb >= 0) {
+                        // the table entries of the next candidate point are fetched before the current block's
+                        // arithmetic (an entry of generation 0 never matches)
                         int p = my_sl;
+                        unsigned i = 0u, j = 0u;
+                        auto probe = [&](int pp) {
+                            if (pp < npts) {
+                                i = tab[pp * ncams + la];
+                                j = tab[pp * ncams + lb];
+                            }
+                        };
+                        probe(p);
                         while (true) {
-                            unsigned i = 0u, j = 0u;
-                            while (p < npts) {
-                                i = tab[p * ncams + la];
-                                j = tab[p * ncams + lb];
-                                if ((i >> 8) == gen && (j >> 8) == gen) break;
+                            while (p < npts && !((i >> 8) == gen && (j >> 8) == gen)) {
                                 p += run_ns;
+                                probe(p);
                             }
                             if (p >= npts) break;
                             run_touched = true;
                             const int si = (int)(i & 255u), sj = (int)(j & 255u);
-                            sbuild_block(sJ, s_pm, si, sj, sacc);
                             p += run_ns;
+                            probe(p);
+                            sbuild_block(sJ, s_pm, si, sj, sacc);
                         }
                     }
                 }
@@ -1427,6 +1459,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
     if (MODE == M_SBUILD && timing) {
         lap(7);
         for (int k = 0; k < 8; ++k) A.dbg[16 + k] += phc[k];
+        for (int k = 0; k < 6; ++k) A.dbg[32 + k] += flc[k];
         A.dbg[24] += t_end - t_begin;
     }
 #endif

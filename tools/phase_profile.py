@@ -30,3 +30,8 @@ for name in sys.argv[1:] or ["C4", "C2"]:
     print(f"  S-build CTA 0: {tiles} tile visits ({r.nit} launches), {tot / tiles:.0f} cycles per tile")
     for k, nm in enumerate(SB):
         print(f"    {nm:26s} {c[16 + k] / tiles:8.0f} cycles")
+    nfl = max(c[40], 1)
+    print(f"  flushes: {c[40]} ({tiles / nfl:.1f} tiles per flush); cycles per flush:")
+    for k, nm in enumerate(["rhs reduce", "block index", "stage+barrier", "slice sums+RED", "barrier", "tail"]):
+        print(f"    {nm:26s} {c[32 + k] / nfl:8.0f} cycles")
+    print(f"    {'block lookup (run start)':26s} {c[41] / nfl:8.0f} cycles")
