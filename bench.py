@@ -222,8 +222,10 @@ def algorithmic_bytes(kernel, nc, npts, nobs, nnz_up=0):
         "build": 184 * nobs + 96 * npts + 264 * nc,
         "schur_matvec": 152 * nobs + 48 * npts + 96 * nc,
         "schur_rhs": 152 * nobs + 72 * npts + 264 * nc,
-        "backsub": 152 * nobs + 96 * npts + 48 * nc,
-        "jv": 152 * nobs + 2 * (24 * npts + 48 * nc),
+        # back-substitution + the subspace Gram sums: J, metadata and J u1 (16 B/obs, stored by the JV pass) in
+        "backsub": 168 * nobs + 96 * npts + 48 * nc,
+        # ||J u1||^2 of the Cauchy step; J u1 per observation out (16 B/obs)
+        "jv": 168 * nobs + 24 * npts + 48 * nc,
         "resid": 24 * nobs + 24 * npts + 48 * nc,
     }[kernel]
 

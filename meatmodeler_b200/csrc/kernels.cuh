@@ -93,6 +93,10 @@ struct Traits {
     static constexpr int kStages = is_project(MODE) ? 4 : MODE == M_SBUILD ? 3 : 2;   // SBUILD: one CTA per SM
     static constexpr int kThreads = kConsumers + 32 * kStages;
     static constexpr bool kLoadUV = !kLoadJ;
+    // BACKSUB also takes the Gram sums of J [u1 u2] (u2 = the step it completes): J u1 per observation, stored by the
+    // JV1 pass, comes with the tile (16 B/observation instead of a third pass over J)
+    static constexpr bool kLoadAux = MODE == M_BACKSUB;
+    static constexpr int kPtBufs = MODE == M_BACKSUB ? 3 : 2;     // rotating per-point accumulators
     // doubles gathered per camera into shared memory, and the (odd, conflict-free) smem stride
     static constexpr int kCamRows = is_build(MODE) ? 21 : (MODE == M_RESID || MODE == M_RESID_STORE) ? 12
                                   : (MODE == M_RHS || MODE == M_SBUILD) ? 0 : MODE == M_JV2 ? 12 : 6;
@@ -148,6 +152,8 @@ struct ModeArgs {
     double* scal;          // scalar slots                   BUILD (S_COST) JV (S_JV*)
     double* cost;          // trial cost slot                RESID
     const int* done;       // PCG converged flag             MATVEC
+    double* aux_w;         // [tile][2][256] J u1 per observation (written)      JV1
+    const double* aux;     // the same, read with the tile                       BACKSUB
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -171,7 +177,7 @@ __host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts, int
     L.off_meta = o;
     o += align_up((int)sizeof(TileMeta), 128);
     L.off_uv = o;
-    if (T::kLoadUV) o += kUVTileBytes;
+    if (T::kLoadUV || T::kLoadAux) o += kUVTileBytes;
     L.off_camid = o;
     o += align_up(max_cams * 4, 16);
     L.off_camvec = o;
@@ -184,7 +190,7 @@ __host__ __device__ inline SmemLayout smem_layout(int max_cams, int max_pts, int
     L.off_stages = 128;                                   // mbarriers live in the first 128 bytes
     o = L.off_stages + n_stages * L.stage_bytes;
     L.off_pt = o;
-    o += 2 * align_up(max_pts * T::kPtAcc * 8, 16);       // two parities (see the MATVEC / BACKSUB flow)
+    o += T::kPtBufs * align_up(max_pts * T::kPtAcc * 8, 16);   // rotating buffers (see the MATVEC / BACKSUB flow)
     L.off_z = o;
     L.off_buf = o;
     o += T::kStageBufs * T::kStageRows * kBufStride * 8;
@@ -587,7 +593,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
     }
     if (T::kPtAcc) {
         double* s_pt = reinterpret_cast<double*>(smem + L.off_pt);
-        for (int i = tid; i < 2 * align_up(A.max_pts * T::kPtAcc * 8, 16) / 8; i += kThreads) s_pt[i] = 0.0;
+        for (int i = tid; i < T::kPtBufs * align_up(A.max_pts * T::kPtAcc * 8, 16) / 8; i += kThreads) s_pt[i] = 0.0;
     }
     __syncthreads();
 
@@ -681,6 +687,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                 if (T::kLoadJ) bulk_g2s(st + L.off_J, P.J + (int64_t)t * kJRows * kT, kJTileBytes, &full[stage]);
                 bulk_g2s(st + L.off_meta, &A.meta[t], (unsigned)sizeof(TileMeta), &full[stage]);
                 if (T::kLoadUV) bulk_g2s(st + L.off_uv, A.uv + (int64_t)t * 2 * kT, kUVTileBytes, &full[stage]);
+                if (T::kLoadAux) bulk_g2s(st + L.off_uv, P.aux + (int64_t)t * 2 * kT, kUVTileBytes, &full[stage]);
             }
             if (first) {
                 // the first tile's bulk copies are already in flight while its header chain resolves
@@ -717,7 +724,8 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
             }
             __syncwarp();
             if (lane == 0) {
-                const unsigned tx = (T::kLoadJ ? kJTileBytes : 0) + (unsigned)sizeof(TileMeta) + (T::kLoadUV ? kUVTileBytes : 0);
+                const unsigned tx = (T::kLoadJ ? kJTileBytes : 0) + (unsigned)sizeof(TileMeta) +
+                                    ((T::kLoadUV || T::kLoadAux) ? kUVTileBytes : 0);
                 mbar_arrive_expect_tx(&full[stage], tx);
             }
             phase ^= 1;
@@ -1027,6 +1035,11 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                 e[v][1] = valid ? e1 : 0.0;
             }
             acc[0] += e[0][0] * e[0][0] + e[0][1] * e[0][1];
+            if (MODE == M_JV1 && P.aux_w) {
+                double* o = P.aux_w + (int64_t)t * 2 * kT;
+                o[tid] = e[0][0];
+                o[kT + tid] = e[0][1];
+            }
             if (NV == 2) {
                 acc[1] += e[0][0] * e[NV - 1][0] + e[0][1] * e[NV - 1][1];
                 acc[2] += e[NV - 1][0] * e[NV - 1][0] + e[NV - 1][1] * e[NV - 1][1];
@@ -1334,10 +1347,13 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
             double uu0 = 0, uu1 = 0;
             double cvy[6] = {0, 0, 0, 0, 0, 0};   // RHS: the y contribution rides in the first Sd round
             if constexpr (MODE != M_RHS) {
-                // u = Jc xt_c ; w = Jp^T u ; t_p = sum over the point's observations.  The per-point
-                // accumulator has two parities: tile i's sums are read after its barrier while tile
-                // i+1 already accumulates into the other one; each parity is re-zeroed by its readers.
-                double* s_ptp = s_pt + par * (align_up(A.max_pts * T::kPtAcc * 8, 16) / 8);
+                // u = Jc xt_c ; w = Jp^T u ; t_p = sum over the point's observations.  The per-point accumulators
+                // rotate: tile i's sums are read after its barrier while tile i+1 already accumulates into the next
+                // buffer.  MATVEC (two buffers): each is re-zeroed by its readers before the scatter round's barrier.
+                // BACKSUB (three buffers, one barrier per tile): after the barrier of tile i the buffer of tile i+2 is
+                // zeroed — its last readers (tile i-1) are past that barrier, its next writers wait for the one of tile i+1.
+                const int pt_buf = align_up(A.max_pts * T::kPtAcc * 8, 16) / 8;
+                double* s_ptp = s_pt + par * pt_buf;
                 const double* xc = s_cv + lc * T::kCamStride;
                 double u0 = 0, u1 = 0;
 #pragma unroll
@@ -1353,18 +1369,32 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                 tile_point_reduce<3>(w, lp, s_ptp);
                 consumer_sync();
                 if constexpr (MODE == M_BACKSUB) {
-                    // one thread per point: dp = M (g - t)
-                    if (tid < npts) {
-                        const double t0 = s_pb[tid * 3] - s_ptp[tid * 3], t1 = s_pb[tid * 3 + 1] - s_ptp[tid * 3 + 1],
-                                     t2 = s_pb[tid * 3 + 2] - s_ptp[tid * 3 + 2];
-                        s_ptp[tid * 3] = 0.0;
-                        s_ptp[tid * 3 + 1] = 0.0;
-                        s_ptp[tid * 3 + 2] = 0.0;
-                        const double* m = s_pa + tid * 6;
-                        double* o = P.dp + ((int64_t)pt0 + tid) * 3;
-                        o[0] = m[0] * t0 + m[1] * t1 + m[2] * t2;
-                        o[1] = m[1] * t0 + m[3] * t1 + m[4] * t2;
-                        o[2] = m[2] * t0 + m[4] * t1 + m[5] * t2;
+                    // every observation forms its point's step dp = M (g - t) itself; the first slot of a point stores it
+                    const double t0 = s_pb[lps * 3] - s_ptp[lps * 3], t1 = s_pb[lps * 3 + 1] - s_ptp[lps * 3 + 1],
+                                 t2 = s_pb[lps * 3 + 2] - s_ptp[lps * 3 + 2];
+                    const double* m = s_pa + lps * 6;
+                    const double d0 = m[0] * t0 + m[1] * t1 + m[2] * t2;
+                    const double d1 = m[1] * t0 + m[3] * t1 + m[4] * t2;
+                    const double d2 = m[2] * t0 + m[4] * t1 + m[5] * t2;
+                    if (valid && (tid == 0 || mt->slot_pt[tid - 1] != lp)) {
+                        double* o = P.dp + ((int64_t)pt0 + lps) * 3;
+                        o[0] = d0;
+                        o[1] = d1;
+                        o[2] = d2;
+                    }
+                    {
+                        double* s_ptz = s_pt + ((par + 2) % 3) * pt_buf;
+                        for (int i = tid; i < A.max_pts * 3; i += kConsumers) s_ptz[i] = 0.0;
+                    }
+                    if (P.aux) {
+                        // Gram sums of J [u1 u2]: J u2 = Jc xt_c + Jp dp_p (u2 = the unscaled Gauss-Newton step),
+                        // J u1 from the JV1 pass (trf.py:498-499)
+                        const double* s_ju = reinterpret_cast<const double*>(st + L.off_uv);
+                        const double e10 = valid ? s_ju[tid] : 0.0, e11 = valid ? s_ju[kT + tid] : 0.0;
+                        const double e20 = valid ? uu0 + jp[0] * d0 + jp[1] * d1 + jp[2] * d2 : 0.0;
+                        const double e21 = valid ? uu1 + jp[3] * d0 + jp[4] * d1 + jp[5] * d2 : 0.0;
+                        acc[1] += e10 * e20 + e11 * e21;
+                        acc[2] += e20 * e20 + e21 * e21;
                     }
                     z0 = z1 = z2 = 0.0;
                 } else {
@@ -1443,7 +1473,7 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
             }
         }
         // all reads of this stage are done: hand it back to the producer
-        par ^= 1;
+        par = T::kPtBufs == 3 ? (par + 1) % 3 : par ^ 1;
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == nst) {
@@ -1490,6 +1520,12 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
     } else if constexpr (MODE == M_JV2) {
         double* outp[3] = {P.scal + S_JV00, P.scal + S_JV01, P.scal + S_JV11};
         consumer_accumulate<3>(acc, s_red, outp);
+    } else if constexpr (MODE == M_BACKSUB) {
+        if (P.aux) {
+            double c[2] = {acc[1], acc[2]};
+            double* outp[2] = {P.scal + S_JV01, P.scal + S_JV11};
+            consumer_accumulate<2>(c, s_red, outp);
+        }
     }
 }
 

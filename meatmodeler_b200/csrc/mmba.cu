@@ -110,6 +110,7 @@ struct Dev {
     double* uv;
     // linearisation
     double *J, *res;
+    double* ju1;       // [slots][2] J u1 per observation (JV1 -> BACKSUB, subspace Gram sums)
     double *x, *xn, *x0, *camtab, *camtab_n;
     double *U, *Ud, *g, *V, *M, *zg, *dp;
     // n-vectors (camera part first, then the local points)
@@ -341,6 +342,7 @@ void carve(mmba_handle* h, Arena& a) {
     d.uv = dp.uvt;
     d.J = a.take<double>(18 * ns);
     d.res = a.take<double>(2 * ns);
+    d.ju1 = a.take<double>(2 * ns);
     d.x = a.take<double>(nloc);
     d.xn = a.take<double>(nloc);
     d.x0 = a.take<double>(nloc);
@@ -745,22 +747,8 @@ int jv1(mmba_handle* h, const double* v) {
     P.cam0 = v;
     P.ptA = v + 6 * h->Nc;
     P.scal = d.scal;
+    P.aux_w = d.ju1;
     TRY(launch_tile<M_JV1>(h, MMBA_K_JV, P));
-    TRY(allreduce(h, {{d.scal + S_JV00, 3, false}}));
-    return MMBA_OK;
-}
-
-int jv2(mmba_handle* h, const double* va, const double* vb) {
-    Dev& d = h->d;
-    TRY(zero(h, d.scal + S_JV00, 3));
-    ModeArgs P{};
-    P.J = d.J;
-    P.cam0 = va;
-    P.ptA = va + 6 * h->Nc;
-    P.cam1 = vb;
-    P.ptB = vb + 6 * h->Nc;
-    P.scal = d.scal;
-    TRY(launch_tile<M_JV2>(h, MMBA_K_JV, P));
     TRY(allreduce(h, {{d.scal + S_JV00, 3, false}}));
     return MMBA_OK;
 }
@@ -802,6 +790,8 @@ ModeArgs backsub_args(mmba_handle* h) {
     P.ptA = d.M;
     P.ptB = d.g + 6 * h->Nc;
     P.dp = d.dp;
+    P.aux = d.ju1;       // J u1 of the preceding JV1 pass: the pass also leaves (J u1).(J u2), ||J u2||^2 in S_JV01, S_JV11
+    P.scal = d.scal;
     return P;
 }
 
@@ -1070,12 +1060,13 @@ int run_trf(mmba_handle* h, mmba_result* out) {
         // s1 = g_h / ||g_h||, s2 = (gn_h - c1 s1) / n2 with c1 = s1.gn_h, n2^2 = ||gn_h||^2 - c1^2; it is never formed:
         // with u1 = d o g_h (d.tmp) and u2 = d o gn_h (d.gn) the products J_h s1 = J u1 / ||g_h|| and
         // J_h s2 = (J u2 - kappa J u1) / n2, kappa = c1 / ||g_h||, follow from the Gram matrix of J [u1 u2]
-        // (one J pass) and five dot products (one vector pass): one host round trip instead of three.
+        // and five dot products (one vector pass): one host round trip instead of three.  The Gram matrix needs no
+        // pass of its own: ||J u1||^2 is the Cauchy step's (JV1, which also stores J u1 per observation) and the
+        // back-substitution pass, which completes u2, adds (J u1).(J u2) and ||J u2||^2 on its way.
         TRY(zero(h, d.scal + S_DOT0, 10));
         LAUNCH(MMBA_K_VEC, subspace_dots_kernel, std::min(gv, 8 * h->sm_count), 256, 0, d.gh, d.tmp, d.sinv, d.px, d.pxt, d.dp, d.gn,
                ncam, nloc, d.scal, lead);
-        TRY(allreduce(h, {{d.scal + S_DOT0, 5, false}}));
-        TRY(jv2(h, d.tmp, d.gn));
+        TRY(allreduce(h, {{d.scal + S_DOT0, 5, false}, {d.scal + S_JV01, 2, false}}));
         TRY(read_scalars(h));
         const double D0 = h->h_scal[S_DOT0], D1 = h->h_scal[S_DOT1];
         const double U11 = h->h_scal[S_DOT2], U12 = h->h_scal[S_DOT3], U22 = h->h_scal[S_DOT4];
