@@ -435,12 +435,14 @@ int stage_commit(mmba_handle* h, int idx) {
 void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     parallel_ranges((int64_t)bytes, (int64_t)1 << 20, [&](int64_t b, int64_t e, int) {
         std::memcpy(static_cast<char*>(dst) + b, static_cast<const char*>(src) + b, (size_t)(e - b));
-    });
+    }, 16, true);
 }
+// pieces of the generic pageable copies: small enough that the DMA of one piece overlaps the host copy of the next
+constexpr size_t kCopyPiece = (size_t)8 << 20;
 // pageable host -> device; the caller's buffer is fully consumed on return
 int h2d(mmba_handle* h, void* dst, const void* src, size_t bytes) {
-    for (size_t off = 0; off < bytes; off += kStageSlotBytes) {
-        const size_t n = std::min(kStageSlotBytes, bytes - off);
+    for (size_t off = 0; off < bytes; off += kCopyPiece) {
+        const size_t n = std::min(kCopyPiece, bytes - off);
         int idx;
         char* slot;
         TRY(stage_acquire(h, &idx, &slot));
@@ -463,9 +465,9 @@ int d2h(mmba_handle* h, void* dst, const void* src, size_t bytes) {
         --npend;
         return MMBA_OK;
     };
-    for (size_t off = 0; off < bytes; off += kStageSlotBytes) {
+    for (size_t off = 0; off < bytes; off += kCopyPiece) {
         if (npend == kStageSlots - 1) TRY(drain_one());
-        const size_t n = std::min(kStageSlotBytes, bytes - off);
+        const size_t n = std::min(kCopyPiece, bytes - off);
         int idx;
         char* slot;
         TRY(stage_acquire(h, &idx, &slot));
@@ -729,11 +731,12 @@ int scale_and_grad(mmba_handle* h, bool first) {
     auto sg_cam = scale_grad_kernel<6, false>;
     auto sg_pt = scale_grad_kernel<3, true>;
     const int cap = 8 * h->sm_count;      // grid-stride kernels: a few CTAs per SM, one atomic per CTA and result
-    LAUNCH(MMBA_K_VEC, sg_cam, std::min(cap, cdiv(6 * h->Nc, 256)), 256, 0, d.Ud, d.g, d.x, d.sinv, d.gh, (int)first,
+    // (also leaves u1 = d o g_h in d.tmp)
+    LAUNCH(MMBA_K_VEC, sg_cam, std::min(cap, cdiv(6 * h->Nc, 256)), 256, 0, d.Ud, d.g, d.x, d.sinv, d.gh, d.tmp, (int)first,
            6 * h->Nc, d.scal, lead);
     if (h->npl)
         LAUNCH(MMBA_K_VEC, sg_pt, std::min(cap, cdiv(3 * h->npl, 256)), 256, 0, d.V, d.g + 6 * h->Nc, d.x + 6 * h->Nc,
-               d.sinv + 6 * h->Nc, d.gh + 6 * h->Nc, (int)first, 3 * h->npl, d.scal, 1);
+               d.sinv + 6 * h->Nc, d.gh + 6 * h->Nc, d.tmp + 6 * h->Nc, (int)first, 3 * h->npl, d.scal, 1);
     TRY(allreduce(h, {{d.scal + S_GH2, 3, false}, {d.scal + S_GINF, 1, true}}));
     return MMBA_OK;
 }
@@ -1040,7 +1043,7 @@ int run_trf(mmba_handle* h, mmba_result* out) {
         if (status != -1 || nfev >= max_nfev) break;
 
         // Cauchy-step regulariser (trf.py:488-492): a = 0.5 ||J_h g_h||^2, b = -||g_h||^2
-        LAUNCH(MMBA_K_VEC, unscale_kernel, gv, 256, 0, d.gh, d.sinv, 1.0, d.tmp, nloc);
+        // (u1 = d o g_h is in d.tmp: scale_and_grad)
         TRY(jv1(h, d.tmp));
         TRY(read_scalars(h));
         const double qa = 0.5 * h->h_scal[S_JV00], qb = -gh2;
@@ -1210,7 +1213,8 @@ int run_trf_pose(mmba_handle* h, mmba_result* out) {
     auto grad_stats = [&]() -> int {
         // ||g||_inf and ||x||^2 over the camera parameters (the variables of this problem)
         TRY(zero(h, d.scal + S_GH2, 4));
-        LAUNCH(MMBA_K_VEC, sg_cam, std::min(8 * h->sm_count, cdiv(ncam, 256)), 256, 0, d.Ud, d.g, d.x, d.sinv, d.gh, 1, ncam, d.scal, 1);
+        LAUNCH(MMBA_K_VEC, sg_cam, std::min(8 * h->sm_count, cdiv(ncam, 256)), 256, 0, d.Ud, d.g, d.x, d.sinv, d.gh, (double*)nullptr, 1, ncam,
+               d.scal, 1);
         return MMBA_OK;
     };
     TRY(linearise(h, true));
@@ -1539,7 +1543,8 @@ static int upload_observations(mmba_handle* h, int64_t n_cams, int64_t n_points,
         int32_t* s_cam = reinterpret_cast<int32_t*>(slot);
         int32_t* s_pt = s_cam + m;
         double* s_uv = reinterpret_cast<double*>(slot + 8 * (size_t)((m + 1) / 2 * 2));
-        int64_t bad[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+        int64_t bad[16];
+        for (int w = 0; w < 16; ++w) bad[w] = -1;
         parallel_ranges(m, 32768, [&](int64_t i0, int64_t i1, int worker) {
             for (int64_t i = i0; i < i1; ++i) {
                 const int64_t c = cam_idx[b + i], p = pt_idx[b + i];
@@ -1553,8 +1558,8 @@ static int upload_observations(mmba_handle* h, int64_t n_cams, int64_t n_points,
                 }
             }
             std::memcpy(s_uv + 2 * i0, uv + 2 * (b + i0), (size_t)(i1 - i0) * 16);
-        });
-        for (int w = 0; w < 8; ++w)
+        }, 16, true);
+        for (int w = 0; w < 16; ++w)
             if (bad[w] >= 0 && (first_bad < 0 || bad[w] < first_bad)) first_bad = bad[w];
         CU(cudaMemcpyAsync(P.cam + (b - o0), s_cam, (size_t)m * 4, cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(P.pt + (b - o0), s_pt, (size_t)m * 4, cudaMemcpyHostToDevice, h->stream));

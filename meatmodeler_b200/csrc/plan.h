@@ -6,6 +6,9 @@
 #pragma once
 #include <cstdint>
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -56,24 +59,101 @@ struct Plan {
     int64_t n_points_local() const { return pt_end - pt_begin; }
 };
 
-// Static-chunked parallel loop over [0, n) on short-lived std::threads (at most 8): fn(begin, end, worker).
-// No thread pool is left spinning between calls (an OpenMP runtime's idle workers were measured to slow
-// the surrounding CUDA calls by several times).
+// A small pool of SLEEPING workers (condition variable, no spinning: an OpenMP runtime's spinning idle workers were
+// measured to slow the surrounding CUDA calls by several times; spawning std::threads per call cost ~15 us per thread,
+// 2-3 ms per adjustPoints call over the staged copies).  One job at a time: a second concurrent caller (the pattern
+// thread next to the main thread) falls back to short-lived threads.
+class WorkerPool {
+public:
+    static WorkerPool& get() {
+        static WorkerPool pool;
+        return pool;
+    }
+    // fn(w) for w in [0, n): w = 0 on the calling thread, the rest on pool workers; returns false if the pool is busy
+    template <typename F>
+    bool run(int n, F&& fn) {
+        std::unique_lock<std::mutex> owner(busy_, std::try_to_lock);
+        if (!owner.owns_lock()) return false;
+        {
+            std::lock_guard<std::mutex> g(m_);
+            while ((int)threads_.size() < n - 1) {
+                const int id = (int)threads_.size() + 1;
+                threads_.emplace_back([this, id]() { loop(id); });
+            }
+            job_ = [&fn](int w) { fn(w); };
+            job_n_ = n;
+            pending_ = n - 1;
+            ++gen_;
+        }
+        cv_work_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> g(m_);
+        cv_done_.wait(g, [this]() { return pending_ == 0; });
+        job_ = nullptr;
+        return true;
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+            ++gen_;
+        }
+        cv_work_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+
+private:
+    void loop(int id) {
+        uint64_t seen = 0;
+        {
+            std::lock_guard<std::mutex> g(m_);
+            seen = gen_ - 1;      // created inside run(): the current generation is this worker's first job
+        }
+        while (true) {
+            std::function<void(int)> job;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_work_.wait(g, [&]() { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                if (id >= job_n_) continue;
+                job = job_;
+            }
+            job(id);
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0) cv_done_.notify_one();
+            }
+        }
+    }
+    std::mutex busy_, m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> threads_;
+    std::function<void(int)> job_;
+    int job_n_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+// Static-chunked parallel loop over [0, n): fn(begin, end, worker), at most max_workers workers (half of the cores
+// unless all_cores: memory-bound copies scale past that, the plan's compute phases do not).
 template <typename F>
-inline void parallel_ranges(int64_t n, int64_t min_chunk, F&& fn) {
+inline void parallel_ranges(int64_t n, int64_t min_chunk, F&& fn, unsigned max_workers = 8, bool all_cores = false) {
     unsigned hw = std::thread::hardware_concurrency();
-    int64_t workers = std::min<int64_t>(std::max(1u, std::min(8u, hw ? hw / 2 : 1u)), std::max<int64_t>(1, n / std::max<int64_t>(1, min_chunk)));
+    const unsigned want = all_cores ? (hw ? hw : 1u) : (hw ? hw / 2 : 1u);
+    int64_t workers = std::min<int64_t>(std::max(1u, std::min(max_workers, want)), std::max<int64_t>(1, n / std::max<int64_t>(1, min_chunk)));
     if (workers <= 1) {
         fn((int64_t)0, n, 0);
         return;
     }
-    std::vector<std::thread> pool;
     const int64_t step = (n + workers - 1) / workers;
-    for (int64_t w = 0; w < workers; ++w) {
+    auto part = [&](int w) {
         const int64_t b = w * step, e = std::min(n, b + step);
-        if (b >= e) break;
-        pool.emplace_back([&fn, b, e, w]() { fn(b, e, (int)w); });
-    }
+        if (b < e) fn(b, e, w);
+    };
+    if (WorkerPool::get().run((int)workers, part)) return;
+    std::vector<std::thread> pool;
+    for (int64_t w = 0; w < workers; ++w) pool.emplace_back([&part, w]() { part((int)w); });
     for (auto& t : pool) t.join();
 }
 

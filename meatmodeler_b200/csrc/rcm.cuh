@@ -122,6 +122,7 @@ __device__ __forceinline__ double warp_sum_all(double v) {
     return v;
 }
 
+constexpr int kRcmRowStride = 7;         // doubles per 6-entry block row of S in shared memory (lanes 7 apart hit 16 distinct banks)
 constexpr int kRcmPcgThreads = 512;      // 16 warps, one CTA per SM: every phase of an iteration is latency bound, more warps hide it
 
 // shared-memory carve-up of rcm_pcg_kernel (same arithmetic on the host)
@@ -132,7 +133,7 @@ __host__ __device__ inline RcmSmem rcm_smem(int cpc, int nblk_max, int nh_max, i
     RcmSmem L{};
     int o = 0;
     L.off_S = o;
-    if (s_in_smem) o += nblk_max * 36 * 8;
+    if (s_in_smem) o += nblk_max * 6 * kRcmRowStride * 8;   // block rows padded to 7 doubles: conflict-free row products
     L.off_pinv = o;
     o += cpc * 21 * 8;
     L.off_vec = o;
@@ -206,8 +207,8 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
     const int h0 = A.halo_ptr[blockIdx.x], nh = A.halo_ptr[blockIdx.x + 1] - h0;
     if (tid == 0) s_dead = 0;
     if (A.s_in_smem) {
+        // block rows (6 doubles) land kRcmRowStride apart
         const double2* src = reinterpret_cast<const double2*>(A.S + (int64_t)e0 * 36);
-        double2* dst = reinterpret_cast<double2*>(S_s);
         const int n2 = nblk * 18;
         for (int i = tid; i < n2; i += 4 * blockDim.x) {
             double2 v[4];
@@ -215,8 +216,14 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
             for (int u = 0; u < 4; ++u)
                 if (i + u * blockDim.x < n2) v[u] = __ldg(src + i + u * blockDim.x);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i + u * blockDim.x < n2) dst[i + u * blockDim.x] = v[u];
+            for (int u = 0; u < 4; ++u) {
+                const int i2 = i + u * (int)blockDim.x;
+                if (i2 < n2) {
+                    const int row = i2 / 3, k = (i2 - row * 3) * 2;
+                    S_s[row * kRcmRowStride + k] = v[u].x;
+                    S_s[row * kRcmRowStride + k + 1] = v[u].y;
+                }
+            }
         }
     }
     for (int i = tid; i < nblk; i += blockDim.x) lcol_s[i] = A.lcol[e0 + i];
@@ -249,12 +256,24 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
     // Publish: the per-thread partial sums v[0..nv) of the row warps are reduced over the CTA and stored to this
     // CTA's slot (every CTA later adds the published CTA totals in CTA order: identical bits everywhere).
     auto publish = [&](const double (&v)[kRcmSums], int nv, unsigned seq) {
+        // all (up to eight) sums in one butterfly: every step halves the values a lane carries, 9 shuffles instead
+        // of 5 per value; afterwards lane l holds the warp total of value (l >> 2) (bit-reversed over lane bits 4, 3, 2)
+        {
+            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+            double a4[4], a2[2];
 #pragma unroll
-        for (int i = 0; i < kRcmSums; ++i)
-            if (i < nv) {
-                const double w = warp_sum_all(v[i]);
-                if (lane == 0) s_part[warp][i] = w;
+            for (int i = 0; i < 4; ++i) {
+                const double lo = v[i], hi = i + 4 < kRcmSums ? v[i + 4] : 0.0;
+                a4[i] = (h16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, h16 ? lo : hi, 16);
             }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) a2[i] = (h8 ? a4[i + 2] : a4[i]) + __shfl_xor_sync(0xffffffffu, h8 ? a4[i] : a4[i + 2], 8);
+            double a1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+            const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if ((lane & 3) == 0 && idx < kRcmSums) s_part[warp][idx] = a1;
+        }
         row_sync();
         if (tid < nv) {
             double t = 0;
@@ -391,8 +410,9 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                 const int u1 = u0 + blockDim.x;
                 const bool two = u1 < n_units;
                 const int ea = u0 / 6, eb = two ? u1 / 6 : ea;
-                const double* sa = S_rows + (int64_t)ea * 36 + (u0 - ea * 6) * 6;
-                const double* sb = S_rows + (int64_t)eb * 36 + ((two ? u1 : u0) - eb * 6) * 6;
+                const int rs = A.s_in_smem ? kRcmRowStride : 6;
+                const double* sa = S_rows + (int64_t)u0 * rs;
+                const double* sb = S_rows + (int64_t)(two ? u1 : u0) * rs;
                 const double* pa = ph + lcol_s[ea] * 6;
                 const double* pb = ph + lcol_s[eb] * 6;
                 double a0, a1, b0, b1;
@@ -473,7 +493,7 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
             lap(2);
             if (!collect(kRcmSums, seq, wh, tot)) return;
             const double pq = tot[0], rho = tot[5];
-            const double alpha = rho / pq, inv_rho = 1.0 / rho;      // independent divisions
+            const double inv_rho = __drcp_rn(rho), alpha = rho * __drcp_rn(pq);      // independent reciprocals (no division sequence)
             const double rho_n = fma(alpha, fma(alpha, tot[2], -2.0 * tot[1]), rho);
             double rr_n = fma(alpha, fma(alpha, tot[4], -2.0 * tot[3]), tot[6]);
             if (!(pq > 0.0) || !(rho > 0.0) || !isfinite(alpha) || !isfinite(rho_n) || !isfinite(rr_n)) {
@@ -502,7 +522,7 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
                 A.hist[2 * its] = rr_n;
                 A.hist[2 * its + 1] = rho_n;
             }
-            inv_nu2 += rr_n > 0.0 ? 1.0 / rr_n : INFINITY;
+            inv_nu2 += rr_n > 0.0 ? __drcp_rn(rr_n) : INFINITY;
             if (rr_n <= A.rtol2 * b2 || rr_n <= A.atol2f || 1.0 <= inv_nu2 * A.ktol2f * (double)its) {
                 done = 1;
                 break;

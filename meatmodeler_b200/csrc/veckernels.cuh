@@ -46,7 +46,8 @@ __device__ __forceinline__ double sum_partials(const double* __restrict__ part, 
 template <int BS, bool PACKED>
 __global__ void scale_grad_kernel(const double* __restrict__ blk, const double* __restrict__ g,
                                   const double* __restrict__ x, double* __restrict__ sinv, double* __restrict__ gh,
-                                  int first, int64_t n_elem, double* __restrict__ scal, int accumulate) {
+                                  double* __restrict__ u1, int first, int64_t n_elem, double* __restrict__ scal,
+                                  int accumulate) {
     __shared__ double s_red[64];
     __shared__ unsigned long long s_max;
     constexpr int STRIDE = BS * (BS + 1) / 2;
@@ -64,6 +65,7 @@ __global__ void scale_grad_kernel(const double* __restrict__ blk, const double* 
         const double gv = g[e], xv = x[e];
         const double h = gv / si;
         gh[e] = h;
+        if (u1) u1[e] = h / si;      // u1 = d o g_h: the unscaled gradient direction (Cauchy step, subspace basis)
         gabs = fmax(gabs, fabs(gv));
         acc[0] += h * h;
         acc[1] += (xv * si) * (xv * si);
