@@ -31,6 +31,7 @@ FTOL = 1e-4
 XTOL = 1e-8
 GTOL = 1e-8
 VERBOSE = 2          # the reference passes verbose=2: scipy prints its iteration table
+TRACK_LIMIT = 256    # observations of one point (one tile of the streaming layout); longer tracks raise ValueError
 
 #: statistics of the most recent solve (scipy ``OptimizeResult``-like fields)
 last_result = None
@@ -276,9 +277,17 @@ def solve(parameters, camera_matrix, n_frames, n_points, frame_indices, point_in
     success`` plus engine statistics (``log``, ``pcg_iterations``, ``solve_ms``).
     """
     sharded = engine is None and _is_distributed()
-    eng = engine if engine is not None else _engine(
-        camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D,
-        ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=0 if max_nfev is None else int(max_nfev), **options)
+    try:
+        eng = engine if engine is not None else _engine(
+            camera_matrix, n_frames, n_points, frame_indices, point_indices, points_2D,
+            ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=0 if max_nfev is None else int(max_nfev), **options)
+    except _capi.MmbaError as e:
+        if e.code == -5:
+            # documented limit of the engine (DESIGN.md, "Known limits"): a point's observations live in one 256-slot
+            # tile.  The reference has no such limit; the call fails loudly instead of solving a different problem.
+            raise ValueError(f"adjustPoints: {e} - tracks of more than {TRACK_LIMIT} observations are not supported "
+                             "by the B200 engine") from e
+        raise
     try:
         if isinstance(parameters, tuple):
             # (camera parameters, points) as adjustPoints holds them: no packed host copy in either direction; the

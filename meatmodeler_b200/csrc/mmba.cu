@@ -842,6 +842,10 @@ RcmPcgArgs rcm_pcg_args(mmba_handle* h, double f2) {
     A.ktol2f = h->opt.pcg_ktol * h->opt.pcg_ktol * f2;
     A.hist = (d.rcm_hist && h->opt.pcg_maxit <= h->hist_cap) ? d.rcm_hist : nullptr;
     A.phase = (h->opt.profile & 4) ? d.dbg : nullptr;
+    {
+        const char* f = getenv("MMBA_FAULT_PCG_CTA");
+        A.fault_cta = f ? atoi(f) : -1;
+    }
     A.seq0 = h->rcm_seq;
     h->rcm_seq += (unsigned)h->opt.pcg_maxit + 2u;
     return A;

@@ -109,6 +109,7 @@ struct RcmPcgArgs {
     double* hist;               // optional [2 (maxit + 1)]: (||r_k||^2, r_k.z_k) of every iterate, k = 0 first
     long long* phase;           // optional [8]: cycles CTA 0 spent per phase of the iteration loop (diagnostics)
     int n_cams, maxit, cpc, nblk_max, nh_max, s_in_smem;
+    int fault_cta;              // fault injection (tests, MMBA_FAULT_PCG_CTA): this CTA never joins the exchanges; -1 = none
     unsigned seq0;              // sequence numbers of this launch are seq0 + 1 ...: lines of earlier launches never match,
                                 // so neither z nor slots are cleared between launches
     double rtol2;
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__(kRcmPcgThreads, 1) rcm_pcg_kernel(const RcmPcg
     uint16_t* lcol_s = reinterpret_cast<uint16_t*>(rsm + L.off_lcol);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if ((int)blockIdx.x == A.fault_cta) return;    // (tests: a lost CTA must surface as an error code, not as a hang)
     const int a = lane % 6, slot = lane / 6;       // 6-lane groups: five cameras per warp, lanes 30 and 31 idle
     const int c0 = blockIdx.x * A.cpc, ncam = min(A.cpc, A.n_cams - c0);
     const int e0 = A.rowptr[c0], nblk = A.rowptr[c0 + ncam] - e0;

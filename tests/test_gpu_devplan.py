@@ -116,3 +116,15 @@ def test_track_longer_than_a_tile_is_a_documented_error():
         with pytest.raises(_capi.MmbaError) as e:
             eng.set_problem(nc, 2, np.eye(3), fi, pi, uv)
         assert e.value.code == -5 and "point 0" in str(e.value)
+
+
+def test_drop_in_reports_the_track_limit_as_value_error():
+    """adjustPoints on a 257-observation track: a ValueError that names the limit (the reference has none; the
+    drop-in fails loudly rather than solving a different problem)."""
+    from meatmodeler_b200 import bundleAdjuster as mm
+    nc = 300
+    fi = np.concatenate((np.arange(257) % nc, [0, 1]))
+    pi = np.concatenate((np.zeros(257, dtype=np.int64), [1, 1]))
+    ext = np.tile(np.eye(4), (nc, 1, 1))
+    with pytest.raises(ValueError, match="256 observations"):
+        mm.adjustPoints(ext, np.eye(3), np.ones((2, 3)), np.zeros((259, 2)), fi, pi)

@@ -137,3 +137,21 @@ def test_auto_mode_picks_explicit_for_video_like_visibility_only():
         with pytest.raises(_capi.MmbaError) as e:
             eng.reduced_system(problem_x0(dense), np.ones(problem_x0(dense).size), 1e-3)
         assert e.value.code == -3
+
+
+def test_lost_pcg_cta_is_an_error_code_not_a_hang(monkeypatch):
+    """The one-kernel PCG exchanges through spin-polled lines; a CTA that never publishes (fault injection) makes
+    the others give up after their spin limit (~1 s): the solve returns MMBA_ERR_CUDA, and the handle stays usable."""
+    prob = synth.make_problem(40, 3000, 24000, seed=21, hard=True)
+    x0 = problem_x0(prob)
+    ext, K, pts, uv, fi, pi = prob.args()
+    with _capi.Engine(schur_mode=_capi.SCHUR_EXPLICIT) as eng:
+        eng.set_problem(len(ext), len(pts), K, fi, pi, uv)
+        if eng.rcm_pattern()["n_ctas"] < 2:
+            pytest.skip("needs at least two PCG CTAs")
+        monkeypatch.setenv("MMBA_FAULT_PCG_CTA", "1")
+        with pytest.raises(_capi.MmbaError, match="timed out"):
+            eng.solve(x0)
+        monkeypatch.delenv("MMBA_FAULT_PCG_CTA")
+        x, r, _ = eng.solve(x0)
+        assert r.status > 0 and np.isfinite(r.cost)
