@@ -1,7 +1,7 @@
 // Device code of libmmba.so — float64 CUDA kernels for sm_100a (B200): the observation-streaming
 // kernels.  (Small-vector kernels: veckernels.cuh.)
 //
-// Data layout in HBM, per shard (built by plan.cpp)
+// Data layout in HBM, per shard (built on the device by devplan.cu; plan.cpp is the host statement of the same plan)
 //   * observations are reordered into point-aligned TILES of kT = 256 slots; a point's observations
 //     are contiguous and never straddle a tile.  Everything per-observation is tile-major, so one
 //     tile is one contiguous block that a single TMA bulk copy moves:
@@ -9,23 +9,23 @@
 //                                                  w0 w1 w2 t0 t1 t2), rows 12..17 = 2x3 point block
 //       uv   [tile][2][256]  f64    4 096 B/tile   observed pixel
 //       res  [tile][2][256]  f64                   residual (du, dv)
-//       meta [tile] TileMeta        2 064 B/tile   header + 4 x u16 per slot: local camera slot, local
-//                                                  point, and the tile's camera-sorted order (source
-//                                                  slot, key) that drives the warp-shuffle scatter
+//       ju1  [tile][2][256]  f64                   J u1 of the JV1 pass (read back by BACKSUB for the subspace Gram sums)
+//       meta [tile] TileMeta        2 592 B/tile   header + 5 x u16 per slot: local camera slot, local point, the
+//                                                  tile's camera-sorted order and its camera runs (start, camera)
 //       tile_cams [tile][cam_stride] i32           global camera ids of the tile's local camera slots
 //   * cameras: camtab[Nc][24] = R (9) | t (3) | Q (9) from cam_prep_kernel (rotate's trigonometry
 //     hoisted from per-observation to per-camera); camera vectors are [Nc][6].
-//   * points (internal order, tile-contiguous): x_p[3], V[6], g_p[3], M[6] (damped inverse), ...
+//   * points (internal order, tile-contiguous): x_p[3], V[6], g_p[3], M[6] (damped inverse), zg[3] = M g_p
 //
 // Kernel structure: ONE persistent, warp-specialised kernel template (tile_kernel<MODE>).  Each CTA
-// owns a contiguous range of tiles and runs a kStages-deep mbarrier pipeline:
-//   * producer warp (warp 8): cp.async.bulk (TMA bulk copy, SASS UBLKCP) of the tile's J block and
-//     metadata into shared memory, plus the gather of the cameras the tile touches (rotation rows or
-//     PCG vector entries) and of the tile's point payloads, completing on the stage's "full" barrier;
+// owns a contiguous range of tiles and runs a 2..4-stage mbarrier pipeline:
+//   * producer warps (one per stage): cp.async.bulk (TMA bulk copy, SASS UBLKCP) of the tile's J block,
+//     metadata (and uv / ju1) into shared memory, plus the gather of the cameras the tile touches (rotation rows
+//     or vector entries) and of the tile's point payloads, completing on the stage's "full" barrier;
 //   * 8 consumer warps: one thread per observation slot; per-point sums by warp-shuffle segmented
-//     reduction over the contiguous point runs, per-camera sums by re-reading the staged values in
-//     the tile's camera-sorted order, reducing runs with warp shuffles and issuing one f64 RED per
-//     (run, component).
+//     reduction over the contiguous point runs, per-camera sums by staging the values in shared memory and
+//     summing the tile's precomputed camera runs, one f64 RED per (run, component).  The S-build (SBUILD)
+//     instead accumulates whole 6x6 blocks of the reduced camera matrix in registers across tiles.
 // Every pass is therefore a streaming pass at 24..184 B/observation with all latency (tile header ->
 // camera list -> camera rows) hidden behind the previous tile's arithmetic.
 //
@@ -1133,12 +1133,11 @@ __global__ void __launch_bounds__(Traits<MODE>::kThreads, Traits<MODE>::kMinBloc
                 consumer_sync();
                 lap(3);
                 const int flags = s_flag[0], n_missing = s_flag[1];
-                // Re-pack: the second tile in a row that uses at most 3/4 of the run's pairs restarts the run on its own
-                // cameras (tighter capacity -> more point slices, no idle pair lanes); a single such tile does not.
-                const bool repack = false;      // measured: the extra flushes cost more than the tighter lanes gain (pairs are latency-bound)
-                if ((flags & 1) || repack) {
+                // (Restarting the run on a subset tile's own cameras — tighter capacity, no idle pair lanes — was measured:
+                // the extra flushes cost more than the lanes gain, profiles/r2_sbuild_phases_repack_experiment.log.)
+                if (flags & 1) {
                     const int new_n = run_n + n_missing;
-                    if (!repack && run_n > 0 && !(flags & 2) && new_n <= 31 && run_pairs(new_n) <= run_P) {
+                    if (run_n > 0 && !(flags & 2) && new_n <= 31 && run_pairs(new_n) <= run_P) {
                         // extend: the missing cameras are the last n_missing of the tile's (ascending) list
                         if (tid >= ncams - n_missing && tid < ncams) {
                             const int pos = run_n + (tid - (ncams - n_missing));

@@ -1079,17 +1079,18 @@ int run_trf(mmba_handle* h, mmba_result* out) {
         const double U11 = h->h_scal[S_DOT2], U12 = h->h_scal[S_DOT3], U22 = h->h_scal[S_DOT4];
         const double G11 = h->h_scal[S_JV00], G12 = h->h_scal[S_JV01], G22 = h->h_scal[S_JV11];
         const double inv_gh = gh_norm > 0 ? 1.0 / gh_norm : 0.0;
-        const double kappa = D0 * inv_gh * inv_gh;                  // c1 / ||g_h||
         const double n2sq = D1 - D0 * D0 * inv_gh * inv_gh;         // ||s2||^2 before normalisation
-        // second basis vector is s2 / n2; degenerate (gn_h parallel to g_h up to rounding, or not finite) -> 1-D
-        // problem along s1
-        const bool two_d = std::isfinite(n2sq) && std::isfinite(D1) && n2sq > 1e-24 * D1 && D1 > 0.0;
+        // second basis vector is s2 / n2; degenerate (gn_h parallel to g_h up to rounding, or not finite after a PCG
+        // breakdown) -> 1-D problem along s1: every term that carries gn_h is switched off, not multiplied by zero
+        const bool two_d = std::isfinite(n2sq) && std::isfinite(D0) && std::isfinite(D1) && n2sq > 1e-24 * D1 && D1 > 0.0 &&
+                           std::isfinite(G12) && std::isfinite(G22) && std::isfinite(U12) && std::isfinite(U22);
+        const double kappa = two_d ? D0 * inv_gh * inv_gh : 0.0;    // c1 / ||g_h||
         const double i2 = two_d ? 1.0 / std::sqrt(n2sq) : 0.0;
-        double B[3] = {G11 * inv_gh * inv_gh, (G12 - kappa * G11) * inv_gh * i2,
-                       (G22 - 2.0 * kappa * G12 + kappa * kappa * G11) * i2 * i2};
+        double B[3] = {G11 * inv_gh * inv_gh, two_d ? (G12 - kappa * G11) * inv_gh * i2 : 0.0,
+                       two_d ? (G22 - 2.0 * kappa * G12 + kappa * kappa * G11) * i2 * i2 : 1.0};
         double gS[2] = {gh_norm, 0.0};                              // S^T g_h = (||g_h||, 0)
-        const double vv00 = U11 * inv_gh * inv_gh, vv01 = (U12 - kappa * U11) * inv_gh * i2,
-                     vv11 = (U22 - 2.0 * kappa * U12 + kappa * kappa * U11) * i2 * i2;
+        const double vv00 = U11 * inv_gh * inv_gh, vv01 = two_d ? (U12 - kappa * U11) * inv_gh * i2 : 0.0,
+                     vv11 = two_d ? (U22 - 2.0 * kappa * U12 + kappa * kappa * U11) * i2 * i2 : 0.0;
         if (i2 == 0.0) {
             B[1] = 0.0;
             B[2] = 1.0;
