@@ -35,6 +35,18 @@ def golden_mid():
     return dict(np.load(os.path.join(GOLDEN, "mid.npz")))
 
 
+@pytest.fixture(scope="session")
+def golden_chain_tight():
+    """300-camera chain, the unmodified reference with converged inner solves (tests/golden/make_golden_tight.py)."""
+    return dict(np.load(os.path.join(GOLDEN, "chain_tight.npz")))
+
+
+def chain_problem():
+    """The problem of chain_tight.npz: 300 ring cameras, windows of 5 neighbours per point (a long camera chain)."""
+    from meatmodeler_b200 import synth
+    return synth.make_problem(300, 6000, 30000, seed=33, hard=True)
+
+
 def problem_x0(prob):
     """Parameter vector the reference packs (bundleAdjuster.py:172-176) for a synth.Problem."""
     from meatmodeler_b200 import bundleAdjuster as mm

@@ -257,6 +257,33 @@ def test_full_size_solve_vs_reference_golden(name):
         assert rms == pytest.approx(float(g["ref_rms"]), rel=tol)
 
 
+def test_long_chain_with_converged_inner_solves_vs_reference_golden(golden_chain_tight):
+    """The north-star bar on a long camera chain, where it is well defined: the unmodified reference with LSMR run to
+    convergence (1e-11 instead of scipy's 1e-6; tests/golden/make_golden_tight.py) against the engine with its PCG run
+    to convergence (threshold rules off).  Same nfev / status, final cost and RMS within 1e-6 relative; intermediate
+    costs within 1e-4 (finite-difference vs analytic Jacobian on systems whose regulariser falls to 1e-12).  At their
+    default tolerances both codes stop their inner solves early: the reference's own default-tolerance result ends
+    1.0e-4 above this converged cost, the engine's default result must end no further away than that."""
+    from conftest import chain_problem
+    g = golden_chain_tight
+    prob = chain_problem()
+    assert abs(problem_x0(prob).sum() - float(g["x0_checksum"])) < 1e-9
+    res = _solve(prob, pcg_rtol=1e-9, pcg_atol=0.0, pcg_ktol=0.0, pcg_maxit=20000)
+    costs = np.array([row["cost"] for row in res.log])
+    ref = g["ref_costs"]
+    assert res.nfev == int(g["ref_nfev"]) and res.status == int(g["ref_status"]) and len(costs) == len(ref)
+    assert max(row["pcg_iterations"] for row in res.log) < 20000        # every inner solve converged
+    np.testing.assert_allclose(costs, ref, rtol=1e-4)
+    assert res.cost == pytest.approx(float(g["ref_cost"]), rel=1e-6)
+    rms = np.sqrt(np.mean(np.sum(res.fun.reshape(-1, 2) ** 2, axis=1)))
+    assert rms == pytest.approx(float(g["ref_rms"]), rel=1e-6)
+    # default rules (LSMR-like early stop): same nfev as the reference's default run, final cost between the converged
+    # value and the reference's default-tolerance value
+    dflt = _solve(prob)
+    assert dflt.nfev == int(g["ref_default_nfev"]) and dflt.status == int(g["ref_default_status"])
+    assert float(g["ref_cost"]) * (1 - 1e-9) <= dflt.cost <= float(g["ref_default_cost"]) * (1 + 1e-6)
+
+
 def test_solve_vs_oracle_trf(case):
     """Same algorithm on both sides (analytic J, Schur PCG, TRF rules): per-iteration costs agree
     to 1e-9, i.e. far inside the 1e-6 bar; the reference comparison is the golden test above."""
