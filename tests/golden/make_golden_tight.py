@@ -11,7 +11,8 @@ the north-star bar.  The default-tolerance trajectory of the same problem rides 
 Run in the build container only (needs /root/reference), single-threaded BLAS (the sparse products are serial anyway):
     OMP_NUM_THREADS=1 OPENBLAS_NUM_THREADS=1 python tests/golden/make_golden_tight.py [chain] [c4s]
   chain: 300 cameras on the ring, 6 000 points, 30 000 observations (windows of 5 neighbours) — about 2 minutes
-  c4s  : BASELINE configs[3] scaled to 5 % of its points, all 1 778 cameras kept (250 k observations) — about an hour
+  chain1k: 1 000 cameras, 20 000 points, 100 000 observations (windows of 5 neighbours), LSMR at 1e-10
+  c4s  : BASELINE configs[3] scaled to 5 % of its points, all 1 778 cameras kept (250 k observations) — hours
 Writes tests/golden/<name>_tight.npz.  Nothing at test time reads /root/reference.
 """
 import os
@@ -33,8 +34,10 @@ TOL = 1e-11
 
 PROBLEMS = {
     "chain": lambda: synth.make_problem(300, 6000, 30000, seed=33, hard=True),
+    "chain1k": lambda: synth.make_problem(1000, 20000, 100000, seed=34, hard=True),
     "c4s": lambda: synth.make_config("C4", hard=True, scale=0.05),
 }
+TOLS = {"chain1k": 1e-10}
 
 
 def trajectory(prob, tol):
@@ -70,17 +73,18 @@ def main(names):
         prob = PROBLEMS[name]()
         uv = prob.args()[3]
         t0 = time.perf_counter()
-        x0, res, costs, its, rms = trajectory(prob, TOL)
+        tol = TOLS.get(name, TOL)
+        x0, res, costs, its, rms = trajectory(prob, tol)
         wall = time.perf_counter() - t0
         _, res_d, costs_d, its_d, rms_d = trajectory(prob, None)
         np.savez_compressed(
             os.path.join(HERE, name + "_tight.npz"), sizes=np.array(prob.sizes), x0_checksum=float(np.sum(x0)),
-            uv_checksum=float(np.sum(uv)), lsmr_tol=TOL, ref_costs=costs, ref_cost=res.cost, ref_nfev=res.nfev,
+            uv_checksum=float(np.sum(uv)), lsmr_tol=tol, ref_costs=costs, ref_cost=res.cost, ref_nfev=res.nfev,
             ref_status=res.status, ref_rms=rms, ref_lsmr_its=its, ref_wall_s=wall,
             ref_default_costs=costs_d, ref_default_cost=res_d.cost, ref_default_nfev=res_d.nfev,
             ref_default_status=res_d.status, ref_default_rms=rms_d, ref_default_lsmr_its=its_d,
             versions=np.array([np.__version__, scipy.__version__]))
-        print(name, prob.sizes, f"tol {TOL:g}: nfev {res.nfev} status {res.status} cost {res.cost:.9f} lsmr {its.tolist()} "
+        print(name, prob.sizes, f"tol {tol:g}: nfev {res.nfev} status {res.status} cost {res.cost:.9f} lsmr {its.tolist()} "
               f"{wall:.0f} s | default: nfev {res_d.nfev} cost {res_d.cost:.9f} lsmr {its_d.tolist()}", flush=True)
 
 

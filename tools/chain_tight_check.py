@@ -13,6 +13,7 @@ from meatmodeler_b200 import bundleAdjuster as mm
 
 PROBLEMS = {
     "chain": lambda: synth.make_problem(300, 6000, 30000, seed=33, hard=True),
+    "chain1k": lambda: synth.make_problem(1000, 20000, 100000, seed=34, hard=True),
     "c4s": lambda: synth.make_config("C4", hard=True, scale=0.05),
 }
 TIGHT = dict(pcg_atol=0.0, pcg_ktol=0.0, pcg_maxit=20000)
