@@ -35,16 +35,27 @@ def golden_mid():
     return dict(np.load(os.path.join(GOLDEN, "mid.npz")))
 
 
+# Long camera chains with the reference's inner solves converged (tests/golden/make_golden_tight.py): name ->
+# (problem, PCG iteration cap of the converged engine solve)
+CHAIN_PROBLEMS = {
+    "chain": ((300, 6000, 30000, 33), 20000),        # 300 ring cameras, windows of 5 neighbours per point
+    "chain1k": ((1000, 20000, 100000, 34), 100000),  # 1 000 cameras: inner solves of up to 28 k LSMR / 23 k PCG iterations
+}
+
+
+def chain_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + "_tight.npz")))
+
+
 @pytest.fixture(scope="session")
 def golden_chain_tight():
-    """300-camera chain, the unmodified reference with converged inner solves (tests/golden/make_golden_tight.py)."""
-    return dict(np.load(os.path.join(GOLDEN, "chain_tight.npz")))
+    return chain_golden("chain")
 
 
-def chain_problem():
-    """The problem of chain_tight.npz: 300 ring cameras, windows of 5 neighbours per point (a long camera chain)."""
+def chain_problem(name="chain"):
     from meatmodeler_b200 import synth
-    return synth.make_problem(300, 6000, 30000, seed=33, hard=True)
+    nc, npts, nobs, seed = CHAIN_PROBLEMS[name][0]
+    return synth.make_problem(nc, npts, nobs, seed=seed, hard=True)
 
 
 def problem_x0(prob):

@@ -257,23 +257,27 @@ def test_full_size_solve_vs_reference_golden(name):
         assert rms == pytest.approx(float(g["ref_rms"]), rel=tol)
 
 
-def test_long_chain_with_converged_inner_solves_vs_reference_golden(golden_chain_tight):
-    """The north-star bar on a long camera chain, where it is well defined: the unmodified reference with LSMR run to
-    convergence (1e-11 instead of scipy's 1e-6; tests/golden/make_golden_tight.py) against the engine with its PCG run
-    to convergence (threshold rules off).  Same nfev / status, final cost and RMS within 1e-6 relative; intermediate
-    costs within 1e-4 (finite-difference vs analytic Jacobian on systems whose regulariser falls to 1e-12).  At their
-    default tolerances both codes stop their inner solves early: the reference's own default-tolerance result ends
-    1.0e-4 above this converged cost, the engine's default result must end no further away than that."""
-    from conftest import chain_problem
-    g = golden_chain_tight
-    prob = chain_problem()
+@pytest.mark.parametrize("name", ["chain", "chain1k"])
+def test_long_chain_with_converged_inner_solves_vs_reference_golden(name):
+    """The north-star bar on long camera chains, where it is well defined: the unmodified reference with LSMR run to
+    convergence (1e-11 / 1e-10 instead of scipy's 1e-6; tests/golden/make_golden_tight.py) against the engine with its
+    PCG run to convergence (threshold rules off).  Same nfev / status, final cost and RMS within 1e-6 relative
+    (measured on B200: 1e-11 on the 300-camera chain, 1.3e-7 on the 1 000-camera one, where LSMR at 1e-10 is the
+    looser of the two solves); intermediate costs within 1e-4 / 2e-4 (finite-difference vs analytic Jacobian on systems
+    whose regulariser falls to 1e-12; measured 1.4e-5 / 5.0e-5).  At their default tolerances both codes stop their
+    inner solves early: the reference's own default-tolerance result ends 1.0e-4 / 3.8e-4 above this converged cost,
+    the engine's default result (same nfev as the reference's default run) 3.3e-5 / 6.1e-5 above."""
+    from conftest import CHAIN_PROBLEMS, chain_golden, chain_problem
+    g = chain_golden(name)
+    prob = chain_problem(name)
+    maxit = CHAIN_PROBLEMS[name][1]
     assert abs(problem_x0(prob).sum() - float(g["x0_checksum"])) < 1e-9
-    res = _solve(prob, pcg_rtol=1e-9, pcg_atol=0.0, pcg_ktol=0.0, pcg_maxit=20000)
+    res = _solve(prob, pcg_rtol=1e-9, pcg_atol=0.0, pcg_ktol=0.0, pcg_maxit=maxit)
     costs = np.array([row["cost"] for row in res.log])
     ref = g["ref_costs"]
     assert res.nfev == int(g["ref_nfev"]) and res.status == int(g["ref_status"]) and len(costs) == len(ref)
-    assert max(row["pcg_iterations"] for row in res.log) < 20000        # every inner solve converged
-    np.testing.assert_allclose(costs, ref, rtol=1e-4)
+    assert max(row["pcg_iterations"] for row in res.log) < maxit        # every inner solve converged
+    np.testing.assert_allclose(costs, ref, rtol=1e-4 if name == "chain" else 2e-4)
     assert res.cost == pytest.approx(float(g["ref_cost"]), rel=1e-6)
     rms = np.sqrt(np.mean(np.sum(res.fun.reshape(-1, 2) ** 2, axis=1)))
     assert rms == pytest.approx(float(g["ref_rms"]), rel=1e-6)
@@ -281,7 +285,7 @@ def test_long_chain_with_converged_inner_solves_vs_reference_golden(golden_chain
     # value and the reference's default-tolerance value
     dflt = _solve(prob)
     assert dflt.nfev == int(g["ref_default_nfev"]) and dflt.status == int(g["ref_default_status"])
-    assert float(g["ref_cost"]) * (1 - 1e-9) <= dflt.cost <= float(g["ref_default_cost"]) * (1 + 1e-6)
+    assert float(g["ref_cost"]) * (1 - 1e-6) <= dflt.cost <= float(g["ref_default_cost"]) * (1 + 1e-6)
 
 
 def test_solve_vs_oracle_trf(case):

@@ -16,7 +16,7 @@ PROBLEMS = {
     "chain1k": lambda: synth.make_problem(1000, 20000, 100000, seed=34, hard=True),
     "c4s": lambda: synth.make_config("C4", hard=True, scale=0.05),
 }
-TIGHT = dict(pcg_atol=0.0, pcg_ktol=0.0, pcg_maxit=20000)
+TIGHT = dict(pcg_atol=0.0, pcg_ktol=0.0, pcg_maxit=100000)
 SETTINGS = [
     ("default rules", {}),
     ("converged, rtol 1e-8", dict(TIGHT, pcg_rtol=1e-8)),
