@@ -37,7 +37,7 @@ PROBLEMS = {
     "chain1k": lambda: synth.make_problem(1000, 20000, 100000, seed=34, hard=True),
     "c4s": lambda: synth.make_config("C4", hard=True, scale=0.05),
 }
-TOLS = {"chain1k": 1e-10}
+TOLS = {"chain1k": 1e-10, "c4s": 1e-10}
 
 
 def trajectory(prob, tol):
