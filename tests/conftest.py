@@ -40,6 +40,7 @@ def golden_mid():
 CHAIN_PROBLEMS = {
     "chain": ((300, 6000, 30000, 33), 20000),        # 300 ring cameras, windows of 5 neighbours per point
     "chain1k": ((1000, 20000, 100000, 34), 100000),  # 1 000 cameras: inner solves of up to 28 k LSMR / 23 k PCG iterations
+    "c4s": ("C4", 400000),                           # BASELINE configs[3] at 5 % of its points, all 1 778 cameras kept
 }
 
 
@@ -54,7 +55,10 @@ def golden_chain_tight():
 
 def chain_problem(name="chain"):
     from meatmodeler_b200 import synth
-    nc, npts, nobs, seed = CHAIN_PROBLEMS[name][0]
+    spec = CHAIN_PROBLEMS[name][0]
+    if isinstance(spec, str):
+        return synth.make_config(spec, hard=True, scale=0.05)
+    nc, npts, nobs, seed = spec
     return synth.make_problem(nc, npts, nobs, seed=seed, hard=True)
 
 

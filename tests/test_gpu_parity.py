@@ -257,7 +257,7 @@ def test_full_size_solve_vs_reference_golden(name):
         assert rms == pytest.approx(float(g["ref_rms"]), rel=tol)
 
 
-@pytest.mark.parametrize("name", ["chain", "chain1k"])
+@pytest.mark.parametrize("name", ["chain", "chain1k", "c4s"])
 def test_long_chain_with_converged_inner_solves_vs_reference_golden(name):
     """The north-star bar on long camera chains, where it is well defined: the unmodified reference with LSMR run to
     convergence (1e-11 / 1e-10 instead of scipy's 1e-6; tests/golden/make_golden_tight.py) against the engine with its
@@ -267,7 +267,10 @@ def test_long_chain_with_converged_inner_solves_vs_reference_golden(name):
     whose regulariser falls to 1e-12; measured 1.4e-5 / 5.0e-5).  At their default tolerances both codes stop their
     inner solves early: the reference's own default-tolerance result ends 1.0e-4 / 3.8e-4 above this converged cost,
     the engine's default result (same nfev as the reference's default run) 3.3e-5 / 6.1e-5 above."""
-    from conftest import CHAIN_PROBLEMS, chain_golden, chain_problem
+    import os
+    from conftest import CHAIN_PROBLEMS, GOLDEN, chain_golden, chain_problem
+    if not os.path.exists(os.path.join(GOLDEN, name + "_tight.npz")):
+        pytest.skip(f"{name}_tight.npz not generated (hours of CPU: tests/golden/make_golden_tight.py)")
     g = chain_golden(name)
     prob = chain_problem(name)
     maxit = CHAIN_PROBLEMS[name][1]
@@ -277,7 +280,7 @@ def test_long_chain_with_converged_inner_solves_vs_reference_golden(name):
     ref = g["ref_costs"]
     assert res.nfev == int(g["ref_nfev"]) and res.status == int(g["ref_status"]) and len(costs) == len(ref)
     assert max(row["pcg_iterations"] for row in res.log) < maxit        # every inner solve converged
-    np.testing.assert_allclose(costs, ref, rtol=1e-4 if name == "chain" else 2e-4)
+    np.testing.assert_allclose(costs, ref, rtol={"chain": 1e-4, "chain1k": 2e-4}.get(name, 5e-4))
     assert res.cost == pytest.approx(float(g["ref_cost"]), rel=1e-6)
     rms = np.sqrt(np.mean(np.sum(res.fun.reshape(-1, 2) ** 2, axis=1)))
     assert rms == pytest.approx(float(g["ref_rms"]), rel=1e-6)

@@ -1,5 +1,5 @@
 """Engine vs the unmodified reference with CONVERGED inner solves on long camera chains (prints, no assertions).
-    python tools/chain_tight_check.py [chain] [c4s]
+    python tools/chain_tight_check.py [--quick] [chain] [chain1k] [c4s]      (--quick: default rules + one converged setting)
 Goldens: tests/golden/<name>_tight.npz (make_golden_tight.py: LSMR at 1e-11 instead of scipy's 1e-6).  For every
 setting of the engine's inner solve: nfev / status, final cost and its relative deviation from the converged reference,
 largest relative deviation along the trajectory, PCG iterations per inner solve, device time."""
@@ -25,7 +25,10 @@ SETTINGS = [
     ("converged, rtol 1e-9, implicit Schur product", dict(TIGHT, pcg_rtol=1e-9, schur_mode=_capi.SCHUR_IMPLICIT)),
 ]
 
-for name in sys.argv[1:] or ["chain"]:
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+if "--quick" in sys.argv:
+    SETTINGS = [SETTINGS[0], ("converged, rtol 1e-9", dict(TIGHT, pcg_rtol=1e-9, pcg_maxit=400000))]
+for name in args or ["chain"]:
     path = os.path.join(ROOT, "tests", "golden", name + "_tight.npz")
     if not os.path.exists(path):
         print(name, "no golden", path)
