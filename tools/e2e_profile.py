@@ -4,7 +4,7 @@ import contextlib, io, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from meatmodeler_b200 import _capi, synth
+from meatmodeler_b200 import synth
 from meatmodeler_b200 import bundleAdjuster as mm
 
 for name in sys.argv[1:] or ["C2"]:

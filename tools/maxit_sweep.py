@@ -1,4 +1,4 @@
-import os, sys
+import sys
 import numpy as np
 sys.path.insert(0, "/root/repo")
 from meatmodeler_b200 import synth

@@ -1,6 +1,6 @@
 """GPU: residual history of the reduced-system PCG on the full-size configs and a sweep of the LSMR-like
 k-dependent stop (pcg_ktol) against the reference's golden trajectories.  Writes gpurun_out/pcg_hist_<cfg>.npz."""
-import os, sys, time
+import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
