@@ -182,6 +182,27 @@ def test_plan_edge_cases():
     assert e.value.code == -5
 
 
+def test_plan_fuzz_ragged_duplicates_and_full_tiles():
+    """Seeded random problems across the awkward shapes: duplicate (camera, point) pairs, unobserved points and
+    cameras, tracks of exactly one tile (256 observations, the documented limit), single-camera problems, more ranks
+    than tiles, unsorted observation order."""
+    rng = np.random.default_rng(11)
+    for case in range(40):
+        nc = int(rng.integers(1, 40))
+        npts = int(rng.integers(1, 120))
+        lens = rng.integers(0, 12, size=npts)
+        if case % 5 == 0:
+            lens[rng.integers(npts)] = 256          # a track that fills a tile exactly
+        if case % 7 == 0:
+            lens[rng.integers(npts)] = 255
+        if lens.sum() == 0:
+            lens[0] = 1
+        pi = np.repeat(np.arange(npts, dtype=np.int64), lens)
+        fi = rng.integers(0, nc, size=len(pi)).astype(np.int64)      # duplicates of (camera, point) are allowed
+        order = rng.permutation(len(pi))
+        _check_plan(nc, npts, fi[order], pi[order], int(rng.integers(1, 5)))
+
+
 # ---- block pattern of the reduced camera matrix ---------------------------------------------------
 @pytest.mark.parametrize("windowed", [True, False])
 def test_rcm_pattern_is_the_covisibility_graph(windowed):
@@ -201,6 +222,29 @@ def test_rcm_pattern_is_the_covisibility_graph(windowed):
     assert nnz_full == cov.sum()
     L = np.bincount(pi, minlength=npts)
     assert pairs == int((L * (L + 1) // 2).sum())
+
+
+def test_rcm_pattern_fuzz_against_the_covisibility_graph():
+    """Seeded random problems (duplicates, unobserved cameras and points, single-camera and single-point shapes):
+    the block pattern is the upper triangle of the co-visibility graph plus every diagonal block."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        nc, npts = int(rng.integers(1, 30)), int(rng.integers(1, 80))
+        nobs = int(rng.integers(1, 400))
+        fi = rng.integers(0, nc, size=nobs).astype(np.int64)
+        pi = rng.integers(0, npts, size=nobs).astype(np.int64)
+        rowptr, cols, nnz_full, pairs = _capi.host_rcm_pattern(nc, npts, fi, pi)
+        vis = sp.csr_matrix((np.ones(nobs), (fi, pi)), shape=(nc, npts))
+        cov = ((vis @ vis.T).toarray() > 0) | np.eye(nc, dtype=bool)
+        dense = np.zeros((nc, nc), dtype=bool)
+        for i in range(nc):
+            c = cols[rowptr[i]:rowptr[i + 1]]
+            assert c[0] == i and np.all(np.diff(c) > 0)
+            dense[i, c] = True
+        assert np.array_equal(dense, np.triu(cov)) and nnz_full == cov.sum()
+        L = np.bincount(pi, minlength=npts)
+        assert pairs == int((L * (L + 1) // 2).sum())
 
 
 def test_rcm_pattern_unobserved_camera_keeps_its_diagonal():
