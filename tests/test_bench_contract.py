@@ -23,6 +23,14 @@ def test_reference_arm_prints_the_contract_line():
     assert "workload" in line["config"]
 
 
+def test_reference_arm_runs_on_rank_zero_only():
+    """Under torchrun (N > 1) rank 0 alone runs and prints the reference arm; the other ranks exit 0 without work."""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == "", (out.stdout, out.stderr[-2000:])
+
+
 def test_engine_arm_needs_a_gpu():
     import torch
     if torch.cuda.is_available():
